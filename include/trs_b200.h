@@ -1,0 +1,163 @@
+/*
+ * trs_b200.h — C ABI of the B200-native batched observation path for Triton-Racer-Sim.
+ *
+ * The reference (pure Python) has no FFI of its own: its boundary for this path is the
+ * `Component` plugin API (TritonRacerSim/components/component.py:3-28).  The Python mirror of
+ * that API lives in triton-racer-sim_b200/components.py and reaches the sm_100a kernels only
+ * through the entry points declared here (ctypes).  Every entry point names
+ * the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - every function returns int: 0 = ok, >0 = cudaError_t, <0 = TRS_E_* argument error;
+ *     trs_last_error() returns a thread-local message for the last non-zero return
+ *   - "_dev" pointers are device pointers (contiguous); frame pointers should be 16-byte aligned
+ *   - work is enqueued on the caller's stream (a cudaStream_t passed as void*) and the call
+ *     returns without synchronising; the *_host entry points synchronise before returning
+ *   - frames are (N,H,W,3) uint8 RGB, HWC interleaved: the input contract of
+ *     TritonRacerSim/components/gyminterface.py:95-104
+ */
+#ifndef TRS_B200_H
+#define TRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRS_VERSION 100
+
+#define TRS_E_ARG      (-1)  /* null pointer / bad size / bad enum                */
+#define TRS_E_STATE    (-2)  /* e.g. locate before set_track                       */
+#define TRS_E_RANGE    (-3)  /* frame too large for the on-chip working set        */
+#define TRS_E_NODEVICE (-4)  /* no sm_100 device                                   */
+
+#define TRS_MAX_HSV 4        /* colour ranges accepted (only the last writer of each channel matters) */
+
+typedef struct trs_ctx trs_ctx;
+
+/* Parameters of ImgPreprocessing — names follow core/config.py:15-28 (preprocessing_*). */
+typedef struct trs_preproc_params {
+    double contrast_ratio;        /* preprocessing_contrast_enhancement_ratio   (config.py:18) */
+    double contrast_offset;       /* preprocessing_contrast_enhancement_offset  (config.py:19) */
+    double brightness_baseline;   /* preprocessing_brightness_baseline          (config.py:21) */
+    int32_t dynamic_brightness;   /* preprocessing_dynamic_brightness_enabled   (config.py:20) */
+    int32_t color_filter_enabled; /* preprocessing_color_filter_enabled         (config.py:22) */
+    int32_t n_hsv;                /* len(preprocessing_color_filter_hsvs)       (config.py:23) */
+    int32_t edge_enabled;         /* preprocessing_edge_detection_enabled       (config.py:25) */
+    double hsv_lo[TRS_MAX_HSV][3];/* lower (H,S,V) bound of each range, compared as reals      */
+    double hsv_hi[TRS_MAX_HSV][3];/* upper (H,S,V) bound, inclusive                              */
+    int32_t color_dest[TRS_MAX_HSV]; /* preprocessing_color_filter_destination_channels (config.py:24) */
+    int32_t edge_dest;            /* preprocessing_edge_detection_destination_channel (config.py:28) */
+    double canny_a;               /* preprocessing_edge_detection_threshold_a   (config.py:26) */
+    double canny_b;               /* preprocessing_edge_detection_threshold_b   (config.py:27) */
+} trs_preproc_params;
+
+/* Parameters of the pilots' speed-control tail — core/config.py:65-66,76-80. */
+typedef struct trs_spd_params {
+    double threshold;             /* spd_ctl_threshold            */
+    double reverse_multiplier;    /* spd_ctl_reverse_multiplier   */
+    double break_multiplier;      /* spd_ctl_break_multiplier     */
+    int32_t use_break;            /* spd_ctl_break                */
+    int32_t smooth_steering;      /* smooth_steering_enabled      */
+    double smooth_threshold;      /* smooth_steering_threshold    */
+} trs_spd_params;
+
+/* Per-call statistics written by trs_preprocess (all counters are sums over the N frames). */
+enum {
+    TRS_STAT_FRAMES = 0,     /* frames processed                                   */
+    TRS_STAT_MASK0 = 1,      /* set pixels of colour range 0..3                    */
+    TRS_STAT_MASK1 = 2,
+    TRS_STAT_MASK2 = 3,
+    TRS_STAT_MASK3 = 4,
+    TRS_STAT_EDGE = 5,       /* Canny edge pixels after hysteresis                 */
+    TRS_STAT_STRONG = 6,     /* pixels above the high threshold after NMS          */
+    TRS_STAT_CAND = 7,       /* NMS survivors above the low threshold              */
+    TRS_STAT_HYST_SWEEPS = 8,/* hysteresis sweeps summed over frames               */
+    TRS_STAT_ROI_SUM = 9,    /* sum of all ROI bytes (brightness statistic)        */
+    TRS_STAT_COUNT = 16
+};
+
+int trs_version(void);
+const char* trs_last_error(void);
+
+/* One context per GPU.  Holds the uploaded parameter tables and the waypoint table. */
+int trs_ctx_create(int device, trs_ctx** out);
+int trs_ctx_destroy(trs_ctx* ctx);
+/* Properties of the device the context is bound to (SM count, opt-in shared memory per block). */
+int trs_ctx_device_info(trs_ctx* ctx, int* sm_count, int* smem_optin_bytes, int* cc_major, int* cc_minor);
+
+/* Replaces reading self.cfg[...] inside ImgPreprocessing (img_preprocessing.py:41-50,66-68,77-78,84-86). */
+int trs_set_preproc_params(trs_ctx* ctx, const trs_preproc_params* p);
+
+/*
+ * Replaces ImgPreprocessing.__process (img_preprocessing.py:37-54) for N frames, fused with the
+ * pilot's float normalisation (keras_pilot.py:49-50) when out_f32_dev is given.
+ *   in_dev      (N,H,W,3) u8
+ *   out_u8_dev  (N,H,W,3) u8  `cam/processed_img`            — nullable
+ *   out_f32_dev (N,H,W,3) f32 `processed_img / 255`          — nullable
+ *   stats_dev   TRS_STAT_COUNT x u64, accumulated atomically  — nullable
+ */
+int trs_preprocess(trs_ctx* ctx, const uint8_t* in_dev, int n, int h, int w,
+                   uint8_t* out_u8_dev, float* out_f32_dev, unsigned long long* stats_dev,
+                   void* stream);
+
+/*
+ * Replaces the camera resize (camera.py:36, nearest neighbour), a rows/cols window crop and the
+ * float normalisation (keras_pilot.py:49-50, keras_train.py:41-42) for N frames.
+ *   in_dev (N,h_in,w_in,3) u8; window rows [roi_y0,roi_y1) cols [roi_x0,roi_x1) of the source;
+ *   the window is scaled to (h_out,w_out) with src = floor(dst*size_src/size_dst);
+ *   out_f32_dev (N,h_out,w_out,3) f32 = u8/255 — nullable; out_u8_dev same shape u8 — nullable.
+ */
+int trs_normalise(trs_ctx* ctx, const uint8_t* in_dev, int n, int h_in, int w_in,
+                  int roi_y0, int roi_y1, int roi_x0, int roi_x1, int h_out, int w_out,
+                  float* out_f32_dev, uint8_t* out_u8_dev, void* stream);
+
+/* Replaces LocationTracker.__init__ (track_data_process.py:69-75): upload the centre line (host pointer, n_wp x 3 f64). */
+int trs_set_track(trs_ctx* ctx, const double* wp_xyz_host, int n_wp, double min_map, double max_map);
+
+/*
+ * Replaces LocationTracker.step/localize/__find_closest/__map (track_data_process.py:77-107) for N cars.
+ *   xyz_dev (N,3) f64; idx_dev (N) i32 — nullable; segment_dev (N) f64 — nullable.
+ */
+int trs_locate(trs_ctx* ctx, const double* xyz_dev, int n, int32_t* idx_dev, double* segment_dev,
+               void* stream);
+
+/*
+ * Replaces the speed-control tail of KerasPilot.step (keras_pilot.py:80-95,99-118,142-153) and
+ * calcThrottle/calcBreak (utils/mapping.py:23-35) for N cars.
+ *   cur_spd_dev (N) f64 `gym/speed`; model_spd_dev (N) f32 = the model's speed output (before x20);
+ *   model_steer_dev (N) f32 = the model's steering output;
+ *   outputs (N) f64 each: `ai/steering`, `ai/throttle`, `ai/breaking`;
+ *   spd_feature_dev (N) f32 = gym/speed / 20 (keras_pilot.py:68,100) — nullable.
+ */
+int trs_speed_control(trs_ctx* ctx, const double* cur_spd_dev, const float* model_spd_dev,
+                      const float* model_steer_dev, int n, const trs_spd_params* p,
+                      double* steering_dev, double* throttle_dev, double* breaking_dev,
+                      float* spd_feature_dev, void* stream);
+
+/*
+ * Host-buffer form of trs_preprocess: copies frames host->device in chunks, runs the kernels and
+ * copies the requested outputs back, overlapping the three on internal streams; synchronises before
+ * returning.  Host buffers may be pageable (slower) or pinned (trs_host_alloc).
+ *   keep_f32_dev: optional device buffer (N,H,W,3) f32 that receives the normalised tensor and
+ *   stays on the GPU for the pilot's model — nullable.
+ */
+int trs_preprocess_host(trs_ctx* ctx, const uint8_t* in_host, int n, int h, int w,
+                        uint8_t* out_u8_host, float* out_f32_host, float* keep_f32_dev,
+                        unsigned long long* stats_host);
+
+/* Pinned host allocations for the *_host entry points. */
+int trs_host_alloc(void** out, unsigned long long bytes);
+int trs_host_free(void* p);
+
+/* Debug taps used by the parity tests: intermediate planes of the edge filter for ONE frame.
+ *   mag_dev (H,W) u16 selected-channel L1 magnitude; map_dev (H,W) u8: 0 none, 1 candidate, 2 strong. */
+int trs_debug_canny_stages(trs_ctx* ctx, const uint8_t* in_dev, int h, int w,
+                           uint16_t* mag_dev, uint8_t* map_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRS_B200_H */

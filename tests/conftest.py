@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_images():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "images.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_tracks():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "tracks.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_speed():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "speed.npz"))
