@@ -81,6 +81,8 @@ enum {
 
 int trs_version(void);
 const char* trs_last_error(void);
+/* Number of kernels this library has launched in this process (all contexts); bench.py reports it. */
+unsigned long long trs_kernel_launches(void);
 
 /* One context per GPU.  Holds the uploaded parameter tables and the waypoint table. */
 int trs_ctx_create(int device, trs_ctx** out);

@@ -1,0 +1,278 @@
+"""Parity of the CUDA path (through the C ABI / Component classes) against the oracle and the reference's golden
+vectors.  Bit-exact for uint8 frames, masks and waypoint indices; float32 normalised tensors are compared exactly
+too (they are correctly rounded divisions); speed-control outputs within 1e-5 relative (north_star tolerance)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.helpers import cfg_for, golden_pairs, speed_cases
+from triton_racer_sim_b200 import FrameNormalise, ImgPreprocessing, LocationTracker, SpeedControl, synth
+from triton_racer_sim_b200 import _native as nat
+from triton_racer_sim_b200.config import full_house_config
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-5          # BASELINE.json north_star: "within 1e-5 relative for normalised float tensors and PID outputs"
+
+
+def run_device(cfg, frames, want_f32=True):
+    comp = ImgPreprocessing(cfg, device=0, normalised_key='cam/normalised_img' if want_f32 else None)
+    u8, f32 = comp.process_device(torch.from_numpy(frames).to(DEV))
+    torch.cuda.synchronize()
+    comp.onShutdown()
+    return u8.cpu().numpy(), (f32.cpu().numpy() if f32 is not None else None)
+
+
+def describe(got, want):
+    bad = np.argwhere(got != want)
+    return f"{len(bad)} of {got.size} differ; first at {bad[:5].tolist()}"
+
+
+def test_library_is_the_cuda_one():
+    assert torch.cuda.is_available()
+    ctx = nat.Context(0)
+    assert ctx.cc[0] >= 10 and ctx.sm_count > 0
+    ctx.close()
+
+
+def test_golden_images_device_path(golden_images):
+    count = 0
+    for sname, cname, cfg, frames, expected in golden_pairs(golden_images):
+        got, f32 = run_device(cfg, frames)
+        assert np.array_equal(got, expected), f"{sname}/{cname}: {describe(got, expected)}"
+        assert np.array_equal(f32, oracle.normalise(expected)), f"{sname}/{cname} f32"
+        count += 1
+    assert count >= 30
+
+
+def test_golden_images_host_path(golden_images):
+    for sname, cname, cfg, frames, expected in golden_pairs(golden_images):
+        if cname not in ("full_house", "exotic"):
+            continue
+        comp = ImgPreprocessing(cfg, device=0, normalised_key='cam/normalised_img', collect_stats=True)
+        u8, f32 = comp.step(frames)
+        assert np.array_equal(u8, expected), f"{sname}/{cname}: {describe(u8, expected)}"
+        assert np.array_equal(f32, oracle.normalise(expected))
+        assert comp.last_stats["frames"] == frames.shape[0]
+        comp.onShutdown()
+
+
+def test_canny_stage_taps_match_oracle(golden_images):
+    """Intermediate planes (selected-channel magnitude, NMS map) for single frames, incl. odd sizes."""
+    cfg = full_house_config()
+    comp = ImgPreprocessing(cfg, device=0)
+    for sname in ("f120", "f240", "odd_7x9", "odd_33x50", "odd_121x163", "odd_64x96"):
+        for img in golden_images[f"in/{sname}"][:4]:
+            h, w, _ = img.shape
+            _, mag, mp = oracle.canny3(img, 60, 100, taps=True)
+            d_img = torch.from_numpy(img).to(DEV)
+            d_mag = torch.zeros((h, w), dtype=torch.int16, device=DEV)
+            d_map = torch.zeros((h, w), dtype=torch.uint8, device=DEV)
+            nat.check(comp.ctx.lib.trs_debug_canny_stages(comp.ctx.handle, C.c_void_p(d_img.data_ptr()), h, w, C.c_void_p(d_mag.data_ptr()),
+                                                          C.c_void_p(d_map.data_ptr()), None), "debug")
+            torch.cuda.synchronize()
+            got_mag = d_mag.cpu().numpy().view(np.uint16)
+            assert np.array_equal(got_mag, mag), f"{sname} mag: {describe(got_mag, mag)}"
+            assert np.array_equal(d_map.cpu().numpy(), mp), f"{sname} map: {describe(d_map.cpu().numpy(), mp)}"
+    comp.onShutdown()
+
+
+@pytest.mark.parametrize("h,w,n", [(120, 160, 96), (240, 320, 24), (17, 23, 5), (41, 64, 7), (119, 8, 3), (1, 40, 2), (40, 1, 2),
+                                   (480, 640, 3), (130, 2000, 2)])
+def test_fresh_frames_against_oracle(h, w, n):
+    frames = synth.frame_pool(n, h, w, seed=1000 + h + w)
+    for over in (dict(), dict(preprocessing_dynamic_brightness_enabled=True, preprocessing_contrast_enhancement_ratio=1.6,
+                              preprocessing_contrast_enhancement_offset=90, preprocessing_edge_detection_threshold_a=33.3,
+                              preprocessing_edge_detection_threshold_b=210)):
+        cfg = full_house_config(**over)
+        want = oracle.process_batch(frames, cfg)
+        got, f32 = run_device(cfg, frames)
+        assert np.array_equal(got, want), describe(got, want)
+        assert np.array_equal(f32, oracle.normalise(want))
+
+
+def test_adversarial_hysteresis_chains():
+    """Serpentine weak chains hanging off a single strong pixel: the worst case for iterative flood fill."""
+    h, w = 120, 160
+    frames = []
+    for period in (4, 6, 10):
+        img = np.full((h, w, 3), 90, np.uint8)
+        for y in range(4, h - 4, period):
+            img[y, 4:w - 4] = 112
+            x = (w - 5) if (y // period) % 2 == 0 else 4
+            img[y:y + period, x] = 112
+        img[4, 4:8] = 255
+        frames.append(img)
+    frames = np.stack(frames)
+    cfg = full_house_config(preprocessing_edge_detection_threshold_a=30, preprocessing_edge_detection_threshold_b=200)
+    want = oracle.process_batch(frames, cfg)
+    got, _ = run_device(cfg, frames, want_f32=False)
+    assert np.array_equal(got, want), describe(got, want)
+    assert want[..., 2].sum() > 0
+
+
+def test_component_drop_in_single_frame_and_none():
+    cfg = full_house_config()
+    comp = ImgPreprocessing(cfg, device=0)
+    assert comp.step_inputs == ['cam/img'] and comp.step_outputs == ['cam/processed_img']
+    assert comp.getName() == 'Image Preprocessing'
+    assert comp.step(None) == (None,)
+    img = synth.frame_pool(1, 120, 160, seed=77)[0]
+    keep = img.copy()
+    out, = comp.step(img)
+    assert isinstance(out, np.ndarray) and out.shape == (120, 160, 3) and out.dtype == np.uint8
+    assert np.array_equal(img, keep)                                  # the caller's frame is never modified
+    assert np.array_equal(out, oracle.process_frame(img, cfg))
+    t_out, = comp.step(torch.from_numpy(img).to(DEV))
+    assert t_out.is_cuda and np.array_equal(t_out.cpu().numpy(), out)
+    comp.onShutdown()
+    lag = ImgPreprocessing(cfg, device=0, emulate_latency=True)       # the reference's one-tick lag (img_preprocessing.py:18-21)
+    assert lag.step(img) == (None,)
+    second, = lag.step(np.zeros_like(img))
+    assert np.array_equal(second, out)
+    lag.onShutdown()
+
+
+def test_bad_arguments_raise():
+    with pytest.raises(ValueError):
+        ImgPreprocessing(full_house_config(preprocessing_color_filter_destination_channels=[0, 5]), device=0)
+    with pytest.raises(AssertionError):
+        ImgPreprocessing(full_house_config(preprocessing_color_filter_destination_channels=[0]), device=0)
+    comp = ImgPreprocessing(full_house_config(), device=0)
+    with pytest.raises(ValueError):
+        comp.process_device(torch.zeros((2, 8, 8, 4), dtype=torch.uint8, device=DEV))
+    empty_u8, _ = comp.process_device(torch.zeros((0, 120, 160, 3), dtype=torch.uint8, device=DEV))
+    assert empty_u8.shape[0] == 0
+    comp.onShutdown()
+    with pytest.raises(FileNotFoundError):
+        LocationTracker('/nonexistent/track.json', device=0)
+
+
+def test_statistics_match_oracle_counts():
+    cfg = full_house_config()
+    frames = synth.frame_pool(64, 120, 160, seed=5)
+    want = oracle.process_batch(frames, cfg)
+    comp = ImgPreprocessing(cfg, device=0, collect_stats=True)
+    comp.process_device(torch.from_numpy(frames).to(DEV))
+    st = comp.stats()
+    assert st["frames"] == 64
+    assert st["mask0"] == int((want[..., 0] == 255).sum())
+    assert st["mask1"] == int((want[..., 1] == 255).sum())
+    assert st["edge"] == int((want[..., 2] == 255).sum())
+    comp.onShutdown()
+
+
+def test_normalise_and_crop_resize():
+    frames = synth.frame_pool(6, 240, 320, seed=3)
+    d = torch.from_numpy(frames).to(DEV)
+    ident = FrameNormalise(device=0)
+    out, = ident.step(d)
+    assert np.array_equal(out.cpu().numpy(), oracle.normalise(frames))
+    all_bytes = np.arange(256, dtype=np.uint8).repeat(3 * 5).reshape(1, 5, 256, 3)      # every byte value, true division
+    assert np.array_equal(ident.step(all_bytes)[0], oracle.normalise(all_bytes))
+    ident.onShutdown()
+    cam = FrameNormalise(device=0, out_hw=(120, 160))                                   # camera.py:36 case: 320x240 -> 160x120
+    u8_want, f32_want = oracle.crop_resize(frames, (0, 240, 0, 320), (120, 160))
+    f32, u8 = cam.normalise_device(d, want_u8=True)
+    assert np.array_equal(u8.cpu().numpy(), u8_want) and np.array_equal(f32.cpu().numpy(), f32_want)
+    assert np.array_equal(u8_want, frames[:, ::2, ::2])
+    cam.onShutdown()
+    for roi, out_hw in (((40, 119, 0, 320), None), ((10, 230, 17, 301), (77, 131)), ((0, 240, 0, 320), (300, 333))):
+        comp = FrameNormalise(device=0, roi=roi, out_hw=out_hw)
+        ho, wo = out_hw if out_hw else (roi[1] - roi[0], roi[3] - roi[2])
+        u8_want, f32_want = oracle.crop_resize(frames, roi, (ho, wo))
+        f32, u8 = comp.normalise_device(d, want_u8=True)
+        assert np.array_equal(u8.cpu().numpy(), u8_want) and np.array_equal(f32.cpu().numpy(), f32_want)
+        comp.onShutdown()
+    odd = synth.frame_pool(3, 7, 9, seed=1)                                              # 189 bytes per frame: unaligned tail path
+    comp = FrameNormalise(device=0)
+    assert np.array_equal(comp.step(odd)[0], oracle.normalise(odd))
+    comp.onShutdown()
+
+
+def test_locate_golden_tracks(golden_tracks):
+    for name in ("generated_track", "mountain_track"):
+        wp, xyz = golden_tracks[f"wp/{name}"], golden_tracks[f"xyz/{name}"]
+        trk = LocationTracker(wp, 0, 10, device=0)
+        idx, seg = trk.locate_device(torch.from_numpy(xyz).to(DEV))
+        assert np.array_equal(idx.cpu().numpy(), golden_tracks[f"idx/{name}"])
+        assert np.array_equal(seg.cpu().numpy(), golden_tracks[f"seg/{name}/0_10"])
+        # N = 1 python floats, like Car would pass them
+        s, = trk.step(float(xyz[5, 0]), float(xyz[5, 1]), float(xyz[5, 2]))
+        assert isinstance(s, float) and s == golden_tracks[f"seg/{name}/0_10"][5]
+        trk.onShutdown()
+        trk2 = LocationTracker(wp, -2.5, 7.25, device=0)
+        seg2, = trk2.step(torch.from_numpy(xyz[:, 0].copy()).to(DEV), torch.from_numpy(xyz[:, 1].copy()).to(DEV), torch.from_numpy(xyz[:, 2].copy()).to(DEV))
+        assert np.array_equal(seg2.cpu().numpy(), golden_tracks[f"seg/{name}/m2p5_7p25"])
+        trk2.onShutdown()
+
+
+def test_locate_large_batch_against_oracle(golden_tracks):
+    for name, n in (("generated_track", 200_000), ("mountain_track", 100_000)):
+        wp = golden_tracks[f"wp/{name}"]
+        xyz, _, _, _ = synth.car_states(wp, n, seed=17)
+        idx_want, seg_want = oracle.locate(wp, xyz)
+        trk = LocationTracker(wp, device=0)
+        idx, seg = trk.locate_device(torch.from_numpy(xyz).to(DEV))
+        assert np.array_equal(idx.cpu().numpy(), idx_want)
+        assert np.array_equal(seg.cpu().numpy(), seg_want)
+        assert (idx_want == 0).sum() >= n // 200                      # the > 100 sentinel cases are present
+        trk.onShutdown()
+    # more waypoints than one shared-memory tile
+    wp = synth.synthetic_track(5000)
+    xyz, _, _, _ = synth.car_states(wp, 5000, seed=3)
+    trk = LocationTracker(wp, device=0)
+    idx, _ = trk.locate_device(torch.from_numpy(xyz).to(DEV))
+    assert np.array_equal(idx.cpu().numpy(), oracle.locate(wp, xyz)[0])
+    trk.onShutdown()
+
+
+def test_speed_control_golden(golden_speed):
+    cur, ms, st = golden_speed["cur"], golden_speed["model_spd"], golden_speed["model_steer"]
+    for cname, over in speed_cases(golden_speed).items():
+        cfg = cfg_for(over)
+        comp = SpeedControl(cfg, device=0)
+        s, t, b, feat = comp.control_device(torch.from_numpy(cur).to(DEV), torch.from_numpy(st).to(DEV), torch.from_numpy(ms).to(DEV), want_feature=True)
+        want = golden_speed[f"out/{cname}"]
+        s, t, b = s.cpu().numpy(), t.cpu().numpy(), b.cpu().numpy()
+        assert np.array_equal(s, want[:, 0]), cname
+        # the law is discontinuous at the dead-bands (-0.2, 0 for throttle; 0.4 for brake): the float32 speed gap is computed
+        # identically, so only atan's last ulp can move a state across; require equality of the zeroing decision away from the edges
+        for got, ref in ((t, want[:, 1]), (b, want[:, 2])):
+            differs = ~(np.abs(got - ref) <= RTOL * np.abs(ref))
+            assert differs.sum() == 0, f"{cname}: {differs.sum()} states outside {RTOL} relative"
+        assert np.array_equal(feat.cpu().numpy(), golden_speed["feature"])
+        out = comp.step(float(cur[3]), float(st[3]), float(ms[3]))
+        assert all(isinstance(v, float) for v in out) and abs(out[1] - want[3, 1]) <= RTOL * abs(want[3, 1])
+        assert comp.step(None, None, None) == (0.0, 0.0, 0.0)
+        comp.onShutdown()
+
+
+def test_full_size_properties():
+    """BASELINE-size batch (65,536 x 120x160): shard invariance, idempotence of masks, counters — no CPU oracle needed."""
+    cfg = full_house_config()
+    pool = torch.from_numpy(synth.frame_pool(256, 120, 160)).to(DEV)
+    n = 65536
+    frames = synth.expand_torch(pool, n)
+    comp = ImgPreprocessing(cfg, device=0, collect_stats=True)
+    u8, f32 = comp.process_device(frames, want_f32=True)
+    st = comp.stats()
+    assert st["frames"] == n
+    # (1) every output byte is 0 or 255 and the float tensor is exactly u8/255
+    assert bool(((u8 == 0) | (u8 == 255)).all())
+    assert bool((f32 == u8.to(torch.float32) / 255).all())
+    # (2) counters agree with the written planes
+    assert st["mask0"] == int((u8[..., 0] == 255).sum()) and st["mask1"] == int((u8[..., 1] == 255).sum())
+    assert st["edge"] == int((u8[..., 2] == 255).sum()) and st["edge"] <= st["cand"] and st["strong"] <= st["edge"]
+    # (3) a re-run of any sub-range gives the same bytes (shard invariance: rank r of 8 computes rows [r*N/8,(r+1)*N/8))
+    lo, hi = 5 * n // 8, 6 * n // 8
+    part, _ = comp.process_device(frames[lo:hi], want_f32=False)
+    assert torch.equal(part, u8[lo:hi])
+    # (4) a sample of frames against the CPU oracle
+    pick = np.random.default_rng(0).integers(0, n, size=48)
+    want = oracle.process_batch(frames[pick].cpu().numpy(), cfg)
+    assert np.array_equal(u8[pick].cpu().numpy(), want)
+    comp.onShutdown()

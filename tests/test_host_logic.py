@@ -1,0 +1,107 @@
+"""Host-side logic that needs no GPU: sharding, workload generator, plugin API mirror, 2-rank gloo plumbing."""
+import inspect
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from triton_racer_sim_b200 import Component, default_config, sharding, synth
+
+
+def test_shard_ranges_partition_everything():
+    for n in (0, 1, 7, 8, 1000, 1048576):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (s0, e0), (s1, e1) in zip(spans, spans[1:]):
+                assert e0 == s1
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synth_is_deterministic_and_shard_invariant():
+    pool = synth.frame_pool(8, 24, 32)
+    assert np.array_equal(pool, synth.frame_pool(8, 24, 32))
+    whole = synth.expand_numpy(pool, 40)
+    parts = [synth.expand_numpy(pool, e - s, start=s) for s, e in (sharding.shard_range(40, r, 3) for r in range(3))]
+    assert np.array_equal(whole, np.concatenate(parts))
+    t = synth.expand_torch(torch.from_numpy(pool), 40)
+    assert np.array_equal(t.numpy(), whole)
+    wp = synth.synthetic_track(300)
+    xyz, cur, ms, st = synth.car_states(wp, 1000)
+    assert xyz.shape == (1000, 3) and xyz.dtype == np.float64 and ms.dtype == np.float32 and st.dtype == np.float32
+    assert len(np.unique(wp, axis=0)) < len(wp)            # duplicates present -> ties
+
+
+def test_component_base_mirrors_reference_api():
+    # TritonRacerSim/components/component.py:3-28
+    c = Component(inputs=['a'], outputs=['b', 'c'], threaded=True)
+    assert c.step_inputs == ['a'] and c.step_outputs == ['b', 'c'] and c.threaded is True
+    src = ['a']
+    c2 = Component(inputs=src)
+    c2.step_inputs[0] = 'z'
+    assert src == ['a']                                      # lists are copied (callers mutate them: manage.py:50,104)
+    for hook in ('onStart', 'step', 'thread_step', 'onShutdown', 'getName'):
+        assert callable(getattr(c, hook))
+    assert c.getName() == 'Generic Component'
+    assert c.step(1, 2) is None and c.onStart() is None
+    assert list(inspect.signature(Component.__init__).parameters) == ['self', 'inputs', 'outputs', 'threaded']
+
+
+def test_config_defaults_match_reference_values():
+    cfg = default_config()
+    # core/config.py:8-28,65-66,76-80
+    assert (cfg['img_w'], cfg['img_h'], cfg['cam_resolution']) == (160, 120, [320, 240])
+    assert cfg['preprocessing_contrast_enhancement_ratio'] == 1.0 and cfg['preprocessing_contrast_enhancement_offset'] == 125
+    assert cfg['preprocessing_brightness_baseline'] == 550 and cfg['preprocessing_dynamic_brightness_enabled'] is False
+    assert cfg['preprocessing_color_filter_hsvs'] == [((0, 0, 130), (180, 64, 255)), ((25, 180, 155), (43, 255, 255))]
+    assert cfg['preprocessing_color_filter_destination_channels'] == [0, 1]
+    assert (cfg['preprocessing_edge_detection_threshold_a'], cfg['preprocessing_edge_detection_threshold_b'],
+            cfg['preprocessing_edge_detection_destination_channel']) == (60, 100, 2)
+    assert (cfg['spd_ctl_threshold'], cfg['spd_ctl_reverse_multiplier'], cfg['spd_ctl_break'], cfg['spd_ctl_break_multiplier']) == (1.1, 1.0, False, 1.0)
+    assert (cfg['smooth_steering_enabled'], cfg['smooth_steering_threshold']) == (False, 0.9)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, w, _ = sharding.init_distributed("gloo")
+    assert (r, w) == (rank, world)
+    s, e = sharding.shard_range(n_total, rank, world)
+    pool = synth.frame_pool(4, 8, 12)
+    local = torch.from_numpy(synth.expand_numpy(pool, e - s, start=s))       # each rank builds only its own block
+    stats = torch.zeros(16, dtype=torch.int64)
+    stats[0] = e - s
+    stats[5] = int(local.sum())
+    total = sharding.reduce_stats(stats)
+    whole = sharding.gather_shards(local, n_total)
+    slowest = sharding.max_over_ranks(1.0 + rank)
+    if rank == 0:
+        ref = synth.expand_numpy(pool, n_total)
+        q.put((int(total[0]), int(total[5]) == int(ref.astype(np.int64).sum()), bool(np.array_equal(whole.numpy(), ref)), slowest))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_stats():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 37, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    frames, sum_ok, equal, slowest = q.get(timeout=10)
+    assert frames == 37 and sum_ok and equal and slowest == 2.0

@@ -1,0 +1,158 @@
+"""ctypes binding of libtrs_b200.so (the C ABI in include/trs_b200.h).
+
+There is no fallback: if the library is missing, cannot be loaded, or no sm_100 GPU is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtrs_b200.so")
+MAX_HSV = 4
+STAT_COUNT = 16
+STAT_NAMES = ["frames", "mask0", "mask1", "mask2", "mask3", "edge", "strong", "cand", "hyst_sweeps", "roi_sum"]
+
+# every symbol include/trs_b200.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "trs_version", "trs_last_error", "trs_kernel_launches", "trs_ctx_create", "trs_ctx_destroy", "trs_ctx_device_info",
+    "trs_set_preproc_params", "trs_preprocess", "trs_normalise", "trs_set_track", "trs_locate", "trs_speed_control",
+    "trs_preprocess_host", "trs_host_alloc", "trs_host_free", "trs_debug_canny_stages",
+]
+
+
+class PreprocParams(C.Structure):
+    _fields_ = [
+        ("contrast_ratio", C.c_double), ("contrast_offset", C.c_double), ("brightness_baseline", C.c_double),
+        ("dynamic_brightness", C.c_int32), ("color_filter_enabled", C.c_int32), ("n_hsv", C.c_int32),
+        ("edge_enabled", C.c_int32),
+        ("hsv_lo", (C.c_double * 3) * MAX_HSV), ("hsv_hi", (C.c_double * 3) * MAX_HSV),
+        ("color_dest", C.c_int32 * MAX_HSV), ("edge_dest", C.c_int32),
+        ("canny_a", C.c_double), ("canny_b", C.c_double),
+    ]
+
+
+class SpdParams(C.Structure):
+    _fields_ = [
+        ("threshold", C.c_double), ("reverse_multiplier", C.c_double), ("break_multiplier", C.c_double),
+        ("use_break", C.c_int32), ("smooth_steering", C.c_int32), ("smooth_threshold", C.c_double),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises with a build hint when it is absent (never falls back to a CPU path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(f"{LIB_PATH} is missing: build it with `python -m triton_racer_sim_b200.build` "
+                          "(nvcc, sm_100a). There is no CPU implementation of this path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u64p = C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)
+    lib.trs_version.restype = C.c_int
+    lib.trs_last_error.restype = C.c_char_p
+    lib.trs_kernel_launches.restype = C.c_ulonglong
+    lib.trs_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    lib.trs_ctx_destroy.argtypes = [vp]
+    lib.trs_ctx_device_info.argtypes = [vp] + [C.POINTER(C.c_int)] * 4
+    lib.trs_set_preproc_params.argtypes = [vp, C.POINTER(PreprocParams)]
+    lib.trs_preprocess.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.trs_normalise.argtypes = [vp, vp] + [i32] * 9 + [vp, vp, vp]
+    lib.trs_set_track.argtypes = [vp, vp, i32, C.c_double, C.c_double]
+    lib.trs_locate.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.trs_speed_control.argtypes = [vp, vp, vp, vp, i32, C.POINTER(SpdParams), vp, vp, vp, vp, vp]
+    lib.trs_preprocess_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.trs_host_alloc.argtypes = [C.POINTER(vp), C.c_ulonglong]
+    lib.trs_host_free.argtypes = [vp]
+    lib.trs_debug_canny_stages.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    for name in SYMBOLS:
+        getattr(lib, name)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    msg = load().trs_last_error().decode(errors="replace")
+    if rc < 0:
+        if rc == -4:
+            raise NativeError(f"{what}: {msg}")
+        raise ValueError(f"{what}: {msg}")
+    raise NativeError(f"{what}: CUDA error {rc}: {msg}")
+
+
+class Context:
+    """One per GPU (trs_ctx).  Owns the uploaded parameters and the centre line."""
+
+    _by_device: dict = {}
+
+    def __init__(self, device: int = 0):
+        lib = load()
+        h = C.c_void_p()
+        check(lib.trs_ctx_create(int(device), C.byref(h)), "trs_ctx_create")
+        self.lib, self.handle, self.device = lib, h, int(device)
+        sm, smem, maj, mnr = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib.trs_ctx_device_info(h, C.byref(sm), C.byref(smem), C.byref(maj), C.byref(mnr)), "trs_ctx_device_info")
+        self.sm_count, self.smem_optin, self.cc = sm.value, smem.value, (maj.value, mnr.value)
+
+    def close(self):
+        if self.handle:
+            self.lib.trs_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def kernel_launches() -> int:
+    return int(load().trs_kernel_launches())
+
+
+def preproc_params_from_cfg(cfg: dict) -> PreprocParams:
+    """Reference key names (core/config.py:15-28); bounds may be lists after the JSON round trip (img_preprocessing.py:71)."""
+    p = PreprocParams()
+    p.contrast_ratio = float(cfg['preprocessing_contrast_enhancement_ratio'])
+    p.contrast_offset = float(cfg['preprocessing_contrast_enhancement_offset'])
+    p.brightness_baseline = float(cfg['preprocessing_brightness_baseline'])
+    p.dynamic_brightness = int(bool(cfg['preprocessing_dynamic_brightness_enabled']))
+    p.color_filter_enabled = int(bool(cfg['preprocessing_color_filter_enabled']))
+    p.edge_enabled = int(bool(cfg['preprocessing_edge_detection_enabled']))
+    if p.color_filter_enabled:
+        hsvs = cfg['preprocessing_color_filter_hsvs']
+        dests = cfg['preprocessing_color_filter_destination_channels']
+        assert len(hsvs) == len(dests)          # img_preprocessing.py:59 (the reference asserts in __merge)
+        if len(hsvs) > MAX_HSV:
+            raise ValueError(f"at most {MAX_HSV} colour ranges are supported, got {len(hsvs)}")
+        p.n_hsv = len(hsvs)
+        for k, (lo, hi) in enumerate(hsvs):
+            lo, hi = tuple(lo), tuple(hi)
+            for c in range(3):
+                p.hsv_lo[k][c] = float(lo[c])
+                p.hsv_hi[k][c] = float(hi[c])
+            p.color_dest[k] = int(dests[k])
+    p.edge_dest = int(cfg['preprocessing_edge_detection_destination_channel'])
+    p.canny_a = float(cfg['preprocessing_edge_detection_threshold_a'])
+    p.canny_b = float(cfg['preprocessing_edge_detection_threshold_b'])
+    return p
+
+
+def spd_params_from_cfg(cfg: dict) -> SpdParams:
+    p = SpdParams()
+    p.threshold = float(cfg['spd_ctl_threshold'])
+    p.reverse_multiplier = float(cfg['spd_ctl_reverse_multiplier'])
+    p.break_multiplier = float(cfg['spd_ctl_break_multiplier'])
+    p.use_break = int(bool(cfg['spd_ctl_break']))
+    p.smooth_steering = int(bool(cfg['smooth_steering_enabled']))
+    p.smooth_threshold = float(cfg['smooth_steering_threshold'])
+    return p

@@ -1,0 +1,315 @@
+"""Batched drop-ins for the reference's hot-path components (same class names, keys, config names, hooks).
+
+Every positional ``step`` argument gains a leading N (cars / tub records); N = 1 inputs in the reference's own
+types (numpy HWC frame, python floats) still work and give the reference's result types back, so the classes
+can be added to the reference's ``Car`` as they are.  All arithmetic runs in the sm_100a kernels behind
+``libtrs_b200.so``; there is no CPU path here.
+
+  ImgPreprocessing   components/img_preprocessing.py:9-108       cam/img -> cam/processed_img
+  LocationTracker    components/track_data_process.py:68-107     gym/x, gym/y, gym/z -> loc/segment
+  SpeedControl       components/keras_pilot.py:80-95,99-118,142-153 + utils/mapping.py:23-35
+  FrameNormalise     components/camera.py:36 + keras_pilot.py:49-50 / keras_train.py:41-42
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .component import Component
+from .config import default_config
+
+
+def _device_index(device):
+    if device is None:
+        return torch.cuda.current_device()
+    if isinstance(device, torch.device):
+        return device.index if device.index is not None else torch.cuda.current_device()
+    return int(device)
+
+
+def _stream_ptr(dev: int):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class ImgPreprocessing(Component):
+    """Batched ``ImgPreprocessing``: brightness/contrast, HSV colour masks, 3-channel Canny, merge [+ /255].
+
+    ``step(frames)`` accepts
+      * ``None``                                  -> ``(None,)``                       (img_preprocessing.py:20-21)
+      * numpy uint8 (H,W,3)                       -> numpy uint8 (H,W,3)               (N = 1 drop-in)
+      * numpy uint8 (N,H,W,3) (pageable/pinned)   -> numpy uint8 (N,H,W,3)             (host pipeline, chunked copies)
+      * CUDA uint8 tensor (N,H,W,3) or (H,W,3)    -> CUDA tensor, same shape           (stream-ordered, no sync)
+    The result is the one for *this* call.  The reference hands back the previous frame's result because its
+    worker thread lags (img_preprocessing.py:18-35); ``emulate_latency=True`` reproduces that.
+    ``normalised_key`` adds a second output: the float32 ``/255`` tensor the pilots consume (keras_pilot.py:49-50).
+    """
+
+    def __init__(self, cfg={}, device=None, emulate_latency=False, normalised_key=None, collect_stats=False):
+        outputs = ['cam/processed_img'] + ([normalised_key] if normalised_key else [])
+        Component.__init__(self, inputs=['cam/img'], outputs=outputs, threaded=False)
+        self.running = True
+        self.cfg = default_config()
+        self.cfg.update(cfg)
+        self.device = _device_index(device)
+        self.ctx = nat.Context(self.device)
+        self.emulate_latency = bool(emulate_latency)
+        self.want_f32 = normalised_key is not None
+        self.collect_stats = bool(collect_stats)
+        self.processed_img = None          # same attribute name as the reference (img_preprocessing.py:14)
+        self.normalised_img = None
+        self.last_stats = None
+        self._stats_dev = None
+        self._apply_cfg()
+
+    def _apply_cfg(self):
+        p = nat.preproc_params_from_cfg(self.cfg)
+        nat.check(self.ctx.lib.trs_set_preproc_params(self.ctx.handle, C.byref(p)), "trs_set_preproc_params")
+
+    # -- device path ------------------------------------------------------------------------------------
+    def process_device(self, frames: torch.Tensor, out_u8=None, out_f32=None, want_u8=True, want_f32=None):
+        """(N,H,W,3) uint8 CUDA tensor -> (u8 tensor or None, f32 tensor or None).  Enqueued on the current stream."""
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+            raise ValueError(f"expected (N,H,W,3) uint8 frames, got {tuple(frames.shape)} {frames.dtype}")
+        if not frames.is_cuda or frames.device.index != self.device:
+            raise ValueError(f"frames must live on cuda:{self.device}")
+        frames = frames.contiguous()
+        n, h, w, _ = frames.shape
+        want_f32 = self.want_f32 if want_f32 is None else want_f32
+        if want_u8 and out_u8 is None:
+            out_u8 = torch.empty_like(frames)
+        if want_f32 and out_f32 is None:
+            out_f32 = torch.empty(frames.shape, dtype=torch.float32, device=frames.device)
+        stats = None
+        if self.collect_stats:
+            if self._stats_dev is None:
+                self._stats_dev = torch.zeros(nat.STAT_COUNT, dtype=torch.int64, device=frames.device)
+            self._stats_dev.zero_()
+            stats = self._stats_dev
+        nat.check(self.ctx.lib.trs_preprocess(self.ctx.handle, _ptr(frames), n, h, w, _ptr(out_u8), _ptr(out_f32), _ptr(stats),
+                                              _stream_ptr(self.device)), "trs_preprocess")
+        return out_u8, out_f32
+
+    def stats(self) -> dict:
+        """Counters of the last call (synchronises)."""
+        if self._stats_dev is None:
+            return {}
+        v = self._stats_dev.cpu().tolist()
+        return dict(zip(nat.STAT_NAMES, v))
+
+    # -- host path --------------------------------------------------------------------------------------
+    def process_host(self, frames: np.ndarray, out_u8=None, out_f32=None, keep_f32_dev=None, want_u8=True):
+        """(N,H,W,3) uint8 numpy -> numpy.  H2D copy, kernels and D2H copy are pipelined in chunks inside the library."""
+        if frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[-1] != 3:
+            raise ValueError(f"expected (N,H,W,3) uint8 frames, got {frames.shape} {frames.dtype}")
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        if want_u8 and out_u8 is None:
+            out_u8 = np.empty_like(frames)
+        stats = (C.c_ulonglong * nat.STAT_COUNT)() if self.collect_stats else None
+        nat.check(self.ctx.lib.trs_preprocess_host(self.ctx.handle, _np_ptr(frames), n, h, w, _np_ptr(out_u8), _np_ptr(out_f32),
+                                                   _ptr(keep_f32_dev), stats), "trs_preprocess_host")
+        if stats is not None:
+            self.last_stats = dict(zip(nat.STAT_NAMES, list(stats)))
+        return out_u8, out_f32
+
+    # -- Component API ----------------------------------------------------------------------------------
+    def step(self, *args):
+        img = args[0]
+        if img is None:
+            result = (None, None)
+        elif isinstance(img, torch.Tensor):
+            single = img.dim() == 3
+            u8, f32 = self.process_device(img[None] if single else img)
+            result = (u8[0], f32[0] if f32 is not None else None) if single else (u8, f32)
+        else:
+            arr = np.asarray(img)
+            single = arr.ndim == 3
+            batch = arr[None] if single else arr
+            f32 = np.empty(batch.shape, np.float32) if self.want_f32 else None
+            u8, f32 = self.process_host(batch, out_f32=f32)
+            result = (u8[0], f32[0] if f32 is not None else None) if single else (u8, f32)
+        if self.emulate_latency:
+            previous = (self.processed_img, self.normalised_img)
+            self.processed_img, self.normalised_img = result
+            result = previous
+        else:
+            self.processed_img, self.normalised_img = result
+        return (result[0], result[1]) if self.want_f32 else (result[0],)
+
+    def thread_step(self):
+        """The reference polls a hand-off slot from a worker thread (img_preprocessing.py:23-35); here `step` does the
+        work itself on the GPU stream, so there is nothing to run."""
+        return
+
+    def onShutdown(self):
+        self.running = False
+        self.ctx.close()
+
+    def getName(self):
+        return 'Image Preprocessing'
+
+
+class LocationTracker(Component):
+    """Batched ``LocationTracker``: nearest waypoint (L1, float64, first index on ties, sentinel 100) -> segment."""
+
+    def __init__(self, track_data_path, min_map=0, max_map=10, device=None):
+        Component.__init__(self, inputs=['gym/x', 'gym/y', 'gym/z'], outputs=['loc/segment'])
+        if isinstance(track_data_path, (str, bytes)) or hasattr(track_data_path, "__fspath__"):
+            with open(track_data_path, 'r') as input_file:        # FileNotFoundError propagates (track_data_process.py:72)
+                self.data = json.load(input_file)
+        else:
+            self.data = np.asarray(track_data_path, np.float64).tolist()
+        self.max = max_map
+        self.min = min_map
+        self.device = _device_index(device)
+        self.ctx = nat.Context(self.device)
+        wp = np.ascontiguousarray(np.asarray(self.data, dtype=np.float64).reshape(-1, 3))
+        # (max - min) is evaluated in python like the reference (ints stay exact), then handed over as doubles
+        nat.check(self.ctx.lib.trs_set_track(self.ctx.handle, _np_ptr(wp), wp.shape[0], float(min_map), float(max_map)),
+                  "trs_set_track")
+        self.n_wp = wp.shape[0]
+
+    def locate_device(self, xyz: torch.Tensor, want_idx=True, want_segment=True):
+        """xyz (N,3) float64 CUDA tensor -> (idx int32 (N,), segment float64 (N,))."""
+        if xyz.dtype != torch.float64 or xyz.dim() != 2 or xyz.shape[1] != 3:
+            raise ValueError(f"expected (N,3) float64, got {tuple(xyz.shape)} {xyz.dtype}")
+        xyz = xyz.contiguous()
+        n = xyz.shape[0]
+        idx = torch.empty(n, dtype=torch.int32, device=xyz.device) if want_idx else None
+        seg = torch.empty(n, dtype=torch.float64, device=xyz.device) if want_segment else None
+        nat.check(self.ctx.lib.trs_locate(self.ctx.handle, _ptr(xyz), n, _ptr(idx), _ptr(seg), _stream_ptr(self.device)), "trs_locate")
+        return idx, seg
+
+    def localize(self, point):
+        seg = self.step(point[0], point[1], point[2])[0]
+        return seg, 0.0
+
+    def step(self, *args):
+        x, y, z = args[0], args[1], args[2]
+        if isinstance(x, torch.Tensor) and x.dim() >= 1:
+            xyz = torch.stack([x.to(torch.float64), y.to(torch.float64), z.to(torch.float64)], dim=1)
+            return self.locate_device(xyz, want_idx=False)[1],
+        if isinstance(x, np.ndarray) and x.ndim >= 1:
+            xyz = torch.from_numpy(np.stack([x, y, z], axis=1).astype(np.float64)).to(f"cuda:{self.device}")
+            return self.locate_device(xyz, want_idx=False)[1].cpu().numpy(),
+        xyz = torch.tensor([[float(x), float(y), float(z)]], dtype=torch.float64, device=f"cuda:{self.device}")  # TypeError on None, like the reference
+        return float(self.locate_device(xyz, want_idx=False)[1].item()),
+
+    def onShutdown(self):
+        self.ctx.close()
+
+    def getName(self):
+        return 'Location Tracker'
+
+
+class SpeedControl(Component):
+    """The pilots' post-model glue for ``cnn_2d_speed_control`` / ``cnn_2d_full_house``, batched.
+
+    step(gym/speed (N,) f64, model steering (N,) f32, model speed (N,) f32) -> ai/steering, ai/throttle, ai/breaking (f64).
+    ``features(gym/speed)`` gives the float32 ``speed / 20`` model input (keras_pilot.py:68,100).
+    """
+
+    def __init__(self, cfg={}, device=None):
+        Component.__init__(self, inputs=['gym/speed', 'pilot/steering', 'pilot/speed'],
+                           outputs=['ai/steering', 'ai/throttle', 'ai/breaking'])
+        self.cfg = default_config()
+        self.cfg.update(cfg)
+        self.device = _device_index(device)
+        self.ctx = nat.Context(self.device)
+        self.params = nat.spd_params_from_cfg(self.cfg)
+        self.last_feature = None
+
+    def control_device(self, cur: torch.Tensor, steer: torch.Tensor, spd: torch.Tensor, want_feature=False):
+        n = cur.shape[0]
+        cur = cur.to(torch.float64).contiguous()
+        steer = steer.to(torch.float32).contiguous()
+        spd = spd.to(torch.float32).contiguous()
+        out = torch.empty((3, n), dtype=torch.float64, device=cur.device)
+        feat = torch.empty(n, dtype=torch.float32, device=cur.device) if want_feature else None
+        nat.check(self.ctx.lib.trs_speed_control(self.ctx.handle, _ptr(cur), _ptr(spd), _ptr(steer), n, C.byref(self.params),
+                                                 _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(feat), _stream_ptr(self.device)),
+                  "trs_speed_control")
+        return out[0], out[1], out[2], feat
+
+    def step(self, *args):
+        cur, steer, spd = args[0], args[1], args[2]
+        if cur is None:
+            return 0.0, 0.0, 0.0                                   # keras_pilot.py:46-47
+        if isinstance(cur, torch.Tensor) and cur.dim() >= 1:
+            s, t, b, _ = self.control_device(cur, steer, spd)
+            return s, t, b
+        dev = f"cuda:{self.device}"
+        if isinstance(cur, np.ndarray) and cur.ndim >= 1:
+            s, t, b, _ = self.control_device(torch.from_numpy(np.asarray(cur, np.float64)).to(dev),
+                                             torch.from_numpy(np.asarray(steer, np.float32)).to(dev),
+                                             torch.from_numpy(np.asarray(spd, np.float32)).to(dev))
+            return s.cpu().numpy(), t.cpu().numpy(), b.cpu().numpy()
+        s, t, b, _ = self.control_device(torch.tensor([float(cur)], dtype=torch.float64, device=dev),
+                                         torch.tensor([float(steer)], dtype=torch.float32, device=dev),
+                                         torch.tensor([float(spd)], dtype=torch.float32, device=dev))
+        return float(s.item()), float(t.item()), float(b.item())
+
+    def onShutdown(self):
+        self.ctx.close()
+
+    def getName(self):
+        return 'Speed Control'
+
+
+class FrameNormalise(Component):
+    """Camera-side resize (nearest, camera.py:36), optional window crop, and the ``/255`` float32 normalisation
+    (keras_pilot.py:49-50, keras_train.py:41-42) for N frames: cam/img -> cam/normalised_img."""
+
+    def __init__(self, cfg={}, device=None, roi=None, out_hw=None):
+        Component.__init__(self, inputs=['cam/img'], outputs=['cam/normalised_img'])
+        self.cfg = default_config()
+        self.cfg.update(cfg)
+        self.device = _device_index(device)
+        self.ctx = nat.Context(self.device)
+        self.roi = roi                                  # (y0, y1, x0, x1) in source pixels, or None = whole frame
+        self.out_hw = out_hw                            # (h, w) or None = window size (no resize)
+
+    def normalise_device(self, frames: torch.Tensor, want_u8=False):
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+            raise ValueError(f"expected (N,H,W,3) uint8 frames, got {tuple(frames.shape)} {frames.dtype}")
+        frames = frames.contiguous()
+        n, h, w, _ = frames.shape
+        y0, y1, x0, x1 = self.roi if self.roi is not None else (0, h, 0, w)
+        ho, wo = self.out_hw if self.out_hw is not None else (y1 - y0, x1 - x0)
+        out = torch.empty((n, ho, wo, 3), dtype=torch.float32, device=frames.device)
+        u8 = torch.empty((n, ho, wo, 3), dtype=torch.uint8, device=frames.device) if want_u8 else None
+        nat.check(self.ctx.lib.trs_normalise(self.ctx.handle, _ptr(frames), n, h, w, y0, y1, x0, x1, ho, wo, _ptr(out), _ptr(u8),
+                                             _stream_ptr(self.device)), "trs_normalise")
+        return (out, u8) if want_u8 else out
+
+    def step(self, *args):
+        img = args[0]
+        if img is None:
+            return None,
+        if isinstance(img, torch.Tensor):
+            single = img.dim() == 3
+            out = self.normalise_device(img[None] if single else img)
+            return (out[0] if single else out),
+        arr = np.asarray(img)
+        single = arr.ndim == 3
+        t = torch.from_numpy(np.ascontiguousarray(arr[None] if single else arr)).to(f"cuda:{self.device}")
+        out = self.normalise_device(t).cpu().numpy()
+        return (out[0] if single else out),
+
+    def onShutdown(self):
+        self.ctx.close()
+
+    def getName(self):
+        return 'Frame Normalise'

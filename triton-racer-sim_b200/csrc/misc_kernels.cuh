@@ -1,0 +1,189 @@
+// misc_kernels.cuh — normalise/crop/resize, waypoint lookup, speed control (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace trs {
+
+// ------------------------------------------------------------------------------------------------------
+// K1a: pure streaming normalise, u8 -> f32 (keras_pilot.py:49-50; keras_train.py:41-42).
+// One thread converts 16 input bytes (one 128-bit load) into four 128-bit stores; consecutive lanes take
+// consecutive 16-byte chunks so a warp reads 512 contiguous bytes and writes 2 KB contiguous.
+// 1/255 is not exactly representable: true division (div.rn) is required, 126 of 256 inputs differ otherwise.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float norm255(uint32_t b) { return __fdiv_rn((float)b, 255.0f); }
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, float4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float4 norm_word(uint32_t w)
+{
+    return make_float4(norm255(w & 0xff), norm255((w >> 8) & 0xff), norm255((w >> 16) & 0xff), norm255(w >> 24));
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_normalise_stream(const uint4* __restrict__ in, float4* __restrict__ out, size_t n_chunks)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < n_chunks; i += UNROLL * stride) {
+        uint4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) v[u] = ldg_stream(in + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            float4* o = out + 4 * (i + u * stride);
+            stg_stream(o, norm_word(v[u].x));
+            stg_stream(o + 1, norm_word(v[u].y));
+            stg_stream(o + 2, norm_word(v[u].z));
+            stg_stream(o + 3, norm_word(v[u].w));
+        }
+    }
+    for (; i < n_chunks; i += stride) {
+        const uint4 v = ldg_stream(in + i);
+        float4* o = out + 4 * i;
+        stg_stream(o, norm_word(v.x)); stg_stream(o + 1, norm_word(v.y));
+        stg_stream(o + 2, norm_word(v.z)); stg_stream(o + 3, norm_word(v.w));
+    }
+}
+
+// tail / unaligned fallback: one byte per thread
+__global__ void k_normalise_bytes(const uint8_t* __restrict__ in, float* __restrict__ out, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = norm255(in[i]);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1b: window crop + nearest resize (camera.py:36: src = floor(dst * size_src / size_dst)) + normalise.
+// One thread per output pixel; lanes walk along the output row so the source reads of a warp fall in one
+// or two source rows (2:1 down-scale touches every other pixel: half of each fetched sector is used).
+// ------------------------------------------------------------------------------------------------------
+struct ResizeParams {
+    const uint8_t* in;
+    float* out_f32;
+    uint8_t* out_u8;
+    int n, h_in, w_in, y0, x0, hs, ws, h_out, w_out;
+};
+
+__global__ void __launch_bounds__(256) k_crop_resize(const __grid_constant__ ResizeParams p)
+{
+    const size_t total = (size_t)p.n * p.h_out * p.w_out;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int x = (int)(i % p.w_out);
+        const size_t t = i / p.w_out;
+        const int y = (int)(t % p.h_out);
+        const size_t f = t / p.h_out;
+        const int sy = p.y0 + (int)(((long long)y * p.hs) / p.h_out);
+        const int sx = p.x0 + (int)(((long long)x * p.ws) / p.w_out);
+        const uint8_t* s = p.in + ((f * p.h_in + sy) * p.w_in + sx) * 3;
+        const uint8_t r = s[0], g = s[1], b = s[2];
+        if (p.out_u8) { uint8_t* o = p.out_u8 + i * 3; o[0] = r; o[1] = g; o[2] = b; }
+        if (p.out_f32) { float* o = p.out_f32 + i * 3; o[0] = norm255(r); o[1] = norm255(g); o[2] = norm255(b); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K6: nearest waypoint, L1 distance in float64, first index wins ties, running minimum starts at 100
+// (track_data_process.py:89-107).  The centre line sits in shared memory as (x,y,z,pad) f64 quads; every lane
+// of a warp reads the same waypoint (broadcast), each thread carries CARS cars so one shared-memory read
+// feeds CARS distance evaluations.  Distances are summed left to right exactly as the reference does.
+// ------------------------------------------------------------------------------------------------------
+enum { LOC_THREADS = 256, LOC_CARS = 2, LOC_TILE = 1024 };
+
+__global__ void __launch_bounds__(LOC_THREADS) k_locate(const double* __restrict__ wp, int n_wp, double min_map, double max_map,
+                                                       const double* __restrict__ xyz, int n, int32_t* __restrict__ idx_out,
+                                                       double* __restrict__ seg_out)
+{
+    __shared__ double4 s_wp[LOC_TILE];
+    const int base = (blockIdx.x * LOC_THREADS + threadIdx.x) * LOC_CARS;
+    double px[LOC_CARS], py[LOC_CARS], pz[LOC_CARS], best[LOC_CARS];
+    int sel[LOC_CARS];
+#pragma unroll
+    for (int c = 0; c < LOC_CARS; ++c) {
+        const int k = min(base + c, n - 1);
+        px[c] = xyz[3 * (size_t)k]; py[c] = xyz[3 * (size_t)k + 1]; pz[c] = xyz[3 * (size_t)k + 2];
+        best[c] = 100.0; sel[c] = 0;
+    }
+    for (int t0 = 0; t0 < n_wp; t0 += LOC_TILE) {
+        const int tn = min(LOC_TILE, n_wp - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn; i += LOC_THREADS)
+            s_wp[i] = make_double4(wp[3 * (size_t)(t0 + i)], wp[3 * (size_t)(t0 + i) + 1], wp[3 * (size_t)(t0 + i) + 2], 0.0);
+        __syncthreads();
+#pragma unroll 4
+        for (int i = 0; i < tn; ++i) {
+            const double4 q = s_wp[i];
+#pragma unroll
+            for (int c = 0; c < LOC_CARS; ++c) {
+                const double d = __dadd_rn(__dadd_rn(fabs(__dsub_rn(px[c], q.x)), fabs(__dsub_rn(py[c], q.y))), fabs(__dsub_rn(pz[c], q.z)));
+                if (d < best[c]) { best[c] = d; sel[c] = t0 + i; }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < LOC_CARS; ++c) {
+        const int k = base + c;
+        if (k < n) {
+            if (idx_out) idx_out[k] = sel[c];
+            if (seg_out) {
+                const double q = __ddiv_rn((double)sel[c], (double)n_wp);
+                seg_out[k] = __dadd_rn(__dmul_rn(q, __dsub_rn(max_map, min_map)), min_map);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K7: speed-control tail of the pilots (keras_pilot.py:80-95 == 99-118, 142-153; utils/mapping.py:23-35).
+// Types follow numpy >= 2 promotion with np.float32 model outputs: the products and the speed difference are
+// float32, atan and everything after it float64.
+// ------------------------------------------------------------------------------------------------------
+struct SpdKParams {
+    double threshold, reverse_multiplier, break_multiplier, smooth_threshold;
+    int use_break, smooth_steering;
+};
+
+__global__ void __launch_bounds__(256) k_speed_control(const double* __restrict__ cur, const float* __restrict__ model_spd,
+                                                      const float* __restrict__ model_steer, int n, const SpdKParams p,
+                                                      double* __restrict__ steer_out, double* __restrict__ thr_out,
+                                                      double* __restrict__ brk_out, float* __restrict__ feat_out)
+{
+    const double half_pi = 3.141592653589793 / 2.0;
+    const int stride = gridDim.x * blockDim.x;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const double real_spd = cur[k];
+        const float steer_f = model_steer[k];
+        double steering = (double)steer_f;
+        if (steer_f < -1.0f) steering = -1.0; else if (steer_f > 1.0f) steering = 1.0;
+        const float predicted = __fmul_rn(model_spd[k], 20.0f);
+        const float target = __fmul_rn(predicted, (float)p.threshold);
+        const float real_f = (float)real_spd;
+        const float delta = __fsub_rn(target, real_f);
+        double throttle = __ddiv_rn(__dmul_rn(p.reverse_multiplier, atan((double)__fmul_rn(delta, 2.0f))), half_pi);
+        if (-0.2 < throttle && throttle < 0.0) throttle = 0.0;
+        double breaking = 0.0;
+        if (p.use_break) {
+            throttle = (__fsub_rn(predicted, real_f) > 0.0f) ? 1.0 : 0.0;
+            breaking = __ddiv_rn(__dmul_rn(__dmul_rn(-1.0, p.break_multiplier), atan((double)delta)), half_pi);
+            if (breaking < 0.4) breaking = 0.0;
+        }
+        if (p.smooth_steering) {
+            if (steering > p.smooth_threshold) steering = 1.0;
+            else if (steering < p.smooth_threshold * -1.0) steering = -1.0;
+        }
+        steer_out[k] = steering; thr_out[k] = throttle; brk_out[k] = breaking;
+        if (feat_out) feat_out[k] = (float)__ddiv_rn(real_spd, 20.0);
+    }
+}
+
+}  // namespace trs

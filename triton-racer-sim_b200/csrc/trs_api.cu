@@ -1,0 +1,465 @@
+// trs_api.cu — the C ABI declared in include/trs_b200.h, over the sm_100a kernels.
+//
+// Host-side mirror of what the reference's Python does around its library calls: parameter validation and
+// derivation (threshold swap/floor, bound rounding, merge order), launch geometry, and the host-buffer pipeline.
+// No CPU implementation of any stage lives here: if there is no sm_100 device the calls fail.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <new>
+
+#include "../../include/trs_b200.h"
+#include "misc_kernels.cuh"
+#include "preproc_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    snprintf(g_err, sizeof g_err, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e > 0 ? (int)e : 1;
+}
+
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
+    } while (0)
+
+// cvRound semantics of OpenCV's scalar -> int32 conversion (half-to-even; out of range -> INT_MIN)
+int32_t round_bound(double v)
+{
+    if (!(v > -2147483648.5 && v < 2147483647.5)) return INT32_MIN;
+    return (int32_t)nearbyint(v);
+}
+
+enum { HOST_STREAMS = 3 };
+
+}  // namespace
+
+struct trs_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    int cc_major = 0, cc_minor = 0;
+    std::mutex mu;
+    // preprocessing
+    bool have_params = false;
+    trs_preproc_params user{};
+    trs::PreKParams kp{};              // derived, geometry fields filled per call
+    // track
+    double* wp_dev = nullptr;
+    int n_wp = 0;
+    double min_map = 0, max_map = 10;
+    // host pipeline
+    cudaStream_t hs[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    uint8_t* st_in[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    uint8_t* st_u8[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    float* st_f32[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    size_t st_in_cap = 0, st_u8_cap = 0, st_f32_cap = 0;
+    unsigned long long* stats_dev = nullptr;
+};
+
+namespace {
+
+void default_params(trs_preproc_params* p)
+{
+    memset(p, 0, sizeof *p);
+    p->contrast_ratio = 1.0;
+    p->contrast_offset = 125;
+    p->brightness_baseline = 550;
+    p->edge_dest = 2;
+    p->canny_a = 60;
+    p->canny_b = 100;
+}
+
+int derive_params(trs_ctx* ctx, const trs_preproc_params* u)
+{
+    trs::PreKParams k{};
+    if (u->color_filter_enabled && (u->n_hsv < 0 || u->n_hsv > TRS_MAX_HSV))
+        return fail(TRS_E_ARG, "n_hsv=%d outside [0,%d]", u->n_hsv, TRS_MAX_HSV);
+    // brightness / contrast (img_preprocessing.py:81-102)
+    k.dynamic = u->dynamic_brightness ? 1 : 0;
+    k.foff = (float)u->contrast_offset;
+    k.fratio = (float)u->contrast_ratio;
+    k.baseline = u->brightness_baseline;
+    k.lut_identity = 1;
+    for (int i = 0; i < 256; ++i) {
+        k.lut[i] = trs::adjust_entry(i, false, 0.0f, k.foff, k.fratio);
+        if (k.lut[i] != i) k.lut_identity = 0;
+    }
+    // merge order (img_preprocessing.py:44-53,57-62): colour layers in list order, then the edge layer; later wins
+    int src[3] = {trs::SRC_PIXEL, trs::SRC_PIXEL, trs::SRC_PIXEL};
+    const int n_hsv = u->color_filter_enabled ? u->n_hsv : 0;
+    for (int i = 0; i < n_hsv; ++i) {
+        int ch = u->color_dest[i];
+        if (ch < -3 || ch > 2) return fail(TRS_E_ARG, "colour destination channel %d out of range for an RGB frame", ch);
+        if (ch < 0) ch += 3;                        // numpy negative index
+        src[ch] = trs::SRC_MASK0 + i;
+    }
+    k.edge_enabled = u->edge_enabled ? 1 : 0;
+    if (k.edge_enabled) {
+        int ch = u->edge_dest;
+        if (ch < -3 || ch > 2) return fail(TRS_E_ARG, "edge destination channel %d out of range for an RGB frame", ch);
+        if (ch < 0) ch += 3;
+        src[ch] = trs::SRC_EDGE;
+    }
+    // keep only colour ranges that still reach the output
+    k.n_ranges = 0;
+    for (int i = 0; i < n_hsv; ++i) {
+        bool used = false;
+        for (int c = 0; c < 3; ++c) used |= (src[c] == trs::SRC_MASK0 + i);
+        if (!used) continue;
+        const int slot = k.n_ranges++;
+        for (int c = 0; c < 3; ++c) {
+            k.ranges[slot].lo[c] = round_bound(u->hsv_lo[i][c]);
+            k.ranges[slot].hi[c] = round_bound(u->hsv_hi[i][c]);
+            if (src[c] == trs::SRC_MASK0 + i) src[c] = -(slot + 1);      // temporary marker
+        }
+        k.range_stat[slot] = i;
+    }
+    k.need_pixels = 0;
+    for (int c = 0; c < 3; ++c) {
+        if (src[c] < 0) src[c] = trs::SRC_MASK0 + (-src[c] - 1);
+        k.src[c] = src[c];
+        if (src[c] == trs::SRC_PIXEL) k.need_pixels = 1;
+    }
+    // cv2.Canny(img, a, b): swap if a > b, then floor (L1 norm)
+    double a = u->canny_a, b = u->canny_b;
+    if (a > b) { double t = a; a = b; b = t; }
+    if (!(a > -2e9 && b < 2e9)) return fail(TRS_E_ARG, "edge thresholds out of range");
+    k.low = (int)floor(a);
+    k.high = (int)floor(b);
+    ctx->kp = k;
+    ctx->user = *u;
+    ctx->have_params = true;
+    return 0;
+}
+
+struct Geometry {
+    int band_h, row_stride, mag_stride, wwords, smem, ctas_per_sm;
+};
+
+int plan_geometry(trs_ctx* ctx, int h, int w, int n_ranges, Geometry* g)
+{
+    g->wwords = (w + 31) / 32;
+    g->row_stride = ((w * 3 + 15) & ~15) + 16;
+    g->mag_stride = (w + 3) & ~1;
+    const int budget2 = (ctx->smem_optin + 1024) / 2 - 1024;       // two CTAs per SM (1 KB per-CTA reserve)
+    auto fits = [&](int band_h, int budget) {
+        return trs::pre_smem_layout(h, w, band_h, g->row_stride, g->mag_stride, g->wwords, n_ranges).total <= budget;
+    };
+    auto largest = [&](int budget) {
+        int lo = 0, hi = h;
+        while (lo < hi) { int mid = (lo + hi + 1) / 2; if (fits(mid, budget)) lo = mid; else hi = mid - 1; }
+        return lo;
+    };
+    int band = largest(budget2);
+    if (band < (h < 16 ? h : 16)) band = largest(ctx->smem_optin);
+    if (band < 1) return fail(TRS_E_RANGE, "frame %dx%d does not fit the on-chip working set (%d B shared memory)", h, w, ctx->smem_optin);
+    const int nb = (h + band - 1) / band;
+    g->band_h = (h + nb - 1) / nb;
+    g->smem = trs::pre_smem_layout(h, w, g->band_h, g->row_stride, g->mag_stride, g->wwords, n_ranges).total;
+    return 0;
+}
+
+int launch_preprocess(trs_ctx* ctx, const uint8_t* in, int n, int h, int w, uint8_t* out_u8, float* out_f32,
+                      unsigned long long* stats, uint16_t* dbg_mag, uint8_t* dbg_map, bool force_edge, cudaStream_t st)
+{
+    trs::PreKParams k = ctx->kp;
+    if (force_edge && !k.edge_enabled) { k.edge_enabled = 1; }
+    Geometry g;
+    int rc = plan_geometry(ctx, h, w, k.n_ranges, &g);
+    if (rc) return rc;
+    k.in = in; k.out_u8 = out_u8; k.out_f32 = out_f32; k.stats = stats; k.dbg_mag = dbg_mag; k.dbg_map = dbg_map;
+    k.n = n; k.h = h; k.w = w;
+    k.band_h = g.band_h; k.row_stride = g.row_stride; k.mag_stride = g.mag_stride; k.wwords = g.wwords;
+    const size_t frame_bytes = (size_t)h * w * 3;
+    k.word_io = ((w * 3) % 4 == 0) && (((uintptr_t)in & 15) == 0) && (!out_u8 || ((uintptr_t)out_u8 & 15) == 0) &&
+                (!out_f32 || ((uintptr_t)out_f32 & 15) == 0) && (frame_bytes % 4 == 0);
+    CU(cudaFuncSetAttribute(trs::k_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trs::k_preprocess, trs::PRE_THREADS, g.smem));
+    if (per_sm < 1) return fail(TRS_E_RANGE, "kernel does not fit an SM with %d B shared memory", g.smem);
+    int grid = ctx->sm_count * per_sm;
+    if (grid > n) grid = n;
+    trs::k_preprocess<<<grid, trs::PRE_THREADS, g.smem, st>>>(k);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int bind(trs_ctx* ctx)
+{
+    if (!ctx) return fail(TRS_E_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int trs_version(void) { return TRS_VERSION; }
+const char* trs_last_error(void) { return g_err; }
+unsigned long long trs_kernel_launches(void) { return g_launches.load(); }
+
+int trs_ctx_create(int device, trs_ctx** out)
+{
+    if (!out) return fail(TRS_E_ARG, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(TRS_E_NODEVICE, "no CUDA device (%s): this library has no CPU path", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(TRS_E_ARG, "device %d of %d", device, count);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(TRS_E_NODEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+    trs_ctx* c = new (std::nothrow) trs_ctx();
+    if (!c) return fail(TRS_E_ARG, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c->cc_major = prop.major; c->cc_minor = prop.minor;
+    trs_preproc_params d;
+    default_params(&d);
+    derive_params(c, &d);
+    *out = c;
+    return 0;
+}
+
+int trs_ctx_destroy(trs_ctx* ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < HOST_STREAMS; ++i) {
+        if (ctx->hs[i]) cudaStreamDestroy(ctx->hs[i]);
+        cudaFree(ctx->st_in[i]); cudaFree(ctx->st_u8[i]); cudaFree(ctx->st_f32[i]);
+    }
+    cudaFree(ctx->wp_dev);
+    cudaFree(ctx->stats_dev);
+    delete ctx;
+    return 0;
+}
+
+int trs_ctx_device_info(trs_ctx* ctx, int* sm_count, int* smem_optin_bytes, int* cc_major, int* cc_minor)
+{
+    if (!ctx) return fail(TRS_E_ARG, "null context");
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (smem_optin_bytes) *smem_optin_bytes = ctx->smem_optin;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    return 0;
+}
+
+int trs_set_preproc_params(trs_ctx* ctx, const trs_preproc_params* p)
+{
+    if (!ctx || !p) return fail(TRS_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return derive_params(ctx, p);
+}
+
+int trs_preprocess(trs_ctx* ctx, const uint8_t* in_dev, int n, int h, int w, uint8_t* out_u8_dev, float* out_f32_dev,
+                   unsigned long long* stats_dev, void* stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0 || h < 0 || w < 0) return fail(TRS_E_ARG, "negative size n=%d h=%d w=%d", n, h, w);
+    if (n == 0 || h == 0 || w == 0) return 0;
+    if (!in_dev) return fail(TRS_E_ARG, "null input");
+    if (!out_u8_dev && !out_f32_dev && !stats_dev) return fail(TRS_E_ARG, "no output requested");
+    return launch_preprocess(ctx, in_dev, n, h, w, out_u8_dev, out_f32_dev, stats_dev, nullptr, nullptr, false, (cudaStream_t)stream);
+}
+
+int trs_debug_canny_stages(trs_ctx* ctx, const uint8_t* in_dev, int h, int w, uint16_t* mag_dev, uint8_t* map_dev, void* stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!in_dev || h <= 0 || w <= 0) return fail(TRS_E_ARG, "bad argument");
+    return launch_preprocess(ctx, in_dev, 1, h, w, nullptr, nullptr, nullptr, mag_dev, map_dev, true, (cudaStream_t)stream);
+}
+
+int trs_normalise(trs_ctx* ctx, const uint8_t* in_dev, int n, int h_in, int w_in, int roi_y0, int roi_y1, int roi_x0, int roi_x1,
+                  int h_out, int w_out, float* out_f32_dev, uint8_t* out_u8_dev, void* stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0 || h_in < 0 || w_in < 0 || h_out < 0 || w_out < 0) return fail(TRS_E_ARG, "negative size");
+    if (roi_y0 < 0 || roi_x0 < 0 || roi_y1 > h_in || roi_x1 > w_in || roi_y1 < roi_y0 || roi_x1 < roi_x0)
+        return fail(TRS_E_ARG, "window rows [%d,%d) cols [%d,%d) outside a %dx%d frame", roi_y0, roi_y1, roi_x0, roi_x1, h_in, w_in);
+    if (n == 0 || h_out == 0 || w_out == 0) return 0;
+    if (roi_y1 == roi_y0 || roi_x1 == roi_x0) return fail(TRS_E_ARG, "empty source window for a non-empty output");
+    if (!in_dev || (!out_f32_dev && !out_u8_dev)) return fail(TRS_E_ARG, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool identity = roi_y0 == 0 && roi_x0 == 0 && roi_y1 == h_in && roi_x1 == w_in && h_out == h_in && w_out == w_in;
+    const size_t total = (size_t)n * h_out * w_out * 3;
+    if (identity && out_f32_dev && !out_u8_dev && ((uintptr_t)in_dev & 15) == 0 && ((uintptr_t)out_f32_dev & 15) == 0) {
+        const size_t chunks = total / 16;
+        if (chunks) {
+            size_t want = (chunks + 256 * 4 - 1) / (256 * 4);
+            const size_t cap = (size_t)ctx->sm_count * 32;
+            const int grid = (int)(want < cap ? want : cap);
+            trs::k_normalise_stream<4><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(in_dev), reinterpret_cast<float4*>(out_f32_dev), chunks);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        const size_t done = chunks * 16;
+        if (done < total) {
+            trs::k_normalise_bytes<<<1, 32, 0, st>>>(in_dev + done, out_f32_dev + done, total - done);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        CU(cudaGetLastError());
+        return 0;
+    }
+    trs::ResizeParams p{in_dev, out_f32_dev, out_u8_dev, n, h_in, w_in, roi_y0, roi_x0, roi_y1 - roi_y0, roi_x1 - roi_x0, h_out, w_out};
+    const size_t px = total / 3;
+    size_t want = (px + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    trs::k_crop_resize<<<(int)(want < cap ? want : cap), 256, 0, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trs_set_track(trs_ctx* ctx, const double* wp_xyz_host, int n_wp, double min_map, double max_map)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!wp_xyz_host || n_wp <= 0) return fail(TRS_E_ARG, "empty centre line");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaFree(ctx->wp_dev);
+    ctx->wp_dev = nullptr;
+    CU(cudaMalloc(&ctx->wp_dev, sizeof(double) * 3 * (size_t)n_wp));
+    CU(cudaMemcpy(ctx->wp_dev, wp_xyz_host, sizeof(double) * 3 * (size_t)n_wp, cudaMemcpyHostToDevice));
+    ctx->n_wp = n_wp;
+    ctx->min_map = min_map;
+    ctx->max_map = max_map;
+    return 0;
+}
+
+int trs_locate(trs_ctx* ctx, const double* xyz_dev, int n, int32_t* idx_dev, double* segment_dev, void* stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!ctx->wp_dev) return fail(TRS_E_STATE, "trs_locate before trs_set_track");
+    if (n < 0) return fail(TRS_E_ARG, "negative n");
+    if (n == 0) return 0;
+    if (!xyz_dev || (!idx_dev && !segment_dev)) return fail(TRS_E_ARG, "null pointer");
+    const int per_block = trs::LOC_THREADS * trs::LOC_CARS;
+    const int grid = (n + per_block - 1) / per_block;
+    trs::k_locate<<<grid, trs::LOC_THREADS, 0, (cudaStream_t)stream>>>(ctx->wp_dev, ctx->n_wp, ctx->min_map, ctx->max_map, xyz_dev, n, idx_dev, segment_dev);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trs_speed_control(trs_ctx* ctx, const double* cur_spd_dev, const float* model_spd_dev, const float* model_steer_dev, int n,
+                      const trs_spd_params* p, double* steering_dev, double* throttle_dev, double* breaking_dev,
+                      float* spd_feature_dev, void* stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0 || !p) return fail(TRS_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    if (!cur_spd_dev || !model_spd_dev || !model_steer_dev || !steering_dev || !throttle_dev || !breaking_dev)
+        return fail(TRS_E_ARG, "null pointer");
+    trs::SpdKParams k{p->threshold, p->reverse_multiplier, p->break_multiplier, p->smooth_threshold, p->use_break ? 1 : 0,
+                      p->smooth_steering ? 1 : 0};
+    int grid = (n + 255) / 256;
+    const int cap = ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    trs::k_speed_control<<<grid, 256, 0, (cudaStream_t)stream>>>(cur_spd_dev, model_spd_dev, model_steer_dev, n, k, steering_dev,
+                                                                  throttle_dev, breaking_dev, spd_feature_dev);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trs_host_alloc(void** out, unsigned long long bytes)
+{
+    if (!out) return fail(TRS_E_ARG, "null out pointer");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+
+int trs_host_free(void* p)
+{
+    if (p) CU(cudaFreeHost(p));
+    return 0;
+}
+
+int trs_preprocess_host(trs_ctx* ctx, const uint8_t* in_host, int n, int h, int w, uint8_t* out_u8_host, float* out_f32_host,
+                        float* keep_f32_dev, unsigned long long* stats_host)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0 || h < 0 || w < 0) return fail(TRS_E_ARG, "negative size");
+    if (stats_host) memset(stats_host, 0, sizeof(unsigned long long) * TRS_STAT_COUNT);
+    if (n == 0 || h == 0 || w == 0) return 0;
+    if (!in_host) return fail(TRS_E_ARG, "null input");
+    if (!out_u8_host && !out_f32_host && !keep_f32_dev && !stats_host) return fail(TRS_E_ARG, "no output requested");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t fb = (size_t)h * w * 3;
+    size_t chunk = (size_t)(24u << 20) / fb;                   // ~24 MB of frames per chunk
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)n) chunk = n;
+    chunk = (chunk + 3) & ~(size_t)3;                          // keeps every chunk base 16-byte aligned when fb % 4 == 0
+    for (int i = 0; i < HOST_STREAMS; ++i)
+        if (!ctx->hs[i]) CU(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
+    const bool need_f32 = out_f32_host != nullptr;
+    if (ctx->st_in_cap < chunk * fb) {
+        for (int i = 0; i < HOST_STREAMS; ++i) { cudaFree(ctx->st_in[i]); ctx->st_in[i] = nullptr; CU(cudaMalloc(&ctx->st_in[i], chunk * fb)); }
+        ctx->st_in_cap = chunk * fb;
+    }
+    if (out_u8_host && ctx->st_u8_cap < chunk * fb) {
+        for (int i = 0; i < HOST_STREAMS; ++i) { cudaFree(ctx->st_u8[i]); ctx->st_u8[i] = nullptr; CU(cudaMalloc(&ctx->st_u8[i], chunk * fb)); }
+        ctx->st_u8_cap = chunk * fb;
+    }
+    if (need_f32 && !keep_f32_dev && ctx->st_f32_cap < chunk * fb * 4) {
+        for (int i = 0; i < HOST_STREAMS; ++i) { cudaFree(ctx->st_f32[i]); ctx->st_f32[i] = nullptr; CU(cudaMalloc(&ctx->st_f32[i], chunk * fb * 4)); }
+        ctx->st_f32_cap = chunk * fb * 4;
+    }
+    if (stats_host) {
+        if (!ctx->stats_dev) CU(cudaMalloc(&ctx->stats_dev, sizeof(unsigned long long) * TRS_STAT_COUNT));
+        CU(cudaMemsetAsync(ctx->stats_dev, 0, sizeof(unsigned long long) * TRS_STAT_COUNT, ctx->hs[0]));
+        CU(cudaStreamSynchronize(ctx->hs[0]));
+    }
+    int ci = 0;
+    for (size_t f0 = 0; f0 < (size_t)n; f0 += chunk, ++ci) {
+        const int s = ci % HOST_STREAMS;
+        const size_t cn = (size_t)n - f0 < chunk ? (size_t)n - f0 : chunk;
+        cudaStream_t st = ctx->hs[s];
+        CU(cudaMemcpyAsync(ctx->st_in[s], in_host + f0 * fb, cn * fb, cudaMemcpyHostToDevice, st));
+        uint8_t* du8 = out_u8_host ? ctx->st_u8[s] : nullptr;
+        float* df32 = keep_f32_dev ? keep_f32_dev + f0 * fb : (need_f32 ? ctx->st_f32[s] : nullptr);
+        rc = launch_preprocess(ctx, ctx->st_in[s], (int)cn, h, w, du8, df32, stats_host ? ctx->stats_dev : nullptr, nullptr, nullptr, false, st);
+        if (rc) return rc;
+        if (out_u8_host) CU(cudaMemcpyAsync(out_u8_host + f0 * fb, du8, cn * fb, cudaMemcpyDeviceToHost, st));
+        if (need_f32) CU(cudaMemcpyAsync(out_f32_host + f0 * fb, df32, cn * fb * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < HOST_STREAMS; ++i) CU(cudaStreamSynchronize(ctx->hs[i]));
+    if (stats_host) CU(cudaMemcpy(stats_host, ctx->stats_dev, sizeof(unsigned long long) * TRS_STAT_COUNT, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"
