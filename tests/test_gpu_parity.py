@@ -276,3 +276,14 @@ def test_full_size_properties():
     want = oracle.process_batch(frames[pick].cpu().numpy(), cfg)
     assert np.array_equal(u8[pick].cpu().numpy(), want)
     comp.onShutdown()
+
+
+def test_generic_banded_kernel_still_matches(golden_images, monkeypatch):
+    """The frame-resident fast path takes the aligned 32-multiple widths; force the generic banded kernel on the same data."""
+    monkeypatch.setenv("TRS_FORCE_GENERIC", "1")
+    for sname, cname, cfg, frames, expected in golden_pairs(golden_images):
+        if sname not in ("f120", "f240") or cname not in ("full_house", "exotic", "edge_only"):
+            continue
+        got, f32 = run_device(cfg, frames)
+        assert np.array_equal(got, expected), f"{sname}/{cname}: {describe(got, expected)}"
+        assert np.array_equal(f32, oracle.normalise(expected))

@@ -8,6 +8,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -17,6 +18,7 @@
 #include "../../include/trs_b200.h"
 #include "misc_kernels.cuh"
 #include "preproc_kernel.cuh"
+#include "preproc_fast.cuh"
 
 namespace {
 
@@ -181,11 +183,66 @@ int plan_geometry(trs_ctx* ctx, int h, int w, int n_ranges, Geometry* g)
     return 0;
 }
 
+// Frame-resident fast path (preproc_fast.cuh): whole frame + magnitude plane + bit planes in one CTA's shared memory,
+// width a multiple of 32, everything 16-byte aligned.  Returns 1 if launched, 0 if not eligible, <0 / >1 on error.
+template <int NR, bool EDGE>
+int launch_fast_t(const trs::FastParams& fp, int grid, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_fast<NR, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fast)");
+    trs::k_preprocess_fast<NR, EDGE><<<grid, fp.g.threads, fp.g.total, st>>>(fp);
+    return 0;
+}
+
+int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w, cudaStream_t st)
+{
+    if (getenv("TRS_FORCE_GENERIC")) return 0;
+    if (!k.word_io || (w % 32) != 0 || (((size_t)h * w * 3) % 16) != 0) return 0;
+    if (!k.edge_enabled && k.n_ranges == 0) return 0;
+    const int nsg = w / 32;
+    const int max_warps = trs::FAST_MAX_THREADS / 32;
+    if (nsg > max_warps) return 0;
+    const int quads = max_warps / nsg;
+    const int seg_rows = (h + 4 * quads - 1) / (4 * quads);
+    trs::FastParams fp;
+    fp.k = k;
+    fp.g = trs::fast_geometry(h, w, k.n_ranges, seg_rows < 1 ? 1 : seg_rows);
+    const int budget2 = (ctx->smem_optin + 1024) / 2 - 1024;
+    if (fp.g.total > budget2 || fp.g.threads > trs::FAST_MAX_THREADS) return 0;
+    int grid = ctx->sm_count * 2;
+    if (grid > n) grid = n;
+    int rc;
+    switch (k.n_ranges * 2 + (k.edge_enabled ? 1 : 0)) {
+    case 1: rc = launch_fast_t<0, true>(fp, grid, st); break;
+    case 2: rc = launch_fast_t<1, false>(fp, grid, st); break;
+    case 3: rc = launch_fast_t<1, true>(fp, grid, st); break;
+    case 4: rc = launch_fast_t<2, false>(fp, grid, st); break;
+    case 5: rc = launch_fast_t<2, true>(fp, grid, st); break;
+    case 6: rc = launch_fast_t<3, false>(fp, grid, st); break;
+    default: return 0;
+    }
+    if (rc) return rc < 0 ? rc : -100 - rc;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cuda_fail(e, "k_preprocess_fast launch"); return -100 - (int)e; }
+    return 1;
+}
+
 int launch_preprocess(trs_ctx* ctx, const uint8_t* in, int n, int h, int w, uint8_t* out_u8, float* out_f32,
                       unsigned long long* stats, uint16_t* dbg_mag, uint8_t* dbg_map, bool force_edge, cudaStream_t st)
 {
     trs::PreKParams k = ctx->kp;
     if (force_edge && !k.edge_enabled) { k.edge_enabled = 1; }
+    if (!dbg_mag && !dbg_map) {
+        trs::PreKParams kf = k;
+        kf.in = in; kf.out_u8 = out_u8; kf.out_f32 = out_f32; kf.stats = stats; kf.dbg_mag = nullptr; kf.dbg_map = nullptr;
+        kf.n = n; kf.h = h; kf.w = w;
+        kf.word_io = ((w * 3) % 4 == 0) && (((uintptr_t)in & 15) == 0) && (!out_u8 || ((uintptr_t)out_u8 & 15) == 0) &&
+                     (!out_f32 || ((uintptr_t)out_f32 & 15) == 0) && (((size_t)h * w * 3) % 4 == 0);
+        const int fr = try_launch_fast(ctx, kf, n, h, w, st);
+        if (fr == 1) return 0;
+        if (fr < 0) return fr <= -100 ? -(fr + 100) : fr;
+    }
     Geometry g;
     int rc = plan_geometry(ctx, h, w, k.n_ranges, &g);
     if (rc) return rc;
