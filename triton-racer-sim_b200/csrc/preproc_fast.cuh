@@ -7,10 +7,11 @@
 //    (cp.async.bulk + mbarrier) and the next frame's copy is issued as soon as the pixels are dead, so it
 //    overlaps non-maximum suppression, hysteresis and the output stores of the current frame
 //  * a thread owns a 4-pixel-wide column strip and walks down SEG rows with a rolling 3-row window held in
-//    registers; an 8-lane group covers 32 pixels = one bit-plane word
+//    registers; two adjacent lanes make one byte (8 pixels) of a bit plane with a single shuffle
 //  * the Sobel arithmetic runs two pixels per instruction on the FMA pipe: a u8 value zero-extended to 16 bits
 //    is a valid fp16 subnormal (n * 2^-24) and every intermediate stays below 2048, so HADD2/HFMA2 on the raw bit
-//    patterns are exact integer add/sub/scale with free |x| and -x operand modifiers (results are sign-magnitude)
+//    patterns are exact integer add/sub/scale with free |x| and -x operand modifiers (results are sign-magnitude);
+//    HSET2 on the same patterns gives packed compares for the range tests and the non-maximum suppression
 //  * HSV: max/min/delta and the hue numerator are computed packed (VIMNMX3.U16x2, IADD3), the two fixed-point
 //    multiplies per pixel stay scalar (IMAD) — bit-exact with OpenCV's integer path
 //  * colour masks, NMS candidates and strong pixels live as bit planes; hysteresis is a word-parallel flood fill
@@ -43,11 +44,11 @@ __host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, in
     int o = 0;
     g.off_pix = o;    o += ((h * w * 3 + 15) & ~15) + 16;
     g.off_mag = o;    o += (((h + 2) * g.mag_stride * 2) + 15) & ~15;
-    const int plane = ((h * g.nsg * 4) + 15) & ~15;
+    const int plane = (((h + 2) * g.nsg * 4) + 15) & ~15;          // one zero row above and below (hysteresis reads y-1 / y+1)
     g.off_cand = o;   o += plane;
     g.off_edge = o;   o += plane;
     g.off_mask = o;   o += plane * n_ranges;
-    g.off_tab = o;    o += 2048;
+    g.off_tab = o;    o += 1024 + 2048;                            // sdiv[256] int32, hue table[256] int2
     g.off_lut = o;    o += 256;
     g.off_f32lut = o; o += 128;
     g.off_bar = o;    o += 16;
@@ -56,9 +57,18 @@ __host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, in
     return g;
 }
 
+// packed-compare form of one colour range: fp16-subnormal bit patterns duplicated in both halves
+struct FastRange {
+    uint32_t lo[3], hi[3];
+    uint32_t flags;                  // bit 2c: the lower bound of channel c can fail; bit 2c+1: the upper bound can fail
+};
+
 struct FastParams {
     PreKParams k;
     FastGeom g;
+    FastRange fr[3];
+    uint32_t low2, high2;            // edge thresholds as packed patterns
+    int need_hue;                    // some range has a hue bound that can fail
 };
 
 // ---- small PTX helpers --------------------------------------------------------------------------------
@@ -101,6 +111,8 @@ __device__ __forceinline__ uint32_t hx2p(uint32_t a, uint32_t b) { return u32(__
 __device__ __forceinline__ uint32_t habsadd(uint32_t a, uint32_t b) { return u32(__hadd2(__habs2(h2(a)), __habs2(h2(b)))); }     // |a| + |b|
 __device__ __forceinline__ uint32_t hmaxu(uint32_t a, uint32_t b) { return u32(__hmax2(h2(a), h2(b))); }
 __device__ __forceinline__ uint32_t hgt_mask(uint32_t a, uint32_t b) { return __hgt2_mask(h2(a), h2(b)); }
+__device__ __forceinline__ uint32_t hge_mask(uint32_t a, uint32_t b) { return __hge2_mask(h2(a), h2(b)); }
+__device__ __forceinline__ uint32_t hle_mask(uint32_t a, uint32_t b) { return __hle2_mask(h2(a), h2(b)); }
 __device__ __forceinline__ uint32_t heq_mask(uint32_t a, uint32_t b) { return __heq2_mask(h2(a), h2(b)); }
 __device__ __forceinline__ uint32_t bsel(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }                      // one LOP3
 
@@ -116,10 +128,21 @@ __device__ __forceinline__ uint32_t dir_code(uint32_t ax, uint32_t ay, uint32_t 
     return code;
 }
 
-// linear 32-pixel word of one 8-lane group from the four per-pixel ballots (bit l of b[q] = lane l, pixel q of its strip)
-__device__ __forceinline__ uint32_t group_word(uint32_t bq, int lane, int grp)
+// same classes as dir_code, computed from sign bits: h <=> ay*2^15 - ax*13573 < 0, v <=> ax*79109 - ay*2^15 < 0
+__device__ __forceinline__ uint32_t dir_bits(uint32_t ax, uint32_t ay, uint32_t sdiff)
 {
-    return __ballot_sync(0xffffffffu, (bq >> (8 * grp + (lane >> 2))) & 1u);
+    const int t22 = (int)(ax * 13573u);
+    const int nu = (int)(ay * 32768u) - t22;                 // < 0: horizontal
+    const int wv = t22 + (int)(ax * 65536u) - (int)(ay * 32768u);   // < 0: vertical
+    const uint32_t H = (uint32_t)(nu >> 31), V = (uint32_t)(wv >> 31);
+    return ~H & ((V & 1u) | (~V & (2u | sdiff)));
+}
+
+// four 0xffff/0 half masks (pixels 0,2 in `a`; pixels 1,3 in `b`) -> nibble, bit q = pixel q
+__device__ __forceinline__ uint32_t nibble_of(uint32_t a, uint32_t b)
+{
+    const uint32_t x = (a & 0x00040001u) | (b & 0x00080002u);
+    return (x | (x >> 16)) & 0xfu;
 }
 
 enum { FAST_MAX_THREADS = 320 };
@@ -132,11 +155,14 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
     const FastGeom& G = P.g;
     uint8_t* s_pix = smem + G.off_pix;
     uint16_t* s_mag = reinterpret_cast<uint16_t*>(smem + G.off_mag);
-    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + G.off_cand);
-    uint32_t* s_edge = reinterpret_cast<uint32_t*>(smem + G.off_edge);
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + G.off_mask);
+    const int h = p.h, w = p.w, ww = G.nsg;
+    // bit planes: row y at word row y + 1; rows 0 and h + 1 stay zero
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + G.off_cand) + ww;
+    uint32_t* s_edge = reinterpret_cast<uint32_t*>(smem + G.off_edge) + ww;
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + G.off_mask) + ww;
+    const int plane_stride = (((h + 2) * ww * 4 + 15) & ~15) >> 2;        // words between consecutive mask planes
     int32_t* s_sdiv = reinterpret_cast<int32_t*>(smem + G.off_tab);
-    int32_t* s_hdiv = s_sdiv + 256;
+    int2* s_hue = reinterpret_cast<int2*>(smem + G.off_tab + 1024);
     uint8_t* s_lut = smem + G.off_lut;
     float4* s_f32lut = reinterpret_cast<float4*>(smem + G.off_f32lut);
     unsigned long long* s_red = reinterpret_cast<unsigned long long*>(smem + G.off_red);
@@ -144,13 +170,13 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int h = p.h, w = p.w, ww = G.nsg;
     const int row_bytes = w * 3;
+    const int prb = w >> 3;                                  // plane bytes per row
     const uint32_t frame_bytes = (uint32_t)h * row_bytes;
     const int plane_words = h * ww;
     const int MS = G.mag_stride;
 
-    // thread -> (strip, segment): an 8-lane group is 8 adjacent strips (one plane word) of one segment
+    // thread -> (strip, segment): an 8-lane group is 8 adjacent strips (32 pixels) of one segment
     const int grp = lane >> 3;
     const int strip = 8 * (warp % ww) + (lane & 7);
     const int seg = 4 * (warp / ww) + grp;
@@ -158,17 +184,23 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
     const int r1 = min(h, r0 + G.seg_rows);
     const bool seg_ok = r0 < h;
     const int nstrips = w >> 2;
+    const bool store_lane = seg_ok && !(lane & 1);           // even lanes store the byte shared with the odd neighbour
 
-    // ---- one-time tables ---------------------------------------------------------------------------------
+    // ---- one-time tables and zero borders --------------------------------------------------------------------
     for (int i = tid; i < 256; i += nthr) {
         s_sdiv[i] = i ? __double2int_rn((double)(255 << 12) / (double)i) : 0;
-        s_hdiv[i] = i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
+        const int hd = i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
+        s_hue[i] = make_int2(hd, 2048 - 2048 * hd);           // ((h0 + 2048) * hd + (2048 - 2048 hd)) >> 12 == (h0 * hd + 2048) >> 12
         s_lut[i] = p.lut[i];
     }
     if (tid < 8) s_f32lut[tid] = make_float4((tid & 1) ? 1.0f : 0.0f, (tid & 2) ? 1.0f : 0.0f, (tid & 4) ? 1.0f : 0.0f, 0.0f);
     if (EDGE) {   // zero borders of the magnitude plane: rows 0 and h+1, columns x = -1 and x = w
         for (int i = tid; i < MS; i += nthr) { s_mag[i] = 0; s_mag[(h + 1) * MS + i] = 0; }
         for (int i = tid; i < h + 2; i += nthr) { s_mag[i * MS + 3] = 0; s_mag[i * MS + 4 + w] = 0; }
+        for (int i = tid; i < ww; i += nthr) {
+            s_cand[-ww + i] = 0; s_cand[h * ww + i] = 0;
+            s_edge[-ww + i] = 0; s_edge[h * ww + i] = 0;
+        }
     }
     if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
@@ -238,6 +270,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
 #pragma unroll
                 for (int j = 0; j < 6; ++j) { D[i][j] = 0; Hs[i][j] = 0; }
             const uint8_t* strip_base = s_pix + 12 * strip;
+            uint8_t* mask_base = reinterpret_cast<uint8_t*>(s_mask) + (strip >> 1);
 
             auto row_step = [&](int k, uint32_t (&Dn)[6], uint32_t (&Hn)[6], const uint32_t (&D0)[6], const uint32_t (&D1)[6],
                                 const uint32_t (&H0)[6]) {
@@ -254,65 +287,75 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
                 const uint32_t E1 = w1 & 0x00ff00ffu, O1 = prmt(w1, 0, 0x4341);
                 const uint32_t E2 = w2 & 0x00ff00ffu, O2 = prmt(w2, 0, 0x4341);
                 // planar pairs: A = pixels (0,2), B = pixels (1,3) of the strip, per channel
-                uint32_t A[3], B[3], Lh[3], Rh[3];
+                uint32_t A[3], B[3];
                 A[0] = prmt(E0, E1, 0x7610); A[1] = prmt(O0, O1, 0x7610); A[2] = prmt(E0, E2, 0x5432);
                 B[0] = prmt(O0, O2, 0x5432); B[1] = prmt(E1, E2, 0x7610); B[2] = prmt(O1, O2, 0x7610);
-                // neighbours: Lh = pixels (-1,1), Rh = pixels (2,4)
-                Lh[0] = prmt(wl, B[0], selL0); Lh[1] = prmt(wl, B[1], selL1); Lh[2] = prmt(wl, B[2], selL2);
-                Rh[0] = prmt(A[0], wr, selR0); Rh[1] = prmt(A[1], wr, selR1); Rh[2] = prmt(A[2], wr, selR2);
+                if (EDGE) {
+                    // neighbours: Lh = pixels (-1,1), Rh = pixels (2,4)
+                    uint32_t Lh[3], Rh[3];
+                    Lh[0] = prmt(wl, B[0], selL0); Lh[1] = prmt(wl, B[1], selL1); Lh[2] = prmt(wl, B[2], selL2);
+                    Rh[0] = prmt(A[0], wr, selR0); Rh[1] = prmt(A[1], wr, selR1); Rh[2] = prmt(A[2], wr, selR2);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (EDGE) {
+                    for (int c = 0; c < 3; ++c) {
                         Dn[c] = hsub(B[c], Lh[c]);                      // pixels (0,2): p[x+1] - p[x-1]
                         Dn[3 + c] = hsub(Rh[c], A[c]);                  // pixels (1,3)
                         Hn[c] = hadd(hx2p(A[c], Lh[c]), B[c]);          // p[x-1] + 2 p[x] + p[x+1]
                         Hn[3 + c] = hadd(hx2p(B[c], A[c]), Rh[c]);
                     }
                 }
-                const bool row_in = seg_ok && (r0 - 1 + k) >= r0 && (r0 - 1 + k) < r1;      // the loaded row belongs to this segment
+                const int y_row = r0 - 1 + k;
+                const bool row_in = k >= 1 && y_row < r1;                // the loaded row belongs to this segment
                 // ---- colour masks for the loaded row ---------------------------------------------------------
                 if (NR > 0) {
-                    uint32_t bits[NR > 0 ? NR : 1][4];
+                    uint32_t okm[NR > 0 ? NR : 1][2];                    // per range: half masks for pixels (0,2) and (1,3)
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         const uint32_t* X = half ? B : A;
                         const uint32_t v2 = __vimax3_u16x2(X[0], X[1], X[2]);
                         const uint32_t mn2 = __vimin3_u16x2(X[0], X[1], X[2]);
                         const uint32_t d2 = v2 - mn2;
-                        // hue numerator + 2048 (always positive): g-b | b-r+2d | r-g+4d, chosen by v==r, then v==g
-                        const uint32_t gb = X[1] + 0x08000800u - X[2];
-                        const uint32_t br = X[2] + 0x08000800u - X[0] + d2 + d2;
-                        const uint32_t rg = X[0] + 0x08000800u - X[1] + (d2 << 2);
-                        const uint32_t eqr = heq_mask(v2, X[0]), eqg = heq_mask(v2, X[1]);
-                        const uint32_t h02 = bsel(eqr, gb, bsel(eqg, br, rg));
+                        uint32_t s2, hh2 = 0;
+                        {
+                            const uint32_t vlo = v2 & 0xffffu, vhi = v2 >> 16, dlo = d2 & 0xffffu, dhi = d2 >> 16;
+                            const uint32_t slo = (uint32_t)(((int)dlo * s_sdiv[vlo] + 2048) >> 12);
+                            const uint32_t shi = (uint32_t)(((int)dhi * s_sdiv[vhi] + 2048) >> 12);
+                            s2 = slo | (shi << 16);
+                            if (P.need_hue) {
+                                // hue numerator + 2048 (always positive): g-b | b-r+2d | r-g+4d, chosen by v==r, then v==g
+                                const uint32_t gb = X[1] + 0x08000800u - X[2];
+                                const uint32_t br = X[2] + 0x08000800u - X[0] + d2 + d2;
+                                const uint32_t rg = X[0] + 0x08000800u - X[1] + (d2 << 2);
+                                const uint32_t eqr = heq_mask(v2, X[0]), eqg = heq_mask(v2, X[1]);
+                                const uint32_t h02 = bsel(eqr, gb, bsel(eqg, br, rg));
+                                const int2 tl = s_hue[dlo], th = s_hue[dhi];
+                                int hlo = ((int)(h02 & 0xffffu) * tl.x + tl.y) >> 12;
+                                int hhi = ((int)(h02 >> 16) * th.x + th.y) >> 12;
+                                hlo += (hlo >> 31) & 180;
+                                hhi += (hhi >> 31) & 180;
+                                hh2 = (uint32_t)hlo | ((uint32_t)hhi << 16);
+                            }
+                        }
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int v = q ? (v2 >> 16) : (v2 & 0xffffu);
-                            const int d = q ? (d2 >> 16) : (d2 & 0xffffu);
-                            const int h0 = (int)(q ? (h02 >> 16) : (h02 & 0xffffu)) - 2048;
-                            const int s = (d * s_sdiv[v] + 2048) >> 12;
-                            int hh = (h0 * s_hdiv[d] + 2048) >> 12;
-                            hh += (hh < 0) ? 180 : 0;
-#pragma unroll
-                            for (int r = 0; r < NR; ++r)
-                                bits[r][2 * q + half] = in_range_px(hh, s, v, p.ranges[r]) ? 1u : 0u;     // pixel index = 2q + half
+                        for (int r = 0; r < NR; ++r) {
+                            const FastRange& R = P.fr[r];
+                            uint32_t ok = 0xffffffffu;
+                            if (R.flags & 1u) ok &= hge_mask(hh2, R.lo[0]);
+                            if (R.flags & 2u) ok &= hle_mask(hh2, R.hi[0]);
+                            if (R.flags & 4u) ok &= hge_mask(s2, R.lo[1]);
+                            if (R.flags & 8u) ok &= hle_mask(s2, R.hi[1]);
+                            if (R.flags & 16u) ok &= hge_mask(v2, R.lo[2]);
+                            if (R.flags & 32u) ok &= hle_mask(v2, R.hi[2]);
+                            okm[r][half] = ok;
                         }
                     }
+                    uint32_t v = 0;
 #pragma unroll
-                    for (int r = 0; r < NR; ++r) {
-                        const uint32_t b0 = __ballot_sync(0xffffffffu, bits[r][0] && row_in);
-                        const uint32_t b1 = __ballot_sync(0xffffffffu, bits[r][1] && row_in);
-                        const uint32_t b2 = __ballot_sync(0xffffffffu, bits[r][2] && row_in);
-                        const uint32_t b3 = __ballot_sync(0xffffffffu, bits[r][3] && row_in);
-                        const int q = lane & 3;
-                        const uint32_t bq = q == 0 ? b0 : (q == 1 ? b1 : (q == 2 ? b2 : b3));
-                        uint32_t mine = 0;
+                    for (int r = 0; r < NR; ++r) v |= nibble_of(okm[r][0], okm[r][1]) << (8 * r);
+                    const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
+                    v |= other << 4;
+                    if (store_lane && row_in) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint32_t wd = group_word(bq, lane, g);
-                            mine = (g == grp) ? wd : mine;
-                        }
-                        if ((lane & 7) == 0 && row_in) s_mask[r * plane_words + (r0 - 1 + k) * ww + (warp % ww)] = mine;
+                        for (int r = 0; r < NR; ++r) mask_base[(r * plane_stride) * 4 + y_row * prb] = (uint8_t)(v >> (8 * r));
                     }
                 }
                 // ---- Sobel combine for output row y = r0 + k - 2 ----------------------------------------------
@@ -337,21 +380,18 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
                         bx = bsel(g2, dx[2], bx); by = bsel(g2, dy[2], by);
                         mg[half] = mm; dxs[half] = bx; dys[half] = by;
                     }
-                    // per pixel direction class; pixel order 0..3 = (A.lo, B.lo, A.hi, B.hi)
-                    uint32_t out16[4];
-#pragma unroll
-                    for (int px = 0; px < 4; ++px) {
-                        const int half = px & 1, hi = px >> 1;
-                        const uint32_t m = hi ? (mg[half] >> 16) : (mg[half] & 0xffffu);
-                        const uint32_t xs = hi ? (dxs[half] >> 16) : (dxs[half] & 0xffffu);
-                        const uint32_t ys = hi ? (dys[half] >> 16) : (dys[half] & 0xffffu);
-                        const uint32_t code = dir_code(xs & 0x7fffu, ys & 0x7fffu, ((xs ^ ys) >> 15) & 1u);
-                        out16[px] = m | (code << 11);
-                    }
+                    // per pixel direction class (pixel_math.cuh canny_dir), branch-free; pixel order 0..3 = (A.lo, B.lo, A.hi, B.hi)
+                    const uint32_t ax0 = dxs[0] & 0x7fff7fffu, ay0 = dys[0] & 0x7fff7fffu;
+                    const uint32_t ax1 = dxs[1] & 0x7fff7fffu, ay1 = dys[1] & 0x7fff7fffu;
+                    const uint32_t sd0 = ((dxs[0] ^ dys[0]) >> 15) & 0x00010001u, sd1 = ((dxs[1] ^ dys[1]) >> 15) & 0x00010001u;
+                    const uint32_t c0 = dir_bits(ax0 & 0xffffu, ay0 & 0xffffu, sd0 & 1u);      // pixel 0
+                    const uint32_t c1 = dir_bits(ax1 & 0xffffu, ay1 & 0xffffu, sd1 & 1u);      // pixel 1
+                    const uint32_t c2 = dir_bits(ax0 >> 16, ay0 >> 16, sd0 >> 16);             // pixel 2
+                    const uint32_t c3 = dir_bits(ax1 >> 16, ay1 >> 16, sd1 >> 16);             // pixel 3
                     if (seg_ok && y < r1) {
                         uint2 v;
-                        v.x = out16[0] | (out16[1] << 16);
-                        v.y = out16[2] | (out16[3] << 16);
+                        v.x = prmt(mg[0], mg[1], 0x5410) | (c0 << 11) | (c1 << 27);        // (m0, m1) + codes
+                        v.y = prmt(mg[0], mg[1], 0x7632) | (c2 << 11) | (c3 << 27);        // (m2, m3) + codes
                         *reinterpret_cast<uint2*>(s_mag + (y + 1) * MS + 4 + 4 * strip) = v;
                     }
                 }
@@ -367,66 +407,68 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
         __syncthreads();
         if (!p.need_pixels && tid == 0 && f + (int)gridDim.x < p.n) issue_load(f + gridDim.x);   // pixels are dead: prefetch
 
-        // ---- P2: non-maximum suppression, same strip walk over the magnitude plane ---------------------------
+        // ---- P2: non-maximum suppression, same strip walk over the magnitude plane, two pixels per compare ------
         if (EDGE) {
             const uint16_t* mbase = s_mag + 4 + 4 * strip;
-            auto load_row = [&](int y, uint32_t (&m)[6]) {      // magnitudes (with direction bits) of x0-1 .. x0+4 at image row y
+            uint8_t* cbase = reinterpret_cast<uint8_t*>(s_cand) + (strip >> 1);
+            uint8_t* ebase = reinterpret_cast<uint8_t*>(s_edge) + (strip >> 1);
+            // one row as packed pairs of magnitudes: P01=(m0,m1) P23=(m2,m3) L01=(m-1,m0) M12=(m1,m2) R23=(m3,m4); raw keeps the codes
+            struct Row { uint32_t p01, p23, l01, m12, r23, raw01, raw23; };
+            auto load_row = [&](int y) {
                 const uint16_t* rp = mbase + (y + 1) * MS;
                 const uint2 c = *reinterpret_cast<const uint2*>(rp);
-                m[0] = rp[-1]; m[1] = c.x & 0xffffu; m[2] = c.x >> 16; m[3] = c.y & 0xffffu; m[4] = c.y >> 16; m[5] = rp[4];
+                const uint32_t ml = rp[-1] & 0x7ffu, mr = rp[4] & 0x7ffu;
+                Row r;
+                r.raw01 = c.x; r.raw23 = c.y;
+                r.p01 = c.x & 0x07ff07ffu; r.p23 = c.y & 0x07ff07ffu;
+                r.l01 = prmt(ml, r.p01, 0x5410);
+                r.m12 = prmt(r.p01, r.p23, 0x5432);
+                r.r23 = prmt(r.p23, mr, 0x5432);
+                return r;
             };
-            uint32_t up[6], ce[6], dn[6];
             const int ya = seg_ok ? r0 : 0;
-            load_row(ya - 1, up);
-            load_row(ya, ce);
+            Row up = load_row(ya - 1), ce = load_row(ya);
 #pragma unroll 1
             for (int k = 0; k < G.seg_rows; ++k) {
                 const int y = ya + k;
-                const bool row_in = seg_ok && y < r1;
-                load_row(min(y + 1, h), dn);
-                uint32_t cnib = 0, snib = 0;
+                const bool row_in = y < r1;
+                const Row dn = load_row(min(y + 1, h));
+                uint32_t cm[2], sm[2];
 #pragma unroll
-                for (int px = 0; px < 4; ++px) {
-                    const uint32_t cw = ce[px + 1];
-                    const int m = cw & 0x7ff;
-                    const uint32_t code = cw >> 11;
-                    const uint32_t a = code == 0 ? ce[px] : (code == 1 ? up[px + 1] : (code == 2 ? up[px] : up[px + 2]));
-                    const uint32_t b = code == 0 ? ce[px + 2] : (code == 1 ? dn[px + 1] : (code == 2 ? dn[px + 2] : dn[px]));
-                    const int am = a & 0x7ff, bm = (b & 0x7ff) + (code >> 1);      // diagonals: strict on both sides
-                    const bool cand = (m > p.low) & (m > am) & (m >= bm);
-                    cnib |= (cand ? 1u : 0u) << px;
-                    snib |= ((cand && m > p.high) ? 1u : 0u) << px;
+                for (int pr = 0; pr < 2; ++pr) {
+                    const uint32_t C = pr ? ce.p23 : ce.p01;
+                    const uint32_t raw = pr ? ce.raw23 : ce.raw01;
+                    const uint32_t L = pr ? ce.m12 : ce.l01, Rr = pr ? ce.r23 : ce.m12;
+                    const uint32_t U = pr ? up.p23 : up.p01, Dw = pr ? dn.p23 : dn.p01;
+                    const uint32_t UL = pr ? up.m12 : up.l01, DR = pr ? dn.r23 : dn.m12;
+                    const uint32_t UR = pr ? up.r23 : up.m12, DL = pr ? dn.m12 : dn.l01;
+                    const uint32_t t0 = hgt_mask(C, L) & hge_mask(C, Rr);          // horizontal:  m > left, m >= right
+                    const uint32_t t1 = hgt_mask(C, U) & hge_mask(C, Dw);          // vertical:    m > up,   m >= down
+                    const uint32_t t2 = hgt_mask(C, UL) & hgt_mask(C, DR);         // diagonal s=+1, strict on both sides
+                    const uint32_t t3 = hgt_mask(C, UR) & hgt_mask(C, DL);         // diagonal s=-1
+                    const uint32_t b0 = ((raw >> 11) & 0x00010001u) * 0xffffu;
+                    const uint32_t b1 = ((raw >> 12) & 0x00010001u) * 0xffffu;
+                    const uint32_t pick = bsel(b1, bsel(b0, t3, t2), bsel(b0, t1, t0));
+                    cm[pr] = pick & hgt_mask(C, P.low2);
+                    sm[pr] = cm[pr] & hgt_mask(C, P.high2);
                 }
-#pragma unroll
-                for (int j = 0; j < 6; ++j) { up[j] = ce[j]; ce[j] = dn[j]; }
-                // per-pixel ballots -> one linear plane word per 8-lane group
-                uint32_t cword = 0, sword = 0;
-                {
-                    const int q = lane & 3;
-                    const uint32_t c0 = __ballot_sync(0xffffffffu, cnib & 1u), c1 = __ballot_sync(0xffffffffu, cnib & 2u);
-                    const uint32_t c2 = __ballot_sync(0xffffffffu, cnib & 4u), c3 = __ballot_sync(0xffffffffu, cnib & 8u);
-                    const uint32_t s0 = __ballot_sync(0xffffffffu, snib & 1u), s1 = __ballot_sync(0xffffffffu, snib & 2u);
-                    const uint32_t s2 = __ballot_sync(0xffffffffu, snib & 4u), s3 = __ballot_sync(0xffffffffu, snib & 8u);
-                    const uint32_t cq = q == 0 ? c0 : (q == 1 ? c1 : (q == 2 ? c2 : c3));
-                    const uint32_t sq = q == 0 ? s0 : (q == 1 ? s1 : (q == 2 ? s2 : s3));
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const uint32_t cw_g = group_word(cq, lane, g), sw_g = group_word(sq, lane, g);
-                        cword = (g == grp) ? cw_g : cword;
-                        sword = (g == grp) ? sw_g : sword;
-                    }
-                }
-                if ((lane & 7) == 0 && row_in) {
-                    s_cand[y * ww + (warp % ww)] = cword;
-                    s_edge[y * ww + (warp % ww)] = sword;
-                    st_cand += __popc(cword);
-                    st_strong += __popc(sword);
+                up = ce; ce = dn;
+                // pixels (0,1) sit in cm[0] halves, (2,3) in cm[1]: nibble bit q = pixel q
+                uint32_t x = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u);
+                uint32_t z = (sm[0] & 0x00020001u) | (sm[1] & 0x00080004u);
+                uint32_t v = ((x | (x >> 16)) & 0xfu) | (((z | (z >> 16)) & 0xfu) << 8);
+                const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
+                v |= other << 4;
+                if (store_lane && row_in) {
+                    cbase[y * prb] = (uint8_t)v;
+                    ebase[y * prb] = (uint8_t)(v >> 8);
+                    if (p.stats) st_strong += __popc((v >> 8) & 0xffu);
                 }
             }
         }
         __syncthreads();
 
-        // ---- P3: hysteresis ----------------------------------------------------------------------------------
+        // ---- P3: hysteresis: grow the strong set through candidates, one plane word per thread per sweep -------
         if (EDGE) {
             volatile uint32_t* E = s_edge;
             int any;
@@ -435,20 +477,16 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
                 for (int t = tid; t < plane_words; t += nthr) {
                     const uint32_t c = s_cand[t];
                     const uint32_t e = E[t];
-                    if (c == e) continue;
-                    const int y = t / ww, wi = t - y * ww;
-                    uint32_t mid = e, lft = 0, rgt = 0;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        const int yy = y + dy;
-                        if (yy < 0 || yy >= h) continue;
-                        mid |= E[yy * ww + wi];
-                        if (wi > 0) lft |= E[yy * ww + wi - 1];
-                        if (wi + 1 < ww) rgt |= E[yy * ww + wi + 1];
+                    if (c != e) {
+                        const int wi = t % ww;
+                        uint32_t mid = e | E[t - ww] | E[t + ww];
+                        uint32_t lft = 0, rgt = 0;
+                        if (wi > 0) lft = E[t - 1] | E[t - ww - 1] | E[t + ww - 1];
+                        if (wi + 1 < ww) rgt = E[t + 1] | E[t - ww + 1] | E[t + ww + 1];
+                        const uint32_t spread = mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
+                        const uint32_t ne = flood_word((spread & c) | e, c);
+                        if (ne != e) { E[t] = ne; changed = 1; }
                     }
-                    const uint32_t spread = mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
-                    const uint32_t ne = flood_word((spread & c) | e, c);
-                    if (ne != e) { E[t] = ne; changed = 1; }
                 }
                 any = __syncthreads_or(changed);
                 if (tid == 0) ++st_sweeps;
@@ -459,49 +497,55 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
         {
             uint8_t* __restrict__ gout = p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr;
             float* __restrict__ gf32 = p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr;
-            const uint32_t* planes[3];
+            const uint8_t* planes[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-                planes[c] = p.src[c] == SRC_EDGE ? s_edge : (p.src[c] >= SRC_MASK0 ? s_mask + (p.src[c] - SRC_MASK0) * plane_words : nullptr);
-            const int gpr = w >> 2;
+                planes[c] = reinterpret_cast<const uint8_t*>(p.src[c] == SRC_EDGE ? s_edge : (p.src[c] >= SRC_MASK0 ? s_mask + (p.src[c] - SRC_MASK0) * plane_stride : nullptr));
+            const int npb = h * prb;                        // groups of 8 pixels = plane bytes
             if (!p.need_pixels) {
-                // all three channels are bit planes: bytes by multiply-spread, floats from the {0,1}^3 table
-                for (int g = tid; g < h * gpr; g += nthr) {
-                    const int y = g / gpr, sx = g - y * gpr;
-                    const int wi = sx >> 3, sh = (sx & 7) * 4;
-                    uint32_t by[3];
+                // all three channels are bit planes: bytes by multiply-spread, floats as bit * 0x3f800000 (masks are 0.0 / 1.0)
+                int poff[3];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const uint32_t nib = (planes[c][y * ww + wi] >> sh) & 0xfu;
-                        by[c] = (nib * 0x00204081u) & 0x01010101u;                      // bit q -> byte q
+                for (int c = 0; c < 3; ++c)
+                    poff[c] = (p.src[c] == SRC_EDGE ? G.off_edge : G.off_mask + (p.src[c] - SRC_MASK0) * plane_stride * 4) + ww * 4;
+                for (int g = tid; g < npb; g += nthr) {
+                    const uint32_t b0 = smem[poff[0] + g], b1 = smem[poff[1] + g], b2 = smem[poff[2] + g];     // 8 pixels of each channel
+                    uint32_t r4[2], g4[2], l4[2];
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        r4[hf] = (((b0 >> (4 * hf)) & 0xfu) * 0x00204081u) & 0x01010101u;      // bit q -> byte q
+                        g4[hf] = (((b1 >> (4 * hf)) & 0xfu) * 0x00204081u) & 0x01010101u;
+                        l4[hf] = (((b2 >> (4 * hf)) & 0xfu) * 0x00204081u) & 0x01010101u;
                     }
                     if (gout) {
-                        const uint32_t R = by[0] * 255u, Gc = by[1] * 255u, Bc = by[2] * 255u;    // planar bytes 0 / 255
-                        uint32_t* dst = reinterpret_cast<uint32_t*>(gout + (size_t)y * row_bytes + sx * 12);
-                        dst[0] = prmt(prmt(R, Gc, 0x1040), Bc, 0x3410);     // R0 G0 B0 R1
-                        dst[1] = prmt(prmt(Gc, Bc, 0x2051), R, 0x3610);     // G1 B1 R2 G2
-                        dst[2] = prmt(prmt(Bc, R, 0x3072), Gc, 0x3710);     // B2 R3 G3 B3
+                        uint32_t wv[6];
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const uint32_t R = r4[hf] * 255u, Gc = g4[hf] * 255u, Bc = l4[hf] * 255u;     // planar bytes 0 / 255
+                            wv[3 * hf + 0] = prmt(prmt(R, Gc, 0x1040), Bc, 0x3410);     // R0 G0 B0 R1
+                            wv[3 * hf + 1] = prmt(prmt(Gc, Bc, 0x2051), R, 0x3610);     // G1 B1 R2 G2
+                            wv[3 * hf + 2] = prmt(prmt(Bc, R, 0x3072), Gc, 0x3710);     // B2 R3 G3 B3
+                        }
+                        uint2* dst = reinterpret_cast<uint2*>(gout + (size_t)g * 24);
+                        dst[0] = make_uint2(wv[0], wv[1]); dst[1] = make_uint2(wv[2], wv[3]); dst[2] = make_uint2(wv[4], wv[5]);
                     }
                     if (gf32) {
-                        const uint32_t idx = (by[0] | (by[1] << 1) | (by[2] << 2)) << 4;     // byte q = 16 * (r | g<<1 | b<<2) of pixel q
-                        const uint8_t* lut = reinterpret_cast<const uint8_t*>(s_f32lut);
-                        const float4 a0 = *reinterpret_cast<const float4*>(lut + (idx & 0xffu));
-                        const float4 a1 = *reinterpret_cast<const float4*>(lut + ((idx >> 8) & 0xffu));
-                        const float4 a2 = *reinterpret_cast<const float4*>(lut + ((idx >> 16) & 0xffu));
-                        const float4 a3 = *reinterpret_cast<const float4*>(lut + (idx >> 24));
-                        float4* dst = reinterpret_cast<float4*>(gf32 + (size_t)y * row_bytes + sx * 12);
-                        dst[0] = make_float4(a0.x, a0.y, a0.z, a1.x);
-                        dst[1] = make_float4(a1.y, a1.z, a2.x, a2.y);
-                        dst[2] = make_float4(a2.z, a3.x, a3.y, a3.z);
+                        uint4* dst = reinterpret_cast<uint4*>(gf32 + (size_t)g * 24);
+                        const uint32_t one = 0x3f800000u;
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const uint32_t R = r4[hf], Gc = g4[hf], Bc = l4[hf];
+                            dst[3 * hf + 0] = make_uint4((R & 0xffu) * one, (Gc & 0xffu) * one, (Bc & 0xffu) * one, prmt(R, 0, 0x4441) * one);
+                            dst[3 * hf + 1] = make_uint4(prmt(Gc, 0, 0x4441) * one, prmt(Bc, 0, 0x4441) * one, prmt(R, 0, 0x4442) * one, prmt(Gc, 0, 0x4442) * one);
+                            dst[3 * hf + 2] = make_uint4(prmt(Bc, 0, 0x4442) * one, (R >> 24) * one, (Gc >> 24) * one, (Bc >> 24) * one);
+                        }
                     }
                 }
             } else {
                 // some channel keeps the adjusted pixel: bytes from the resident frame, floats by correctly rounded x/255
                 const float rcp = 1.0f / 255.0f;
-                for (int g = tid; g < h * gpr; g += nthr) {
-                    const int y = g / gpr, sx = g - y * gpr;
-                    const int wi = sx >> 3, sh = (sx & 7) * 4;
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(s_pix + y * row_bytes + sx * 12);
+                for (int g = tid; g < 2 * npb; g += nthr) {          // groups of 4 pixels
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(s_pix + (size_t)g * 12);
                     uint32_t wv[3] = {src[0], src[1], src[2]};
                     uint8_t b[12];
 #pragma unroll
@@ -509,13 +553,13 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         if (planes[c]) {
-                            const uint32_t bits = planes[c][y * ww + wi] >> sh;
+                            const uint32_t bits = (uint32_t)planes[c][g >> 1] >> ((g & 1) * 4);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) b[q * 3 + c] = ((bits >> q) & 1u) ? 255 : 0;
                         }
                     }
                     if (gout) {
-                        uint32_t* dst = reinterpret_cast<uint32_t*>(gout + (size_t)y * row_bytes + sx * 12);
+                        uint32_t* dst = reinterpret_cast<uint32_t*>(gout + (size_t)g * 12);
 #pragma unroll
                         for (int k = 0; k < 3; ++k)
                             dst[k] = (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) | ((uint32_t)b[4 * k + 3] << 24);
@@ -529,7 +573,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
                             const float q0 = __fmul_rn(x, rcp);
                             fv[k] = __fmaf_rn(__fmaf_rn(-q0, 255.0f, x), rcp, q0);
                         }
-                        float4* dst = reinterpret_cast<float4*>(gf32 + (size_t)y * row_bytes + sx * 12);
+                        float4* dst = reinterpret_cast<float4*>(gf32 + (size_t)g * 12);
                         dst[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
                         dst[1] = make_float4(fv[4], fv[5], fv[6], fv[7]);
                         dst[2] = make_float4(fv[8], fv[9], fv[10], fv[11]);
@@ -539,9 +583,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
         }
         if (p.stats) {
             for (int i = tid; i < plane_words; i += nthr) {
-                if (EDGE) st_edge += __popc(s_edge[i]);
+                if (EDGE) { st_edge += __popc(s_edge[i]); st_cand += __popc(s_cand[i]); }
 #pragma unroll
-                for (int k = 0; k < NR; ++k) st_mask[k] += __popc(s_mask[k * plane_words + i]);
+                for (int k = 0; k < NR; ++k) st_mask[k] += __popc(s_mask[k * plane_stride + i]);
             }
             if (tid == 0) ++st_frames;
         }

@@ -205,8 +205,30 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     const int quads = max_warps / nsg;
     const int seg_rows = (h + 4 * quads - 1) / (4 * quads);
     trs::FastParams fp;
+    memset(&fp, 0, sizeof fp);
     fp.k = k;
     fp.g = trs::fast_geometry(h, w, k.n_ranges, seg_rows < 1 ? 1 : seg_rows);
+    // integer bounds -> fp16-subnormal bit patterns for the packed compares (values live in [0, 2047];
+    // anything below 0 compares like -1, anything above like 2047, which keeps every outcome unchanged)
+    auto pat = [](long long v) -> uint32_t {
+        const uint32_t q = v < 0 ? 0x8001u : (v > 2047 ? 2047u : (uint32_t)v);
+        return q | (q << 16);
+    };
+    fp.need_hue = 0;
+    for (int r = 0; r < k.n_ranges && r < 3; ++r) {
+        const int top[3] = {179, 255, 255};
+        uint32_t flags = 0;
+        for (int c = 0; c < 3; ++c) {
+            fp.fr[r].lo[c] = pat(k.ranges[r].lo[c]);
+            fp.fr[r].hi[c] = pat(k.ranges[r].hi[c]);
+            if (k.ranges[r].lo[c] > 0) flags |= 1u << (2 * c);
+            if (k.ranges[r].hi[c] < top[c]) flags |= 2u << (2 * c);
+        }
+        fp.fr[r].flags = flags;
+        if (flags & 3u) fp.need_hue = 1;
+    }
+    fp.low2 = pat(k.low);
+    fp.high2 = pat(k.high);
     const int budget2 = (ctx->smem_optin + 1024) / 2 - 1024;
     if (fp.g.total > budget2 || fp.g.threads > trs::FAST_MAX_THREADS) return 0;
     int grid = ctx->sm_count * 2;
