@@ -76,7 +76,15 @@ enum {
     TRS_STAT_CAND = 7,       /* NMS survivors above the low threshold              */
     TRS_STAT_HYST_SWEEPS = 8,/* hysteresis sweeps summed over frames               */
     TRS_STAT_ROI_SUM = 9,    /* sum of all ROI bytes (brightness statistic)        */
-    TRS_STAT_COUNT = 16
+    /* cycle accounting of the warp-specialised kernel (SM clocks, summed over CTAs; one sampling warp per role) */
+    TRS_STAT_T_FRONT_WAIT_FRAME = 10, /* front group: waiting for the TMA frame load           */
+    TRS_STAT_T_FRONT_WAIT_BACK = 11,  /* front group: waiting for the back group to free a buffer */
+    TRS_STAT_T_FRONT_WORK = 12,       /* front group: Sobel strip walk                          */
+    TRS_STAT_T_BACK_WAIT = 13,        /* back group: waiting for frame / magnitude plane        */
+    TRS_STAT_T_BACK_MASKS = 14,       /* back group: HSV colour masks                           */
+    TRS_STAT_T_BACK_EDGE = 15,        /* back group: NMS + hysteresis                           */
+    TRS_STAT_T_BACK_OUT = 16,         /* back group: merge + stores                             */
+    TRS_STAT_COUNT = 24
 };
 
 int trs_version(void);

@@ -10,8 +10,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtrs_b200.so")
 MAX_HSV = 4
-STAT_COUNT = 16
-STAT_NAMES = ["frames", "mask0", "mask1", "mask2", "mask3", "edge", "strong", "cand", "hyst_sweeps", "roi_sum"]
+STAT_COUNT = 24
+STAT_NAMES = ["frames", "mask0", "mask1", "mask2", "mask3", "edge", "strong", "cand", "hyst_sweeps", "roi_sum",
+              "t_front_wait_frame", "t_front_wait_back", "t_front_work", "t_back_wait", "t_back_masks", "t_back_edge", "t_back_out"]
 
 # every symbol include/trs_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = [

@@ -1,22 +1,31 @@
-// preproc_fast.cuh — frame-resident fast path of the fused observation kernel (sm_100a).
+// preproc_fast.cuh — frame-resident fast paths of the fused observation kernel (sm_100a).
 //
-// Same contract as k_preprocess (preproc_kernel.cuh) for frames that (a) fit one CTA's shared memory whole,
-// (b) have a width that is a multiple of 32 and (c) are 16-byte aligned.  Design:
+// Same contract as k_preprocess (preproc_kernel.cuh) for frames that (a) fit shared memory whole, (b) have a
+// width that is a multiple of 32 and (c) are 16-byte aligned.  Two kernels share the phase code below:
 //
-//  * one CTA per frame, persistent over frames, two CTAs per SM; the frame arrives by a TMA bulk copy
-//    (cp.async.bulk + mbarrier) and the next frame's copy is issued as soon as the pixels are dead, so it
-//    overlaps non-maximum suppression, hysteresis and the output stores of the current frame
-//  * a thread owns a 4-pixel-wide column strip and walks down SEG rows with a rolling 3-row window held in
+//  k_preprocess_ws   warp-specialised, one persistent CTA per SM.  "Front" warps run the Sobel strip walk of frame
+//                    j+1 while "back" warps run the colour masks, non-maximum suppression, hysteresis and the output
+//                    stores of frame j.  Frames arrive by TMA bulk copies into a double buffer, the magnitude plane
+//                    is double-buffered too; the two groups hand buffers over through mbarriers (full/empty pairs)
+//                    and never meet at a CTA-wide barrier.
+//  k_preprocess_fast one frame per CTA, two CTAs per SM, phases separated by __syncthreads (used when the double
+//                    buffers do not fit, or when there is no edge filter to overlap with).
+//
+// Common design points:
+//  * a thread owns a 4-pixel-wide column strip and walks down its segment of rows with a rolling 3-row window in
 //    registers; two adjacent lanes make one byte (8 pixels) of a bit plane with a single shuffle
-//  * the Sobel arithmetic runs two pixels per instruction on the FMA pipe: a u8 value zero-extended to 16 bits
-//    is a valid fp16 subnormal (n * 2^-24) and every intermediate stays below 2048, so HADD2/HFMA2 on the raw bit
-//    patterns are exact integer add/sub/scale with free |x| and -x operand modifiers (results are sign-magnitude);
-//    HSET2 on the same patterns gives packed compares for the range tests and the non-maximum suppression
-//  * HSV: max/min/delta and the hue numerator are computed packed (VIMNMX3.U16x2, IADD3), the two fixed-point
+//  * the Sobel arithmetic runs two pixels per instruction on the FMA pipe: a u8 value zero-extended to 16 bits is a
+//    valid fp16 subnormal (n * 2^-24) and every intermediate stays below 2048, so HADD2/HFMA2 on the raw bit patterns
+//    are exact integer add/sub/scale with free |x| and -x operand modifiers (results are sign-magnitude); HSET2 on
+//    the same patterns gives the packed compares of the range tests and of the non-maximum suppression
+//  * HSV: max/min/delta and the hue numerator are computed packed (VIMNMX3.U16x2, IADD3); the two fixed-point
 //    multiplies per pixel stay scalar (IMAD) — bit-exact with OpenCV's integer path
 //  * colour masks, NMS candidates and strong pixels live as bit planes; hysteresis is a word-parallel flood fill
-//  * outputs are written once: u8 bytes expanded from plane nibbles by multiply-spread, f32 pixels fetched from an
-//    8-entry {0,1}^3 table (masks are exactly 0.0/1.0 after /255)
+//  * outputs are written once: u8 bytes expanded from plane nibbles by multiply-spread, f32 as bit * 0x3f800000
+//    (masks are exactly 0.0 / 1.0 after /255)
+//  * every shared-memory access in the hot loops goes through explicit ld.shared / st.shared on 32-bit window
+//    addresses derived from ONE laundered base register: letting the compiler re-derive the window base costs a
+//    S2R SR_CgaCtaId (long-scoreboard latency) inside every loop it decides to rematerialise it in
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -27,32 +36,46 @@
 
 namespace trs {
 
+enum { FAST_MAX_THREADS = 320, WS_MAX_THREADS = 640, WS_MAX_WARPS = 20 };
+
 struct FastGeom {
-    int seg_rows, nseg, nsg, threads;
+    int ws;                          // 1: warp-specialised layout (double buffers)
+    int nsg;                         // strip groups per row (w / 32)
+    int front_warps, back_warps;     // ws: warps per role; resident kernel: front == back == all warps
+    int seg_rows_front, seg_rows_back;
+    int threads;
     int mag_stride;                  // u16 elements per magnitude row (w + 8; pixel x at index x + 4)
-    int off_pix, off_mag, off_cand, off_edge, off_mask, off_tab, off_lut, off_f32lut, off_bar, off_red, total;
+    int plane_bytes;                 // one bit plane incl. a zero row above and below, 16-byte multiple
+    int off_pix[2], off_mag[2], off_mask, off_cand, off_edge, off_sdiv, off_hue, off_lut, off_bar, off_red, total;
 };
 
-__host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, int seg_rows)
+__host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, int ws, int front_warps, int back_warps)
 {
     FastGeom g;
-    g.seg_rows = seg_rows;
-    g.nseg = (h + seg_rows - 1) / seg_rows;
+    g.ws = ws;
     g.nsg = w / 32;
-    g.threads = 32 * g.nsg * ((g.nseg + 3) / 4);
+    g.front_warps = front_warps;
+    g.back_warps = back_warps;
+    const int fsegs = 4 * (front_warps / g.nsg), bsegs = 4 * (back_warps / g.nsg);
+    g.seg_rows_front = (h + fsegs - 1) / fsegs;
+    g.seg_rows_back = (h + bsegs - 1) / bsegs;
+    g.threads = 32 * (ws ? front_warps + back_warps : front_warps);
     g.mag_stride = w + 8;
+    g.plane_bytes = (((h + 2) * g.nsg * 4) + 15) & ~15;
+    const int pix = ((h * w * 3 + 15) & ~15) + 16;
+    const int mag = (((h + 2) * g.mag_stride * 2) + 15) & ~15;
     int o = 0;
-    g.off_pix = o;    o += ((h * w * 3 + 15) & ~15) + 16;
-    g.off_mag = o;    o += (((h + 2) * g.mag_stride * 2) + 15) & ~15;
-    const int plane = (((h + 2) * g.nsg * 4) + 15) & ~15;          // one zero row above and below (hysteresis reads y-1 / y+1)
-    g.off_cand = o;   o += plane;
-    g.off_edge = o;   o += plane;
-    g.off_mask = o;   o += plane * n_ranges;
-    g.off_tab = o;    o += 1024 + 2048;                            // sdiv[256] int32, hue table[256] int2
-    g.off_lut = o;    o += 256;
-    g.off_f32lut = o; o += 128;
-    g.off_bar = o;    o += 16;
-    g.off_red = o;    o += 64;
+    for (int b = 0; b < (ws ? 2 : 1); ++b) { g.off_pix[b] = o; o += pix; }
+    for (int b = 0; b < (ws ? 2 : 1); ++b) { g.off_mag[b] = o; o += mag; }
+    if (!ws) { g.off_pix[1] = g.off_pix[0]; g.off_mag[1] = g.off_mag[0]; }
+    g.off_mask = o; o += g.plane_bytes * n_ranges;                 // masks are made and used by one thread group: single buffer
+    g.off_cand = o; o += g.plane_bytes;
+    g.off_edge = o; o += g.plane_bytes;
+    g.off_sdiv = o; o += 1024;                                     // int32[256]
+    g.off_hue = o;  o += 2048;                                     // int2[256]
+    g.off_lut = o;  o += 256;
+    g.off_bar = o;  o += 64;                                       // 8 mbarriers
+    g.off_red = o;  o += 64;
     g.total = o;
     return g;
 }
@@ -75,6 +98,16 @@ struct FastParams {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 
+// shared-memory accessors on 32-bit window addresses
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -83,6 +116,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done;
@@ -90,9 +127,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"      // %3: suspend-time hint, the warp sleeps instead of spinning
             "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     } while (!done);
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
@@ -101,6 +138,27 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                  "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ int bar_or(int id, int nthreads, int pred)
+{
+    int r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.s32 q, %3, 0;\n"
+        "bar.red.or.pred p, %1, %2, q;\n"
+        "selp.s32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(r) : "r"(id), "r"(nthreads), "r"(pred) : "memory");
+    return r;
+}
+
+// one elected thread: arm the barrier with the byte count, then one bulk copy per 16 KB piece
+__device__ __forceinline__ void issue_frame_load(uint32_t dst, const uint8_t* src, uint32_t frame_bytes, uint32_t bar)
+{
+    fence_proxy_async();
+    mbar_expect_tx(bar, frame_bytes);
+    for (uint32_t o = 0; o < frame_bytes; o += 16384u) tma_load_1d(dst + o, src + o, min(16384u, frame_bytes - o), bar);
+}
 
 // fp16x2 views of 32-bit registers (bit patterns are integers n < 2048 == fp16 subnormals n * 2^-24)
 __device__ __forceinline__ __half2 h2(uint32_t x) { return *reinterpret_cast<__half2*>(&x); }
@@ -116,24 +174,13 @@ __device__ __forceinline__ uint32_t hle_mask(uint32_t a, uint32_t b) { return __
 __device__ __forceinline__ uint32_t heq_mask(uint32_t a, uint32_t b) { return __heq2_mask(h2(a), h2(b)); }
 __device__ __forceinline__ uint32_t bsel(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }                      // one LOP3
 
-// direction class from |dx|, |dy| and the sign-difference flag (pixel_math.cuh: canny_dir)
-__device__ __forceinline__ uint32_t dir_code(uint32_t ax, uint32_t ay, uint32_t sdiff)
-{
-    const int t22 = (int)(ax * 13573u);
-    const int ay15 = (int)(ay << 15);
-    const int t67 = t22 + (int)(ax << 16);
-    uint32_t code = 2u + sdiff;
-    code = (ay15 > t67) ? 1u : code;
-    code = (ay15 < t22) ? 0u : code;
-    return code;
-}
-
-// same classes as dir_code, computed from sign bits: h <=> ay*2^15 - ax*13573 < 0, v <=> ax*79109 - ay*2^15 < 0
+// direction class (pixel_math.cuh canny_dir) from sign bits: horizontal <=> ay*2^15 - ax*13573 < 0,
+// vertical <=> ax*79109 - ay*2^15 < 0, else diagonal 2 + (sign(dx) != sign(dy))
 __device__ __forceinline__ uint32_t dir_bits(uint32_t ax, uint32_t ay, uint32_t sdiff)
 {
     const int t22 = (int)(ax * 13573u);
-    const int nu = (int)(ay * 32768u) - t22;                 // < 0: horizontal
-    const int wv = t22 + (int)(ax * 65536u) - (int)(ay * 32768u);   // < 0: vertical
+    const int nu = (int)(ay * 32768u) - t22;
+    const int wv = t22 + (int)(ax * 65536u) - (int)(ay * 32768u);
     const uint32_t H = (uint32_t)(nu >> 31), V = (uint32_t)(wv >> 31);
     return ~H & ((V & 1u) | (~V & (2u | sdiff)));
 }
@@ -145,463 +192,709 @@ __device__ __forceinline__ uint32_t nibble_of(uint32_t a, uint32_t b)
     return (x | (x >> 16)) & 0xfu;
 }
 
-enum { FAST_MAX_THREADS = 320 };
+// Flood the seed bits along the runs of ones of `c` (seeds must be a subset of c), both directions, O(1).
+__device__ __forceinline__ uint32_t flood_run(uint32_t seeds, uint32_t c)
+{
+    const uint32_t up = (c & ~(c + seeds)) | seeds;          // carry ripples up through each run
+    const uint32_t cr = __brev(c), sr = __brev(seeds);
+    const uint32_t dn = __brev((cr & ~(cr + sr)) | sr);
+    return up | dn;
+}
 
+// which strip / rows a lane owns in a strip walk: an 8-lane group is 8 adjacent strips (32 pixels) of one segment
+struct StripMap {
+    int strip, r0, r1;
+    bool ok, store_lane;
+};
+
+__device__ __forceinline__ StripMap strip_map(int group_warp, int lane, int nsg, int seg_rows, int h)
+{
+    StripMap m;
+    m.strip = 8 * (group_warp % nsg) + (lane & 7);
+    const int seg = 4 * (group_warp / nsg) + (lane >> 3);
+    m.r0 = seg * seg_rows;
+    m.r1 = min(h, m.r0 + seg_rows);
+    m.ok = m.r0 < h;
+    m.store_lane = m.ok && !(lane & 1);          // even lanes store the byte shared with the odd neighbour
+    return m;
+}
+
+// shared-memory addresses (32-bit window) of every buffer, derived once from the laundered base
+struct SmemMap {
+    uint32_t pix[2], mag[2], mask, cand, edge, sdiv, hue, lut, bar, red;      // mask / cand / edge: address of image row 0
+};
+
+__device__ __forceinline__ SmemMap smem_map(uint32_t sb, const FastGeom& G)
+{
+    SmemMap s;
+    s.pix[0] = sb + G.off_pix[0]; s.pix[1] = sb + G.off_pix[1];
+    s.mag[0] = sb + G.off_mag[0]; s.mag[1] = sb + G.off_mag[1];
+    s.mask = sb + G.off_mask + G.nsg * 4;
+    s.cand = sb + G.off_cand + G.nsg * 4;
+    s.edge = sb + G.off_edge + G.nsg * 4;
+    s.sdiv = sb + G.off_sdiv; s.hue = sb + G.off_hue; s.lut = sb + G.off_lut; s.bar = sb + G.off_bar; s.red = sb + G.off_red;
+    return s;
+}
+
+// interleaved RGB words of 4 pixels -> planar zero-extended pairs: A = pixels (0,2), B = pixels (1,3), per channel
+__device__ __forceinline__ void unpack_planar(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t (&A)[3], uint32_t (&B)[3])
+{
+    const uint32_t E0 = w0 & 0x00ff00ffu, O0 = prmt(w0, 0, 0x4341);      // E = (b0,b2), O = (b1,b3)
+    const uint32_t E1 = w1 & 0x00ff00ffu, O1 = prmt(w1, 0, 0x4341);
+    const uint32_t E2 = w2 & 0x00ff00ffu, O2 = prmt(w2, 0, 0x4341);
+    A[0] = prmt(E0, E1, 0x7610); A[1] = prmt(O0, O1, 0x7610); A[2] = prmt(E0, E2, 0x5432);
+    B[0] = prmt(O0, O2, 0x5432); B[1] = prmt(E1, E2, 0x7610); B[2] = prmt(O1, O2, 0x7610);
+}
+
+// =========================================================================================================
+// colour-range tests of 4 pixels given as planar pairs; okm[r][half] = 0xffff/0 half masks
+// =========================================================================================================
+template <int NR>
+__device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t (&A)[3], const uint32_t (&B)[3], uint32_t a_sdiv, uint32_t a_hue,
+                                             uint32_t (&okm)[NR > 0 ? NR : 1][2])
+{
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t* X = half ? B : A;
+        const uint32_t v2 = __vimax3_u16x2(X[0], X[1], X[2]);
+        const uint32_t mn2 = __vimin3_u16x2(X[0], X[1], X[2]);
+        const uint32_t d2 = v2 - mn2;
+        const uint32_t vlo = v2 & 0xffffu, vhi = v2 >> 16, dlo = d2 & 0xffffu, dhi = d2 >> 16;
+        const uint32_t slo = (uint32_t)(((int)dlo * (int)lds32(a_sdiv + 4 * vlo) + 2048) >> 12);
+        const uint32_t shi = (uint32_t)(((int)dhi * (int)lds32(a_sdiv + 4 * vhi) + 2048) >> 12);
+        const uint32_t s2 = slo | (shi << 16);
+        uint32_t hh2 = 0;
+        if (P.need_hue) {
+            // hue numerator + 2048 (always positive): g-b | b-r+2d | r-g+4d, chosen by v==r, then v==g
+            const uint32_t gb = X[1] + 0x08000800u - X[2];
+            const uint32_t br = X[2] + 0x08000800u - X[0] + d2 + d2;
+            const uint32_t rg = X[0] + 0x08000800u - X[1] + (d2 << 2);
+            const uint32_t eqr = heq_mask(v2, X[0]), eqg = heq_mask(v2, X[1]);
+            const uint32_t h02 = bsel(eqr, gb, bsel(eqg, br, rg));
+            const uint2 tl = lds64(a_hue + 8 * dlo), th = lds64(a_hue + 8 * dhi);
+            int hlo = ((int)(h02 & 0xffffu) * (int)tl.x + (int)tl.y) >> 12;
+            int hhi = ((int)(h02 >> 16) * (int)th.x + (int)th.y) >> 12;
+            hlo += (hlo >> 31) & 180;
+            hhi += (hhi >> 31) & 180;
+            hh2 = (uint32_t)hlo | ((uint32_t)hhi << 16);
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const FastRange& R = P.fr[r];
+            uint32_t ok = 0xffffffffu;
+            if (R.flags & 1u) ok &= hge_mask(hh2, R.lo[0]);
+            if (R.flags & 2u) ok &= hle_mask(hh2, R.hi[0]);
+            if (R.flags & 4u) ok &= hge_mask(s2, R.lo[1]);
+            if (R.flags & 8u) ok &= hle_mask(s2, R.hi[1]);
+            if (R.flags & 16u) ok &= hge_mask(v2, R.lo[2]);
+            if (R.flags & 32u) ok &= hle_mask(v2, R.hi[2]);
+            okm[r][half] = ok;
+        }
+    }
+}
+
+// =========================================================================================================
+// P1: strip walk — Sobel / magnitude / direction -> magnitude plane, colour masks -> bit planes
+// =========================================================================================================
+template <int NR, bool EDGE>
+__device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pix, uint32_t a_mag, const SmemMap& S, const StripMap& M, int seg_rows)
+{
+    const int h = P.k.h, w = P.k.w;
+    const int row_bytes = w * 3, prb = w >> 3, MS2 = P.g.mag_stride * 2, nstrips = w >> 2;
+    const int r0 = M.r0, r1 = M.r1;
+    // per-thread constants of the strip walk
+    const bool left_edge = M.strip == 0, right_edge = M.strip == nstrips - 1;
+    const int offL = left_edge ? 0 : -4;                    // word holding the pixel left of the strip (replicated at x = 0)
+    const int offR = right_edge ? 8 : 12;                   // word holding the pixel right of the strip (replicated at x = w-1)
+    const uint32_t selL0 = 0x5450u | (left_edge ? 0u : 1u), selL1 = 0x5450u | (left_edge ? 1u : 2u), selL2 = 0x5450u | (left_edge ? 2u : 3u);
+    const uint32_t selR0 = 0x1012u | ((right_edge ? 5u : 4u) << 8), selR1 = 0x1012u | ((right_edge ? 6u : 5u) << 8),
+                   selR2 = 0x1012u | ((right_edge ? 7u : 6u) << 8);
+    const int nsteps = seg_rows + 2;
+    const uint32_t strip_base = a_pix + 12 * M.strip;
+    const uint32_t mask_base = S.mask + (M.strip >> 1);
+    const uint32_t mag_base = a_mag + 2 * (4 + 4 * M.strip);
+
+    uint32_t D[3][6], Hs[3][6];      // rolling rows: horizontal difference and horizontal smoothing, packed pairs
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { D[i][j] = 0; Hs[i][j] = 0; }
+
+    auto row_step = [&](int k, uint32_t (&Dn)[6], uint32_t (&Hn)[6], const uint32_t (&D0)[6], const uint32_t (&D1)[6], const uint32_t (&H0)[6]) {
+        // load image row r0 - 1 + k (clamped: replicated border) into slot n; emit output row y = r0 + k - 2
+        const int y_row = r0 - 1 + k;
+        const uint32_t rp = strip_base + min(max(y_row, 0), h - 1) * row_bytes;
+        const uint32_t w0 = lds32(rp), w1 = lds32(rp + 4), w2 = lds32(rp + 8);
+        uint32_t A[3], B[3];
+        unpack_planar(w0, w1, w2, A, B);
+        if (EDGE) {
+            const uint32_t wl = lds32(rp + offL), wr = lds32(rp + offR);
+            // neighbours: Lh = pixels (-1,1), Rh = pixels (2,4)
+            uint32_t Lh[3], Rh[3];
+            Lh[0] = prmt(wl, B[0], selL0); Lh[1] = prmt(wl, B[1], selL1); Lh[2] = prmt(wl, B[2], selL2);
+            Rh[0] = prmt(A[0], wr, selR0); Rh[1] = prmt(A[1], wr, selR1); Rh[2] = prmt(A[2], wr, selR2);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                Dn[c] = hsub(B[c], Lh[c]);                      // pixels (0,2): p[x+1] - p[x-1]
+                Dn[3 + c] = hsub(Rh[c], A[c]);                  // pixels (1,3)
+                Hn[c] = hadd(hx2p(A[c], Lh[c]), B[c]);          // p[x-1] + 2 p[x] + p[x+1]
+                Hn[3 + c] = hadd(hx2p(B[c], A[c]), Rh[c]);
+            }
+        }
+        // ---- colour masks for the loaded row ---------------------------------------------------------
+        if (NR > 0) {
+            const bool row_in = k >= 1 && y_row < r1;            // the loaded row belongs to this segment
+            uint32_t okm[NR > 0 ? NR : 1][2];                    // per range: half masks for pixels (0,2) and (1,3)
+            hsv_masks_of<NR>(P, A, B, S.sdiv, S.hue, okm);
+            uint32_t v = 0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) v |= nibble_of(okm[r][0], okm[r][1]) << (8 * r);
+            const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
+            v |= other << 4;
+            if (M.store_lane && row_in) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) sts8(mask_base + r * P.g.plane_bytes + y_row * prb, v >> (8 * r));
+            }
+        }
+        // ---- Sobel combine for output row y = r0 + k - 2 ----------------------------------------------
+        if (EDGE && k >= 2) {
+            const int y = r0 + k - 2;
+            uint32_t mg[2], dxs[2], dys[2];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t m[3], dx[3], dy[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int j = 3 * half + c;
+                    dx[c] = hadd(hx2p(D1[j], D0[j]), Dn[j]);            // D[y-1] + 2 D[y] + D[y+1]
+                    dy[c] = hsub(Hn[j], H0[j]);                          // H[y+1] - H[y-1]
+                    m[c] = habsadd(dx[c], dy[c]);
+                }
+                const uint32_t g1 = hgt_mask(m[1], m[0]);                // strictly greater: the lowest channel wins ties
+                uint32_t mm = hmaxu(m[0], m[1]);
+                uint32_t bx = bsel(g1, dx[1], dx[0]), by = bsel(g1, dy[1], dy[0]);
+                const uint32_t g2 = hgt_mask(m[2], mm);
+                mm = hmaxu(mm, m[2]);
+                bx = bsel(g2, dx[2], bx); by = bsel(g2, dy[2], by);
+                mg[half] = mm; dxs[half] = bx; dys[half] = by;
+            }
+            // per pixel direction class, branch-free; pixel order 0..3 = (A.lo, B.lo, A.hi, B.hi)
+            const uint32_t ax0 = dxs[0] & 0x7fff7fffu, ay0 = dys[0] & 0x7fff7fffu;
+            const uint32_t ax1 = dxs[1] & 0x7fff7fffu, ay1 = dys[1] & 0x7fff7fffu;
+            const uint32_t sd0 = ((dxs[0] ^ dys[0]) >> 15) & 0x00010001u, sd1 = ((dxs[1] ^ dys[1]) >> 15) & 0x00010001u;
+            const uint32_t c0 = dir_bits(ax0 & 0xffffu, ay0 & 0xffffu, sd0 & 1u);      // pixel 0
+            const uint32_t c1 = dir_bits(ax1 & 0xffffu, ay1 & 0xffffu, sd1 & 1u);      // pixel 1
+            const uint32_t c2 = dir_bits(ax0 >> 16, ay0 >> 16, sd0 >> 16);             // pixel 2
+            const uint32_t c3 = dir_bits(ax1 >> 16, ay1 >> 16, sd1 >> 16);             // pixel 3
+            if (M.ok && y < r1) {
+                uint2 v;
+                v.x = prmt(mg[0], mg[1], 0x5410) | (c0 << 11) | (c1 << 27);        // (m0, m1) + codes
+                v.y = prmt(mg[0], mg[1], 0x7632) | (c2 << 11) | (c3 << 27);        // (m2, m3) + codes
+                sts64(mag_base + (y + 1) * MS2, v);
+            }
+        }
+    };
+    // rolling window by register renaming: slots (k % 3)
+#pragma unroll 1
+    for (int k = 0; k < nsteps; k += 3) {
+        row_step(k, D[0], Hs[0], D[1], D[2], Hs[1]);                 // new = slot0, y-1 = slot1, y = slot2
+        if (k + 1 < nsteps) row_step(k + 1, D[1], Hs[1], D[2], D[0], Hs[2]);
+        if (k + 2 < nsteps) row_step(k + 2, D[2], Hs[2], D[0], D[1], Hs[0]);
+    }
+}
+
+// =========================================================================================================
+// P1b: colour masks as a pointwise pass (back group of the warp-specialised kernel): a thread takes 4 consecutive
+// pixels (12 bytes), adjacent lanes take adjacent groups, two lanes make one plane byte.
+// =========================================================================================================
+template <int NR>
+__device__ __forceinline__ void p1b_colour_masks(const FastParams& P, uint32_t a_pix, const SmemMap& S, int t0, int tstride)
+{
+    const int ngroups = (P.k.h * P.k.w) >> 2;
+    const int lane = t0 & 31;
+#pragma unroll 2
+    for (int g0 = t0 - lane; g0 < ngroups; g0 += tstride) {          // warp-uniform trip count (the shuffle needs every lane)
+        const int g = g0 + lane;
+        const bool valid = g < ngroups;
+        const uint32_t src = a_pix + 12 * (valid ? g : 0);
+        uint32_t A[3], B[3];
+        unpack_planar(lds32(src), lds32(src + 4), lds32(src + 8), A, B);
+        uint32_t okm[NR > 0 ? NR : 1][2];
+        hsv_masks_of<NR>(P, A, B, S.sdiv, S.hue, okm);
+        uint32_t v = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) v |= nibble_of(okm[r][0], okm[r][1]) << (8 * r);
+        const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
+        v |= other << 4;
+        if (valid && !(lane & 1)) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) sts8(S.mask + r * P.g.plane_bytes + (g >> 1), v >> (8 * r));
+        }
+    }
+}
+
+// =========================================================================================================
+// P2: non-maximum suppression, strip walk over the magnitude plane, two pixels per compare
+// =========================================================================================================
+__device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, const SmemMap& S, const StripMap& M, int seg_rows,
+                                       unsigned long long& st_strong)
+{
+    const int h = P.k.h, prb = P.k.w >> 3, MS2 = P.g.mag_stride * 2;
+    const uint32_t mbase = a_mag + 2 * (4 + 4 * M.strip);
+    const uint32_t cbase = S.cand + (M.strip >> 1), ebase = S.edge + (M.strip >> 1);
+    // one row as packed pairs of magnitudes: P01=(m0,m1) P23=(m2,m3) L01=(m-1,m0) M12=(m1,m2) R23=(m3,m4); raw keeps the codes
+    struct Row { uint32_t p01, p23, l01, m12, r23, raw01, raw23; };
+    auto load_row = [&](int y) {
+        const uint32_t rp = mbase + (y + 1) * MS2;
+        const uint2 c = lds64(rp);
+        const uint32_t ml = lds16(rp - 2) & 0x7ffu, mr = lds16(rp + 8) & 0x7ffu;
+        Row r;
+        r.raw01 = c.x; r.raw23 = c.y;
+        r.p01 = c.x & 0x07ff07ffu; r.p23 = c.y & 0x07ff07ffu;
+        r.l01 = prmt(ml, r.p01, 0x5410);
+        r.m12 = prmt(r.p01, r.p23, 0x5432);
+        r.r23 = prmt(r.p23, mr, 0x5432);
+        return r;
+    };
+    const int ya = M.ok ? M.r0 : 0;
+    Row up = load_row(ya - 1), ce = load_row(ya);
+#pragma unroll 1
+    for (int k = 0; k < seg_rows; ++k) {
+        const int y = ya + k;
+        const bool row_in = y < M.r1;
+        const Row dn = load_row(min(y + 1, h));
+        uint32_t cm[2], sm[2];
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+            const uint32_t C = pr ? ce.p23 : ce.p01;
+            const uint32_t raw = pr ? ce.raw23 : ce.raw01;
+            const uint32_t L = pr ? ce.m12 : ce.l01, Rr = pr ? ce.r23 : ce.m12;
+            const uint32_t U = pr ? up.p23 : up.p01, Dw = pr ? dn.p23 : dn.p01;
+            const uint32_t UL = pr ? up.m12 : up.l01, DR = pr ? dn.r23 : dn.m12;
+            const uint32_t UR = pr ? up.r23 : up.m12, DL = pr ? dn.m12 : dn.l01;
+            const uint32_t t0 = hgt_mask(C, L) & hge_mask(C, Rr);          // horizontal:  m > left, m >= right
+            const uint32_t t1 = hgt_mask(C, U) & hge_mask(C, Dw);          // vertical:    m > up,   m >= down
+            const uint32_t t2 = hgt_mask(C, UL) & hgt_mask(C, DR);         // diagonal s=+1, strict on both sides
+            const uint32_t t3 = hgt_mask(C, UR) & hgt_mask(C, DL);         // diagonal s=-1
+            const uint32_t b0 = ((raw >> 11) & 0x00010001u) * 0xffffu;
+            const uint32_t b1 = ((raw >> 12) & 0x00010001u) * 0xffffu;
+            const uint32_t pick = bsel(b1, bsel(b0, t3, t2), bsel(b0, t1, t0));
+            cm[pr] = pick & hgt_mask(C, P.low2);
+            sm[pr] = cm[pr] & hgt_mask(C, P.high2);
+        }
+        up = ce; ce = dn;
+        // pixels (0,1) sit in cm[0] halves, (2,3) in cm[1]: nibble bit q = pixel q
+        const uint32_t x = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u);
+        const uint32_t z = (sm[0] & 0x00020001u) | (sm[1] & 0x00080004u);
+        uint32_t v = ((x | (x >> 16)) & 0xfu) | (((z | (z >> 16)) & 0xfu) << 8);
+        const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
+        v |= other << 4;
+        if (M.store_lane && row_in) {
+            sts8(cbase + y * prb, v);
+            sts8(ebase + y * prb, v >> 8);
+            if (P.k.stats) st_strong += __popc((v >> 8) & 0xffu);
+        }
+    }
+}
+
+// =========================================================================================================
+// P3: hysteresis — grow the strong set through candidates, one plane word per thread per sweep, until stable.
+// a_cand / a_edge address row 0; the rows just above and below hold zeros.  Returns the number of sweeps.
+// =========================================================================================================
+template <class OrReduce>
+__device__ __forceinline__ int p3_hysteresis(uint32_t a_cand, uint32_t a_edge, int plane_words, int ww, int t0, int tstride, OrReduce group_or)
+{
+    int sweeps = 0, any;
+    const int rowb = ww * 4;
+    do {
+        int changed = 0;
+        for (int t = t0; t < plane_words; t += tstride) {
+            const uint32_t c = lds32(a_cand + 4 * t);
+            const uint32_t ea = a_edge + 4 * t;
+            const uint32_t e = lds32(ea);
+            if (c != e) {
+                const int wi = t % ww;
+                const uint32_t mid = e | lds32(ea - rowb) | lds32(ea + rowb);
+                uint32_t lft = 0, rgt = 0;
+                if (wi > 0) lft = lds32(ea - 4) | lds32(ea - rowb - 4) | lds32(ea + rowb - 4);
+                if (wi + 1 < ww) rgt = lds32(ea + 4) | lds32(ea - rowb + 4) | lds32(ea + rowb + 4);
+                const uint32_t spread = mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
+                const uint32_t ne = flood_run((spread & c) | e, c);
+                if (ne != e) { sts32(ea, ne); changed = 1; }
+            }
+        }
+        any = group_or(changed);
+        ++sweeps;
+    } while (any);
+    return sweeps;
+}
+
+// =========================================================================================================
+// P4: merge + normalise, written once.  pa[c] = shared address of the bit plane (row 0) feeding output channel c,
+// or 0 if that channel keeps the adjusted pixel.
+// =========================================================================================================
+__device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&pa)[3], uint32_t a_pix, uint8_t* __restrict__ gout,
+                                          float* __restrict__ gf32, int t0, int tstride)
+{
+    const int npb = P.k.h * (P.k.w >> 3);              // groups of 8 pixels = plane bytes
+    if (!P.k.need_pixels) {
+        // All three channels are bit planes.  Six lanes share one plane byte (8 pixels = 24 output items = six 4-item chunks):
+        // lane (g, s) emits chunk s of group g, i.e. one 16-byte f32 store and one 4-byte u8 store, so that consecutive lanes
+        // write consecutive addresses (30 lanes = 480 contiguous f32 bytes per instruction; strided per-thread stores made the
+        // LSU issue 2-3x the ideal sector count and left the output phase store-bound).
+        // Chunk s covers items 4s..4s+3 of (pixel, channel) order: with r = s % 3 and X, Y, Z = planes r, r+1, r+2 (mod 3) it is
+        // (X[p0], Y[p1], Z[p2], X[p0 + 1]); the pixel shifts (p0, p1, p2) are (0,0,0), (1,1,2), (2,3,3), plus 4 for s >= 3.
+        const int lane = t0 & 31, gw = t0 >> 5, nw = tstride >> 5;
+        const int gl = lane / 6, sc = lane - 6 * gl, r = sc % 3, hi4 = 4 * (sc / 3);
+        const bool lane_ok = lane < 30;
+        const uint32_t paX = r == 0 ? pa[0] : (r == 1 ? pa[1] : pa[2]);
+        const uint32_t paY = r == 0 ? pa[1] : (r == 1 ? pa[2] : pa[0]);
+        const uint32_t paZ = r == 0 ? pa[2] : (r == 1 ? pa[0] : pa[1]);
+        const int shX = r + hi4, shY = (r == 2 ? 3 : r) + hi4, shZ = (r == 0 ? 0 : r + 1) + hi4;
+        const int nwi = (npb + 4) / 5;
+        const uint32_t one = 0x3f800000u;
+#pragma unroll 2
+        for (int wi = gw; wi < nwi; wi += nw) {
+            const int g = 5 * wi + gl;
+            if (lane_ok && g < npb) {
+                const uint32_t xs = lds8(paX + g) >> shX, ys = lds8(paY + g) >> shY, zs = lds8(paZ + g) >> shZ;
+                const uint32_t b0 = xs & 1u, b1 = ys & 1u, b2 = zs & 1u, b3x = xs & 2u;
+                const size_t chunk = (size_t)30 * wi + lane;                       // == 6 g + s
+                if (gf32) reinterpret_cast<uint4*>(gf32)[chunk] = make_uint4(b0 * one, b1 * one, b2 * one, b3x * (one >> 1));
+                if (gout) reinterpret_cast<uint32_t*>(gout)[chunk] = b0 * 255u + b1 * (255u << 8) + b2 * (255u << 16) + b3x * (255u << 23);
+            }
+        }
+    } else {
+        // some channel keeps the adjusted pixel: bytes from the resident frame, floats by correctly rounded x/255
+        const float rcp = 1.0f / 255.0f;
+        for (int g = t0; g < 2 * npb; g += tstride) {          // groups of 4 pixels
+            const uint32_t src = a_pix + 12 * g;
+            uint32_t wv[3] = {lds32(src), lds32(src + 4), lds32(src + 8)};
+            uint8_t b[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) b[k] = (uint8_t)(wv[k >> 2] >> ((k & 3) * 8));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (pa[c]) {
+                    const uint32_t bits = lds8(pa[c] + (g >> 1)) >> ((g & 1) * 4);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) b[q * 3 + c] = ((bits >> q) & 1u) ? 255 : 0;
+                }
+            }
+            if (gout) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(gout + (size_t)g * 12);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    dst[k] = (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) | ((uint32_t)b[4 * k + 3] << 24);
+            }
+            if (gf32) {
+                float fv[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    // x/255 correctly rounded without a division: q0 = x*rcp, one fused residual correction (exhaustively checked for 0..255)
+                    const float x = (float)b[k];
+                    const float q0 = __fmul_rn(x, rcp);
+                    fv[k] = __fmaf_rn(__fmaf_rn(-q0, 255.0f, x), rcp, q0);
+                }
+                float4* dst = reinterpret_cast<float4*>(gf32 + (size_t)g * 12);
+                dst[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
+                dst[1] = make_float4(fv[4], fv[5], fv[6], fv[7]);
+                dst[2] = make_float4(fv[8], fv[9], fv[10], fv[11]);
+            }
+        }
+    }
+}
+
+// ---- shared prologue pieces ---------------------------------------------------------------------------------
+__device__ __forceinline__ void init_tables(const PreKParams& p, const SmemMap& S, int t0, int tstride)
+{
+    for (int i = t0; i < 256; i += tstride) {
+        sts32(S.sdiv + 4 * i, i ? (uint32_t)__double2int_rn((double)(255 << 12) / (double)i) : 0u);
+        const int hd = i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
+        sts64(S.hue + 8 * i, make_uint2((uint32_t)hd, (uint32_t)(2048 - 2048 * hd)));      // ((h0 + 2048) hd + (2048 - 2048 hd)) >> 12 == (h0 hd + 2048) >> 12
+        sts8(S.lut + i, p.lut[i]);
+    }
+}
+
+__device__ __forceinline__ void zero_mag_borders(uint32_t a_mag, int h, int w, int MS, int t0, int tstride)
+{
+    for (int i = t0; i < MS; i += tstride) { sts16(a_mag + 2 * i, 0); sts16(a_mag + 2 * ((h + 1) * MS + i), 0); }
+    for (int i = t0; i < h + 2; i += tstride) { sts16(a_mag + 2 * (i * MS + 3), 0); sts16(a_mag + 2 * (i * MS + 4 + w), 0); }
+}
+
+__device__ __forceinline__ void zero_plane_pads(const SmemMap& S, int plane_words, int ww, int t0, int tstride)
+{
+    for (int i = t0; i < ww; i += tstride) {
+        sts32(S.cand - 4 * ww + 4 * i, 0); sts32(S.cand + 4 * (plane_words + i), 0);
+        sts32(S.edge - 4 * ww + 4 * i, 0); sts32(S.edge + 4 * (plane_words + i), 0);
+    }
+}
+
+__device__ __forceinline__ uint32_t lut4s(uint32_t a_lut, uint32_t v)
+{
+    return lds8(a_lut + (v & 0xff)) | (lds8(a_lut + ((v >> 8) & 0xff)) << 8) | (lds8(a_lut + ((v >> 16) & 0xff)) << 16) | (lds8(a_lut + (v >> 24)) << 24);
+}
+
+// brightness / contrast on the resident frame (only when the table is not the identity); `sync` is the barrier of the
+// thread group that owns the frame at this point; s_red = generic pointer to three u64 accumulators
+template <class Sync>
+__device__ __forceinline__ void adjust_in_place(const PreKParams& p, uint32_t a_pix, const SmemMap& S, unsigned long long* s_red, int t0,
+                                                int tstride, int lane, unsigned long long& st_roi, Sync sync)
+{
+    const int h = p.h, w = p.w, row_bytes = w * 3;
+    if (p.dynamic) {
+        const int y0 = min(40, h), y1 = min(119, h);
+        unsigned long long s0 = 0, s1 = 0, s2 = 0;
+        const int npix = (y1 - y0) * w;
+        const uint32_t roi = a_pix + y0 * row_bytes;
+        for (int i = t0; i < npix; i += tstride) { s0 += lds8(roi + 3 * i); s1 += lds8(roi + 3 * i + 1); s2 += lds8(roi + 3 * i + 2); }
+        for (int o = 16; o; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (t0 < 3) s_red[t0] = 0;
+        sync();
+        if (lane == 0) { atomicAdd(&s_red[0], s0); atomicAdd(&s_red[1], s1); atomicAdd(&s_red[2], s2); }
+        sync();
+        const float fdelta = (float)brightness_delta(s_red[0], s_red[1], s_red[2], (double)npix, p.baseline);
+        if (t0 == 0) st_roi += s_red[0] + s_red[1] + s_red[2];
+        for (int i = t0; i < 256; i += tstride) sts8(S.lut + i, adjust_entry(i, true, fdelta, p.foff, p.fratio));
+        sync();
+    }
+    if (p.dynamic || !p.lut_identity) {
+        const int nwords = (h * row_bytes) >> 2;
+        for (int i = t0; i < nwords; i += tstride) sts32(a_pix + 4 * i, lut4s(S.lut, lds32(a_pix + 4 * i)));
+        sync();
+    }
+}
+
+__device__ __forceinline__ void flush_stats(const PreKParams& p, const unsigned long long (&v)[10], int lane)
+{
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        unsigned long long x = v[k];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(&p.stats[k], x);
+    }
+}
+
+__device__ __forceinline__ void plane_sources(const PreKParams& p, const SmemMap& S, int plane_bytes, uint32_t (&pa)[3])
+{
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        pa[c] = p.src[c] == SRC_EDGE ? S.edge : (p.src[c] >= SRC_MASK0 ? S.mask + (p.src[c] - SRC_MASK0) * plane_bytes : 0u);
+}
+
+// population counts of the finished planes (statistics)
+template <int NR, bool EDGE>
+__device__ __forceinline__ void count_planes(const SmemMap& S, int plane_bytes, int plane_words, int t0, int tstride, unsigned long long (&st_mask)[3],
+                                             unsigned long long& st_edge, unsigned long long& st_cand)
+{
+    for (int i = t0; i < plane_words; i += tstride) {
+        if (EDGE) { st_edge += __popc(lds32(S.edge + 4 * i)); st_cand += __popc(lds32(S.cand + 4 * i)); }
+#pragma unroll
+        for (int k = 0; k < NR; ++k) st_mask[k] += __popc(lds32(S.mask + k * plane_bytes + 4 * i));
+    }
+}
+
+// =========================================================================================================
+// Resident kernel: one frame per CTA, two CTAs per SM
+// =========================================================================================================
 template <int NR, bool EDGE>
 __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const __grid_constant__ FastParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const PreKParams& p = P.k;
     const FastGeom& G = P.g;
-    uint8_t* s_pix = smem + G.off_pix;
-    uint16_t* s_mag = reinterpret_cast<uint16_t*>(smem + G.off_mag);
-    const int h = p.h, w = p.w, ww = G.nsg;
-    // bit planes: row y at word row y + 1; rows 0 and h + 1 stay zero
-    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + G.off_cand) + ww;
-    uint32_t* s_edge = reinterpret_cast<uint32_t*>(smem + G.off_edge) + ww;
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + G.off_mask) + ww;
-    const int plane_stride = (((h + 2) * ww * 4 + 15) & ~15) >> 2;        // words between consecutive mask planes
-    int32_t* s_sdiv = reinterpret_cast<int32_t*>(smem + G.off_tab);
-    int2* s_hue = reinterpret_cast<int2*>(smem + G.off_tab + 1024);
-    uint8_t* s_lut = smem + G.off_lut;
-    float4* s_f32lut = reinterpret_cast<float4*>(smem + G.off_f32lut);
+    uint32_t sb = smem_u32(smem);
+    asm volatile("" : "+r"(sb));                       // launder: the window base lives in this register, never re-derived
+    const SmemMap S = smem_map(sb, G);
     unsigned long long* s_red = reinterpret_cast<unsigned long long*>(smem + G.off_red);
-    const uint32_t bar = smem_u32(smem + G.off_bar);
-
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int row_bytes = w * 3;
-    const int prb = w >> 3;                                  // plane bytes per row
-    const uint32_t frame_bytes = (uint32_t)h * row_bytes;
+    const int h = p.h, w = p.w, ww = G.nsg;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t frame_bytes = (uint32_t)h * w * 3;
     const int plane_words = h * ww;
-    const int MS = G.mag_stride;
+    const StripMap M = strip_map(warp, lane, ww, G.seg_rows_front, h);
 
-    // thread -> (strip, segment): an 8-lane group is 8 adjacent strips (32 pixels) of one segment
-    const int grp = lane >> 3;
-    const int strip = 8 * (warp % ww) + (lane & 7);
-    const int seg = 4 * (warp / ww) + grp;
-    const int r0 = seg * G.seg_rows;
-    const int r1 = min(h, r0 + G.seg_rows);
-    const bool seg_ok = r0 < h;
-    const int nstrips = w >> 2;
-    const bool store_lane = seg_ok && !(lane & 1);           // even lanes store the byte shared with the odd neighbour
-
-    // ---- one-time tables and zero borders --------------------------------------------------------------------
-    for (int i = tid; i < 256; i += nthr) {
-        s_sdiv[i] = i ? __double2int_rn((double)(255 << 12) / (double)i) : 0;
-        const int hd = i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
-        s_hue[i] = make_int2(hd, 2048 - 2048 * hd);           // ((h0 + 2048) * hd + (2048 - 2048 hd)) >> 12 == (h0 * hd + 2048) >> 12
-        s_lut[i] = p.lut[i];
+    init_tables(p, S, tid, nthr);
+    if (EDGE) {
+        zero_mag_borders(S.mag[0], h, w, G.mag_stride, tid, nthr);
+        zero_plane_pads(S, plane_words, ww, tid, nthr);
     }
-    if (tid < 8) s_f32lut[tid] = make_float4((tid & 1) ? 1.0f : 0.0f, (tid & 2) ? 1.0f : 0.0f, (tid & 4) ? 1.0f : 0.0f, 0.0f);
-    if (EDGE) {   // zero borders of the magnitude plane: rows 0 and h+1, columns x = -1 and x = w
-        for (int i = tid; i < MS; i += nthr) { s_mag[i] = 0; s_mag[(h + 1) * MS + i] = 0; }
-        for (int i = tid; i < h + 2; i += nthr) { s_mag[i * MS + 3] = 0; s_mag[i * MS + 4 + w] = 0; }
-        for (int i = tid; i < ww; i += nthr) {
-            s_cand[-ww + i] = 0; s_cand[h * ww + i] = 0;
-            s_edge[-ww + i] = 0; s_edge[h * ww + i] = 0;
-        }
-    }
-    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(S.bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
+    if (tid == 0 && (int)blockIdx.x < p.n) issue_frame_load(S.pix[0], p.in + (size_t)blockIdx.x * frame_bytes, frame_bytes, S.bar);
 
-    auto issue_load = [&](int f) {
-        // one elected thread: arm the barrier with the byte count, then one bulk copy per 16 KB piece
-        fence_proxy_async();
-        mbar_expect_tx(bar, frame_bytes);
-        const uint8_t* src = p.in + (size_t)f * frame_bytes;
-        for (uint32_t o = 0; o < frame_bytes; o += 16384u)
-            tma_load_1d(smem_u32(s_pix) + o, src + o, min(16384u, frame_bytes - o), bar);
-    };
-    if (tid == 0 && (int)blockIdx.x < p.n) issue_load(blockIdx.x);
-
-    unsigned long long st_mask[NR > 0 ? NR : 1];
-#pragma unroll
-    for (int k = 0; k < (NR > 0 ? NR : 1); ++k) st_mask[k] = 0;
+    unsigned long long st_mask[3] = {0, 0, 0};
     unsigned long long st_edge = 0, st_strong = 0, st_cand = 0, st_sweeps = 0, st_roi = 0, st_frames = 0;
     uint32_t phase = 0;
-
-    // per-thread constants of the strip walk
-    const bool left_edge = strip == 0, right_edge = strip == nstrips - 1;
-    const int offL = left_edge ? 0 : -4;                    // word holding the pixel left of the strip (replicated at x = 0)
-    const int offR = right_edge ? 8 : 12;                   // word holding the pixel right of the strip (replicated at x = w-1)
-    const uint32_t selL0 = 0x5450u | (left_edge ? 0u : 1u), selL1 = 0x5450u | (left_edge ? 1u : 2u), selL2 = 0x5450u | (left_edge ? 2u : 3u);
-    const uint32_t selR0 = 0x1012u | ((right_edge ? 5u : 4u) << 8), selR1 = 0x1012u | ((right_edge ? 6u : 5u) << 8),
-                   selR2 = 0x1012u | ((right_edge ? 7u : 6u) << 8);
-    const int nsteps = G.seg_rows + 2;
+    uint32_t pa[3];
+    plane_sources(p, S, G.plane_bytes, pa);
 
     for (int f = blockIdx.x; f < p.n; f += gridDim.x) {
-        mbar_wait(bar, phase);
+        mbar_wait(S.bar, phase);
         phase ^= 1u;
-        const bool use_lut = p.dynamic || !p.lut_identity;
-
-        // ---- brightness / contrast on the resident frame (only when the table is not the identity) ----------
-        if (p.dynamic) {
-            const int y0 = min(40, h), y1 = min(119, h);
-            unsigned long long s0 = 0, s1 = 0, s2 = 0;
-            const int npix = (y1 - y0) * w;
-            const uint8_t* roi = s_pix + y0 * row_bytes;
-            for (int i = tid; i < npix; i += nthr) { s0 += roi[3 * i]; s1 += roi[3 * i + 1]; s2 += roi[3 * i + 2]; }
-            for (int o = 16; o; o >>= 1) {
-                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            if (tid < 3) s_red[tid] = 0;
-            __syncthreads();
-            if (lane == 0) { atomicAdd(&s_red[0], s0); atomicAdd(&s_red[1], s1); atomicAdd(&s_red[2], s2); }
-            __syncthreads();
-            const float fdelta = (float)brightness_delta(s_red[0], s_red[1], s_red[2], (double)npix, p.baseline);
-            if (tid == 0) st_roi += s_red[0] + s_red[1] + s_red[2];
-            for (int i = tid; i < 256; i += nthr) s_lut[i] = adjust_entry(i, true, fdelta, p.foff, p.fratio);
-            __syncthreads();
-        }
-        if (use_lut) {
-            uint32_t* px = reinterpret_cast<uint32_t*>(s_pix);
-            for (int i = tid; i < (int)(frame_bytes >> 2); i += nthr) px[i] = lut4(s_lut, px[i]);
-            __syncthreads();
-        }
-
-        // ---- P1: strip walk — Sobel / magnitude / direction -> s_mag, colour masks -> bit planes --------------
-        if (EDGE || NR > 0) {
-            uint32_t D[3][6], Hs[3][6];      // rolling rows: horizontal difference and horizontal smoothing, packed pairs
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 6; ++j) { D[i][j] = 0; Hs[i][j] = 0; }
-            const uint8_t* strip_base = s_pix + 12 * strip;
-            uint8_t* mask_base = reinterpret_cast<uint8_t*>(s_mask) + (strip >> 1);
-
-            auto row_step = [&](int k, uint32_t (&Dn)[6], uint32_t (&Hn)[6], const uint32_t (&D0)[6], const uint32_t (&D1)[6],
-                                const uint32_t (&H0)[6]) {
-                // load image row y_load = r0 - 1 + k (clamped: replicated border) into slot n; emit output row y = r0 + k - 2
-                const int y_load = min(max(r0 - 1 + k, 0), h - 1);
-                const uint8_t* rp = strip_base + y_load * row_bytes;
-                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(rp);
-                const uint32_t w1 = *reinterpret_cast<const uint32_t*>(rp + 4);
-                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(rp + 8);
-                const uint32_t wl = *reinterpret_cast<const uint32_t*>(rp + offL);
-                const uint32_t wr = *reinterpret_cast<const uint32_t*>(rp + offR);
-                // interleaved bytes -> zero-extended pairs: E = (b0,b2), O = (b1,b3)
-                const uint32_t E0 = w0 & 0x00ff00ffu, O0 = prmt(w0, 0, 0x4341);
-                const uint32_t E1 = w1 & 0x00ff00ffu, O1 = prmt(w1, 0, 0x4341);
-                const uint32_t E2 = w2 & 0x00ff00ffu, O2 = prmt(w2, 0, 0x4341);
-                // planar pairs: A = pixels (0,2), B = pixels (1,3) of the strip, per channel
-                uint32_t A[3], B[3];
-                A[0] = prmt(E0, E1, 0x7610); A[1] = prmt(O0, O1, 0x7610); A[2] = prmt(E0, E2, 0x5432);
-                B[0] = prmt(O0, O2, 0x5432); B[1] = prmt(E1, E2, 0x7610); B[2] = prmt(O1, O2, 0x7610);
-                if (EDGE) {
-                    // neighbours: Lh = pixels (-1,1), Rh = pixels (2,4)
-                    uint32_t Lh[3], Rh[3];
-                    Lh[0] = prmt(wl, B[0], selL0); Lh[1] = prmt(wl, B[1], selL1); Lh[2] = prmt(wl, B[2], selL2);
-                    Rh[0] = prmt(A[0], wr, selR0); Rh[1] = prmt(A[1], wr, selR1); Rh[2] = prmt(A[2], wr, selR2);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        Dn[c] = hsub(B[c], Lh[c]);                      // pixels (0,2): p[x+1] - p[x-1]
-                        Dn[3 + c] = hsub(Rh[c], A[c]);                  // pixels (1,3)
-                        Hn[c] = hadd(hx2p(A[c], Lh[c]), B[c]);          // p[x-1] + 2 p[x] + p[x+1]
-                        Hn[3 + c] = hadd(hx2p(B[c], A[c]), Rh[c]);
-                    }
-                }
-                const int y_row = r0 - 1 + k;
-                const bool row_in = k >= 1 && y_row < r1;                // the loaded row belongs to this segment
-                // ---- colour masks for the loaded row ---------------------------------------------------------
-                if (NR > 0) {
-                    uint32_t okm[NR > 0 ? NR : 1][2];                    // per range: half masks for pixels (0,2) and (1,3)
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t* X = half ? B : A;
-                        const uint32_t v2 = __vimax3_u16x2(X[0], X[1], X[2]);
-                        const uint32_t mn2 = __vimin3_u16x2(X[0], X[1], X[2]);
-                        const uint32_t d2 = v2 - mn2;
-                        uint32_t s2, hh2 = 0;
-                        {
-                            const uint32_t vlo = v2 & 0xffffu, vhi = v2 >> 16, dlo = d2 & 0xffffu, dhi = d2 >> 16;
-                            const uint32_t slo = (uint32_t)(((int)dlo * s_sdiv[vlo] + 2048) >> 12);
-                            const uint32_t shi = (uint32_t)(((int)dhi * s_sdiv[vhi] + 2048) >> 12);
-                            s2 = slo | (shi << 16);
-                            if (P.need_hue) {
-                                // hue numerator + 2048 (always positive): g-b | b-r+2d | r-g+4d, chosen by v==r, then v==g
-                                const uint32_t gb = X[1] + 0x08000800u - X[2];
-                                const uint32_t br = X[2] + 0x08000800u - X[0] + d2 + d2;
-                                const uint32_t rg = X[0] + 0x08000800u - X[1] + (d2 << 2);
-                                const uint32_t eqr = heq_mask(v2, X[0]), eqg = heq_mask(v2, X[1]);
-                                const uint32_t h02 = bsel(eqr, gb, bsel(eqg, br, rg));
-                                const int2 tl = s_hue[dlo], th = s_hue[dhi];
-                                int hlo = ((int)(h02 & 0xffffu) * tl.x + tl.y) >> 12;
-                                int hhi = ((int)(h02 >> 16) * th.x + th.y) >> 12;
-                                hlo += (hlo >> 31) & 180;
-                                hhi += (hhi >> 31) & 180;
-                                hh2 = (uint32_t)hlo | ((uint32_t)hhi << 16);
-                            }
-                        }
-#pragma unroll
-                        for (int r = 0; r < NR; ++r) {
-                            const FastRange& R = P.fr[r];
-                            uint32_t ok = 0xffffffffu;
-                            if (R.flags & 1u) ok &= hge_mask(hh2, R.lo[0]);
-                            if (R.flags & 2u) ok &= hle_mask(hh2, R.hi[0]);
-                            if (R.flags & 4u) ok &= hge_mask(s2, R.lo[1]);
-                            if (R.flags & 8u) ok &= hle_mask(s2, R.hi[1]);
-                            if (R.flags & 16u) ok &= hge_mask(v2, R.lo[2]);
-                            if (R.flags & 32u) ok &= hle_mask(v2, R.hi[2]);
-                            okm[r][half] = ok;
-                        }
-                    }
-                    uint32_t v = 0;
-#pragma unroll
-                    for (int r = 0; r < NR; ++r) v |= nibble_of(okm[r][0], okm[r][1]) << (8 * r);
-                    const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
-                    v |= other << 4;
-                    if (store_lane && row_in) {
-#pragma unroll
-                        for (int r = 0; r < NR; ++r) mask_base[(r * plane_stride) * 4 + y_row * prb] = (uint8_t)(v >> (8 * r));
-                    }
-                }
-                // ---- Sobel combine for output row y = r0 + k - 2 ----------------------------------------------
-                if (EDGE && k >= 2) {
-                    const int y = r0 + k - 2;
-                    uint32_t mg[2], dxs[2], dys[2];
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t m[3], dx[3], dy[3];
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const int j = 3 * half + c;
-                            dx[c] = hadd(hx2p(D1[j], D0[j]), Dn[j]);            // D[y-1] + 2 D[y] + D[y+1]
-                            dy[c] = hsub(Hn[j], H0[j]);                          // H[y+1] - H[y-1]
-                            m[c] = habsadd(dx[c], dy[c]);
-                        }
-                        const uint32_t g1 = hgt_mask(m[1], m[0]);                // strictly greater: the lowest channel wins ties
-                        uint32_t mm = hmaxu(m[0], m[1]);
-                        uint32_t bx = bsel(g1, dx[1], dx[0]), by = bsel(g1, dy[1], dy[0]);
-                        const uint32_t g2 = hgt_mask(m[2], mm);
-                        mm = hmaxu(mm, m[2]);
-                        bx = bsel(g2, dx[2], bx); by = bsel(g2, dy[2], by);
-                        mg[half] = mm; dxs[half] = bx; dys[half] = by;
-                    }
-                    // per pixel direction class (pixel_math.cuh canny_dir), branch-free; pixel order 0..3 = (A.lo, B.lo, A.hi, B.hi)
-                    const uint32_t ax0 = dxs[0] & 0x7fff7fffu, ay0 = dys[0] & 0x7fff7fffu;
-                    const uint32_t ax1 = dxs[1] & 0x7fff7fffu, ay1 = dys[1] & 0x7fff7fffu;
-                    const uint32_t sd0 = ((dxs[0] ^ dys[0]) >> 15) & 0x00010001u, sd1 = ((dxs[1] ^ dys[1]) >> 15) & 0x00010001u;
-                    const uint32_t c0 = dir_bits(ax0 & 0xffffu, ay0 & 0xffffu, sd0 & 1u);      // pixel 0
-                    const uint32_t c1 = dir_bits(ax1 & 0xffffu, ay1 & 0xffffu, sd1 & 1u);      // pixel 1
-                    const uint32_t c2 = dir_bits(ax0 >> 16, ay0 >> 16, sd0 >> 16);             // pixel 2
-                    const uint32_t c3 = dir_bits(ax1 >> 16, ay1 >> 16, sd1 >> 16);             // pixel 3
-                    if (seg_ok && y < r1) {
-                        uint2 v;
-                        v.x = prmt(mg[0], mg[1], 0x5410) | (c0 << 11) | (c1 << 27);        // (m0, m1) + codes
-                        v.y = prmt(mg[0], mg[1], 0x7632) | (c2 << 11) | (c3 << 27);        // (m2, m3) + codes
-                        *reinterpret_cast<uint2*>(s_mag + (y + 1) * MS + 4 + 4 * strip) = v;
-                    }
-                }
-            };
-            // rolling window by register renaming: slots (k % 3)
-#pragma unroll 1
-            for (int k = 0; k < nsteps; k += 3) {
-                row_step(k, D[0], Hs[0], D[1], D[2], Hs[1]);                 // new = slot0, y-1 = slot1, y = slot2
-                if (k + 1 < nsteps) row_step(k + 1, D[1], Hs[1], D[2], D[0], Hs[2]);
-                if (k + 2 < nsteps) row_step(k + 2, D[2], Hs[2], D[0], D[1], Hs[0]);
-            }
-        }
+        adjust_in_place(p, S.pix[0], S, s_red, tid, nthr, lane, st_roi, [] { __syncthreads(); });
+        p1_strip_walk<NR, EDGE>(P, S.pix[0], S.mag[0], S, M, G.seg_rows_front);
         __syncthreads();
-        if (!p.need_pixels && tid == 0 && f + (int)gridDim.x < p.n) issue_load(f + gridDim.x);   // pixels are dead: prefetch
-
-        // ---- P2: non-maximum suppression, same strip walk over the magnitude plane, two pixels per compare ------
+        if (!p.need_pixels && tid == 0 && f + (int)gridDim.x < p.n)       // pixels are dead: prefetch the next frame
+            issue_frame_load(S.pix[0], p.in + (size_t)(f + gridDim.x) * frame_bytes, frame_bytes, S.bar);
         if (EDGE) {
-            const uint16_t* mbase = s_mag + 4 + 4 * strip;
-            uint8_t* cbase = reinterpret_cast<uint8_t*>(s_cand) + (strip >> 1);
-            uint8_t* ebase = reinterpret_cast<uint8_t*>(s_edge) + (strip >> 1);
-            // one row as packed pairs of magnitudes: P01=(m0,m1) P23=(m2,m3) L01=(m-1,m0) M12=(m1,m2) R23=(m3,m4); raw keeps the codes
-            struct Row { uint32_t p01, p23, l01, m12, r23, raw01, raw23; };
-            auto load_row = [&](int y) {
-                const uint16_t* rp = mbase + (y + 1) * MS;
-                const uint2 c = *reinterpret_cast<const uint2*>(rp);
-                const uint32_t ml = rp[-1] & 0x7ffu, mr = rp[4] & 0x7ffu;
-                Row r;
-                r.raw01 = c.x; r.raw23 = c.y;
-                r.p01 = c.x & 0x07ff07ffu; r.p23 = c.y & 0x07ff07ffu;
-                r.l01 = prmt(ml, r.p01, 0x5410);
-                r.m12 = prmt(r.p01, r.p23, 0x5432);
-                r.r23 = prmt(r.p23, mr, 0x5432);
-                return r;
-            };
-            const int ya = seg_ok ? r0 : 0;
-            Row up = load_row(ya - 1), ce = load_row(ya);
-#pragma unroll 1
-            for (int k = 0; k < G.seg_rows; ++k) {
-                const int y = ya + k;
-                const bool row_in = y < r1;
-                const Row dn = load_row(min(y + 1, h));
-                uint32_t cm[2], sm[2];
-#pragma unroll
-                for (int pr = 0; pr < 2; ++pr) {
-                    const uint32_t C = pr ? ce.p23 : ce.p01;
-                    const uint32_t raw = pr ? ce.raw23 : ce.raw01;
-                    const uint32_t L = pr ? ce.m12 : ce.l01, Rr = pr ? ce.r23 : ce.m12;
-                    const uint32_t U = pr ? up.p23 : up.p01, Dw = pr ? dn.p23 : dn.p01;
-                    const uint32_t UL = pr ? up.m12 : up.l01, DR = pr ? dn.r23 : dn.m12;
-                    const uint32_t UR = pr ? up.r23 : up.m12, DL = pr ? dn.m12 : dn.l01;
-                    const uint32_t t0 = hgt_mask(C, L) & hge_mask(C, Rr);          // horizontal:  m > left, m >= right
-                    const uint32_t t1 = hgt_mask(C, U) & hge_mask(C, Dw);          // vertical:    m > up,   m >= down
-                    const uint32_t t2 = hgt_mask(C, UL) & hgt_mask(C, DR);         // diagonal s=+1, strict on both sides
-                    const uint32_t t3 = hgt_mask(C, UR) & hgt_mask(C, DL);         // diagonal s=-1
-                    const uint32_t b0 = ((raw >> 11) & 0x00010001u) * 0xffffu;
-                    const uint32_t b1 = ((raw >> 12) & 0x00010001u) * 0xffffu;
-                    const uint32_t pick = bsel(b1, bsel(b0, t3, t2), bsel(b0, t1, t0));
-                    cm[pr] = pick & hgt_mask(C, P.low2);
-                    sm[pr] = cm[pr] & hgt_mask(C, P.high2);
-                }
-                up = ce; ce = dn;
-                // pixels (0,1) sit in cm[0] halves, (2,3) in cm[1]: nibble bit q = pixel q
-                uint32_t x = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u);
-                uint32_t z = (sm[0] & 0x00020001u) | (sm[1] & 0x00080004u);
-                uint32_t v = ((x | (x >> 16)) & 0xfu) | (((z | (z >> 16)) & 0xfu) << 8);
-                const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
-                v |= other << 4;
-                if (store_lane && row_in) {
-                    cbase[y * prb] = (uint8_t)v;
-                    ebase[y * prb] = (uint8_t)(v >> 8);
-                    if (p.stats) st_strong += __popc((v >> 8) & 0xffu);
-                }
-            }
+            p2_nms(P, S.mag[0], S, M, G.seg_rows_front, st_strong);
+            __syncthreads();
+            const int sw = p3_hysteresis(S.cand, S.edge, plane_words, ww, tid, nthr, [](int c) { return __syncthreads_or(c); });
+            if (tid == 0) st_sweeps += sw;
         }
-        __syncthreads();
-
-        // ---- P3: hysteresis: grow the strong set through candidates, one plane word per thread per sweep -------
-        if (EDGE) {
-            volatile uint32_t* E = s_edge;
-            int any;
-            do {
-                int changed = 0;
-                for (int t = tid; t < plane_words; t += nthr) {
-                    const uint32_t c = s_cand[t];
-                    const uint32_t e = E[t];
-                    if (c != e) {
-                        const int wi = t % ww;
-                        uint32_t mid = e | E[t - ww] | E[t + ww];
-                        uint32_t lft = 0, rgt = 0;
-                        if (wi > 0) lft = E[t - 1] | E[t - ww - 1] | E[t + ww - 1];
-                        if (wi + 1 < ww) rgt = E[t + 1] | E[t - ww + 1] | E[t + ww + 1];
-                        const uint32_t spread = mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
-                        const uint32_t ne = flood_word((spread & c) | e, c);
-                        if (ne != e) { E[t] = ne; changed = 1; }
-                    }
-                }
-                any = __syncthreads_or(changed);
-                if (tid == 0) ++st_sweeps;
-            } while (any);
-        }
-
-        // ---- P4: merge + normalise, written once ---------------------------------------------------------------
-        {
-            uint8_t* __restrict__ gout = p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr;
-            float* __restrict__ gf32 = p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr;
-            const uint8_t* planes[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                planes[c] = reinterpret_cast<const uint8_t*>(p.src[c] == SRC_EDGE ? s_edge : (p.src[c] >= SRC_MASK0 ? s_mask + (p.src[c] - SRC_MASK0) * plane_stride : nullptr));
-            const int npb = h * prb;                        // groups of 8 pixels = plane bytes
-            if (!p.need_pixels) {
-                // all three channels are bit planes: bytes by multiply-spread, floats as bit * 0x3f800000 (masks are 0.0 / 1.0)
-                int poff[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    poff[c] = (p.src[c] == SRC_EDGE ? G.off_edge : G.off_mask + (p.src[c] - SRC_MASK0) * plane_stride * 4) + ww * 4;
-                for (int g = tid; g < npb; g += nthr) {
-                    const uint32_t b0 = smem[poff[0] + g], b1 = smem[poff[1] + g], b2 = smem[poff[2] + g];     // 8 pixels of each channel
-                    uint32_t r4[2], g4[2], l4[2];
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        r4[hf] = (((b0 >> (4 * hf)) & 0xfu) * 0x00204081u) & 0x01010101u;      // bit q -> byte q
-                        g4[hf] = (((b1 >> (4 * hf)) & 0xfu) * 0x00204081u) & 0x01010101u;
-                        l4[hf] = (((b2 >> (4 * hf)) & 0xfu) * 0x00204081u) & 0x01010101u;
-                    }
-                    if (gout) {
-                        uint32_t wv[6];
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            const uint32_t R = r4[hf] * 255u, Gc = g4[hf] * 255u, Bc = l4[hf] * 255u;     // planar bytes 0 / 255
-                            wv[3 * hf + 0] = prmt(prmt(R, Gc, 0x1040), Bc, 0x3410);     // R0 G0 B0 R1
-                            wv[3 * hf + 1] = prmt(prmt(Gc, Bc, 0x2051), R, 0x3610);     // G1 B1 R2 G2
-                            wv[3 * hf + 2] = prmt(prmt(Bc, R, 0x3072), Gc, 0x3710);     // B2 R3 G3 B3
-                        }
-                        uint2* dst = reinterpret_cast<uint2*>(gout + (size_t)g * 24);
-                        dst[0] = make_uint2(wv[0], wv[1]); dst[1] = make_uint2(wv[2], wv[3]); dst[2] = make_uint2(wv[4], wv[5]);
-                    }
-                    if (gf32) {
-                        uint4* dst = reinterpret_cast<uint4*>(gf32 + (size_t)g * 24);
-                        const uint32_t one = 0x3f800000u;
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            const uint32_t R = r4[hf], Gc = g4[hf], Bc = l4[hf];
-                            dst[3 * hf + 0] = make_uint4((R & 0xffu) * one, (Gc & 0xffu) * one, (Bc & 0xffu) * one, prmt(R, 0, 0x4441) * one);
-                            dst[3 * hf + 1] = make_uint4(prmt(Gc, 0, 0x4441) * one, prmt(Bc, 0, 0x4441) * one, prmt(R, 0, 0x4442) * one, prmt(Gc, 0, 0x4442) * one);
-                            dst[3 * hf + 2] = make_uint4(prmt(Bc, 0, 0x4442) * one, (R >> 24) * one, (Gc >> 24) * one, (Bc >> 24) * one);
-                        }
-                    }
-                }
-            } else {
-                // some channel keeps the adjusted pixel: bytes from the resident frame, floats by correctly rounded x/255
-                const float rcp = 1.0f / 255.0f;
-                for (int g = tid; g < 2 * npb; g += nthr) {          // groups of 4 pixels
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(s_pix + (size_t)g * 12);
-                    uint32_t wv[3] = {src[0], src[1], src[2]};
-                    uint8_t b[12];
-#pragma unroll
-                    for (int k = 0; k < 12; ++k) b[k] = (uint8_t)(wv[k >> 2] >> ((k & 3) * 8));
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (planes[c]) {
-                            const uint32_t bits = (uint32_t)planes[c][g >> 1] >> ((g & 1) * 4);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) b[q * 3 + c] = ((bits >> q) & 1u) ? 255 : 0;
-                        }
-                    }
-                    if (gout) {
-                        uint32_t* dst = reinterpret_cast<uint32_t*>(gout + (size_t)g * 12);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-                            dst[k] = (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) | ((uint32_t)b[4 * k + 3] << 24);
-                    }
-                    if (gf32) {
-                        float fv[12];
-#pragma unroll
-                        for (int k = 0; k < 12; ++k) {
-                            // x/255 correctly rounded without a division: q0 = x*rcp, one fused residual correction (exhaustively checked for 0..255)
-                            const float x = (float)b[k];
-                            const float q0 = __fmul_rn(x, rcp);
-                            fv[k] = __fmaf_rn(__fmaf_rn(-q0, 255.0f, x), rcp, q0);
-                        }
-                        float4* dst = reinterpret_cast<float4*>(gf32 + (size_t)g * 12);
-                        dst[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
-                        dst[1] = make_float4(fv[4], fv[5], fv[6], fv[7]);
-                        dst[2] = make_float4(fv[8], fv[9], fv[10], fv[11]);
-                    }
-                }
-            }
-        }
+        p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr,
+                  tid, nthr);
         if (p.stats) {
-            for (int i = tid; i < plane_words; i += nthr) {
-                if (EDGE) { st_edge += __popc(s_edge[i]); st_cand += __popc(s_cand[i]); }
-#pragma unroll
-                for (int k = 0; k < NR; ++k) st_mask[k] += __popc(s_mask[k * plane_stride + i]);
-            }
+            count_planes<NR, EDGE>(S, G.plane_bytes, plane_words, tid, nthr, st_mask, st_edge, st_cand);
             if (tid == 0) ++st_frames;
         }
         __syncthreads();
-        if (p.need_pixels && tid == 0 && f + (int)gridDim.x < p.n) issue_load(f + gridDim.x);
+        if (p.need_pixels && tid == 0 && f + (int)gridDim.x < p.n)
+            issue_frame_load(S.pix[0], p.in + (size_t)(f + gridDim.x) * frame_bytes, frame_bytes, S.bar);
     }
-
     if (p.stats) {
         unsigned long long v[10] = {st_frames, 0, 0, 0, 0, st_edge, st_strong, st_cand, st_sweeps, st_roi};
 #pragma unroll
         for (int k = 0; k < NR; ++k) v[1 + p.range_stat[k]] = st_mask[k];
+        flush_stats(p, v, lane);
+    }
+}
+
+// =========================================================================================================
+// Warp-specialised kernel: one CTA per SM; front warps = Sobel strip walk of frame j+1, back warps = colour masks +
+// NMS + hysteresis + output of frame j; TMA double buffer for frames, double-buffered magnitude plane, mbarrier hand-over.
+// =========================================================================================================
+enum { BAR_FULL_PIX = 0, BAR_EMPTY_PIX = 2, BAR_FULL_MAG = 4, BAR_EMPTY_MAG = 6 };
+
+template <int NR>
+__global__ void __launch_bounds__(WS_MAX_THREADS, 1) k_preprocess_ws(const __grid_constant__ FastParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const PreKParams& p = P.k;
+    const FastGeom& G = P.g;
+    uint32_t sb = smem_u32(smem);
+    asm volatile("" : "+r"(sb));
+    const SmemMap S = smem_map(sb, G);
+    unsigned long long* s_red = reinterpret_cast<unsigned long long*>(smem + G.off_red);
+    const int h = p.h, w = p.w, ww = G.nsg;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t frame_bytes = (uint32_t)h * w * 3;
+    const int plane_words = h * ww;
+    const int NF = G.front_warps, NB = G.back_warps;
+    const int nfr = (int)blockIdx.x < p.n ? (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const bool use_lut = p.dynamic || !p.lut_identity;
+
+    init_tables(p, S, tid, nthr);
+    zero_mag_borders(S.mag[0], h, w, G.mag_stride, tid, nthr);
+    zero_mag_borders(S.mag[1], h, w, G.mag_stride, tid, nthr);
+    zero_plane_pads(S, plane_words, ww, tid, nthr);
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(S.bar + 8 * (BAR_FULL_PIX + b), 1);
+            mbar_init(S.bar + 8 * (BAR_EMPTY_PIX + b), NF + NB);
+            mbar_init(S.bar + 8 * (BAR_FULL_MAG + b), NF);
+            mbar_init(S.bar + 8 * (BAR_EMPTY_MAG + b), NB);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < NF) {
+        // ------------------------------------------- front: Sobel strip walk ---------------------------------------
+        const StripMap M = strip_map(warp, lane, ww, G.seg_rows_front, h);
+        const int fn = NF * 32;
+        unsigned long long st_roi = 0;
+        long long tm_wait_pix = 0, tm_wait_mag = 0, tm_work = 0;       // cycle accounting of warp 0 (TRS_STAT_T_* slots)
+        if (tid == 0) {
+            for (int j = 0; j < 2 && j < nfr; ++j)
+                issue_frame_load(S.pix[j], p.in + (size_t)(blockIdx.x + j * gridDim.x) * frame_bytes, frame_bytes, S.bar + 8 * (BAR_FULL_PIX + j));
+        }
+        for (int j = 0; j < nfr; ++j) {
+            const int b = j & 1;
+            const uint32_t par = (uint32_t)(j >> 1) & 1u;
+            const long long tk0 = clock64();
+            mbar_wait(S.bar + 8 * (BAR_FULL_PIX + b), par);
+            const long long tk1 = clock64();
+            if (j >= 2) mbar_wait(S.bar + 8 * (BAR_EMPTY_MAG + b), par ^ 1u);       // back is done with this buffer's previous frame
+            const long long tk2 = clock64();
+            adjust_in_place(p, S.pix[b], S, s_red, tid, fn, lane, st_roi, [fn] { bar_sync(1, fn); });
+            p1_strip_walk<0, true>(P, S.pix[b], S.mag[b], S, M, G.seg_rows_front);
+            __syncwarp();
+            tm_wait_pix += tk1 - tk0; tm_wait_mag += tk2 - tk1; tm_work += clock64() - tk2;
+            if (lane == 0) {
+                mbar_arrive(S.bar + 8 * (BAR_FULL_MAG + b));
+                mbar_arrive(S.bar + 8 * (BAR_EMPTY_PIX + b));
+            }
+            if (tid == 0 && j + 2 < nfr) {
+                mbar_wait(S.bar + 8 * (BAR_EMPTY_PIX + b), par);                    // every reader of this frame buffer is done
+                issue_frame_load(S.pix[b], p.in + (size_t)(blockIdx.x + (size_t)(j + 2) * gridDim.x) * frame_bytes, frame_bytes,
+                                 S.bar + 8 * (BAR_FULL_PIX + b));
+            }
+            __syncwarp();
+        }
+        if (p.stats && tid == 0) {
+            if (st_roi) atomicAdd(&p.stats[9], st_roi);
+            atomicAdd(&p.stats[10], (unsigned long long)tm_wait_pix);
+            atomicAdd(&p.stats[11], (unsigned long long)tm_wait_mag);
+            atomicAdd(&p.stats[12], (unsigned long long)tm_work);
+        }
+    } else {
+        // ------------------------------------------- back: colour masks, NMS, hysteresis, output ---------------------
+        const int bw = warp - NF, bt = tid - NF * 32, bn = NB * 32;
+        const StripMap M = strip_map(bw, lane, ww, G.seg_rows_back, h);
+        unsigned long long st_mask[3] = {0, 0, 0};
+        unsigned long long st_edge = 0, st_strong = 0, st_cand = 0, st_sweeps = 0, st_frames = 0;
+        long long tb_wait = 0, tb_hsv = 0, tb_edge = 0, tb_out = 0;
+        uint32_t pa[3];
+        plane_sources(p, S, G.plane_bytes, pa);
+        for (int j = 0; j < nfr; ++j) {
+            const int b = j & 1;
+            const uint32_t par = (uint32_t)(j >> 1) & 1u;
+            const size_t f = blockIdx.x + (size_t)j * gridDim.x;
+            const long long tk0 = clock64();
+            mbar_wait(S.bar + 8 * (BAR_FULL_PIX + b), par);
+            if (use_lut) mbar_wait(S.bar + 8 * (BAR_FULL_MAG + b), par);            // the front group adjusts the frame in place first
+            const long long tk1 = clock64();
+            if (NR > 0) p1b_colour_masks<NR>(P, S.pix[b], S, bt, bn);
+            if (!p.need_pixels) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(S.bar + 8 * (BAR_EMPTY_PIX + b));
+            }
+            const long long tk2 = clock64();
+            mbar_wait(S.bar + 8 * (BAR_FULL_MAG + b), par);
+            const long long tk3 = clock64();
+            p2_nms(P, S.mag[b], S, M, G.seg_rows_back, st_strong);
+            bar_sync(2, bn);
+            const int sw = p3_hysteresis(S.cand, S.edge, plane_words, ww, bt, bn, [bn](int c) { return bar_or(2, bn, c); });
+            if (bt == 0) st_sweeps += sw;
+            const long long tk4 = clock64();
+            p4_output(P, pa, S.pix[b], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, bt, bn);
+            if (p.stats) {
+                count_planes<NR, true>(S, G.plane_bytes, plane_words, bt, bn, st_mask, st_edge, st_cand);
+                if (bt == 0) ++st_frames;
+            }
+            bar_sync(2, bn);                       // cand / edge / mask planes are reused by the next frame
+            tb_wait += (tk1 - tk0) + (tk3 - tk2); tb_hsv += tk2 - tk1; tb_edge += tk4 - tk3; tb_out += clock64() - tk4;
+            if (lane == 0) {
+                mbar_arrive(S.bar + 8 * (BAR_EMPTY_MAG + b));
+                if (p.need_pixels) mbar_arrive(S.bar + 8 * (BAR_EMPTY_PIX + b));
+            }
+        }
+        if (p.stats) {
+            unsigned long long v[10] = {st_frames, 0, 0, 0, 0, st_edge, st_strong, st_cand, st_sweeps, 0};
 #pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            unsigned long long x = v[k];
-            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if (lane == 0 && x) atomicAdd(&p.stats[k], x);
+            for (int k = 0; k < NR; ++k) v[1 + p.range_stat[k]] = st_mask[k];
+            flush_stats(p, v, lane);
+            if (bt == 0) {
+                atomicAdd(&p.stats[13], (unsigned long long)tb_wait);
+                atomicAdd(&p.stats[14], (unsigned long long)tb_hsv);
+                atomicAdd(&p.stats[15], (unsigned long long)tb_edge);
+                atomicAdd(&p.stats[16], (unsigned long long)tb_out);
+            }
         }
     }
 }

@@ -188,6 +188,12 @@ int plan_geometry(trs_ctx* ctx, int h, int w, int n_ranges, Geometry* g)
 template <int NR, bool EDGE>
 int launch_fast_t(const trs::FastParams& fp, int grid, cudaStream_t st)
 {
+    if (fp.g.ws) {
+        cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_ws<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ws)");
+        trs::k_preprocess_ws<NR><<<grid, fp.g.threads, fp.g.total, st>>>(fp);
+        return 0;
+    }
     cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_fast<NR, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fast)");
     trs::k_preprocess_fast<NR, EDGE><<<grid, fp.g.threads, fp.g.total, st>>>(fp);
@@ -200,14 +206,30 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     if (!k.word_io || (w % 32) != 0 || (((size_t)h * w * 3) % 16) != 0) return 0;
     if (!k.edge_enabled && k.n_ranges == 0) return 0;
     const int nsg = w / 32;
-    const int max_warps = trs::FAST_MAX_THREADS / 32;
-    if (nsg > max_warps) return 0;
-    const int quads = max_warps / nsg;
-    const int seg_rows = (h + 4 * quads - 1) / (4 * quads);
     trs::FastParams fp;
     memset(&fp, 0, sizeof fp);
     fp.k = k;
-    fp.g = trs::fast_geometry(h, w, k.n_ranges, seg_rows < 1 ? 1 : seg_rows);
+    // preferred: warp-specialised kernel, one CTA per SM, double-buffered frames / magnitude / masks
+    bool planned = false;
+    if (!getenv("TRS_NO_WS") && k.edge_enabled && nsg <= trs::WS_MAX_WARPS / 2) {
+        int qb = 2;
+        if (const char* e = getenv("TRS_WS_QB")) qb = atoi(e) > 0 ? atoi(e) : 1;      // tuning knob: back-group segment quads
+        int qf = (trs::WS_MAX_WARPS - nsg * qb) / nsg;
+        if (qf < 1) { qf = 1; qb = (trs::WS_MAX_WARPS - nsg) / nsg; }
+        while (qf > 1 && 4 * (qf - 1) >= h) --qf;
+        const trs::FastGeom g = trs::fast_geometry(h, w, k.n_ranges, 1, nsg * qf, nsg * qb);
+        if (g.total <= ctx->smem_optin && g.threads <= trs::WS_MAX_THREADS) { fp.g = g; planned = true; }
+    }
+    if (!planned) {
+        // resident kernel: one frame per CTA, two CTAs per SM
+        const int max_warps = trs::FAST_MAX_THREADS / 32;
+        if (nsg > max_warps) return 0;
+        const int quads = max_warps / nsg;
+        const trs::FastGeom g = trs::fast_geometry(h, w, k.n_ranges, 0, nsg * quads, nsg * quads);
+        const int budget2 = (ctx->smem_optin + 1024) / 2 - 1024;
+        if (g.total > budget2 || g.threads > trs::FAST_MAX_THREADS) return 0;
+        fp.g = g;
+    }
     // integer bounds -> fp16-subnormal bit patterns for the packed compares (values live in [0, 2047];
     // anything below 0 compares like -1, anything above like 2047, which keeps every outcome unchanged)
     auto pat = [](long long v) -> uint32_t {
@@ -229,9 +251,7 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     }
     fp.low2 = pat(k.low);
     fp.high2 = pat(k.high);
-    const int budget2 = (ctx->smem_optin + 1024) / 2 - 1024;
-    if (fp.g.total > budget2 || fp.g.threads > trs::FAST_MAX_THREADS) return 0;
-    int grid = ctx->sm_count * 2;
+    int grid = ctx->sm_count * (fp.g.ws ? 1 : 2);
     if (grid > n) grid = n;
     int rc;
     switch (k.n_ranges * 2 + (k.edge_enabled ? 1 : 0)) {
