@@ -278,10 +278,10 @@ def test_full_size_properties():
     comp.onShutdown()
 
 
-@pytest.mark.parametrize("env", ["TRS_FORCE_GENERIC", "TRS_NO_WS"])
+@pytest.mark.parametrize("env", ["TRS_FORCE_GENERIC", "TRS_WS"])
 def test_other_kernels_still_match(golden_images, monkeypatch, env):
-    """The warp-specialised kernel takes the aligned 32-multiple widths by default; force the resident two-CTA kernel
-    (TRS_NO_WS) and the generic banded kernel (TRS_FORCE_GENERIC) on the same data."""
+    """The resident two-CTA kernel takes the aligned 32-multiple widths by default; force the warp-specialised kernel
+    (TRS_WS) and the generic banded kernel (TRS_FORCE_GENERIC) on the same data."""
     monkeypatch.setenv(env, "1")
     for sname, cname, cfg, frames, expected in golden_pairs(golden_images):
         if sname not in ("f120", "f240") or cname not in ("full_house", "exotic", "edge_only"):

@@ -31,6 +31,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "pixel_math.cuh"
 #include "preproc_kernel.cuh"
 
@@ -97,6 +99,13 @@ struct FastParams {
 // ---- small PTX helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+// PTX prmt in its default mode: a selector nibble with bit 3 set replicates the sign bit of the selected byte over the output byte
+__device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 
 // shared-memory accessors on 32-bit window addresses
 __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -247,56 +256,87 @@ __device__ __forceinline__ void unpack_planar(uint32_t w0, uint32_t w1, uint32_t
 }
 
 // =========================================================================================================
-// colour-range tests of 4 pixels given as planar pairs; okm[r][half] = 0xffff/0 half masks
+// colour-range tests of 4 pixels given as planar pairs; okm[r][half] = 0xffff/0 half masks.
+// FLAGSk >= 0 bakes the "which bounds can fail" word of range k into the code (only the live compares are emitted);
+// -1 reads it from the parameters.  The hue (two table reads, two multiplies per pixel) is computed only if some
+// pixel of the warp survived the saturation / value tests of a range that has a live hue bound.
 // =========================================================================================================
-template <int NR>
+template <int F>
+__device__ __forceinline__ uint32_t live_flags(const FastRange& R) { return F >= 0 ? (uint32_t)F : R.flags; }
+
+template <int NR, int F0, int F1>
 __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t (&A)[3], const uint32_t (&B)[3], uint32_t a_sdiv, uint32_t a_hue,
                                              uint32_t (&okm)[NR > 0 ? NR : 1][2])
 {
+    uint32_t fl[NR > 0 ? NR : 1];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) fl[r] = r == 0 ? live_flags<F0>(P.fr[0]) : (r == 1 ? live_flags<F1>(P.fr[1]) : P.fr[r].flags);
+    uint32_t any_s = 0, any_h = 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { any_s |= fl[r] & 12u; any_h |= fl[r] & 3u; }
+    uint32_t v2[2], d2[2];
+    uint32_t alive = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const uint32_t* X = half ? B : A;
-        const uint32_t v2 = __vimax3_u16x2(X[0], X[1], X[2]);
-        const uint32_t mn2 = __vimin3_u16x2(X[0], X[1], X[2]);
-        const uint32_t d2 = v2 - mn2;
-        const uint32_t vlo = v2 & 0xffffu, vhi = v2 >> 16, dlo = d2 & 0xffffu, dhi = d2 >> 16;
-        const uint32_t slo = (uint32_t)(((int)dlo * (int)lds32(a_sdiv + 4 * vlo) + 2048) >> 12);
-        const uint32_t shi = (uint32_t)(((int)dhi * (int)lds32(a_sdiv + 4 * vhi) + 2048) >> 12);
-        const uint32_t s2 = slo | (shi << 16);
-        uint32_t hh2 = 0;
-        if (P.need_hue) {
-            // hue numerator + 2048 (always positive): g-b | b-r+2d | r-g+4d, chosen by v==r, then v==g
-            const uint32_t gb = X[1] + 0x08000800u - X[2];
-            const uint32_t br = X[2] + 0x08000800u - X[0] + d2 + d2;
-            const uint32_t rg = X[0] + 0x08000800u - X[1] + (d2 << 2);
-            const uint32_t eqr = heq_mask(v2, X[0]), eqg = heq_mask(v2, X[1]);
-            const uint32_t h02 = bsel(eqr, gb, bsel(eqg, br, rg));
-            const uint2 tl = lds64(a_hue + 8 * dlo), th = lds64(a_hue + 8 * dhi);
-            int hlo = ((int)(h02 & 0xffffu) * (int)tl.x + (int)tl.y) >> 12;
-            int hhi = ((int)(h02 >> 16) * (int)th.x + (int)th.y) >> 12;
-            hlo += (hlo >> 31) & 180;
-            hhi += (hhi >> 31) & 180;
-            hh2 = (uint32_t)hlo | ((uint32_t)hhi << 16);
+        v2[half] = __vimax3_u16x2(X[0], X[1], X[2]);
+        d2[half] = v2[half] - __vimin3_u16x2(X[0], X[1], X[2]);
+        uint32_t s2 = 0;
+        if (any_s) {
+            const uint32_t vlo = v2[half] & 0xffffu, vhi = v2[half] >> 16, dlo = d2[half] & 0xffffu, dhi = d2[half] >> 16;
+            const uint32_t slo = (uint32_t)(((int)dlo * (int)lds32(a_sdiv + 4 * vlo) + 2048) >> 12);
+            const uint32_t shi = (uint32_t)(((int)dhi * (int)lds32(a_sdiv + 4 * vhi) + 2048) >> 12);
+            s2 = slo | (shi << 16);
         }
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             const FastRange& R = P.fr[r];
             uint32_t ok = 0xffffffffu;
-            if (R.flags & 1u) ok &= hge_mask(hh2, R.lo[0]);
-            if (R.flags & 2u) ok &= hle_mask(hh2, R.hi[0]);
-            if (R.flags & 4u) ok &= hge_mask(s2, R.lo[1]);
-            if (R.flags & 8u) ok &= hle_mask(s2, R.hi[1]);
-            if (R.flags & 16u) ok &= hge_mask(v2, R.lo[2]);
-            if (R.flags & 32u) ok &= hle_mask(v2, R.hi[2]);
+            if (fl[r] & 4u) ok &= hge_mask(s2, R.lo[1]);
+            if (fl[r] & 8u) ok &= hle_mask(s2, R.hi[1]);
+            if (fl[r] & 16u) ok &= hge_mask(v2[half], R.lo[2]);
+            if (fl[r] & 32u) ok &= hle_mask(v2[half], R.hi[2]);
             okm[r][half] = ok;
+            if (fl[r] & 3u) alive |= ok;
         }
+    }
+    if (any_h && __any_sync(0xffffffffu, alive != 0u)) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t* X = half ? B : A;
+            // hue numerator + 2048 (always positive): g-b | b-r+2d | r-g+4d, chosen by v==r, then v==g
+            const uint32_t gb = X[1] + 0x08000800u - X[2];
+            const uint32_t br = X[2] + 0x08000800u - X[0] + d2[half] + d2[half];
+            const uint32_t rg = X[0] + 0x08000800u - X[1] + (d2[half] << 2);
+            const uint32_t eqr = heq_mask(v2[half], X[0]), eqg = heq_mask(v2[half], X[1]);
+            const uint32_t h02 = bsel(eqr, gb, bsel(eqg, br, rg));
+            const uint2 tl = lds64(a_hue + 8 * (d2[half] & 0xffffu)), th = lds64(a_hue + 8 * (d2[half] >> 16));
+            int hlo = ((int)(h02 & 0xffffu) * (int)tl.x + (int)tl.y) >> 12;
+            int hhi = ((int)(h02 >> 16) * (int)th.x + (int)th.y) >> 12;
+            hlo += (hlo >> 31) & 180;
+            hhi += (hhi >> 31) & 180;
+            const uint32_t hh2 = (uint32_t)hlo | ((uint32_t)hhi << 16);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const FastRange& R = P.fr[r];
+                uint32_t ok = okm[r][half];
+                if (fl[r] & 1u) ok &= hge_mask(hh2, R.lo[0]);
+                if (fl[r] & 2u) ok &= hle_mask(hh2, R.hi[0]);
+                okm[r][half] = ok;
+            }
+        }
+    } else if (any_h) {
+        // no pixel of the warp can pass a range with a live hue bound: those ranges are all-zero here
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            if (fl[r] & 3u) { okm[r][0] = 0; okm[r][1] = 0; }
     }
 }
 
 // =========================================================================================================
 // P1: strip walk — Sobel / magnitude / direction -> magnitude plane, colour masks -> bit planes
 // =========================================================================================================
-template <int NR, bool EDGE>
+template <int NR, bool EDGE, int F0, int F1>
 __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pix, uint32_t a_mag, const SmemMap& S, const StripMap& M, int seg_rows)
 {
     const int h = P.k.h, w = P.k.w;
@@ -345,7 +385,7 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
         if (NR > 0) {
             const bool row_in = k >= 1 && y_row < r1;            // the loaded row belongs to this segment
             uint32_t okm[NR > 0 ? NR : 1][2];                    // per range: half masks for pixels (0,2) and (1,3)
-            hsv_masks_of<NR>(P, A, B, S.sdiv, S.hue, okm);
+            hsv_masks_of<NR, F0, F1>(P, A, B, S.sdiv, S.hue, okm);
             uint32_t v = 0;
 #pragma unroll
             for (int r = 0; r < NR; ++r) v |= nibble_of(okm[r][0], okm[r][1]) << (8 * r);
@@ -407,7 +447,7 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
 // P1b: colour masks as a pointwise pass (back group of the warp-specialised kernel): a thread takes 4 consecutive
 // pixels (12 bytes), adjacent lanes take adjacent groups, two lanes make one plane byte.
 // =========================================================================================================
-template <int NR>
+template <int NR, int F0, int F1>
 __device__ __forceinline__ void p1b_colour_masks(const FastParams& P, uint32_t a_pix, const SmemMap& S, int t0, int tstride)
 {
     const int ngroups = (P.k.h * P.k.w) >> 2;
@@ -420,7 +460,7 @@ __device__ __forceinline__ void p1b_colour_masks(const FastParams& P, uint32_t a
         uint32_t A[3], B[3];
         unpack_planar(lds32(src), lds32(src + 4), lds32(src + 8), A, B);
         uint32_t okm[NR > 0 ? NR : 1][2];
-        hsv_masks_of<NR>(P, A, B, S.sdiv, S.hue, okm);
+        hsv_masks_of<NR, F0, F1>(P, A, B, S.sdiv, S.hue, okm);
         uint32_t v = 0;
 #pragma unroll
         for (int r = 0; r < NR; ++r) v |= nibble_of(okm[r][0], okm[r][1]) << (8 * r);
@@ -472,14 +512,12 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, cons
             const uint32_t U = pr ? up.p23 : up.p01, Dw = pr ? dn.p23 : dn.p01;
             const uint32_t UL = pr ? up.m12 : up.l01, DR = pr ? dn.r23 : dn.m12;
             const uint32_t UR = pr ? up.r23 : up.m12, DL = pr ? dn.m12 : dn.l01;
-            const uint32_t t0 = hgt_mask(C, L) & hge_mask(C, Rr);          // horizontal:  m > left, m >= right
-            const uint32_t t1 = hgt_mask(C, U) & hge_mask(C, Dw);          // vertical:    m > up,   m >= down
-            const uint32_t t2 = hgt_mask(C, UL) & hgt_mask(C, DR);         // diagonal s=+1, strict on both sides
-            const uint32_t t3 = hgt_mask(C, UR) & hgt_mask(C, DL);         // diagonal s=-1
-            const uint32_t b0 = ((raw >> 11) & 0x00010001u) * 0xffffu;
-            const uint32_t b1 = ((raw >> 12) & 0x00010001u) * 0xffffu;
-            const uint32_t pick = bsel(b1, bsel(b0, t3, t2), bsel(b0, t1, t0));
-            cm[pr] = pick & hgt_mask(C, P.low2);
+            // direction class bits as half masks: shift the bit to the half's sign position, replicate the sign over the half
+            const uint32_t b0 = prmt_sx(raw << 4, 0, 0xbb99), b1 = prmt_sx(raw << 3, 0, 0xbb99);
+            // the two neighbours along the gradient: a must be strictly below m; b may tie except on the diagonals
+            const uint32_t na = bsel(b1, bsel(b0, UR, UL), bsel(b0, U, L));
+            const uint32_t nb = bsel(b1, bsel(b0, DL, DR), bsel(b0, Dw, Rr)) + (b1 & 0x00010001u);     // m > b  <=>  m >= b + 1
+            cm[pr] = hgt_mask(C, na) & hge_mask(C, nb) & hgt_mask(C, P.low2);
             sm[pr] = cm[pr] & hgt_mask(C, P.high2);
         }
         up = ce; ce = dn;
@@ -551,18 +589,30 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&
         const uint32_t paY = r == 0 ? pa[1] : (r == 1 ? pa[2] : pa[0]);
         const uint32_t paZ = r == 0 ? pa[2] : (r == 1 ? pa[0] : pa[1]);
         const int shX = r + hi4, shY = (r == 2 ? 3 : r) + hi4, shZ = (r == 0 ? 0 : r + 1) + hi4;
-        const int nwi = (npb + 4) / 5;
         const uint32_t one = 0x3f800000u;
+        if (lane_ok) {
+            const int nwi = (npb + 4) / 5;
+            auto emit = [&](auto has_f32, auto has_u8) {
+                // running addresses: plane byte of (warp iteration, group), output chunk of (warp iteration, lane)
+                uint32_t ax = paX + 5 * gw + gl, ay = paY + 5 * gw + gl, az = paZ + 5 * gw + gl;
+                uint4* fp = reinterpret_cast<uint4*>(gf32) + 30 * gw + lane;
+                uint32_t* up = reinterpret_cast<uint32_t*>(gout) + 30 * gw + lane;
+                int g = 5 * gw + gl;
 #pragma unroll 2
-        for (int wi = gw; wi < nwi; wi += nw) {
-            const int g = 5 * wi + gl;
-            if (lane_ok && g < npb) {
-                const uint32_t xs = lds8(paX + g) >> shX, ys = lds8(paY + g) >> shY, zs = lds8(paZ + g) >> shZ;
-                const uint32_t b0 = xs & 1u, b1 = ys & 1u, b2 = zs & 1u, b3x = xs & 2u;
-                const size_t chunk = (size_t)30 * wi + lane;                       // == 6 g + s
-                if (gf32) reinterpret_cast<uint4*>(gf32)[chunk] = make_uint4(b0 * one, b1 * one, b2 * one, b3x * (one >> 1));
-                if (gout) reinterpret_cast<uint32_t*>(gout)[chunk] = b0 * 255u + b1 * (255u << 8) + b2 * (255u << 16) + b3x * (255u << 23);
-            }
+                for (int wi = gw; wi < nwi; wi += nw) {
+                    if (g < npb) {
+                        const uint32_t xs = lds8(ax) >> shX, ys = lds8(ay) >> shY, zs = lds8(az) >> shZ;
+                        const uint32_t b0 = xs & 1u, b1 = ys & 1u, b2 = zs & 1u, b3x = xs & 2u;
+                        if (decltype(has_f32)::value) *fp = make_uint4(b0 * one, b1 * one, b2 * one, b3x * (one >> 1));
+                        if (decltype(has_u8)::value) *up = b0 * 255u + b1 * (255u << 8) + b2 * (255u << 16) + b3x * (255u << 23);
+                    }
+                    ax += 5 * nw; ay += 5 * nw; az += 5 * nw; g += 5 * nw;
+                    fp += 30 * nw; up += 30 * nw;
+                }
+            };
+            if (gf32 && gout) emit(std::true_type{}, std::true_type{});
+            else if (gf32) emit(std::true_type{}, std::false_type{});
+            else if (gout) emit(std::false_type{}, std::true_type{});
         }
     } else {
         // some channel keeps the adjusted pixel: bytes from the resident frame, floats by correctly rounded x/255
@@ -701,7 +751,7 @@ __device__ __forceinline__ void count_planes(const SmemMap& S, int plane_bytes, 
 // =========================================================================================================
 // Resident kernel: one frame per CTA, two CTAs per SM
 // =========================================================================================================
-template <int NR, bool EDGE>
+template <int NR, bool EDGE, int F0, int F1>
 __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const __grid_constant__ FastParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -736,7 +786,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
         mbar_wait(S.bar, phase);
         phase ^= 1u;
         adjust_in_place(p, S.pix[0], S, s_red, tid, nthr, lane, st_roi, [] { __syncthreads(); });
-        p1_strip_walk<NR, EDGE>(P, S.pix[0], S.mag[0], S, M, G.seg_rows_front);
+        p1_strip_walk<NR, EDGE, F0, F1>(P, S.pix[0], S.mag[0], S, M, G.seg_rows_front);
         __syncthreads();
         if (!p.need_pixels && tid == 0 && f + (int)gridDim.x < p.n)       // pixels are dead: prefetch the next frame
             issue_frame_load(S.pix[0], p.in + (size_t)(f + gridDim.x) * frame_bytes, frame_bytes, S.bar);
@@ -770,7 +820,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
 // =========================================================================================================
 enum { BAR_FULL_PIX = 0, BAR_EMPTY_PIX = 2, BAR_FULL_MAG = 4, BAR_EMPTY_MAG = 6 };
 
-template <int NR>
+template <int NR, int F0, int F1>
 __global__ void __launch_bounds__(WS_MAX_THREADS, 1) k_preprocess_ws(const __grid_constant__ FastParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -822,7 +872,7 @@ __global__ void __launch_bounds__(WS_MAX_THREADS, 1) k_preprocess_ws(const __gri
             if (j >= 2) mbar_wait(S.bar + 8 * (BAR_EMPTY_MAG + b), par ^ 1u);       // back is done with this buffer's previous frame
             const long long tk2 = clock64();
             adjust_in_place(p, S.pix[b], S, s_red, tid, fn, lane, st_roi, [fn] { bar_sync(1, fn); });
-            p1_strip_walk<0, true>(P, S.pix[b], S.mag[b], S, M, G.seg_rows_front);
+            p1_strip_walk<0, true, -1, -1>(P, S.pix[b], S.mag[b], S, M, G.seg_rows_front);
             __syncwarp();
             tm_wait_pix += tk1 - tk0; tm_wait_mag += tk2 - tk1; tm_work += clock64() - tk2;
             if (lane == 0) {
@@ -859,7 +909,7 @@ __global__ void __launch_bounds__(WS_MAX_THREADS, 1) k_preprocess_ws(const __gri
             mbar_wait(S.bar + 8 * (BAR_FULL_PIX + b), par);
             if (use_lut) mbar_wait(S.bar + 8 * (BAR_FULL_MAG + b), par);            // the front group adjusts the frame in place first
             const long long tk1 = clock64();
-            if (NR > 0) p1b_colour_masks<NR>(P, S.pix[b], S, bt, bn);
+            if (NR > 0) p1b_colour_masks<NR, F0, F1>(P, S.pix[b], S, bt, bn);
             if (!p.need_pixels) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(S.bar + 8 * (BAR_EMPTY_PIX + b));

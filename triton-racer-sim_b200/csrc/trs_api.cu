@@ -185,19 +185,31 @@ int plan_geometry(trs_ctx* ctx, int h, int w, int n_ranges, Geometry* g)
 
 // Frame-resident fast path (preproc_fast.cuh): whole frame + magnitude plane + bit planes in one CTA's shared memory,
 // width a multiple of 32, everything 16-byte aligned.  Returns 1 if launched, 0 if not eligible, <0 / >1 on error.
+template <int NR, bool EDGE, int F0, int F1>
+int launch_fast_tf(const trs::FastParams& fp, int grid, cudaStream_t st)
+{
+    if (fp.g.ws) {
+        cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_ws<NR, F0, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ws)");
+        trs::k_preprocess_ws<NR, F0, F1><<<grid, fp.g.threads, fp.g.total, st>>>(fp);
+        return 0;
+    }
+    cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_fast<NR, EDGE, F0, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fast)");
+    trs::k_preprocess_fast<NR, EDGE, F0, F1><<<grid, fp.g.threads, fp.g.total, st>>>(fp);
+    return 0;
+}
+
+// The reference's default colour ranges (core/config.py:23: white = S <= 64 & V >= 130, yellow = 25 <= H <= 43 & S >= 180 & V >= 155)
+// get a variant with the live-bound words baked in; every other configuration reads them at run time.
+enum { DEFAULT_F0 = 8 | 16, DEFAULT_F1 = 1 | 2 | 4 | 16 };
+
 template <int NR, bool EDGE>
 int launch_fast_t(const trs::FastParams& fp, int grid, cudaStream_t st)
 {
-    if (fp.g.ws) {
-        cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_ws<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ws)");
-        trs::k_preprocess_ws<NR><<<grid, fp.g.threads, fp.g.total, st>>>(fp);
-        return 0;
-    }
-    cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_fast<NR, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fast)");
-    trs::k_preprocess_fast<NR, EDGE><<<grid, fp.g.threads, fp.g.total, st>>>(fp);
-    return 0;
+    if (NR == 2 && fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1)
+        return launch_fast_tf<NR, EDGE, (NR == 2 ? (int)DEFAULT_F0 : -1), (NR == 2 ? (int)DEFAULT_F1 : -1)>(fp, grid, st);
+    return launch_fast_tf<NR, EDGE, -1, -1>(fp, grid, st);
 }
 
 int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w, cudaStream_t st)
@@ -211,7 +223,8 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     fp.k = k;
     // preferred: warp-specialised kernel, one CTA per SM, double-buffered frames / magnitude / masks
     bool planned = false;
-    if (!getenv("TRS_NO_WS") && k.edge_enabled && nsg <= trs::WS_MAX_WARPS / 2) {
+    // opt-in (TRS_WS=1): measured slower than the resident two-CTA kernel at 120x160 (7.4 vs 8.2 M frames/s), see DESIGN.md
+    if (getenv("TRS_WS") && !getenv("TRS_NO_WS") && k.edge_enabled && nsg <= trs::WS_MAX_WARPS / 2) {
         int qb = 2;
         if (const char* e = getenv("TRS_WS_QB")) qb = atoi(e) > 0 ? atoi(e) : 1;      // tuning knob: back-group segment quads
         int qf = (trs::WS_MAX_WARPS - nsg * qb) / nsg;
