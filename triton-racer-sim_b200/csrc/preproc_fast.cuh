@@ -418,18 +418,27 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
                 bx = bsel(g2, dx[2], bx); by = bsel(g2, dy[2], by);
                 mg[half] = mm; dxs[half] = bx; dys[half] = by;
             }
-            // per pixel direction class, branch-free; pixel order 0..3 = (A.lo, B.lo, A.hi, B.hi)
-            const uint32_t ax0 = dxs[0] & 0x7fff7fffu, ay0 = dys[0] & 0x7fff7fffu;
-            const uint32_t ax1 = dxs[1] & 0x7fff7fffu, ay1 = dys[1] & 0x7fff7fffu;
-            const uint32_t sd0 = ((dxs[0] ^ dys[0]) >> 15) & 0x00010001u, sd1 = ((dxs[1] ^ dys[1]) >> 15) & 0x00010001u;
-            const uint32_t c0 = dir_bits(ax0 & 0xffffu, ay0 & 0xffffu, sd0 & 1u);      // pixel 0
-            const uint32_t c1 = dir_bits(ax1 & 0xffffu, ay1 & 0xffffu, sd1 & 1u);      // pixel 1
-            const uint32_t c2 = dir_bits(ax0 >> 16, ay0 >> 16, sd0 >> 16);             // pixel 2
-            const uint32_t c3 = dir_bits(ax1 >> 16, ay1 >> 16, sd1 >> 16);             // pixel 3
+            // direction class of each pixel pair, branch-free, mostly on the FMA pipe (pixel_math.cuh canny_dir):
+            //   horizontal <=> |dy| 2^15 - |dx| 13573 < 0,  vertical <=> |dx| 79109 - |dy| 2^15 < 0,  else diagonal 2 + (sign dx != sign dy)
+            // the halves are widened to fp32 (exact: n * 2^-24) and each test is ONE fused multiply-add whose sign is exact
+            // (the rounding of an fma never changes the sign of a non-zero exact result and an exact zero stays +0)
+            uint32_t code[2];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const __half2 hx = h2(dxs[half]), hy = h2(dys[half]);
+                const float ax_lo = fabsf(__low2float(hx)), ax_hi = fabsf(__high2float(hx));
+                const float ay_lo = fabsf(__low2float(hy)) * 32768.0f, ay_hi = fabsf(__high2float(hy)) * 32768.0f;
+                const uint32_t nu_lo = __float_as_uint(__fmaf_rn(ax_lo, -13573.0f, ay_lo)), nu_hi = __float_as_uint(__fmaf_rn(ax_hi, -13573.0f, ay_hi));
+                const uint32_t wv_lo = __float_as_uint(__fmaf_rn(ax_lo, 79109.0f, -ay_lo)), wv_hi = __float_as_uint(__fmaf_rn(ax_hi, 79109.0f, -ay_hi));
+                const uint32_t H2 = prmt_sx(nu_lo, nu_hi, 0xffbb), V2 = prmt_sx(wv_lo, wv_hi, 0xffbb);       // sign of each result spread over its half
+                const uint32_t SD = prmt_sx(dxs[half] ^ dys[half], 0, 0xbb99);
+                const uint32_t diag = (SD & 0x00010001u) | 0x00020002u;
+                code[half] = ~H2 & bsel(V2, 0x00010001u, diag);
+            }
             if (M.ok && y < r1) {
-                uint2 v;
-                v.x = prmt(mg[0], mg[1], 0x5410) | (c0 << 11) | (c1 << 27);        // (m0, m1) + codes
-                v.y = prmt(mg[0], mg[1], 0x7632) | (c2 << 11) | (c3 << 27);        // (m2, m3) + codes
+                uint2 v;      // pixel order: (A.lo, B.lo) = pixels (0, 1), (A.hi, B.hi) = pixels (2, 3)
+                v.x = prmt(mg[0], mg[1], 0x5410) | (prmt(code[0], code[1], 0x5410) << 11);
+                v.y = prmt(mg[0], mg[1], 0x7632) | (prmt(code[0], code[1], 0x7632) << 11);
                 sts64(mag_base + (y + 1) * MS2, v);
             }
         }
