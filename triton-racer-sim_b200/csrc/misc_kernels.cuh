@@ -7,16 +7,29 @@ namespace trs {
 
 // ------------------------------------------------------------------------------------------------------
 // K1a: pure streaming normalise, u8 -> f32 (keras_pilot.py:49-50; keras_train.py:41-42).
-// One thread converts 16 input bytes (one 128-bit load) into four 128-bit stores; consecutive lanes take
-// consecutive 16-byte chunks so a warp reads 512 contiguous bytes and writes 2 KB contiguous.
-// 1/255 is not exactly representable: true division (div.rn) is required, 126 of 256 inputs differ otherwise.
+// One thread converts one 32-bit word (4 bytes) into one 128-bit store, so consecutive lanes read consecutive
+// words (128 B per warp load) and write consecutive 16-byte chunks (512 contiguous bytes per warp store); UNROLL
+// independent words per thread keep enough loads in flight.  (A 16-bytes-in / 64-bytes-out per thread mapping
+// makes every store instruction touch 32 half-written sectors and was measured at 47 % of the HBM roofline.)
+// 1/255 is not exactly representable: the quotient must be correctly rounded (126 of 256 inputs differ otherwise).
+// x / 255 = q0 + (x - 255 q0) / 255 with q0 = x * fl(1/255): one fused residual correction gives the correctly
+// rounded quotient for every x in 0..255 (checked exhaustively: tests/test_oracle_golden.py, tests/test_gpu_parity.py).
+// The byte -> float conversion avoids the quarter-rate I2F: 0x4B000000 | b is the float 2^23 + b.
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float norm255(uint32_t b) { return __fdiv_rn((float)b, 255.0f); }
 
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p)
+__device__ __forceinline__ float norm255_fast(uint32_t word, uint32_t sel)
 {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    const float x = __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, sel)), 8388608.0f);
+    const float rcp = 1.0f / 255.0f;
+    const float q0 = __fmul_rn(x, rcp);
+    return __fmaf_rn(__fmaf_rn(-q0, 255.0f, x), rcp, q0);
+}
+
+__device__ __forceinline__ uint32_t ldg_stream32(const uint32_t* p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void stg_stream(float4* p, float4 v)
@@ -26,33 +39,23 @@ __device__ __forceinline__ void stg_stream(float4* p, float4 v)
 
 __device__ __forceinline__ float4 norm_word(uint32_t w)
 {
-    return make_float4(norm255(w & 0xff), norm255((w >> 8) & 0xff), norm255((w >> 16) & 0xff), norm255(w >> 24));
+    // selectors: output byte 0 = source byte k, bytes 1..3 = bytes 5,6,7 of the pair = 0x00,0x00,0x4B
+    return make_float4(norm255_fast(w, 0x7650), norm255_fast(w, 0x7651), norm255_fast(w, 0x7652), norm255_fast(w, 0x7653));
 }
 
 template <int UNROLL>
-__global__ void __launch_bounds__(256) k_normalise_stream(const uint4* __restrict__ in, float4* __restrict__ out, size_t n_chunks)
+__global__ void __launch_bounds__(256) k_normalise_stream(const uint32_t* __restrict__ in, float4* __restrict__ out, size_t n_words)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + (UNROLL - 1) * stride < n_chunks; i += UNROLL * stride) {
-        uint4 v[UNROLL];
+    for (; i + (UNROLL - 1) * stride < n_words; i += UNROLL * stride) {
+        uint32_t v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) v[u] = ldg_stream(in + i + u * stride);
+        for (int u = 0; u < UNROLL; ++u) v[u] = ldg_stream32(in + i + u * stride);
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            float4* o = out + 4 * (i + u * stride);
-            stg_stream(o, norm_word(v[u].x));
-            stg_stream(o + 1, norm_word(v[u].y));
-            stg_stream(o + 2, norm_word(v[u].z));
-            stg_stream(o + 3, norm_word(v[u].w));
-        }
+        for (int u = 0; u < UNROLL; ++u) stg_stream(out + i + u * stride, norm_word(v[u]));
     }
-    for (; i < n_chunks; i += stride) {
-        const uint4 v = ldg_stream(in + i);
-        float4* o = out + 4 * i;
-        stg_stream(o, norm_word(v.x)); stg_stream(o + 1, norm_word(v.y));
-        stg_stream(o + 2, norm_word(v.z)); stg_stream(o + 3, norm_word(v.w));
-    }
+    for (; i < n_words; i += stride) stg_stream(out + i, norm_word(ldg_stream32(in + i)));
 }
 
 // tail / unaligned fallback: one byte per thread

@@ -427,15 +427,15 @@ int trs_normalise(trs_ctx* ctx, const uint8_t* in_dev, int n, int h_in, int w_in
     const bool identity = roi_y0 == 0 && roi_x0 == 0 && roi_y1 == h_in && roi_x1 == w_in && h_out == h_in && w_out == w_in;
     const size_t total = (size_t)n * h_out * w_out * 3;
     if (identity && out_f32_dev && !out_u8_dev && ((uintptr_t)in_dev & 15) == 0 && ((uintptr_t)out_f32_dev & 15) == 0) {
-        const size_t chunks = total / 16;
+        const size_t chunks = total / 4;                    // 32-bit words
         if (chunks) {
-            size_t want = (chunks + 256 * 4 - 1) / (256 * 4);
+            size_t want = (chunks + 256 * 8 - 1) / (256 * 8);
             const size_t cap = (size_t)ctx->sm_count * 32;
             const int grid = (int)(want < cap ? want : cap);
-            trs::k_normalise_stream<4><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(in_dev), reinterpret_cast<float4*>(out_f32_dev), chunks);
+            trs::k_normalise_stream<8><<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(in_dev), reinterpret_cast<float4*>(out_f32_dev), chunks);
             g_launches.fetch_add(1, std::memory_order_relaxed);
         }
-        const size_t done = chunks * 16;
+        const size_t done = chunks * 4;
         if (done < total) {
             trs::k_normalise_bytes<<<1, 32, 0, st>>>(in_dev + done, out_f32_dev + done, total - done);
             g_launches.fetch_add(1, std::memory_order_relaxed);
