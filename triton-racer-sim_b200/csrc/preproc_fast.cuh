@@ -94,6 +94,9 @@ struct FastParams {
     FastRange fr[3];
     uint32_t low2, high2;            // edge thresholds as packed patterns
     int need_hue;                    // some range has a hue bound that can fail
+    uint32_t stagger_half_ns;        // start delay of the CTAs in the second half of the grid (the second CTA of each SM)
+    uint32_t stagger_step_ns;        // plus (blockIdx.x % 4) times this: spreads the store bursts of different SMs
+    int dbg_out_alias;               // experiment only (TRS_DBG_OUT_ALIAS): outputs of frame f go to slot f % alias (results invalid)
 };
 
 // ---- small PTX helpers --------------------------------------------------------------------------------
@@ -382,8 +385,8 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
             }
         }
         // ---- colour masks for the loaded row ---------------------------------------------------------
-        if (NR > 0) {
-            const bool row_in = k >= 1 && y_row < r1;            // the loaded row belongs to this segment
+        if (NR > 0 && k >= 1 && k <= seg_rows) {                 // warp-uniform: the halo rows above and below belong to other segments
+            const bool row_in = y_row < r1;                      // the loaded row belongs to this segment
             uint32_t okm[NR > 0 ? NR : 1][2];                    // per range: half masks for pixels (0,2) and (1,3)
             hsv_masks_of<NR, F0, F1>(P, A, B, S.sdiv, S.hue, okm);
             uint32_t v = 0;
@@ -419,7 +422,7 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
                 mg[half] = mm; dxs[half] = bx; dys[half] = by;
             }
             // direction class of each pixel pair, branch-free, mostly on the FMA pipe (pixel_math.cuh canny_dir):
-            //   horizontal <=> |dy| 2^15 - |dx| 13573 < 0,  vertical <=> |dx| 79109 - |dy| 2^15 < 0,  else diagonal 2 + (sign dx != sign dy)
+            //   horizontal <=> |dy| - |dx| 13573/2^15 < 0,  vertical <=> |dx| 79109/2^15 - |dy| < 0,  else diagonal 2 + (sign dx != sign dy)
             // the halves are widened to fp32 (exact: n * 2^-24) and each test is ONE fused multiply-add whose sign is exact
             // (the rounding of an fma never changes the sign of a non-zero exact result and an exact zero stays +0)
             uint32_t code[2];
@@ -427,9 +430,10 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
             for (int half = 0; half < 2; ++half) {
                 const __half2 hx = h2(dxs[half]), hy = h2(dys[half]);
                 const float ax_lo = fabsf(__low2float(hx)), ax_hi = fabsf(__high2float(hx));
-                const float ay_lo = fabsf(__low2float(hy)) * 32768.0f, ay_hi = fabsf(__high2float(hy)) * 32768.0f;
-                const uint32_t nu_lo = __float_as_uint(__fmaf_rn(ax_lo, -13573.0f, ay_lo)), nu_hi = __float_as_uint(__fmaf_rn(ax_hi, -13573.0f, ay_hi));
-                const uint32_t wv_lo = __float_as_uint(__fmaf_rn(ax_lo, 79109.0f, -ay_lo)), wv_hi = __float_as_uint(__fmaf_rn(ax_hi, 79109.0f, -ay_hi));
+                const float ay_lo = fabsf(__low2float(hy)), ay_hi = fabsf(__high2float(hy));
+                const float T22 = 13573.0f / 32768.0f, T67 = 79109.0f / 32768.0f;      // both exact in fp32 (14- and 17-bit numerators)
+                const uint32_t nu_lo = __float_as_uint(__fmaf_rn(ax_lo, -T22, ay_lo)), nu_hi = __float_as_uint(__fmaf_rn(ax_hi, -T22, ay_hi));
+                const uint32_t wv_lo = __float_as_uint(__fmaf_rn(ax_lo, T67, -ay_lo)), wv_hi = __float_as_uint(__fmaf_rn(ax_hi, T67, -ay_hi));
                 const uint32_t H2 = prmt_sx(nu_lo, nu_hi, 0xffbb), V2 = prmt_sx(wv_lo, wv_hi, 0xffbb);       // sign of each result spread over its half
                 const uint32_t SD = prmt_sx(dxs[half] ^ dys[half], 0, 0xbb99);
                 const uint32_t diag = (SD & 0x00010001u) | 0x00020002u;
@@ -591,32 +595,45 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&
         // LSU issue 2-3x the ideal sector count and left the output phase store-bound).
         // Chunk s covers items 4s..4s+3 of (pixel, channel) order: with r = s % 3 and X, Y, Z = planes r, r+1, r+2 (mod 3) it is
         // (X[p0], Y[p1], Z[p2], X[p0 + 1]); the pixel shifts (p0, p1, p2) are (0,0,0), (1,1,2), (2,3,3), plus 4 for s >= 3.
+        // A warp owns a contiguous run of warp-iterations, so every address of an unrolled trip is base + immediate, and the
+        // bit -> value expansion is one AND (ALU pipe) and multiplies by lane constants (FMA pipe): (x & 1<<sh) * (K >> sh);
+        // the u8 word is assembled as 0x80-per-byte and widened to 0xff by one sign-replicating byte permute.
         const int lane = t0 & 31, gw = t0 >> 5, nw = tstride >> 5;
         const int gl = lane / 6, sc = lane - 6 * gl, r = sc % 3, hi4 = 4 * (sc / 3);
-        const bool lane_ok = lane < 30;
         const uint32_t paX = r == 0 ? pa[0] : (r == 1 ? pa[1] : pa[2]);
         const uint32_t paY = r == 0 ? pa[1] : (r == 1 ? pa[2] : pa[0]);
         const uint32_t paZ = r == 0 ? pa[2] : (r == 1 ? pa[0] : pa[1]);
         const int shX = r + hi4, shY = (r == 2 ? 3 : r) + hi4, shZ = (r == 0 ? 0 : r + 1) + hi4;
         const uint32_t one = 0x3f800000u;
-        if (lane_ok) {
+        const uint32_t mX0 = 1u << shX, mX1 = 2u << shX, mY = 1u << shY, mZ = 1u << shZ;
+        const uint32_t fX0 = one >> shX, fX1 = one >> (shX + 1), fY = one >> shY, fZ = one >> shZ;
+        const uint32_t qX0 = 128u >> shX, qY = (128u >> shY) << 8, qZ = (128u >> shZ) << 16, qX1 = (128u >> (shX + 1)) << 24;
+        if (lane < 30) {
+            const int nfull = npb / 5;                       // warp-iterations whose five groups all exist
             const int nwi = (npb + 4) / 5;
+            const int per = (nwi + nw - 1) / nw;
+            const int w0 = gw * per, w1 = min(nwi, w0 + per), wf = min(nfull, w1);
             auto emit = [&](auto has_f32, auto has_u8) {
-                // running addresses: plane byte of (warp iteration, group), output chunk of (warp iteration, lane)
-                uint32_t ax = paX + 5 * gw + gl, ay = paY + 5 * gw + gl, az = paZ + 5 * gw + gl;
-                uint4* fp = reinterpret_cast<uint4*>(gf32) + 30 * gw + lane;
-                uint32_t* up = reinterpret_cast<uint32_t*>(gout) + 30 * gw + lane;
-                int g = 5 * gw + gl;
-#pragma unroll 2
-                for (int wi = gw; wi < nwi; wi += nw) {
-                    if (g < npb) {
-                        const uint32_t xs = lds8(ax) >> shX, ys = lds8(ay) >> shY, zs = lds8(az) >> shZ;
-                        const uint32_t b0 = xs & 1u, b1 = ys & 1u, b2 = zs & 1u, b3x = xs & 2u;
-                        if (decltype(has_f32)::value) *fp = make_uint4(b0 * one, b1 * one, b2 * one, b3x * (one >> 1));
-                        if (decltype(has_u8)::value) *up = b0 * 255u + b1 * (255u << 8) + b2 * (255u << 16) + b3x * (255u << 23);
-                    }
-                    ax += 5 * nw; ay += 5 * nw; az += 5 * nw; g += 5 * nw;
-                    fp += 30 * nw; up += 30 * nw;
+                uint32_t ax = paX + 5 * w0 + gl, ay = paY + 5 * w0 + gl, az = paZ + 5 * w0 + gl;
+                uint4* fp = reinterpret_cast<uint4*>(gf32) + 30 * w0 + lane;
+                uint32_t* up = reinterpret_cast<uint32_t*>(gout) + 30 * w0 + lane;
+                auto one_iter = [&](int k) {
+                    const uint32_t xs = lds8(ax + 5 * k), ys = lds8(ay + 5 * k), zs = lds8(az + 5 * k);
+                    const uint32_t b0 = xs & mX0, b1 = ys & mY, b2 = zs & mZ, b3 = xs & mX1;
+                    if (decltype(has_f32)::value) fp[30 * k] = make_uint4(b0 * fX0, b1 * fY, b2 * fZ, b3 * fX1);
+                    if (decltype(has_u8)::value) up[30 * k] = prmt_sx(b0 * qX0 + b1 * qY + b2 * qZ + b3 * qX1, 0, 0xba98);
+                };
+                int wi = w0;
+#pragma unroll 1
+                for (; wi + 4 <= wf; wi += 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) one_iter(k);
+                    ax += 20; ay += 20; az += 20; fp += 120; up += 120;
+                }
+#pragma unroll 1
+                for (; wi < w1; ++wi) {
+                    if (5 * wi + gl < npb) one_iter(0);
+                    ax += 5; ay += 5; az += 5; fp += 30; up += 30;
                 }
             };
             if (gf32 && gout) emit(std::true_type{}, std::true_type{});
@@ -784,6 +801,19 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
     if (tid == 0) { mbar_init(S.bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
     if (tid == 0 && (int)blockIdx.x < p.n) issue_frame_load(S.pix[0], p.in + (size_t)blockIdx.x * frame_bytes, frame_bytes, S.bar);
+    // De-phase the CTAs: left alone, all CTAs of the grid (and the two of an SM in particular) run their phases in lockstep, so the
+    // ALU-bound strip walks collide with each other and so do the store-bound output phases.
+    if (P.stagger_half_ns | P.stagger_step_ns) {
+        const uint32_t delay = (blockIdx.x >= (gridDim.x + 1) / 2 ? P.stagger_half_ns : 0u) + (blockIdx.x & 3u) * P.stagger_step_ns;
+        if (delay) {
+            unsigned long long t0, t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                __nanosleep(500);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            } while (t - t0 < delay);
+        }
+    }
 
     unsigned long long st_mask[3] = {0, 0, 0};
     unsigned long long st_edge = 0, st_strong = 0, st_cand = 0, st_sweeps = 0, st_roi = 0, st_frames = 0;
@@ -791,29 +821,52 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
     uint32_t pa[3];
     plane_sources(p, S, G.plane_bytes, pa);
 
+    // cycle accounting of thread 0 (statistics runs only): TRS_STAT_T_* slots 10..15 = frame wait, strip walk, NMS, hysteresis, output, total
+    // (compiled in only with -DTRS_PHASE_TIMERS: the counters cost registers the strip walk does not have to spare)
+    long long tm[6] = {0, 0, 0, 0, 0, 0};
+#ifdef TRS_PHASE_TIMERS
+    const bool timing = p.stats != nullptr && tid == 0;
+#else
+    const bool timing = false;
+#endif
     for (int f = blockIdx.x; f < p.n; f += gridDim.x) {
+        const long long tk0 = timing ? clock64() : 0;
         mbar_wait(S.bar, phase);
         phase ^= 1u;
+        const long long tk1 = timing ? clock64() : 0;
         adjust_in_place(p, S.pix[0], S, s_red, tid, nthr, lane, st_roi, [] { __syncthreads(); });
         p1_strip_walk<NR, EDGE, F0, F1>(P, S.pix[0], S.mag[0], S, M, G.seg_rows_front);
         __syncthreads();
+        const long long tk2 = timing ? clock64() : 0;
         if (!p.need_pixels && tid == 0 && f + (int)gridDim.x < p.n)       // pixels are dead: prefetch the next frame
             issue_frame_load(S.pix[0], p.in + (size_t)(f + gridDim.x) * frame_bytes, frame_bytes, S.bar);
+        long long tk3 = tk2, tk4 = tk2;
         if (EDGE) {
             p2_nms(P, S.mag[0], S, M, G.seg_rows_front, st_strong);
             __syncthreads();
+            tk3 = timing ? clock64() : 0;
             const int sw = p3_hysteresis(S.cand, S.edge, plane_words, ww, tid, nthr, [](int c) { return __syncthreads_or(c); });
             if (tid == 0) st_sweeps += sw;
+            tk4 = timing ? clock64() : 0;
         }
-        p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr,
+        const size_t fo = P.dbg_out_alias ? (size_t)(f % P.dbg_out_alias) : (size_t)f;
+        p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + fo * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + fo * frame_bytes : nullptr,
                   tid, nthr);
         if (p.stats) {
             count_planes<NR, EDGE>(S, G.plane_bytes, plane_words, tid, nthr, st_mask, st_edge, st_cand);
             if (tid == 0) ++st_frames;
         }
         __syncthreads();
+        if (timing) {
+            const long long tk5 = clock64();
+            tm[0] += tk1 - tk0; tm[1] += tk2 - tk1; tm[2] += tk3 - tk2; tm[3] += tk4 - tk3; tm[4] += tk5 - tk4; tm[5] += tk5 - tk0;
+        }
         if (p.need_pixels && tid == 0 && f + (int)gridDim.x < p.n)
             issue_frame_load(S.pix[0], p.in + (size_t)(f + gridDim.x) * frame_bytes, frame_bytes, S.bar);
+    }
+    if (timing) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd(&p.stats[10 + k], (unsigned long long)tm[k]);
     }
     if (p.stats) {
         unsigned long long v[10] = {st_frames, 0, 0, 0, 0, st_edge, st_strong, st_cand, st_sweeps, st_roi};

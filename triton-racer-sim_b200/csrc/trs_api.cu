@@ -262,6 +262,9 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
         fp.fr[r].flags = flags;
         if (flags & 3u) fp.need_hue = 1;
     }
+    if (const char* e = getenv("TRS_STAGGER_HALF_NS")) fp.stagger_half_ns = (uint32_t)atoi(e);
+    if (const char* e = getenv("TRS_STAGGER_STEP_NS")) fp.stagger_step_ns = (uint32_t)atoi(e);
+    if (const char* e = getenv("TRS_DBG_OUT_ALIAS")) fp.dbg_out_alias = atoi(e);
     fp.low2 = pat(k.low);
     fp.high2 = pat(k.high);
     int grid = ctx->sm_count * (fp.g.ws ? 1 : 2);
