@@ -1,5 +1,5 @@
 """Per-phase cycles per frame per CTA of the resident fused kernel (thread 0's clock64 accounting, statistics run)."""
-import sys, torch
+import os, sys, torch
 sys.path.insert(0, '.')
 from triton_racer_sim_b200 import ImgPreprocessing, synth
 from triton_racer_sim_b200.config import full_house_config
@@ -12,6 +12,7 @@ comp = ImgPreprocessing(full_house_config(), device=0, collect_stats=True)
 out_u8 = torch.empty_like(batch); out_f32 = torch.empty(batch.shape, dtype=torch.float32, device='cuda') if want_f32 else None
 comp.process_device(batch, out_u8=out_u8, out_f32=out_f32, want_f32=want_f32)
 st = comp.stats()
-names = ['wait_frame', 'p1_strip_walk', 'p2_nms', 'p3_hysteresis', 'p4_output', 'total']
+names = (['wait_frame', 'p1_strip_walk', 'p2_nms', 'p3_hysteresis', 'p4_output', 'total'] if os.environ.get('TRS_NO_STORE_WARP') else
+         ['wait_frame', 'p1_strip_walk', 'wait_store_warps', 'p2_nms', 'p3_hysteresis', 'total'])
 keys = ["t_front_wait_frame", "t_front_wait_back", "t_front_work", "t_back_wait", "t_back_masks", "t_back_edge"]
 print({nm: round(st[k] / st['frames']) for nm, k in zip(names, keys)}, 'cycles per frame per CTA; sweeps/frame', st['hyst_sweeps'] / st['frames'])

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtrs_b200.so")
+LIB_PATH = os.environ.get("TRS_B200_LIB") or os.path.join(HERE, "libtrs_b200.so")     # (override: instrumented builds of the same library)
 MAX_HSV = 4
 STAT_COUNT = 24
 STAT_NAMES = ["frames", "mask0", "mask1", "mask2", "mask3", "edge", "strong", "cand", "hyst_sweeps", "roi_sum",

@@ -3,13 +3,11 @@
 // Same contract as k_preprocess (preproc_kernel.cuh) for frames that (a) fit shared memory whole, (b) have a
 // width that is a multiple of 32 and (c) are 16-byte aligned.  Two kernels share the phase code below:
 //
-//  k_preprocess_ws   warp-specialised, one persistent CTA per SM.  "Front" warps run the Sobel strip walk of frame
-//                    j+1 while "back" warps run the colour masks, non-maximum suppression, hysteresis and the output
-//                    stores of frame j.  Frames arrive by TMA bulk copies into a double buffer, the magnitude plane
-//                    is double-buffered too; the two groups hand buffers over through mbarriers (full/empty pairs)
-//                    and never meet at a CTA-wide barrier.
-//  k_preprocess_fast one frame per CTA, two CTAs per SM, phases separated by __syncthreads (used when the double
-//                    buffers do not fit, or when there is no edge filter to overlap with).
+//  k_preprocess_fast one frame per CTA, two CTAs per SM, phases separated by __syncthreads.
+//  k_preprocess_sw   the same plus store warps that take the output phase off the compute warps' critical path
+//                    (every output channel a bit plane, edge filter on).
+//  (A front/back warp-specialised kernel with double-buffered frames lived here until round 1 and measured slower:
+//   see profiles/r01_phase_costs.md.)
 //
 // Common design points:
 //  * a thread owns a 4-pixel-wide column strip and walks down its segment of rows with a rolling 3-row window in
@@ -46,12 +44,14 @@ struct FastGeom {
     int front_warps, back_warps;     // ws: warps per role; resident kernel: front == back == all warps
     int seg_rows_front, seg_rows_back;
     int threads;
-    int mag_stride;                  // u16 elements per magnitude row (w + 8; pixel x at index x + 4)
+    int mag_stride;                  // u16 elements per magnitude row (w + 4; pixel x at index x + 4, the zero to the right of a row is
+                                     // element 0 of the next row)
+    int mask_sets;                   // 2: the colour-mask planes are double-buffered by frame parity (store-warp kernel)
     int plane_bytes;                 // one bit plane incl. a zero row above and below, 16-byte multiple
     int off_pix[2], off_mag[2], off_mask, off_cand, off_edge, off_sdiv, off_hue, off_lut, off_bar, off_red, total;
 };
 
-__host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, int ws, int front_warps, int back_warps)
+__host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, int ws, int front_warps, int back_warps, int mask_sets = 1)
 {
     FastGeom g;
     g.ws = ws;
@@ -62,22 +62,23 @@ __host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, in
     g.seg_rows_front = (h + fsegs - 1) / fsegs;
     g.seg_rows_back = (h + bsegs - 1) / bsegs;
     g.threads = 32 * (ws ? front_warps + back_warps : front_warps);
-    g.mag_stride = w + 8;
+    g.mag_stride = w + 4;
+    g.mask_sets = mask_sets;
     g.plane_bytes = (((h + 2) * g.nsg * 4) + 15) & ~15;
     const int pix = ((h * w * 3 + 15) & ~15) + 16;
-    const int mag = (((h + 2) * g.mag_stride * 2) + 15) & ~15;
+    const int mag = ((((h + 2) * g.mag_stride + 4) * 2) + 15) & ~15;
     int o = 0;
     for (int b = 0; b < (ws ? 2 : 1); ++b) { g.off_pix[b] = o; o += pix; }
     for (int b = 0; b < (ws ? 2 : 1); ++b) { g.off_mag[b] = o; o += mag; }
     if (!ws) { g.off_pix[1] = g.off_pix[0]; g.off_mag[1] = g.off_mag[0]; }
-    g.off_mask = o; o += g.plane_bytes * n_ranges;                 // masks are made and used by one thread group: single buffer
+    g.off_mask = o; o += g.plane_bytes * n_ranges * mask_sets;
     g.off_cand = o; o += g.plane_bytes;
     g.off_edge = o; o += g.plane_bytes;
     g.off_sdiv = o; o += 1024;                                     // int32[256]
-    g.off_hue = o;  o += 2048;                                     // int2[256]
+    g.off_hue = o;  o += 1024;                                     // int32[256]
     g.off_lut = o;  o += 256;
     g.off_bar = o;  o += 64;                                       // 8 mbarriers
-    g.off_red = o;  o += 64;
+    g.off_red = o;  o += 32 + 128;                                 // 3 x u64 ROI sums, 16 x u64 statistics
     g.total = o;
     return g;
 }
@@ -96,6 +97,8 @@ struct FastParams {
     int need_hue;                    // some range has a hue bound that can fail
     uint32_t stagger_half_ns;        // start delay of the CTAs in the second half of the grid (the second CTA of each SM)
     uint32_t stagger_step_ns;        // plus (blockIdx.x % 4) times this: spreads the store bursts of different SMs
+    int use_store_warp;              // launch k_preprocess_sw (one extra warp per CTA takes sw_share/256 of the output phase)
+    int sw_share;
     int dbg_out_alias;               // experiment only (TRS_DBG_OUT_ALIAS): outputs of frame f go to slot f % alias (results invalid)
 };
 
@@ -115,6 +118,12 @@ __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile(
 __device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -313,9 +322,10 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
             const uint32_t rg = X[0] + 0x08000800u - X[1] + (d2[half] << 2);
             const uint32_t eqr = heq_mask(v2[half], X[0]), eqg = heq_mask(v2[half], X[1]);
             const uint32_t h02 = bsel(eqr, gb, bsel(eqg, br, rg));
-            const uint2 tl = lds64(a_hue + 8 * (d2[half] & 0xffffu)), th = lds64(a_hue + 8 * (d2[half] >> 16));
-            int hlo = ((int)(h02 & 0xffffu) * (int)tl.x + (int)tl.y) >> 12;
-            int hhi = ((int)(h02 >> 16) * (int)th.x + (int)th.y) >> 12;
+            // ((h0 + 2048) hd + (2048 - 2048 hd)) >> 12 == (h0 hd + 2048) >> 12
+            const int tl = (int)lds32(a_hue + 4 * (d2[half] & 0xffffu)), th = (int)lds32(a_hue + 4 * (d2[half] >> 16));
+            int hlo = ((int)(h02 & 0xffffu) * tl + (2048 - 2048 * tl)) >> 12;
+            int hhi = ((int)(h02 >> 16) * th + (2048 - 2048 * th)) >> 12;
             hlo += (hlo >> 31) & 180;
             hhi += (hhi >> 31) & 180;
             const uint32_t hh2 = (uint32_t)hlo | ((uint32_t)hhi << 16);
@@ -340,7 +350,8 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
 // P1: strip walk — Sobel / magnitude / direction -> magnitude plane, colour masks -> bit planes
 // =========================================================================================================
 template <int NR, bool EDGE, int F0, int F1>
-__device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pix, uint32_t a_mag, const SmemMap& S, const StripMap& M, int seg_rows)
+__device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pix, uint32_t a_mag, uint32_t a_mask, const SmemMap& S, const StripMap& M,
+                                              int seg_rows)
 {
     const int h = P.k.h, w = P.k.w;
     const int row_bytes = w * 3, prb = w >> 3, MS2 = P.g.mag_stride * 2, nstrips = w >> 2;
@@ -354,7 +365,7 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
                    selR2 = 0x1012u | ((right_edge ? 7u : 6u) << 8);
     const int nsteps = seg_rows + 2;
     const uint32_t strip_base = a_pix + 12 * M.strip;
-    const uint32_t mask_base = S.mask + (M.strip >> 1);
+    const uint32_t mask_base = a_mask + (M.strip >> 1);
     const uint32_t mag_base = a_mag + 2 * (4 + 4 * M.strip);
 
     uint32_t D[3][6], Hs[3][6];      // rolling rows: horizontal difference and horizontal smoothing, packed pairs
@@ -456,42 +467,43 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
     }
 }
 
-// =========================================================================================================
-// P1b: colour masks as a pointwise pass (back group of the warp-specialised kernel): a thread takes 4 consecutive
-// pixels (12 bytes), adjacent lanes take adjacent groups, two lanes make one plane byte.
-// =========================================================================================================
-template <int NR, int F0, int F1>
-__device__ __forceinline__ void p1b_colour_masks(const FastParams& P, uint32_t a_pix, const SmemMap& S, int t0, int tstride)
+// statistics live in shared memory (u64 slots after the three ROI sums): counters kept in registers across the frame loop cost the
+// strip walk ~18 registers it does not have
+__device__ __forceinline__ void stat_add(const SmemMap& S, int slot, uint32_t v)
 {
-    const int ngroups = (P.k.h * P.k.w) >> 2;
-    const int lane = t0 & 31;
-#pragma unroll 2
-    for (int g0 = t0 - lane; g0 < ngroups; g0 += tstride) {          // warp-uniform trip count (the shuffle needs every lane)
-        const int g = g0 + lane;
-        const bool valid = g < ngroups;
-        const uint32_t src = a_pix + 12 * (valid ? g : 0);
-        uint32_t A[3], B[3];
-        unpack_planar(lds32(src), lds32(src + 4), lds32(src + 8), A, B);
-        uint32_t okm[NR > 0 ? NR : 1][2];
-        hsv_masks_of<NR, F0, F1>(P, A, B, S.sdiv, S.hue, okm);
-        uint32_t v = 0;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) v |= nibble_of(okm[r][0], okm[r][1]) << (8 * r);
-        const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
-        v |= other << 4;
-        if (valid && !(lane & 1)) {
-#pragma unroll
-            for (int r = 0; r < NR; ++r) sts8(S.mask + r * P.g.plane_bytes + (g >> 1), v >> (8 * r));
-        }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) {
+        unsigned long long x = v;
+        asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(S.red + 32 + 8 * slot), "l"(x) : "memory");
+    }
+}
+
+__device__ __forceinline__ void stat_add_one(const SmemMap& S, int slot, unsigned long long x = 1)     // one thread only
+{
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(S.red + 32 + 8 * slot), "l"(x) : "memory");
+}
+
+__device__ __forceinline__ void stats_zero(const SmemMap& S, int t0)
+{
+    if (t0 < 16) { sts32(S.red + 32 + 8 * t0, 0); sts32(S.red + 36 + 8 * t0, 0); }
+}
+
+// slots: 0 frames, 1..4 colour ranges, 5 edge, 6 strong, 7 cand, 8 sweeps, 9 ROI sum (TRS_STAT_*); call after every thread's last stat_add
+__device__ __forceinline__ void stats_flush(const PreKParams& p, const SmemMap& S, int t0)
+{
+    if (t0 < 10) {
+        const uint2 v = lds64(S.red + 32 + 8 * t0);
+        const unsigned long long x = ((unsigned long long)v.y << 32) | v.x;
+        if (x) atomicAdd(&p.stats[t0], x);
     }
 }
 
 // =========================================================================================================
 // P2: non-maximum suppression, strip walk over the magnitude plane, two pixels per compare
 // =========================================================================================================
-__device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, const SmemMap& S, const StripMap& M, int seg_rows,
-                                       unsigned long long& st_strong)
+__device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, const SmemMap& S, const StripMap& M, int seg_rows)
 {
+    uint32_t n_strong = 0;
     const int h = P.k.h, prb = P.k.w >> 3, MS2 = P.g.mag_stride * 2;
     const uint32_t mbase = a_mag + 2 * (4 + 4 * M.strip);
     const uint32_t cbase = S.cand + (M.strip >> 1), ebase = S.edge + (M.strip >> 1);
@@ -543,9 +555,10 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, cons
         if (M.store_lane && row_in) {
             sts8(cbase + y * prb, v);
             sts8(ebase + y * prb, v >> 8);
-            if (P.k.stats) st_strong += __popc((v >> 8) & 0xffu);
+            if (P.k.stats) n_strong += __popc((v >> 8) & 0xffu);
         }
     }
+    if (P.k.stats) stat_add(S, 6, n_strong);
 }
 
 // =========================================================================================================
@@ -584,8 +597,10 @@ __device__ __forceinline__ int p3_hysteresis(uint32_t a_cand, uint32_t a_edge, i
 // P4: merge + normalise, written once.  pa[c] = shared address of the bit plane (row 0) feeding output channel c,
 // or 0 if that channel keeps the adjusted pixel.
 // =========================================================================================================
+// The all-planes case can be split between thread groups: `part_lo / part_hi` (in 1/256ths of the frame's warp-iterations) select
+// the share this group (threads t0 of tstride) writes; 0 / 256 = the whole frame.
 __device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&pa)[3], uint32_t a_pix, uint8_t* __restrict__ gout,
-                                          float* __restrict__ gf32, int t0, int tstride)
+                                          float* __restrict__ gf32, int t0, int tstride, int part_lo = 0, int part_hi = 256)
 {
     const int npb = P.k.h * (P.k.w >> 3);              // groups of 8 pixels = plane bytes
     if (!P.k.need_pixels) {
@@ -611,8 +626,9 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&
         if (lane < 30) {
             const int nfull = npb / 5;                       // warp-iterations whose five groups all exist
             const int nwi = (npb + 4) / 5;
-            const int per = (nwi + nw - 1) / nw;
-            const int w0 = gw * per, w1 = min(nwi, w0 + per), wf = min(nfull, w1);
+            const int r0 = (nwi * part_lo) >> 8, r1 = (nwi * part_hi) >> 8;
+            const int per = (r1 - r0 + nw - 1) / nw;
+            const int w0 = min(r1, r0 + gw * per), w1 = min(r1, w0 + per), wf = min(nfull, w1);
             auto emit = [&](auto has_f32, auto has_u8) {
                 uint32_t ax = paX + 5 * w0 + gl, ay = paY + 5 * w0 + gl, az = paZ + 5 * w0 + gl;
                 uint4* fp = reinterpret_cast<uint4*>(gf32) + 30 * w0 + lane;
@@ -687,7 +703,7 @@ __device__ __forceinline__ void init_tables(const PreKParams& p, const SmemMap& 
     for (int i = t0; i < 256; i += tstride) {
         sts32(S.sdiv + 4 * i, i ? (uint32_t)__double2int_rn((double)(255 << 12) / (double)i) : 0u);
         const int hd = i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
-        sts64(S.hue + 8 * i, make_uint2((uint32_t)hd, (uint32_t)(2048 - 2048 * hd)));      // ((h0 + 2048) hd + (2048 - 2048 hd)) >> 12 == (h0 hd + 2048) >> 12
+        sts32(S.hue + 4 * i, (uint32_t)hd);
         sts8(S.lut + i, p.lut[i]);
     }
 }
@@ -695,7 +711,8 @@ __device__ __forceinline__ void init_tables(const PreKParams& p, const SmemMap& 
 __device__ __forceinline__ void zero_mag_borders(uint32_t a_mag, int h, int w, int MS, int t0, int tstride)
 {
     for (int i = t0; i < MS; i += tstride) { sts16(a_mag + 2 * i, 0); sts16(a_mag + 2 * ((h + 1) * MS + i), 0); }
-    for (int i = t0; i < h + 2; i += tstride) { sts16(a_mag + 2 * (i * MS + 3), 0); sts16(a_mag + 2 * (i * MS + 4 + w), 0); }
+    // left neighbour of pixel 0 = element 3 of the row; right neighbour of pixel w - 1 = element 4 + w = element 0 of the next row
+    for (int i = t0; i < h + 3; i += tstride) { sts16(a_mag + 2 * (i * MS), 0); if (i < h + 2) sts16(a_mag + 2 * (i * MS + 3), 0); }
 }
 
 __device__ __forceinline__ void zero_plane_pads(const SmemMap& S, int plane_words, int ww, int t0, int tstride)
@@ -715,7 +732,7 @@ __device__ __forceinline__ uint32_t lut4s(uint32_t a_lut, uint32_t v)
 // thread group that owns the frame at this point; s_red = generic pointer to three u64 accumulators
 template <class Sync>
 __device__ __forceinline__ void adjust_in_place(const PreKParams& p, uint32_t a_pix, const SmemMap& S, unsigned long long* s_red, int t0,
-                                                int tstride, int lane, unsigned long long& st_roi, Sync sync)
+                                                int tstride, int lane, Sync sync)
 {
     const int h = p.h, w = p.w, row_bytes = w * 3;
     if (p.dynamic) {
@@ -734,7 +751,7 @@ __device__ __forceinline__ void adjust_in_place(const PreKParams& p, uint32_t a_
         if (lane == 0) { atomicAdd(&s_red[0], s0); atomicAdd(&s_red[1], s1); atomicAdd(&s_red[2], s2); }
         sync();
         const float fdelta = (float)brightness_delta(s_red[0], s_red[1], s_red[2], (double)npix, p.baseline);
-        if (t0 == 0) st_roi += s_red[0] + s_red[1] + s_red[2];
+        if (t0 == 0 && p.stats) s_red[4 + 9] += s_red[0] + s_red[1] + s_red[2];
         for (int i = t0; i < 256; i += tstride) sts8(S.lut + i, adjust_entry(i, true, fdelta, p.foff, p.fratio));
         sync();
     }
@@ -745,33 +762,27 @@ __device__ __forceinline__ void adjust_in_place(const PreKParams& p, uint32_t a_
     }
 }
 
-__device__ __forceinline__ void flush_stats(const PreKParams& p, const unsigned long long (&v)[10], int lane)
-{
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-        unsigned long long x = v[k];
-        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0 && x) atomicAdd(&p.stats[k], x);
-    }
-}
-
-__device__ __forceinline__ void plane_sources(const PreKParams& p, const SmemMap& S, int plane_bytes, uint32_t (&pa)[3])
+__device__ __forceinline__ void plane_sources(const PreKParams& p, const SmemMap& S, uint32_t a_mask, int plane_bytes, uint32_t (&pa)[3])
 {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-        pa[c] = p.src[c] == SRC_EDGE ? S.edge : (p.src[c] >= SRC_MASK0 ? S.mask + (p.src[c] - SRC_MASK0) * plane_bytes : 0u);
+        pa[c] = p.src[c] == SRC_EDGE ? S.edge : (p.src[c] >= SRC_MASK0 ? a_mask + (p.src[c] - SRC_MASK0) * plane_bytes : 0u);
 }
 
 // population counts of the finished planes (statistics)
 template <int NR, bool EDGE>
-__device__ __forceinline__ void count_planes(const SmemMap& S, int plane_bytes, int plane_words, int t0, int tstride, unsigned long long (&st_mask)[3],
-                                             unsigned long long& st_edge, unsigned long long& st_cand)
+__device__ __forceinline__ void count_planes(const PreKParams& p, const SmemMap& S, uint32_t a_mask, int plane_bytes, int plane_words, int t0, int tstride)
 {
+    uint32_t n_edge = 0, n_cand = 0, n_mask[NR > 0 ? NR : 1] = {0};
     for (int i = t0; i < plane_words; i += tstride) {
-        if (EDGE) { st_edge += __popc(lds32(S.edge + 4 * i)); st_cand += __popc(lds32(S.cand + 4 * i)); }
+        if (EDGE) { n_edge += __popc(lds32(S.edge + 4 * i)); n_cand += __popc(lds32(S.cand + 4 * i)); }
 #pragma unroll
-        for (int k = 0; k < NR; ++k) st_mask[k] += __popc(lds32(S.mask + k * plane_bytes + 4 * i));
+        for (int k = 0; k < NR; ++k) n_mask[k] += __popc(lds32(a_mask + k * plane_bytes + 4 * i));
     }
+    if (EDGE) { stat_add(S, 5, n_edge); stat_add(S, 7, n_cand); }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) stat_add(S, 1 + p.range_stat[k], n_mask[k]);
+    if (t0 == 0) stat_add_one(S, 0);
 }
 
 // =========================================================================================================
@@ -794,6 +805,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
     const StripMap M = strip_map(warp, lane, ww, G.seg_rows_front, h);
 
     init_tables(p, S, tid, nthr);
+    stats_zero(S, tid);
     if (EDGE) {
         zero_mag_borders(S.mag[0], h, w, G.mag_stride, tid, nthr);
         zero_plane_pads(S, plane_words, ww, tid, nthr);
@@ -815,11 +827,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
         }
     }
 
-    unsigned long long st_mask[3] = {0, 0, 0};
-    unsigned long long st_edge = 0, st_strong = 0, st_cand = 0, st_sweeps = 0, st_roi = 0, st_frames = 0;
     uint32_t phase = 0;
     uint32_t pa[3];
-    plane_sources(p, S, G.plane_bytes, pa);
+    plane_sources(p, S, S.mask, G.plane_bytes, pa);
 
     // cycle accounting of thread 0 (statistics runs only): TRS_STAT_T_* slots 10..15 = frame wait, strip walk, NMS, hysteresis, output, total
     // (compiled in only with -DTRS_PHASE_TIMERS: the counters cost registers the strip walk does not have to spare)
@@ -834,28 +844,25 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
         mbar_wait(S.bar, phase);
         phase ^= 1u;
         const long long tk1 = timing ? clock64() : 0;
-        adjust_in_place(p, S.pix[0], S, s_red, tid, nthr, lane, st_roi, [] { __syncthreads(); });
-        p1_strip_walk<NR, EDGE, F0, F1>(P, S.pix[0], S.mag[0], S, M, G.seg_rows_front);
+        adjust_in_place(p, S.pix[0], S, s_red, tid, nthr, lane, [] { __syncthreads(); });
+        p1_strip_walk<NR, EDGE, F0, F1>(P, S.pix[0], S.mag[0], S.mask, S, M, G.seg_rows_front);
         __syncthreads();
         const long long tk2 = timing ? clock64() : 0;
         if (!p.need_pixels && tid == 0 && f + (int)gridDim.x < p.n)       // pixels are dead: prefetch the next frame
             issue_frame_load(S.pix[0], p.in + (size_t)(f + gridDim.x) * frame_bytes, frame_bytes, S.bar);
         long long tk3 = tk2, tk4 = tk2;
         if (EDGE) {
-            p2_nms(P, S.mag[0], S, M, G.seg_rows_front, st_strong);
+            p2_nms(P, S.mag[0], S, M, G.seg_rows_front);
             __syncthreads();
             tk3 = timing ? clock64() : 0;
             const int sw = p3_hysteresis(S.cand, S.edge, plane_words, ww, tid, nthr, [](int c) { return __syncthreads_or(c); });
-            if (tid == 0) st_sweeps += sw;
+            if (tid == 0 && p.stats) stat_add_one(S, 8, (unsigned long long)sw);
             tk4 = timing ? clock64() : 0;
         }
         const size_t fo = P.dbg_out_alias ? (size_t)(f % P.dbg_out_alias) : (size_t)f;
         p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + fo * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + fo * frame_bytes : nullptr,
                   tid, nthr);
-        if (p.stats) {
-            count_planes<NR, EDGE>(S, G.plane_bytes, plane_words, tid, nthr, st_mask, st_edge, st_cand);
-            if (tid == 0) ++st_frames;
-        }
+        if (p.stats) count_planes<NR, EDGE>(p, S, S.mask, G.plane_bytes, plane_words, tid, nthr);
         __syncthreads();
         if (timing) {
             const long long tk5 = clock64();
@@ -868,22 +875,30 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
 #pragma unroll
         for (int k = 0; k < 6; ++k) atomicAdd(&p.stats[10 + k], (unsigned long long)tm[k]);
     }
-    if (p.stats) {
-        unsigned long long v[10] = {st_frames, 0, 0, 0, 0, st_edge, st_strong, st_cand, st_sweeps, st_roi};
-#pragma unroll
-        for (int k = 0; k < NR; ++k) v[1 + p.range_stat[k]] = st_mask[k];
-        flush_stats(p, v, lane);
-    }
+    if (p.stats) stats_flush(p, S, tid);          // (the frame loop ends with a CTA-wide barrier)
 }
 
 // =========================================================================================================
-// Warp-specialised kernel: one CTA per SM; front warps = Sobel strip walk of frame j+1, back warps = colour masks +
-// NMS + hysteresis + output of frame j; TMA double buffer for frames, double-buffered magnitude plane, mbarrier hand-over.
+// Store-warp kernel: the resident kernel plus ONE extra warp per CTA that takes most of the output phase off the
+// compute warps' critical path.
+//
+// Why: the SM -> L2 write port sustains ~29 B/clk (tools/ubench_store.cu: any store flavour, any number of SMs), so the
+// 288,000 output bytes of a frame occupy it for ~10 k cycles.  With the output phase run by all warps the CTA sits in
+// it for 13.6 k of its 56 k cycles per frame with almost nothing to issue.  Here the store warp writes the first
+// `sw_share`/256 of frame j while the ten compute warps write the rest and then go straight on to the strip walk of
+// frame j + 1.  What makes that legal without a second copy of every plane:
+//   * the colour-mask planes (written by the strip walk, P1) are double-buffered by frame parity (+4.9 KB);
+//   * the candidate / edge planes are first written by the NMS (P2), one whole strip walk later: the compute warps wait
+//     for the store warp's "done with frame j" (named barrier 3) only before P2 of frame j + 1.
+// Hand-over: named barrier 2 = "planes of frame j are final" (compute warps arrive, store warp syncs).  Compute-only
+// phases use named barrier 1.
 // =========================================================================================================
-enum { BAR_FULL_PIX = 0, BAR_EMPTY_PIX = 2, BAR_FULL_MAG = 4, BAR_EMPTY_MAG = 6 };
+enum { SW_COMPUTE_THREADS = 320, SW_THREADS = 384, SW_MAXREG = 80 };      // register allocation rounds a CTA up to a multiple of 4 warps
+
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 template <int NR, int F0, int F1>
-__global__ void __launch_bounds__(WS_MAX_THREADS, 1) k_preprocess_ws(const __grid_constant__ FastParams P)
+__global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ FastParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const PreKParams& p = P.k;
@@ -896,117 +911,84 @@ __global__ void __launch_bounds__(WS_MAX_THREADS, 1) k_preprocess_ws(const __gri
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t frame_bytes = (uint32_t)h * w * 3;
     const int plane_words = h * ww;
-    const int NF = G.front_warps, NB = G.back_warps;
+    const int NC = SW_COMPUTE_THREADS;
     const int nfr = (int)blockIdx.x < p.n ? (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const bool use_lut = p.dynamic || !p.lut_identity;
+    const uint32_t mask_set_bytes = (uint32_t)(NR * G.plane_bytes);
+    const int share = P.sw_share;
 
     init_tables(p, S, tid, nthr);
+    stats_zero(S, tid);
     zero_mag_borders(S.mag[0], h, w, G.mag_stride, tid, nthr);
-    zero_mag_borders(S.mag[1], h, w, G.mag_stride, tid, nthr);
     zero_plane_pads(S, plane_words, ww, tid, nthr);
-    if (tid == 0) {
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(S.bar + 8 * (BAR_FULL_PIX + b), 1);
-            mbar_init(S.bar + 8 * (BAR_EMPTY_PIX + b), NF + NB);
-            mbar_init(S.bar + 8 * (BAR_FULL_MAG + b), NF);
-            mbar_init(S.bar + 8 * (BAR_EMPTY_MAG + b), NB);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (tid == 0) { mbar_init(S.bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
 
-    if (warp < NF) {
-        // ------------------------------------------- front: Sobel strip walk ---------------------------------------
+    if (tid < NC) {
+        // ------------------------------------------------ compute warps -----------------------------------------------
         const StripMap M = strip_map(warp, lane, ww, G.seg_rows_front, h);
-        const int fn = NF * 32;
-        unsigned long long st_roi = 0;
-        long long tm_wait_pix = 0, tm_wait_mag = 0, tm_work = 0;       // cycle accounting of warp 0 (TRS_STAT_T_* slots)
-        if (tid == 0) {
-            for (int j = 0; j < 2 && j < nfr; ++j)
-                issue_frame_load(S.pix[j], p.in + (size_t)(blockIdx.x + j * gridDim.x) * frame_bytes, frame_bytes, S.bar + 8 * (BAR_FULL_PIX + j));
-        }
+        if (tid == 0 && nfr > 0) issue_frame_load(S.pix[0], p.in + (size_t)blockIdx.x * frame_bytes, frame_bytes, S.bar);
+        uint32_t phase = 0;
+#ifdef TRS_PHASE_TIMERS
+        long long tm[6] = {0, 0, 0, 0, 0, 0};      // thread 0: frame wait, strip walk, wait for the store warps, NMS, hysteresis, total
+        const bool timing = p.stats != nullptr && tid == 0;
+#define TRS_TICK(v) const long long v = timing ? clock64() : 0
+#else
+#define TRS_TICK(v)
+#endif
         for (int j = 0; j < nfr; ++j) {
-            const int b = j & 1;
-            const uint32_t par = (uint32_t)(j >> 1) & 1u;
-            const long long tk0 = clock64();
-            mbar_wait(S.bar + 8 * (BAR_FULL_PIX + b), par);
-            const long long tk1 = clock64();
-            if (j >= 2) mbar_wait(S.bar + 8 * (BAR_EMPTY_MAG + b), par ^ 1u);       // back is done with this buffer's previous frame
-            const long long tk2 = clock64();
-            adjust_in_place(p, S.pix[b], S, s_red, tid, fn, lane, st_roi, [fn] { bar_sync(1, fn); });
-            p1_strip_walk<0, true, -1, -1>(P, S.pix[b], S.mag[b], S, M, G.seg_rows_front);
-            __syncwarp();
-            tm_wait_pix += tk1 - tk0; tm_wait_mag += tk2 - tk1; tm_work += clock64() - tk2;
-            if (lane == 0) {
-                mbar_arrive(S.bar + 8 * (BAR_FULL_MAG + b));
-                mbar_arrive(S.bar + 8 * (BAR_EMPTY_PIX + b));
-            }
-            if (tid == 0 && j + 2 < nfr) {
-                mbar_wait(S.bar + 8 * (BAR_EMPTY_PIX + b), par);                    // every reader of this frame buffer is done
-                issue_frame_load(S.pix[b], p.in + (size_t)(blockIdx.x + (size_t)(j + 2) * gridDim.x) * frame_bytes, frame_bytes,
-                                 S.bar + 8 * (BAR_FULL_PIX + b));
-            }
-            __syncwarp();
-        }
-        if (p.stats && tid == 0) {
-            if (st_roi) atomicAdd(&p.stats[9], st_roi);
-            atomicAdd(&p.stats[10], (unsigned long long)tm_wait_pix);
-            atomicAdd(&p.stats[11], (unsigned long long)tm_wait_mag);
-            atomicAdd(&p.stats[12], (unsigned long long)tm_work);
-        }
-    } else {
-        // ------------------------------------------- back: colour masks, NMS, hysteresis, output ---------------------
-        const int bw = warp - NF, bt = tid - NF * 32, bn = NB * 32;
-        const StripMap M = strip_map(bw, lane, ww, G.seg_rows_back, h);
-        unsigned long long st_mask[3] = {0, 0, 0};
-        unsigned long long st_edge = 0, st_strong = 0, st_cand = 0, st_sweeps = 0, st_frames = 0;
-        long long tb_wait = 0, tb_hsv = 0, tb_edge = 0, tb_out = 0;
-        uint32_t pa[3];
-        plane_sources(p, S, G.plane_bytes, pa);
-        for (int j = 0; j < nfr; ++j) {
-            const int b = j & 1;
-            const uint32_t par = (uint32_t)(j >> 1) & 1u;
             const size_t f = blockIdx.x + (size_t)j * gridDim.x;
-            const long long tk0 = clock64();
-            mbar_wait(S.bar + 8 * (BAR_FULL_PIX + b), par);
-            if (use_lut) mbar_wait(S.bar + 8 * (BAR_FULL_MAG + b), par);            // the front group adjusts the frame in place first
-            const long long tk1 = clock64();
-            if (NR > 0) p1b_colour_masks<NR, F0, F1>(P, S.pix[b], S, bt, bn);
-            if (!p.need_pixels) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(S.bar + 8 * (BAR_EMPTY_PIX + b));
+            const uint32_t a_mask = S.mask + (j & 1) * mask_set_bytes;
+            TRS_TICK(tk0);
+            mbar_wait(S.bar, phase);
+            phase ^= 1u;
+            TRS_TICK(tk1);
+            adjust_in_place(p, S.pix[0], S, s_red, tid, NC, lane, [NC] { bar_sync(1, NC); });
+            p1_strip_walk<NR, true, F0, F1>(P, S.pix[0], S.mag[0], a_mask, S, M, G.seg_rows_front);
+            bar_sync(1, NC);
+            TRS_TICK(tk2);
+            if (tid == 0 && j + 1 < nfr)                                 // pixels are dead: prefetch the next frame
+                issue_frame_load(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, frame_bytes, S.bar);
+            if (j > 0) bar_sync(3, SW_THREADS);                          // the store warps are done with frame j-1's candidate / edge planes
+            TRS_TICK(tk3);
+            p2_nms(P, S.mag[0], S, M, G.seg_rows_front);
+            bar_sync(1, NC);
+            TRS_TICK(tk4);
+            const int sw = p3_hysteresis(S.cand, S.edge, plane_words, ww, tid, NC, [NC](int c) { return bar_or(1, NC, c); });
+            if (tid == 0 && p.stats) stat_add_one(S, 8, (unsigned long long)sw);
+#ifdef TRS_PHASE_TIMERS
+            if (timing) {
+                const long long tk5 = clock64();
+                tm[0] += tk1 - tk0; tm[1] += tk2 - tk1; tm[2] += tk3 - tk2; tm[3] += tk4 - tk3; tm[4] += tk5 - tk4; tm[5] += tk5 - tk0;
             }
-            const long long tk2 = clock64();
-            mbar_wait(S.bar + 8 * (BAR_FULL_MAG + b), par);
-            const long long tk3 = clock64();
-            p2_nms(P, S.mag[b], S, M, G.seg_rows_back, st_strong);
-            bar_sync(2, bn);
-            const int sw = p3_hysteresis(S.cand, S.edge, plane_words, ww, bt, bn, [bn](int c) { return bar_or(2, bn, c); });
-            if (bt == 0) st_sweeps += sw;
-            const long long tk4 = clock64();
-            p4_output(P, pa, S.pix[b], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, bt, bn);
-            if (p.stats) {
-                count_planes<NR, true>(S, G.plane_bytes, plane_words, bt, bn, st_mask, st_edge, st_cand);
-                if (bt == 0) ++st_frames;
-            }
-            bar_sync(2, bn);                       // cand / edge / mask planes are reused by the next frame
-            tb_wait += (tk1 - tk0) + (tk3 - tk2); tb_hsv += tk2 - tk1; tb_edge += tk4 - tk3; tb_out += clock64() - tk4;
-            if (lane == 0) {
-                mbar_arrive(S.bar + 8 * (BAR_EMPTY_MAG + b));
-                if (p.need_pixels) mbar_arrive(S.bar + 8 * (BAR_EMPTY_PIX + b));
-            }
+#endif
+            bar_arrive(2, SW_THREADS);                                   // planes of frame j are final
+            uint32_t pa[3];
+            plane_sources(p, S, a_mask, G.plane_bytes, pa);
+            p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid, NC,
+                      share, 256);
+            if (p.stats) count_planes<NR, true>(p, S, a_mask, G.plane_bytes, plane_words, tid, NC);
+            // (no barrier here: the next strip walk writes the other mask set and the magnitude plane only; the barrier after it orders
+            //  every thread's reads of this frame's candidate / edge planes before the next NMS rewrites them)
         }
         if (p.stats) {
-            unsigned long long v[10] = {st_frames, 0, 0, 0, 0, st_edge, st_strong, st_cand, st_sweeps, 0};
-#pragma unroll
-            for (int k = 0; k < NR; ++k) v[1 + p.range_stat[k]] = st_mask[k];
-            flush_stats(p, v, lane);
-            if (bt == 0) {
-                atomicAdd(&p.stats[13], (unsigned long long)tb_wait);
-                atomicAdd(&p.stats[14], (unsigned long long)tb_hsv);
-                atomicAdd(&p.stats[15], (unsigned long long)tb_edge);
-                atomicAdd(&p.stats[16], (unsigned long long)tb_out);
-            }
+            bar_sync(1, NC);
+            stats_flush(p, S, tid);
+        }
+#ifdef TRS_PHASE_TIMERS
+        if (timing)
+            for (int k = 0; k < 6; ++k) atomicAdd(&p.stats[10 + k], (unsigned long long)tm[k]);
+#endif
+#undef TRS_TICK
+    } else {
+        // ------------------------------------------------ store warp --------------------------------------------------
+        for (int j = 0; j < nfr; ++j) {
+            const size_t f = blockIdx.x + (size_t)j * gridDim.x;
+            uint32_t pa[3];
+            plane_sources(p, S, S.mask + (j & 1) * mask_set_bytes, G.plane_bytes, pa);
+            bar_sync(2, SW_THREADS);
+            p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid - NC,
+                      SW_THREADS - NC, 0, share);
+            if (j + 1 < nfr) bar_arrive(3, SW_THREADS);
         }
     }
 }

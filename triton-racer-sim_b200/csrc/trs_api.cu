@@ -188,10 +188,10 @@ int plan_geometry(trs_ctx* ctx, int h, int w, int n_ranges, Geometry* g)
 template <int NR, bool EDGE, int F0, int F1>
 int launch_fast_tf(const trs::FastParams& fp, int grid, cudaStream_t st)
 {
-    if (fp.g.ws) {
-        cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_ws<NR, F0, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ws)");
-        trs::k_preprocess_ws<NR, F0, F1><<<grid, fp.g.threads, fp.g.total, st>>>(fp);
+    if (EDGE && fp.use_store_warp) {
+        cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_sw<NR, F0, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sw)");
+        trs::k_preprocess_sw<NR, F0, F1><<<grid, trs::SW_THREADS, fp.g.total, st>>>(fp);
         return 0;
     }
     cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_fast<NR, EDGE, F0, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
@@ -221,18 +221,7 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     trs::FastParams fp;
     memset(&fp, 0, sizeof fp);
     fp.k = k;
-    // preferred: warp-specialised kernel, one CTA per SM, double-buffered frames / magnitude / masks
     bool planned = false;
-    // opt-in (TRS_WS=1): measured slower than the resident two-CTA kernel at 120x160 (7.4 vs 8.2 M frames/s), see DESIGN.md
-    if (getenv("TRS_WS") && !getenv("TRS_NO_WS") && k.edge_enabled && nsg <= trs::WS_MAX_WARPS / 2) {
-        int qb = 2;
-        if (const char* e = getenv("TRS_WS_QB")) qb = atoi(e) > 0 ? atoi(e) : 1;      // tuning knob: back-group segment quads
-        int qf = (trs::WS_MAX_WARPS - nsg * qb) / nsg;
-        if (qf < 1) { qf = 1; qb = (trs::WS_MAX_WARPS - nsg) / nsg; }
-        while (qf > 1 && 4 * (qf - 1) >= h) --qf;
-        const trs::FastGeom g = trs::fast_geometry(h, w, k.n_ranges, 1, nsg * qf, nsg * qb);
-        if (g.total <= ctx->smem_optin && g.threads <= trs::WS_MAX_THREADS) { fp.g = g; planned = true; }
-    }
     if (!planned) {
         // resident kernel: one frame per CTA, two CTAs per SM
         const int max_warps = trs::FAST_MAX_THREADS / 32;
@@ -262,12 +251,25 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
         fp.fr[r].flags = flags;
         if (flags & 3u) fp.need_hue = 1;
     }
+    // store-warp variant (k_preprocess_sw): edge filter on, every output channel a bit plane, ten compute warps, and the
+    // double-buffered mask planes still fit two CTAs per SM
+    fp.use_store_warp = 0;
+    if (!fp.g.ws && k.edge_enabled && !k.need_pixels && fp.g.threads == trs::SW_COMPUTE_THREADS && !getenv("TRS_NO_STORE_WARP")) {
+        const trs::FastGeom g2 = trs::fast_geometry(h, w, k.n_ranges, 0, fp.g.front_warps, fp.g.back_warps, 2);
+        const int budget2 = (ctx->smem_optin + 1024) / 2 - 1024;
+        if (g2.total <= budget2) {
+            fp.g = g2;
+            fp.use_store_warp = 1;
+            fp.sw_share = 256;                                           // measured best: the store warps write the whole frame
+            if (const char* e = getenv("TRS_SW_SHARE")) fp.sw_share = atoi(e) < 0 ? 0 : (atoi(e) > 256 ? 256 : atoi(e));
+        }
+    }
     if (const char* e = getenv("TRS_STAGGER_HALF_NS")) fp.stagger_half_ns = (uint32_t)atoi(e);
     if (const char* e = getenv("TRS_STAGGER_STEP_NS")) fp.stagger_step_ns = (uint32_t)atoi(e);
     if (const char* e = getenv("TRS_DBG_OUT_ALIAS")) fp.dbg_out_alias = atoi(e);
     fp.low2 = pat(k.low);
     fp.high2 = pat(k.high);
-    int grid = ctx->sm_count * (fp.g.ws ? 1 : 2);
+    int grid = ctx->sm_count * 2;
     if (grid > n) grid = n;
     int rc;
     switch (k.n_ranges * 2 + (k.edge_enabled ? 1 : 0)) {
