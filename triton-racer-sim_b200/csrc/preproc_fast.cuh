@@ -48,7 +48,9 @@ struct FastGeom {
                                      // element 0 of the next row)
     int mask_sets;                   // 2: the colour-mask planes are double-buffered by frame parity (store-warp kernel)
     int plane_bytes;                 // one bit plane incl. a zero row above and below, 16-byte multiple
-    int off_pix[2], off_mag[2], off_mask, off_cand, off_edge, off_sdiv, off_hue, off_lut, off_bar, off_red, total;
+    int off_pix[2], off_mag[2], off_mask, off_cand, off_edge, off_edge2, off_sdiv, off_hue, off_lut, off_bar, off_red, total;
+    int tail_bytes;                  // store-warp layout: the last tail_bytes of the frame arrive by a second, later bulk copy (their
+                                     // space holds the candidate plane during NMS + hysteresis); 0 = one copy
 };
 
 __host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, int ws, int front_warps, int back_warps, int mask_sets = 1)
@@ -72,7 +74,15 @@ __host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, in
     for (int b = 0; b < (ws ? 2 : 1); ++b) { g.off_mag[b] = o; o += mag; }
     if (!ws) { g.off_pix[1] = g.off_pix[0]; g.off_mag[1] = g.off_mag[0]; }
     g.off_mask = o; o += g.plane_bytes * n_ranges * mask_sets;
-    g.off_cand = o; o += g.plane_bytes;
+    g.tail_bytes = 0;
+    g.off_edge2 = -1;
+    if (mask_sets == 2 && ((h * w * 3) % 16) == 0 && h * w * 3 > 2 * g.plane_bytes) {
+        g.tail_bytes = g.plane_bytes;                                  // a 16-byte multiple
+        g.off_cand = g.off_pix[0] + h * w * 3 - g.plane_bytes;
+        g.off_edge2 = o; o += g.plane_bytes;
+    } else {
+        g.off_cand = o; o += g.plane_bytes;
+    }
     g.off_edge = o; o += g.plane_bytes;
     g.off_sdiv = o; o += 1024;                                     // int32[256]
     g.off_hue = o;  o += 1024;                                     // int32[256]
@@ -180,6 +190,11 @@ __device__ __forceinline__ void issue_frame_load(uint32_t dst, const uint8_t* sr
     mbar_expect_tx(bar, frame_bytes);
     for (uint32_t o = 0; o < frame_bytes; o += 16384u) tma_load_1d(dst + o, src + o, min(16384u, frame_bytes - o), bar);
 }
+// bytes [lo, hi) of a frame (16-byte multiples)
+__device__ __forceinline__ void issue_frame_piece(uint32_t dst, const uint8_t* src, uint32_t lo, uint32_t hi, uint32_t bar)
+{
+    issue_frame_load(dst + lo, src + lo, hi - lo, bar);
+}
 
 // fp16x2 views of 32-bit registers (bit patterns are integers n < 2048 == fp16 subnormals n * 2^-24)
 __device__ __forceinline__ __half2 h2(uint32_t x) { return *reinterpret_cast<__half2*>(&x); }
@@ -242,7 +257,7 @@ __device__ __forceinline__ StripMap strip_map(int group_warp, int lane, int nsg,
 
 // shared-memory addresses (32-bit window) of every buffer, derived once from the laundered base
 struct SmemMap {
-    uint32_t pix[2], mag[2], mask, cand, edge, sdiv, hue, lut, bar, red;      // mask / cand / edge: address of image row 0
+    uint32_t pix[2], mag[2], mask, cand, edge, edge2, sdiv, hue, lut, bar, red;      // mask / cand / edge: address of image row 0
 };
 
 __device__ __forceinline__ SmemMap smem_map(uint32_t sb, const FastGeom& G)
@@ -253,6 +268,7 @@ __device__ __forceinline__ SmemMap smem_map(uint32_t sb, const FastGeom& G)
     s.mask = sb + G.off_mask + G.nsg * 4;
     s.cand = sb + G.off_cand + G.nsg * 4;
     s.edge = sb + G.off_edge + G.nsg * 4;
+    s.edge2 = G.off_edge2 >= 0 ? sb + G.off_edge2 + G.nsg * 4 : s.edge;
     s.sdiv = sb + G.off_sdiv; s.hue = sb + G.off_hue; s.lut = sb + G.off_lut; s.bar = sb + G.off_bar; s.red = sb + G.off_red;
     return s;
 }
@@ -350,8 +366,10 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
 // P1: strip walk — Sobel / magnitude / direction -> magnitude plane, colour masks -> bit planes
 // =========================================================================================================
 template <int NR, bool EDGE, int F0, int F1>
+// tail_bar != 0: the last rows of the frame arrive under a second mbarrier; every thread waits for it at the top of trip `tail_k`
+// (a multiple of 3, before any segment loads such a row)
 __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pix, uint32_t a_mag, uint32_t a_mask, const SmemMap& S, const StripMap& M,
-                                              int seg_rows)
+                                              int seg_rows, uint32_t tail_bar = 0, uint32_t tail_parity = 0, int tail_k = 0)
 {
     const int h = P.k.h, w = P.k.w;
     const int row_bytes = w * 3, prb = w >> 3, MS2 = P.g.mag_stride * 2, nstrips = w >> 2;
@@ -374,10 +392,14 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
 #pragma unroll
         for (int j = 0; j < 6; ++j) { D[i][j] = 0; Hs[i][j] = 0; }
 
+    // running state of the walk: the image row being loaded and the three row addresses that follow it
+    int y_row = r0 - 1;                                                   // may be -1 (frame top) and run past h - 1 (frame bottom): clamped
+    uint32_t rp = strip_base + max(y_row, 0) * row_bytes;                 // pixel row y_row (clamped: replicated border)
+    uint32_t mp = mask_base + y_row * prb;                                // mask plane byte of row y_row
+    uint32_t gp = mag_base + (r0 + 1) * MS2;                              // magnitude row of the next output row (row y lives at row index y + 1)
+
     auto row_step = [&](int k, uint32_t (&Dn)[6], uint32_t (&Hn)[6], const uint32_t (&D0)[6], const uint32_t (&D1)[6], const uint32_t (&H0)[6]) {
-        // load image row r0 - 1 + k (clamped: replicated border) into slot n; emit output row y = r0 + k - 2
-        const int y_row = r0 - 1 + k;
-        const uint32_t rp = strip_base + min(max(y_row, 0), h - 1) * row_bytes;
+        // load image row r0 - 1 + k into slot n; emit output row y = r0 + k - 2
         const uint32_t w0 = lds32(rp), w1 = lds32(rp + 4), w2 = lds32(rp + 8);
         uint32_t A[3], B[3];
         unpack_planar(w0, w1, w2, A, B);
@@ -407,7 +429,7 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
             v |= other << 4;
             if (M.store_lane && row_in) {
 #pragma unroll
-                for (int r = 0; r < NR; ++r) sts8(mask_base + r * P.g.plane_bytes + y_row * prb, v >> (8 * r));
+                for (int r = 0; r < NR; ++r) sts8(mp + r * P.g.plane_bytes, v >> (8 * r));
             }
         }
         // ---- Sobel combine for output row y = r0 + k - 2 ----------------------------------------------
@@ -454,13 +476,19 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
                 uint2 v;      // pixel order: (A.lo, B.lo) = pixels (0, 1), (A.hi, B.hi) = pixels (2, 3)
                 v.x = prmt(mg[0], mg[1], 0x5410) | (prmt(code[0], code[1], 0x5410) << 11);
                 v.y = prmt(mg[0], mg[1], 0x7632) | (prmt(code[0], code[1], 0x7632) << 11);
-                sts64(mag_base + (y + 1) * MS2, v);
+                sts64(gp, v);
             }
+            gp += MS2;
         }
+        // advance to the next image row: the pixel address stays put while the row index is outside [1, h - 1] (replicated borders)
+        ++y_row;
+        if ((unsigned)(y_row - 1) < (unsigned)(h - 1)) rp += row_bytes;
+        mp += prb;
     };
     // rolling window by register renaming: slots (k % 3)
 #pragma unroll 1
     for (int k = 0; k < nsteps; k += 3) {
+        if (tail_bar && k == tail_k) mbar_wait(tail_bar, tail_parity);
         row_step(k, D[0], Hs[0], D[1], D[2], Hs[1]);                 // new = slot0, y-1 = slot1, y = slot2
         if (k + 1 < nsteps) row_step(k + 1, D[1], Hs[1], D[2], D[0], Hs[2]);
         if (k + 2 < nsteps) row_step(k + 2, D[2], Hs[2], D[0], D[1], Hs[0]);
@@ -501,12 +529,12 @@ __device__ __forceinline__ void stats_flush(const PreKParams& p, const SmemMap& 
 // =========================================================================================================
 // P2: non-maximum suppression, strip walk over the magnitude plane, two pixels per compare
 // =========================================================================================================
-__device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, const SmemMap& S, const StripMap& M, int seg_rows)
+__device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint32_t a_cand, uint32_t a_edge, const SmemMap& S, const StripMap& M, int seg_rows)
 {
     uint32_t n_strong = 0;
     const int h = P.k.h, prb = P.k.w >> 3, MS2 = P.g.mag_stride * 2;
     const uint32_t mbase = a_mag + 2 * (4 + 4 * M.strip);
-    const uint32_t cbase = S.cand + (M.strip >> 1), ebase = S.edge + (M.strip >> 1);
+    const uint32_t cbase = a_cand + (M.strip >> 1), ebase = a_edge + (M.strip >> 1);
     // one row as packed pairs of magnitudes: P01=(m0,m1) P23=(m2,m3) L01=(m-1,m0) M12=(m1,m2) R23=(m3,m4); raw keeps the codes
     struct Row { uint32_t p01, p23, l01, m12, r23, raw01, raw23; };
     auto load_row = [&](int y) {
@@ -570,14 +598,15 @@ __device__ __forceinline__ int p3_hysteresis(uint32_t a_cand, uint32_t a_edge, i
 {
     int sweeps = 0, any;
     const int rowb = ww * 4;
+    const int wi0 = t0 % ww, dwi = tstride % ww;          // word column of this thread's first word, and its step (no division per sweep)
     do {
         int changed = 0;
-        for (int t = t0; t < plane_words; t += tstride) {
+        int wi = wi0;
+        for (int t = t0; t < plane_words; t += tstride, wi = wi + dwi >= ww ? wi + dwi - ww : wi + dwi) {
             const uint32_t c = lds32(a_cand + 4 * t);
             const uint32_t ea = a_edge + 4 * t;
             const uint32_t e = lds32(ea);
             if (c != e) {
-                const int wi = t % ww;
                 const uint32_t mid = e | lds32(ea - rowb) | lds32(ea + rowb);
                 uint32_t lft = 0, rgt = 0;
                 if (wi > 0) lft = lds32(ea - 4) | lds32(ea - rowb - 4) | lds32(ea + rowb - 4);
@@ -636,8 +665,14 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&
                 auto one_iter = [&](int k) {
                     const uint32_t xs = lds8(ax + 5 * k), ys = lds8(ay + 5 * k), zs = lds8(az + 5 * k);
                     const uint32_t b0 = xs & mX0, b1 = ys & mY, b2 = zs & mZ, b3 = xs & mX1;
-                    if (decltype(has_f32)::value) fp[30 * k] = make_uint4(b0 * fX0, b1 * fY, b2 * fZ, b3 * fX1);
-                    if (decltype(has_u8)::value) up[30 * k] = prmt_sx(b0 * qX0 + b1 * qY + b2 * qZ + b3 * qX1, 0, 0xba98);
+                    if (decltype(has_f32)::value) {
+                        const uint32_t f0 = b0 * fX0, f1 = b1 * fY, f2 = b2 * fZ, f3 = b3 * fX1;
+                        fp[30 * k] = make_uint4(f0, f1, f2, f3);
+                        // byte 2 of 1.0f is 0x80: its sign bit replicated over a byte is the u8 value
+                        if (decltype(has_u8)::value) up[30 * k] = prmt(prmt_sx(f0, f1, 0x00ea), prmt_sx(f2, f3, 0x00ea), 0x5410);
+                    } else if (decltype(has_u8)::value) {
+                        up[30 * k] = prmt_sx(b0 * qX0 + b1 * qY + b2 * qZ + b3 * qX1, 0, 0xba98);
+                    }
                 };
                 int wi = w0;
 #pragma unroll 1
@@ -718,8 +753,8 @@ __device__ __forceinline__ void zero_mag_borders(uint32_t a_mag, int h, int w, i
 __device__ __forceinline__ void zero_plane_pads(const SmemMap& S, int plane_words, int ww, int t0, int tstride)
 {
     for (int i = t0; i < ww; i += tstride) {
-        sts32(S.cand - 4 * ww + 4 * i, 0); sts32(S.cand + 4 * (plane_words + i), 0);
-        sts32(S.edge - 4 * ww + 4 * i, 0); sts32(S.edge + 4 * (plane_words + i), 0);
+        sts32(S.edge - 4 * ww + 4 * i, 0); sts32(S.edge + 4 * (plane_words + i), 0);       // (the pads of the candidate plane are never read)
+        sts32(S.edge2 - 4 * ww + 4 * i, 0); sts32(S.edge2 + 4 * (plane_words + i), 0);
     }
 }
 
@@ -762,20 +797,21 @@ __device__ __forceinline__ void adjust_in_place(const PreKParams& p, uint32_t a_
     }
 }
 
-__device__ __forceinline__ void plane_sources(const PreKParams& p, const SmemMap& S, uint32_t a_mask, int plane_bytes, uint32_t (&pa)[3])
+__device__ __forceinline__ void plane_sources(const PreKParams& p, uint32_t a_edge, uint32_t a_mask, int plane_bytes, uint32_t (&pa)[3])
 {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-        pa[c] = p.src[c] == SRC_EDGE ? S.edge : (p.src[c] >= SRC_MASK0 ? a_mask + (p.src[c] - SRC_MASK0) * plane_bytes : 0u);
+        pa[c] = p.src[c] == SRC_EDGE ? a_edge : (p.src[c] >= SRC_MASK0 ? a_mask + (p.src[c] - SRC_MASK0) * plane_bytes : 0u);
 }
 
 // population counts of the finished planes (statistics)
 template <int NR, bool EDGE>
-__device__ __forceinline__ void count_planes(const PreKParams& p, const SmemMap& S, uint32_t a_mask, int plane_bytes, int plane_words, int t0, int tstride)
+__device__ __forceinline__ void count_planes(const PreKParams& p, const SmemMap& S, uint32_t a_cand, uint32_t a_edge, uint32_t a_mask, int plane_bytes, int plane_words,
+                                             int t0, int tstride)
 {
     uint32_t n_edge = 0, n_cand = 0, n_mask[NR > 0 ? NR : 1] = {0};
     for (int i = t0; i < plane_words; i += tstride) {
-        if (EDGE) { n_edge += __popc(lds32(S.edge + 4 * i)); n_cand += __popc(lds32(S.cand + 4 * i)); }
+        if (EDGE) { n_edge += __popc(lds32(a_edge + 4 * i)); n_cand += __popc(lds32(a_cand + 4 * i)); }
 #pragma unroll
         for (int k = 0; k < NR; ++k) n_mask[k] += __popc(lds32(a_mask + k * plane_bytes + 4 * i));
     }
@@ -829,7 +865,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
 
     uint32_t phase = 0;
     uint32_t pa[3];
-    plane_sources(p, S, S.mask, G.plane_bytes, pa);
+    plane_sources(p, S.edge, S.mask, G.plane_bytes, pa);
 
     // cycle accounting of thread 0 (statistics runs only): TRS_STAT_T_* slots 10..15 = frame wait, strip walk, NMS, hysteresis, output, total
     // (compiled in only with -DTRS_PHASE_TIMERS: the counters cost registers the strip walk does not have to spare)
@@ -852,7 +888,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
             issue_frame_load(S.pix[0], p.in + (size_t)(f + gridDim.x) * frame_bytes, frame_bytes, S.bar);
         long long tk3 = tk2, tk4 = tk2;
         if (EDGE) {
-            p2_nms(P, S.mag[0], S, M, G.seg_rows_front);
+            p2_nms(P, S.mag[0], S.cand, S.edge, S, M, G.seg_rows_front);
             __syncthreads();
             tk3 = timing ? clock64() : 0;
             const int sw = p3_hysteresis(S.cand, S.edge, plane_words, ww, tid, nthr, [](int c) { return __syncthreads_or(c); });
@@ -862,7 +898,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
         const size_t fo = P.dbg_out_alias ? (size_t)(f % P.dbg_out_alias) : (size_t)f;
         p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + fo * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + fo * frame_bytes : nullptr,
                   tid, nthr);
-        if (p.stats) count_planes<NR, EDGE>(p, S, S.mask, G.plane_bytes, plane_words, tid, nthr);
+        if (p.stats) count_planes<NR, EDGE>(p, S, S.cand, S.edge, S.mask, G.plane_bytes, plane_words, tid, nthr);
         __syncthreads();
         if (timing) {
             const long long tk5 = clock64();
@@ -915,18 +951,30 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
     const int nfr = (int)blockIdx.x < p.n ? (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t mask_set_bytes = (uint32_t)(NR * G.plane_bytes);
     const int share = P.sw_share;
+    const uint32_t main_bytes = frame_bytes - (uint32_t)G.tail_bytes;
+    const uint32_t bar_main = S.bar, bar_tail = S.bar + 8;
 
     init_tables(p, S, tid, nthr);
     stats_zero(S, tid);
     zero_mag_borders(S.mag[0], h, w, G.mag_stride, tid, nthr);
     zero_plane_pads(S, plane_words, ww, tid, nthr);
-    if (tid == 0) { mbar_init(S.bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(bar_main, 1); mbar_init(bar_tail, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
 
     if (tid < NC) {
         // ------------------------------------------------ compute warps -----------------------------------------------
         const StripMap M = strip_map(warp, lane, ww, G.seg_rows_front, h);
-        if (tid == 0 && nfr > 0) issue_frame_load(S.pix[0], p.in + (size_t)blockIdx.x * frame_bytes, frame_bytes, S.bar);
+        const bool use_lut = p.dynamic || !p.lut_identity;
+        // first strip-walk trip (a multiple of 3) in which some segment loads a row of the tail piece
+        const int nsegs = 4 * (G.front_warps / ww);
+        const int tail_row = (int)(main_bytes / (uint32_t)(w * 3));
+        int tail_k = tail_row - (nsegs - 1) * G.seg_rows_front + 1;
+        tail_k = tail_k < 0 ? 0 : (tail_k / 3) * 3;
+        if (tid == 0 && nfr > 0) {
+            const uint8_t* src = p.in + (size_t)blockIdx.x * frame_bytes;
+            issue_frame_piece(S.pix[0], src, 0, main_bytes, bar_main);
+            if (G.tail_bytes) issue_frame_piece(S.pix[0], src, main_bytes, frame_bytes, bar_tail);
+        }
         uint32_t phase = 0;
 #ifdef TRS_PHASE_TIMERS
         long long tm[6] = {0, 0, 0, 0, 0, 0};      // thread 0: frame wait, strip walk, wait for the store warps, NMS, hysteresis, total
@@ -938,37 +986,44 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
         for (int j = 0; j < nfr; ++j) {
             const size_t f = blockIdx.x + (size_t)j * gridDim.x;
             const uint32_t a_mask = S.mask + (j & 1) * mask_set_bytes;
+            const uint32_t a_edge = (j & 1) ? S.edge2 : S.edge;
             TRS_TICK(tk0);
-            mbar_wait(S.bar, phase);
-            phase ^= 1u;
+            mbar_wait(bar_main, phase);
+            if (G.tail_bytes && use_lut) mbar_wait(bar_tail, phase);     // the table pass touches every pixel
             TRS_TICK(tk1);
             adjust_in_place(p, S.pix[0], S, s_red, tid, NC, lane, [NC] { bar_sync(1, NC); });
-            p1_strip_walk<NR, true, F0, F1>(P, S.pix[0], S.mag[0], a_mask, S, M, G.seg_rows_front);
-            bar_sync(1, NC);
             TRS_TICK(tk2);
-            if (tid == 0 && j + 1 < nfr)                                 // pixels are dead: prefetch the next frame
-                issue_frame_load(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, frame_bytes, S.bar);
-            if (j > 0) bar_sync(3, SW_THREADS);                          // the store warps are done with frame j-1's candidate / edge planes
+            if (j >= 2) bar_sync(3, SW_THREADS);                         // the store warps are done with frame j-2: this plane set is free
             TRS_TICK(tk3);
-            p2_nms(P, S.mag[0], S, M, G.seg_rows_front);
+            p1_strip_walk<NR, true, F0, F1>(P, S.pix[0], S.mag[0], a_mask, S, M, G.seg_rows_front, (G.tail_bytes && !use_lut) ? bar_tail : 0u, phase, tail_k);
+            phase ^= 1u;
             bar_sync(1, NC);
             TRS_TICK(tk4);
-            const int sw = p3_hysteresis(S.cand, S.edge, plane_words, ww, tid, NC, [NC](int c) { return bar_or(1, NC, c); });
-            if (tid == 0 && p.stats) stat_add_one(S, 8, (unsigned long long)sw);
+            if (tid == 0 && j + 1 < nfr)                                 // pixels are dead: prefetch the next frame (all but its tail)
+                issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, 0, main_bytes, bar_main);
+            p2_nms(P, S.mag[0], S.cand, a_edge, S, M, G.seg_rows_front);
+            bar_sync(1, NC);
+            TRS_TICK(tk5);
+            const int sw = p3_hysteresis(S.cand, a_edge, plane_words, ww, tid, NC, [NC](int c) { return bar_or(1, NC, c); });
+            if (p.stats) {                                               // (the candidate plane is counted before the tail copy lands on it)
+                if (tid == 0) stat_add_one(S, 8, (unsigned long long)sw);
+                count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid, NC);
+                bar_sync(1, NC);
+            }
+            if (tid == 0 && G.tail_bytes && j + 1 < nfr)                 // the candidate plane is dead: fetch the tail it was sitting in
+                issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, main_bytes, frame_bytes, bar_tail);
 #ifdef TRS_PHASE_TIMERS
             if (timing) {
-                const long long tk5 = clock64();
-                tm[0] += tk1 - tk0; tm[1] += tk2 - tk1; tm[2] += tk3 - tk2; tm[3] += tk4 - tk3; tm[4] += tk5 - tk4; tm[5] += tk5 - tk0;
+                const long long tk6 = clock64();
+                tm[0] += tk1 - tk0; tm[1] += tk4 - tk3; tm[2] += tk3 - tk2; tm[3] += tk5 - tk4; tm[4] += tk6 - tk5; tm[5] += tk6 - tk0;
             }
 #endif
             bar_arrive(2, SW_THREADS);                                   // planes of frame j are final
             uint32_t pa[3];
-            plane_sources(p, S, a_mask, G.plane_bytes, pa);
+            plane_sources(p, a_edge, a_mask, G.plane_bytes, pa);
             p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid, NC,
                       share, 256);
-            if (p.stats) count_planes<NR, true>(p, S, a_mask, G.plane_bytes, plane_words, tid, NC);
-            // (no barrier here: the next strip walk writes the other mask set and the magnitude plane only; the barrier after it orders
-            //  every thread's reads of this frame's candidate / edge planes before the next NMS rewrites them)
+            // (no barrier here: the next strip walk writes the other plane set and the magnitude plane only)
         }
         if (p.stats) {
             bar_sync(1, NC);
@@ -980,15 +1035,15 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
 #endif
 #undef TRS_TICK
     } else {
-        // ------------------------------------------------ store warp --------------------------------------------------
+        // ------------------------------------------------ store warps -------------------------------------------------
         for (int j = 0; j < nfr; ++j) {
             const size_t f = blockIdx.x + (size_t)j * gridDim.x;
             uint32_t pa[3];
-            plane_sources(p, S, S.mask + (j & 1) * mask_set_bytes, G.plane_bytes, pa);
+            plane_sources(p, (j & 1) ? S.edge2 : S.edge, S.mask + (j & 1) * mask_set_bytes, G.plane_bytes, pa);
             bar_sync(2, SW_THREADS);
             p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid - NC,
                       SW_THREADS - NC, 0, share);
-            if (j + 1 < nfr) bar_arrive(3, SW_THREADS);
+            if (j + 2 < nfr) bar_arrive(3, SW_THREADS);
         }
     }
 }
