@@ -278,10 +278,39 @@ def test_full_size_properties():
     comp.onShutdown()
 
 
-@pytest.mark.parametrize("env", ["TRS_FORCE_GENERIC", "TRS_WS"])
+@pytest.mark.parametrize("hsvs", [
+    None,                                                                     # the reference's defaults (core/config.py:23)
+    [[[0, 0, 130], [180, 70, 255]], [[25, 100.5, 155], [43, 255, 255]]],       # same live bounds, other saturation thresholds
+    [[[0, 0, 0], [180, 0, 255]], [[0, 255, 1], [179, 255, 255]]],              # saturation pinned to 0 / to 255
+    [[[0, 0, 130], [180, -3, 255]], [[25, 254.5, 155], [43, 255, 255]]],       # an empty range, a half-to-even bound
+])
+def test_every_colour_through_the_masks(hsvs):
+    """All 2^24 colours (874 frames of 120x160) through the fused kernels: the colour-mask channels of every frame must equal
+    the oracle bit for bit (this pins the saturation-threshold tables of the specialised kernels)."""
+    n_px = 1 << 24
+    per = 120 * 160
+    n = (n_px + per - 1) // per
+    c = np.arange(n * per, dtype=np.uint32) % n_px
+    frames = np.stack([(c >> 16) & 255, (c >> 8) & 255, c & 255], axis=-1).astype(np.uint8).reshape(n, 120, 160, 3)
+    over = {} if hsvs is None else dict(preprocessing_color_filter_hsvs=hsvs)
+    cfg = full_house_config(**over)
+    want = oracle.process_batch(frames, cfg)
+    for env in (None, "TRS_NO_STORE_WARP"):
+        if env:
+            import os
+            os.environ[env] = "1"
+        try:
+            got, _ = run_device(cfg, frames, want_f32=False)
+        finally:
+            if env:
+                del os.environ[env]
+        assert np.array_equal(got, want), f"{env}: {describe(got, want)}"
+
+
+@pytest.mark.parametrize("env", ["TRS_FORCE_GENERIC", "TRS_NO_STORE_WARP"])
 def test_other_kernels_still_match(golden_images, monkeypatch, env):
-    """The resident two-CTA kernel takes the aligned 32-multiple widths by default; force the warp-specialised kernel
-    (TRS_WS) and the generic banded kernel (TRS_FORCE_GENERIC) on the same data."""
+    """The store-warp kernel takes 120x160 full-house frames by default; force the resident kernel without store warps
+    (TRS_NO_STORE_WARP) and the generic banded kernel (TRS_FORCE_GENERIC) on the same data."""
     monkeypatch.setenv(env, "1")
     for sname, cname, cfg, frames, expected in golden_pairs(golden_images):
         if sname not in ("f120", "f240") or cname not in ("full_house", "exotic", "edge_only"):

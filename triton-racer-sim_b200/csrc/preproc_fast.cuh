@@ -292,6 +292,17 @@ __device__ __forceinline__ void unpack_planar(uint32_t w0, uint32_t w1, uint32_t
 template <int F>
 __device__ __forceinline__ uint32_t live_flags(const FastRange& R) { return F >= 0 ? (uint32_t)F : R.flags; }
 
+// Saturation bounds without computing the saturation: s = (d * sdiv[v] + 2048) >> 12 is monotone in d, so "s <= K" is
+// "d <= T_K[v]" with T_K[v] = min(v, (4096 K + 2047) / sdiv[v]) and "s >= K" is "d > T_{K-1}[v]".  When the live-bound words are
+// compile-time constants with at most two saturation bounds, the 256-entry table (in the place of sdiv) holds the two thresholds of a
+// value v as 16-bit halves: one table read per pixel, two packed compares per pixel pair, no multiply / shift / repack.
+// Bounds take table halves in range order, the lower bound of a range before its upper bound.
+template <int NR, int F0, int F1>
+struct SatThresholds {
+    static constexpr int n = (F0 >= 0 && F1 >= 0 && NR == 2) ? ((F0 >> 2) & 1) + ((F0 >> 3) & 1) + ((F1 >> 2) & 1) + ((F1 >> 3) & 1) : 99;
+    static constexpr bool use = n >= 1 && n <= 2;
+};
+
 template <int NR, int F0, int F1>
 __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t (&A)[3], const uint32_t (&B)[3], uint32_t a_sdiv, uint32_t a_hue,
                                              uint32_t (&okm)[NR > 0 ? NR : 1][2])
@@ -309,19 +320,29 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
         const uint32_t* X = half ? B : A;
         v2[half] = __vimax3_u16x2(X[0], X[1], X[2]);
         d2[half] = v2[half] - __vimin3_u16x2(X[0], X[1], X[2]);
-        uint32_t s2 = 0;
-        if (any_s) {
+        uint32_t s2 = 0, T2[2] = {0, 0};
+        constexpr bool TT = SatThresholds<NR, F0, F1>::use;
+        if (TT) {
+            const uint32_t tl = lds32(a_sdiv + 4 * (v2[half] & 0xffffu)), th = lds32(a_sdiv + 4 * (v2[half] >> 16));
+            T2[0] = prmt(tl, th, 0x5410); T2[1] = prmt(tl, th, 0x7632);
+        } else if (any_s) {
             const uint32_t vlo = v2[half] & 0xffffu, vhi = v2[half] >> 16, dlo = d2[half] & 0xffffu, dhi = d2[half] >> 16;
             const uint32_t slo = (uint32_t)(((int)dlo * (int)lds32(a_sdiv + 4 * vlo) + 2048) >> 12);
             const uint32_t shi = (uint32_t)(((int)dhi * (int)lds32(a_sdiv + 4 * vhi) + 2048) >> 12);
             s2 = slo | (shi << 16);
         }
+        int slot = 0;
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             const FastRange& R = P.fr[r];
             uint32_t ok = 0xffffffffu;
-            if (fl[r] & 4u) ok &= hge_mask(s2, R.lo[1]);
-            if (fl[r] & 8u) ok &= hle_mask(s2, R.hi[1]);
+            if (TT) {
+                if (fl[r] & 4u) ok &= hgt_mask(d2[half], T2[slot++ & 1]);
+                if (fl[r] & 8u) ok &= hle_mask(d2[half], T2[slot++ & 1]);
+            } else {
+                if (fl[r] & 4u) ok &= hge_mask(s2, R.lo[1]);
+                if (fl[r] & 8u) ok &= hle_mask(s2, R.hi[1]);
+            }
             if (fl[r] & 16u) ok &= hge_mask(v2[half], R.lo[2]);
             if (fl[r] & 32u) ok &= hle_mask(v2[half], R.hi[2]);
             okm[r][half] = ok;
@@ -733,10 +754,34 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&
 }
 
 // ---- shared prologue pieces ---------------------------------------------------------------------------------
+template <int NR, int F0, int F1>
 __device__ __forceinline__ void init_tables(const PreKParams& p, const SmemMap& S, int t0, int tstride)
 {
     for (int i = t0; i < 256; i += tstride) {
-        sts32(S.sdiv + 4 * i, i ? (uint32_t)__double2int_rn((double)(255 << 12) / (double)i) : 0u);
+        const int sd = i ? __double2int_rn((double)(255 << 12) / (double)i) : 0;
+        if (SatThresholds<NR, F0, F1>::use) {
+            // the live saturation bounds in table order (see SatThresholds); K = the largest admissible saturation of "s <= K"
+            uint32_t entry = 0;
+            int slot = 0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int fl = r == 0 ? F0 : F1;
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {
+                    if (!(fl & (4 << side))) continue;
+                    const long long K = side == 0 ? (long long)p.ranges[r].lo[1] - 1 : (long long)p.ranges[r].hi[1];
+                    uint32_t T;
+                    if (K < 0) T = 0x8001u;                                   // no d qualifies (compares as -1)
+                    else if (i == 0) T = 0u;                                  // v = 0: d = 0, s = 0
+                    else { const long long q = (4096 * K + 2047) / sd; T = (uint32_t)(q < i ? q : i); }
+                    entry |= T << (16 * (slot & 1));
+                    ++slot;
+                }
+            }
+            sts32(S.sdiv + 4 * i, entry);
+        } else {
+            sts32(S.sdiv + 4 * i, (uint32_t)sd);
+        }
         const int hd = i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
         sts32(S.hue + 4 * i, (uint32_t)hd);
         sts8(S.lut + i, p.lut[i]);
@@ -840,7 +885,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
     const int plane_words = h * ww;
     const StripMap M = strip_map(warp, lane, ww, G.seg_rows_front, h);
 
-    init_tables(p, S, tid, nthr);
+    init_tables<NR, F0, F1>(p, S, tid, nthr);
     stats_zero(S, tid);
     if (EDGE) {
         zero_mag_borders(S.mag[0], h, w, G.mag_stride, tid, nthr);
@@ -954,7 +999,7 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
     const uint32_t main_bytes = frame_bytes - (uint32_t)G.tail_bytes;
     const uint32_t bar_main = S.bar, bar_tail = S.bar + 8;
 
-    init_tables(p, S, tid, nthr);
+    init_tables<NR, F0, F1>(p, S, tid, nthr);
     stats_zero(S, tid);
     zero_mag_borders(S.mag[0], h, w, G.mag_stride, tid, nthr);
     zero_plane_pads(S, plane_words, ww, tid, nthr);
