@@ -571,12 +571,12 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
         return r;
     };
     const int ya = M.ok ? M.r0 : 0;
-    Row up = load_row(ya - 1), ce = load_row(ya);
-#pragma unroll 1
-    for (int k = 0; k < seg_rows; ++k) {
+    uint32_t cp = cbase + ya * prb, ep = ebase + ya * prb;          // plane bytes of the row being decided
+    // rolling three-row window by register renaming (three steps per trip): step k decides row ya + k from rows (up, ce) and loads dn
+    auto nms_step = [&](int k, const Row& up, const Row& ce, Row& dn) {
         const int y = ya + k;
         const bool row_in = y < M.r1;
-        const Row dn = load_row(min(y + 1, h));
+        dn = load_row(min(y + 1, h));
         uint32_t cm[2], sm[2];
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
@@ -594,7 +594,6 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
             cm[pr] = hgt_mask(C, na) & hge_mask(C, nb) & hgt_mask(C, P.low2);
             sm[pr] = cm[pr] & hgt_mask(C, P.high2);
         }
-        up = ce; ce = dn;
         // pixels (0,1) sit in cm[0] halves, (2,3) in cm[1]: nibble bit q = pixel q
         const uint32_t x = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u);
         const uint32_t z = (sm[0] & 0x00020001u) | (sm[1] & 0x00080004u);
@@ -602,10 +601,18 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
         const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
         v |= other << 4;
         if (M.store_lane && row_in) {
-            sts8(cbase + y * prb, v);
-            sts8(ebase + y * prb, v >> 8);
+            sts8(cp, v);
+            sts8(ep, v >> 8);
             if (P.k.stats) n_strong += __popc((v >> 8) & 0xffu);
         }
+        cp += prb; ep += prb;
+    };
+    Row ra = load_row(ya - 1), rb = load_row(ya), rc;
+#pragma unroll 1
+    for (int k = 0; k < seg_rows; k += 3) {
+        nms_step(k, ra, rb, rc);
+        if (k + 1 < seg_rows) nms_step(k + 1, rb, rc, ra);
+        if (k + 2 < seg_rows) nms_step(k + 2, rc, ra, rb);
     }
     if (P.k.stats) stat_add(S, 6, n_strong);
 }
@@ -614,33 +621,47 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
 // P3: hysteresis — grow the strong set through candidates, one plane word per thread per sweep, until stable.
 // a_cand / a_edge address row 0; the rows just above and below hold zeros.  Returns the number of sweeps.
 // =========================================================================================================
+// Two-level schedule: a warp owns a band of rows and relaxes it to a local fixed point with warp-level synchronisation only
+// (no CTA barrier, no waiting for other warps); one CTA-wide OR per round then tells whether any band changed, i.e. whether
+// growth may still cross a band boundary.  The fixed point is unique, so the schedule does not affect the result.
 template <class OrReduce>
-__device__ __forceinline__ int p3_hysteresis(uint32_t a_cand, uint32_t a_edge, int plane_words, int ww, int t0, int tstride, OrReduce group_or)
+__device__ __forceinline__ int p3_hysteresis(uint32_t a_cand, uint32_t a_edge, int h, int ww, int t0, int tstride, OrReduce group_or)
 {
-    int sweeps = 0, any;
+    const int lane = t0 & 31, gw = t0 >> 5, nw = tstride >> 5;
+    const int rows_per = (h + nw - 1) / nw;
+    const int y0 = min(h, gw * rows_per), y1 = min(h, y0 + rows_per);
+    const int nwords = (y1 - y0) * ww, base = y0 * ww;
     const int rowb = ww * 4;
-    const int wi0 = t0 % ww, dwi = tstride % ww;          // word column of this thread's first word, and its step (no division per sweep)
+    const int wi0 = lane % ww, dwi = 32 % ww;             // word column of this lane's first word, and its step (no division per sweep)
+    int rounds = 0, any;
     do {
-        int changed = 0;
-        int wi = wi0;
-        for (int t = t0; t < plane_words; t += tstride, wi = wi + dwi >= ww ? wi + dwi - ww : wi + dwi) {
-            const uint32_t c = lds32(a_cand + 4 * t);
-            const uint32_t ea = a_edge + 4 * t;
-            const uint32_t e = lds32(ea);
-            if (c != e) {
-                const uint32_t mid = e | lds32(ea - rowb) | lds32(ea + rowb);
-                uint32_t lft = 0, rgt = 0;
-                if (wi > 0) lft = lds32(ea - 4) | lds32(ea - rowb - 4) | lds32(ea + rowb - 4);
-                if (wi + 1 < ww) rgt = lds32(ea + 4) | lds32(ea - rowb + 4) | lds32(ea + rowb + 4);
-                const uint32_t spread = mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
-                const uint32_t ne = flood_run((spread & c) | e, c);
-                if (ne != e) { sts32(ea, ne); changed = 1; }
+        int round_changed = 0;
+        while (true) {
+            int changed = 0;
+            int wi = wi0;
+            for (int i = lane; i < nwords; i += 32, wi = wi + dwi >= ww ? wi + dwi - ww : wi + dwi) {
+                const int t = base + i;
+                const uint32_t c = lds32(a_cand + 4 * t);
+                const uint32_t ea = a_edge + 4 * t;
+                const uint32_t e = lds32(ea);
+                if (c != e) {
+                    const uint32_t mid = e | lds32(ea - rowb) | lds32(ea + rowb);
+                    uint32_t lft = 0, rgt = 0;
+                    if (wi > 0) lft = lds32(ea - 4) | lds32(ea - rowb - 4) | lds32(ea + rowb - 4);
+                    if (wi + 1 < ww) rgt = lds32(ea + 4) | lds32(ea - rowb + 4) | lds32(ea + rowb + 4);
+                    const uint32_t spread = mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
+                    const uint32_t ne = flood_run((spread & c) | e, c);
+                    if (ne != e) { sts32(ea, ne); changed = 1; }
+                }
             }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, changed)) break;
+            round_changed = 1;
         }
-        any = group_or(changed);
-        ++sweeps;
+        any = group_or(round_changed);
+        ++rounds;
     } while (any);
-    return sweeps;
+    return rounds;
 }
 
 // =========================================================================================================
@@ -936,7 +957,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
             p2_nms(P, S.mag[0], S.cand, S.edge, S, M, G.seg_rows_front);
             __syncthreads();
             tk3 = timing ? clock64() : 0;
-            const int sw = p3_hysteresis(S.cand, S.edge, plane_words, ww, tid, nthr, [](int c) { return __syncthreads_or(c); });
+            const int sw = p3_hysteresis(S.cand, S.edge, h, ww, tid, nthr, [](int c) { return __syncthreads_or(c); });
             if (tid == 0 && p.stats) stat_add_one(S, 8, (unsigned long long)sw);
             tk4 = timing ? clock64() : 0;
         }
@@ -1049,7 +1070,7 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             p2_nms(P, S.mag[0], S.cand, a_edge, S, M, G.seg_rows_front);
             bar_sync(1, NC);
             TRS_TICK(tk5);
-            const int sw = p3_hysteresis(S.cand, a_edge, plane_words, ww, tid, NC, [NC](int c) { return bar_or(1, NC, c); });
+            const int sw = p3_hysteresis(S.cand, a_edge, h, ww, tid, NC, [NC](int c) { return bar_or(1, NC, c); });
             if (p.stats) {                                               // (the candidate plane is counted before the tail copy lands on it)
                 if (tid == 0) stat_add_one(S, 8, (unsigned long long)sw);
                 count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid, NC);
