@@ -109,11 +109,19 @@ struct FastParams {
     uint32_t stagger_step_ns;        // plus (blockIdx.x % 4) times this: spreads the store bursts of different SMs
     int use_store_warp;              // launch k_preprocess_sw (one extra warp per CTA takes sw_share/256 of the output phase)
     int sw_share;
+    int sw_hyst;                     // store-warp kernel: the store warps run the hysteresis as well
     int dbg_out_alias;               // experiment only (TRS_DBG_OUT_ALIAS): outputs of frame f go to slot f % alias (results invalid)
 };
 
 // ---- small PTX helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// a * b + c kept as a multiply-add (FMA pipe) where the compiler would pick a shift-add on the busier ALU pipe
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 // PTX prmt in its default mode: a selector nibble with bit 3 set replicates the sign bit of the selected byte over the output byte
 __device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel)
@@ -228,6 +236,22 @@ __device__ __forceinline__ uint32_t nibble_of(uint32_t a, uint32_t b)
     return (x | (x >> 16)) & 0xfu;
 }
 
+// Two nibbles from eight 0xff/0x00 bytes in one multiply: a = bytes of pixels 0..3 for plane A, b = the same for plane B.
+// Bits 0, 9, 18, 27 of a and 4, 13, 22, 31 of b survive the masks; times 0x01010101 every surviving bit lands once in the top
+// byte (no two partial products share a position, so no carries): top byte = nibble A | nibble B << 4.
+__device__ __forceinline__ uint32_t nibble_pair_top(uint32_t a, uint32_t b)
+{
+    const uint32_t t = b & 0x80402010u;
+    return ((a & 0x08040201u) | t) * 0x01010101u;
+}
+// even lane: bytes for plane A and plane B from its own top byte and the odd neighbour's (low nibble = own 4 pixels)
+__device__ __forceinline__ void merge_nibble_pairs(uint32_t top_own, uint32_t top_other, uint32_t& byteA, uint32_t& byteB)
+{
+    const uint32_t own = top_own >> 24, oth = top_other >> 24;
+    byteA = bsel(0x0fu, own, oth << 4);
+    byteB = bsel(0x0fu, own >> 4, oth);
+}
+
 // Flood the seed bits along the runs of ones of `c` (seeds must be a subset of c), both directions, O(1).
 __device__ __forceinline__ uint32_t flood_run(uint32_t seeds, uint32_t c)
 {
@@ -323,7 +347,7 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
         uint32_t s2 = 0, T2[2] = {0, 0};
         constexpr bool TT = SatThresholds<NR, F0, F1>::use;
         if (TT) {
-            const uint32_t tl = lds32(a_sdiv + 4 * (v2[half] & 0xffffu)), th = lds32(a_sdiv + 4 * (v2[half] >> 16));
+            const uint32_t tl = lds32(mad_u32(v2[half] & 0xffffu, 4u, a_sdiv)), th = lds32(mad_u32(v2[half] >> 16, 4u, a_sdiv));
             T2[0] = prmt(tl, th, 0x5410); T2[1] = prmt(tl, th, 0x7632);
         } else if (any_s) {
             const uint32_t vlo = v2[half] & 0xffffu, vhi = v2[half] >> 16, dlo = d2[half] & 0xffffu, dhi = d2[half] >> 16;
@@ -443,14 +467,26 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
             const bool row_in = y_row < r1;                      // the loaded row belongs to this segment
             uint32_t okm[NR > 0 ? NR : 1][2];                    // per range: half masks for pixels (0,2) and (1,3)
             hsv_masks_of<NR, F0, F1>(P, A, B, S.sdiv, S.hue, okm);
-            uint32_t v = 0;
+            if (NR == 2) {
+                // pixels 0..3 of a range sit in (okm[r][0].lo, okm[r][1].lo, okm[r][0].hi, okm[r][1].hi)
+                const uint32_t top = nibble_pair_top(prmt(okm[0][0], okm[0][1], 0x6240), prmt(okm[NR - 1][0], okm[NR - 1][1], 0x6240));
+                const uint32_t other = __shfl_down_sync(0xffffffffu, top, 1);
+                if (M.store_lane && row_in) {
+                    uint32_t b0, b1;
+                    merge_nibble_pairs(top, other, b0, b1);
+                    sts8(mp, b0);
+                    sts8(mp + P.g.plane_bytes, b1);
+                }
+            } else {
+                uint32_t v = 0;
 #pragma unroll
-            for (int r = 0; r < NR; ++r) v |= nibble_of(okm[r][0], okm[r][1]) << (8 * r);
-            const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
-            v |= other << 4;
-            if (M.store_lane && row_in) {
+                for (int r = 0; r < NR; ++r) v |= nibble_of(okm[r][0], okm[r][1]) << (8 * r);
+                const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
+                v |= other << 4;
+                if (M.store_lane && row_in) {
 #pragma unroll
-                for (int r = 0; r < NR; ++r) sts8(mp + r * P.g.plane_bytes, v >> (8 * r));
+                    for (int r = 0; r < NR; ++r) sts8(mp + r * P.g.plane_bytes, v >> (8 * r));
+                }
             }
         }
         // ---- Sobel combine for output row y = r0 + k - 2 ----------------------------------------------
@@ -594,16 +630,15 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
             cm[pr] = hgt_mask(C, na) & hge_mask(C, nb) & hgt_mask(C, P.low2);
             sm[pr] = cm[pr] & hgt_mask(C, P.high2);
         }
-        // pixels (0,1) sit in cm[0] halves, (2,3) in cm[1]: nibble bit q = pixel q
-        const uint32_t x = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u);
-        const uint32_t z = (sm[0] & 0x00020001u) | (sm[1] & 0x00080004u);
-        uint32_t v = ((x | (x >> 16)) & 0xfu) | (((z | (z >> 16)) & 0xfu) << 8);
-        const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
-        v |= other << 4;
+        // pixels (0,1) sit in the halves of cm[0], (2,3) in cm[1]: one byte per pixel, then both nibbles by one multiply
+        const uint32_t top = nibble_pair_top(prmt(cm[0], cm[1], 0x6420), prmt(sm[0], sm[1], 0x6420));
+        const uint32_t other = __shfl_down_sync(0xffffffffu, top, 1);
         if (M.store_lane && row_in) {
-            sts8(cp, v);
-            sts8(ep, v >> 8);
-            if (P.k.stats) n_strong += __popc((v >> 8) & 0xffu);
+            uint32_t bc, bs;
+            merge_nibble_pairs(top, other, bc, bs);
+            sts8(cp, bc);
+            sts8(ep, bs);
+            if (P.k.stats) n_strong += __popc(bs & 0xffu);
         }
         cp += prb; ep += prb;
     };
@@ -711,6 +746,7 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&
                         const uint32_t f0 = b0 * fX0, f1 = b1 * fY, f2 = b2 * fZ, f3 = b3 * fX1;
                         fp[30 * k] = make_uint4(f0, f1, f2, f3);
                         // byte 2 of 1.0f is 0x80: its sign bit replicated over a byte is the u8 value
+                        // (three ALU-pipe permutes measured 1.3 % faster end to end than four FMA-pipe multiplies + one permute)
                         if (decltype(has_u8)::value) up[30 * k] = prmt(prmt_sx(f0, f1, 0x00ea), prmt_sx(f2, f3, 0x00ea), 0x5410);
                     } else if (decltype(has_u8)::value) {
                         up[30 * k] = prmt_sx(b0 * qX0 + b1 * qY + b2 * qZ + b3 * qX1, 0, 0xba98);
@@ -1070,14 +1106,16 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             p2_nms(P, S.mag[0], S.cand, a_edge, S, M, G.seg_rows_front);
             bar_sync(1, NC);
             TRS_TICK(tk5);
-            const int sw = p3_hysteresis(S.cand, a_edge, h, ww, tid, NC, [NC](int c) { return bar_or(1, NC, c); });
-            if (p.stats) {                                               // (the candidate plane is counted before the tail copy lands on it)
-                if (tid == 0) stat_add_one(S, 8, (unsigned long long)sw);
-                count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid, NC);
-                bar_sync(1, NC);
+            if (!P.sw_hyst) {
+                const int sw = p3_hysteresis(S.cand, a_edge, h, ww, tid, NC, [NC](int c) { return bar_or(1, NC, c); });
+                if (p.stats) {                                           // (the candidate plane is counted before the tail copy lands on it)
+                    if (tid == 0) stat_add_one(S, 8, (unsigned long long)sw);
+                    count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid, NC);
+                    bar_sync(1, NC);
+                }
+                if (tid == 0 && G.tail_bytes && j + 1 < nfr)             // the candidate plane is dead: fetch the tail it was sitting in
+                    issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, main_bytes, frame_bytes, bar_tail);
             }
-            if (tid == 0 && G.tail_bytes && j + 1 < nfr)                 // the candidate plane is dead: fetch the tail it was sitting in
-                issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, main_bytes, frame_bytes, bar_tail);
 #ifdef TRS_PHASE_TIMERS
             if (timing) {
                 const long long tk6 = clock64();
@@ -1091,7 +1129,7 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
                       share, 256);
             // (no barrier here: the next strip walk writes the other plane set and the magnitude plane only)
         }
-        if (p.stats) {
+        if (p.stats && !P.sw_hyst) {
             bar_sync(1, NC);
             stats_flush(p, S, tid);
         }
@@ -1107,9 +1145,26 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             uint32_t pa[3];
             plane_sources(p, (j & 1) ? S.edge2 : S.edge, S.mask + (j & 1) * mask_set_bytes, G.plane_bytes, pa);
             bar_sync(2, SW_THREADS);
+            if (P.sw_hyst) {
+                // the hysteresis too: the compute warps went on to the next frame right after the NMS
+                const int NS = SW_THREADS - NC;
+                const uint32_t a_edge = (j & 1) ? S.edge2 : S.edge, a_mask = S.mask + (j & 1) * mask_set_bytes;
+                const int sw = p3_hysteresis(S.cand, a_edge, h, ww, tid - NC, NS, [NS](int c) { return bar_or(4, NS, c); });
+                if (p.stats) {
+                    if (tid == NC) stat_add_one(S, 8, (unsigned long long)sw);
+                    count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid - NC, NS);
+                    bar_sync(4, NS);
+                }
+                if (tid == NC && G.tail_bytes && j + 1 < nfr)            // the candidate plane is dead: fetch the tail it was sitting in
+                    issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, main_bytes, frame_bytes, bar_tail);
+            }
             p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid - NC,
                       SW_THREADS - NC, 0, share);
             if (j + 2 < nfr) bar_arrive(3, SW_THREADS);
+        }
+        if (p.stats && P.sw_hyst) {
+            bar_sync(4, SW_THREADS - NC);
+            stats_flush(p, S, tid - NC);
         }
     }
 }
