@@ -49,11 +49,13 @@ struct FastGeom {
     int mask_sets;                   // 2: the colour-mask planes are double-buffered by frame parity (store-warp kernel)
     int plane_bytes;                 // one bit plane incl. a zero row above and below, 16-byte multiple
     int off_pix[2], off_mag[2], off_mask, off_cand, off_edge, off_edge2, off_sdiv, off_hue, off_lut, off_bar, off_red, total;
+    int band_h, n_bands;             // banded kernel: image rows per band (band_h == h: the whole frame is resident)
+    int seg_rows_nms;                // banded kernel: rows per segment of the NMS walk (the strip walk also covers one row above and below)
     int tail_bytes;                  // store-warp layout: the last tail_bytes of the frame arrive by a second, later bulk copy (their
                                      // space holds the candidate plane during NMS + hysteresis); 0 = one copy
 };
 
-__host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, int ws, int front_warps, int back_warps, int mask_sets = 1)
+__host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, int ws, int front_warps, int back_warps, int mask_sets = 1, int band_h = 0)
 {
     FastGeom g;
     g.ws = ws;
@@ -61,14 +63,19 @@ __host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, in
     g.front_warps = front_warps;
     g.back_warps = back_warps;
     const int fsegs = 4 * (front_warps / g.nsg), bsegs = 4 * (back_warps / g.nsg);
-    g.seg_rows_front = (h + fsegs - 1) / fsegs;
+    if (band_h <= 0 || band_h >= h) { band_h = h; g.n_bands = 1; } else { g.n_bands = (h + band_h - 1) / band_h; }
+    g.band_h = band_h;
+    const int mag_rows = g.n_bands == 1 ? h : band_h + 2;              // magnitude rows a band's strip walk produces
+    const int pix_rows = g.n_bands == 1 ? h : band_h + 4;              // pixel rows it reads
+    g.seg_rows_front = (mag_rows + fsegs - 1) / fsegs;
     g.seg_rows_back = (h + bsegs - 1) / bsegs;
+    g.seg_rows_nms = (band_h + fsegs - 1) / fsegs;
     g.threads = 32 * (ws ? front_warps + back_warps : front_warps);
     g.mag_stride = w + 4;
     g.mask_sets = mask_sets;
     g.plane_bytes = (((h + 2) * g.nsg * 4) + 15) & ~15;
-    const int pix = ((h * w * 3 + 15) & ~15) + 16;
-    const int mag = ((((h + 2) * g.mag_stride + 4) * 2) + 15) & ~15;
+    const int pix = ((pix_rows * w * 3 + 15) & ~15) + 16;
+    const int mag = ((((mag_rows + 2) * g.mag_stride + 4) * 2) + 15) & ~15;
     int o = 0;
     for (int b = 0; b < (ws ? 2 : 1); ++b) { g.off_pix[b] = o; o += pix; }
     for (int b = 0; b < (ws ? 2 : 1); ++b) { g.off_mag[b] = o; o += mag; }
@@ -76,7 +83,7 @@ __host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, in
     g.off_mask = o; o += g.plane_bytes * n_ranges * mask_sets;
     g.tail_bytes = 0;
     g.off_edge2 = -1;
-    if (mask_sets == 2 && ((h * w * 3) % 16) == 0 && h * w * 3 > 2 * g.plane_bytes) {
+    if (mask_sets == 2 && g.n_bands == 1 && ((h * w * 3) % 16) == 0 && h * w * 3 > 2 * g.plane_bytes) {
         g.tail_bytes = g.plane_bytes;                                  // a 16-byte multiple
         g.off_cand = g.off_pix[0] + h * w * 3 - g.plane_bytes;
         g.off_edge2 = o; o += g.plane_bytes;
@@ -105,12 +112,9 @@ struct FastParams {
     FastRange fr[3];
     uint32_t low2, high2;            // edge thresholds as packed patterns
     int need_hue;                    // some range has a hue bound that can fail
-    uint32_t stagger_half_ns;        // start delay of the CTAs in the second half of the grid (the second CTA of each SM)
-    uint32_t stagger_step_ns;        // plus (blockIdx.x % 4) times this: spreads the store bursts of different SMs
     int use_store_warp;              // launch k_preprocess_sw (one extra warp per CTA takes sw_share/256 of the output phase)
     int sw_share;
     int sw_hyst;                     // store-warp kernel: the store warps run the hysteresis as well
-    int dbg_out_alias;               // experiment only (TRS_DBG_OUT_ALIAS): outputs of frame f go to slot f % alias (results invalid)
 };
 
 // ---- small PTX helpers --------------------------------------------------------------------------------
@@ -267,14 +271,16 @@ struct StripMap {
     bool ok, store_lane;
 };
 
-__device__ __forceinline__ StripMap strip_map(int group_warp, int lane, int nsg, int seg_rows, int h)
+// rows [row_lo, row_hi) split into segments of seg_rows; lanes whose segment starts past the end idle on row_lo (ok = false)
+__device__ __forceinline__ StripMap strip_map(int group_warp, int lane, int nsg, int seg_rows, int row_hi, int row_lo = 0)
 {
     StripMap m;
     m.strip = 8 * (group_warp % nsg) + (lane & 7);
     const int seg = 4 * (group_warp / nsg) + (lane >> 3);
-    m.r0 = seg * seg_rows;
-    m.r1 = min(h, m.r0 + seg_rows);
-    m.ok = m.r0 < h;
+    m.r0 = row_lo + seg * seg_rows;
+    m.ok = m.r0 < row_hi;
+    if (!m.ok) m.r0 = row_lo;
+    m.r1 = m.ok ? min(row_hi, m.r0 + seg_rows) : m.r0;
     m.store_lane = m.ok && !(lane & 1);          // even lanes store the byte shared with the odd neighbour
     return m;
 }
@@ -413,8 +419,11 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
 template <int NR, bool EDGE, int F0, int F1>
 // tail_bar != 0: the last rows of the frame arrive under a second mbarrier; every thread waits for it at the top of trip `tail_k`
 // (a multiple of 3, before any segment loads such a row)
+// Banded use: a_pix / a_mag are VIRTUAL bases (the address image row 0 / magnitude row -1 would have), the segment rows of M lie in the
+// band's magnitude rows, and colour-mask rows are stored only inside [mask_lo, mask_hi).
 __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pix, uint32_t a_mag, uint32_t a_mask, const SmemMap& S, const StripMap& M,
-                                              int seg_rows, uint32_t tail_bar = 0, uint32_t tail_parity = 0, int tail_k = 0)
+                                              int seg_rows, uint32_t tail_bar = 0, uint32_t tail_parity = 0, int tail_k = 0, int mask_lo = 0,
+                                              int mask_hi = 1 << 30)
 {
     const int h = P.k.h, w = P.k.w;
     const int row_bytes = w * 3, prb = w >> 3, MS2 = P.g.mag_stride * 2, nstrips = w >> 2;
@@ -464,7 +473,7 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
         }
         // ---- colour masks for the loaded row ---------------------------------------------------------
         if (NR > 0 && k >= 1 && k <= seg_rows) {                 // warp-uniform: the halo rows above and below belong to other segments
-            const bool row_in = y_row < r1;                      // the loaded row belongs to this segment
+            const bool row_in = y_row < r1 && y_row >= mask_lo && y_row < mask_hi;      // the loaded row belongs to this segment (and band)
             uint32_t okm[NR > 0 ? NR : 1][2];                    // per range: half masks for pixels (0,2) and (1,3)
             hsv_masks_of<NR, F0, F1>(P, A, B, S.sdiv, S.hue, okm);
             if (NR == 2) {
@@ -606,7 +615,7 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
         r.r23 = prmt(r.p23, mr, 0x5432);
         return r;
     };
-    const int ya = M.ok ? M.r0 : 0;
+    const int ya = M.r0;
     uint32_t cp = cbase + ya * prb, ep = ebase + ya * prb;          // plane bytes of the row being decided
     // rolling three-row window by register renaming (three steps per trip): step k decides row ya + k from rows (up, ce) and loads dn
     auto nms_step = [&](int k, const Row& up, const Row& ce, Row& dn) {
@@ -951,20 +960,6 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
     if (tid == 0) { mbar_init(S.bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
     if (tid == 0 && (int)blockIdx.x < p.n) issue_frame_load(S.pix[0], p.in + (size_t)blockIdx.x * frame_bytes, frame_bytes, S.bar);
-    // De-phase the CTAs: left alone, all CTAs of the grid (and the two of an SM in particular) run their phases in lockstep, so the
-    // ALU-bound strip walks collide with each other and so do the store-bound output phases.
-    if (P.stagger_half_ns | P.stagger_step_ns) {
-        const uint32_t delay = (blockIdx.x >= (gridDim.x + 1) / 2 ? P.stagger_half_ns : 0u) + (blockIdx.x & 3u) * P.stagger_step_ns;
-        if (delay) {
-            unsigned long long t0, t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            do {
-                __nanosleep(500);
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            } while (t - t0 < delay);
-        }
-    }
-
     uint32_t phase = 0;
     uint32_t pa[3];
     plane_sources(p, S.edge, S.mask, G.plane_bytes, pa);
@@ -997,8 +992,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
             if (tid == 0 && p.stats) stat_add_one(S, 8, (unsigned long long)sw);
             tk4 = timing ? clock64() : 0;
         }
-        const size_t fo = P.dbg_out_alias ? (size_t)(f % P.dbg_out_alias) : (size_t)f;
-        p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + fo * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + fo * frame_bytes : nullptr,
+        p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr,
                   tid, nthr);
         if (p.stats) count_planes<NR, EDGE>(p, S, S.cand, S.edge, S.mask, G.plane_bytes, plane_words, tid, nthr);
         __syncthreads();
@@ -1014,6 +1008,83 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
         for (int k = 0; k < 6; ++k) atomicAdd(&p.stats[10 + k], (unsigned long long)tm[k]);
     }
     if (p.stats) stats_flush(p, S, tid);          // (the frame loop ends with a CTA-wide barrier)
+}
+
+// =========================================================================================================
+// Banded kernel: frames too large to be resident (240x320: 230 KB) go through the same phases band by band.  Per band of
+// band_h rows: one bulk copy of the band's pixel rows plus a two-row halo, the strip walk over the band's magnitude rows
+// (one extra row above and below, recomputed instead of kept), NMS for the band's rows into the FULL-FRAME candidate /
+// edge planes (colour masks likewise); the next band's copy is issued as soon as the strip walk is done.  After the last
+// band: hysteresis and output over the whole frame from the bit planes.  Every output channel must be a bit plane and the
+// brightness / contrast table the identity (the pixels are gone by the time the output is written).
+// =========================================================================================================
+template <int NR, bool EDGE, int F0, int F1>
+__global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const __grid_constant__ FastParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const PreKParams& p = P.k;
+    const FastGeom& G = P.g;
+    uint32_t sb = smem_u32(smem);
+    asm volatile("" : "+r"(sb));
+    const SmemMap S = smem_map(sb, G);
+    const int h = p.h, w = p.w, ww = G.nsg;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t row_bytes = (uint32_t)w * 3, frame_bytes = (uint32_t)h * row_bytes;
+    const int plane_words = h * ww;
+    const int BH = G.band_h, NB = G.n_bands, MS = G.mag_stride;
+
+    init_tables<NR, F0, F1>(p, S, tid, nthr);
+    stats_zero(S, tid);
+    if (EDGE) {
+        zero_mag_borders(S.mag[0], BH + 2, w, MS, tid, nthr);
+        zero_plane_pads(S, plane_words, ww, tid, nthr);
+    }
+    if (tid == 0) { mbar_init(S.bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    // pixel rows of band b: [max(b BH - 2, 0), min((b + 1) BH + 2, h))
+    auto issue_band = [&](size_t f, int b) {
+        const int p0 = max(b * BH - 2, 0), p1 = min(min((b + 1) * BH, h) + 2, h);
+        issue_frame_load(S.pix[0], p.in + f * frame_bytes + (size_t)p0 * row_bytes, (uint32_t)(p1 - p0) * row_bytes, S.bar);
+    };
+    if (tid == 0 && (int)blockIdx.x < p.n) issue_band(blockIdx.x, 0);
+
+    uint32_t phase = 0;
+    uint32_t pa[3];
+    plane_sources(p, S.edge, S.mask, G.plane_bytes, pa);
+    for (int f = blockIdx.x; f < p.n; f += gridDim.x) {
+        for (int b = 0; b < NB; ++b) {
+            const int by0 = b * BH, by1 = min(by0 + BH, h);
+            const int m0 = EDGE ? max(by0 - 1, 0) : by0, m1 = EDGE ? min(by1 + 1, h) : by1;      // magnitude rows of this band
+            const int p0 = max(by0 - 2, 0);
+            const uint32_t a_pix = S.pix[0] - (uint32_t)p0 * row_bytes;                            // virtual address of image row 0
+            const uint32_t a_mag = S.mag[0] - (uint32_t)(m0 * MS * 2);                            // virtual address of magnitude row -1
+            mbar_wait(S.bar, phase);
+            phase ^= 1u;
+            if (EDGE && m1 == h) {                                  // the zero row below the frame: earlier bands left data there
+                for (int i = tid; i < MS; i += nthr) sts16(a_mag + 2 * ((h + 1) * MS + i), 0);
+            }
+            const StripMap M1 = strip_map(warp, lane, ww, G.seg_rows_front, m1, m0);
+            p1_strip_walk<NR, EDGE, F0, F1>(P, a_pix, a_mag, S.mask, S, M1, G.seg_rows_front, 0u, 0u, 0, by0, by1);
+            __syncthreads();
+            if (tid == 0) {                                         // pixels are dead: fetch the next band (of this or the next frame)
+                if (b + 1 < NB) issue_band(f, b + 1);
+                else if (f + (int)gridDim.x < p.n) issue_band((size_t)f + gridDim.x, 0);
+            }
+            if (EDGE) {
+                const StripMap M2 = strip_map(warp, lane, ww, G.seg_rows_nms, by1, by0);
+                p2_nms(P, a_mag, S.cand, S.edge, S, M2, G.seg_rows_nms);
+                __syncthreads();
+            }
+        }
+        if (EDGE) {
+            const int sw = p3_hysteresis(S.cand, S.edge, h, ww, tid, nthr, [](int c) { return __syncthreads_or(c); });
+            if (tid == 0 && p.stats) stat_add_one(S, 8, (unsigned long long)sw);
+        }
+        p4_output(P, pa, 0u, p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr, tid, nthr);
+        if (p.stats) count_planes<NR, EDGE>(p, S, S.cand, S.edge, S.mask, G.plane_bytes, plane_words, tid, nthr);
+        __syncthreads();
+    }
+    if (p.stats) stats_flush(p, S, tid);
 }
 
 // =========================================================================================================

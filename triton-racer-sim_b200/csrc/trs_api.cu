@@ -194,6 +194,12 @@ int launch_fast_tf(const trs::FastParams& fp, int grid, cudaStream_t st)
         trs::k_preprocess_sw<NR, F0, F1><<<grid, trs::SW_THREADS, fp.g.total, st>>>(fp);
         return 0;
     }
+    if (fp.g.n_bands > 1) {
+        cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_banded<NR, EDGE, F0, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(banded)");
+        trs::k_preprocess_banded<NR, EDGE, F0, F1><<<grid, fp.g.threads, fp.g.total, st>>>(fp);
+        return 0;
+    }
     cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_fast<NR, EDGE, F0, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fast)");
     trs::k_preprocess_fast<NR, EDGE, F0, F1><<<grid, fp.g.threads, fp.g.total, st>>>(fp);
@@ -221,15 +227,25 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     trs::FastParams fp;
     memset(&fp, 0, sizeof fp);
     fp.k = k;
-    bool planned = false;
-    if (!planned) {
-        // resident kernel: one frame per CTA, two CTAs per SM
+    {
+        // resident kernel: one frame per CTA, two CTAs per SM; frames that do not fit whole go band by band (k_preprocess_banded) when
+        // nothing of the pixels is needed after the strip walk
         const int max_warps = trs::FAST_MAX_THREADS / 32;
         if (nsg > max_warps) return 0;
         const int quads = max_warps / nsg;
-        const trs::FastGeom g = trs::fast_geometry(h, w, k.n_ranges, 0, nsg * quads, nsg * quads);
         const int budget2 = (ctx->smem_optin + 1024) / 2 - 1024;
-        if (g.total > budget2 || g.threads > trs::FAST_MAX_THREADS) return 0;
+        trs::FastGeom g = trs::fast_geometry(h, w, k.n_ranges, 0, nsg * quads, nsg * quads);
+        if (g.threads > trs::FAST_MAX_THREADS) return 0;
+        if (g.total > budget2) {
+            if (k.need_pixels || k.dynamic || !k.lut_identity || getenv("TRS_NO_BANDED")) return 0;
+            bool found = false;
+            for (int nb = 2; nb <= h / 4 && !found; ++nb) {
+                const int bh = (h + nb - 1) / nb;
+                g = trs::fast_geometry(h, w, k.n_ranges, 0, nsg * quads, nsg * quads, 1, bh);
+                found = g.n_bands > 1 && g.total <= budget2;
+            }
+            if (!found) return 0;
+        }
         fp.g = g;
     }
     // integer bounds -> fp16-subnormal bit patterns for the packed compares (values live in [0, 2047];
@@ -254,7 +270,7 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     // store-warp variant (k_preprocess_sw): edge filter on, every output channel a bit plane, ten compute warps, and the
     // double-buffered mask planes still fit two CTAs per SM
     fp.use_store_warp = 0;
-    if (!fp.g.ws && k.edge_enabled && !k.need_pixels && fp.g.threads == trs::SW_COMPUTE_THREADS && !getenv("TRS_NO_STORE_WARP")) {
+    if (fp.g.n_bands == 1 && k.edge_enabled && !k.need_pixels && fp.g.threads == trs::SW_COMPUTE_THREADS && !getenv("TRS_NO_STORE_WARP")) {
         const trs::FastGeom g2 = trs::fast_geometry(h, w, k.n_ranges, 0, fp.g.front_warps, fp.g.back_warps, 2);
         const int budget2 = (ctx->smem_optin + 1024) / 2 - 1024;
         if (g2.total <= budget2) {
@@ -265,9 +281,6 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
             if (const char* e = getenv("TRS_SW_SHARE")) fp.sw_share = atoi(e) < 0 ? 0 : (atoi(e) > 256 ? 256 : atoi(e));
         }
     }
-    if (const char* e = getenv("TRS_STAGGER_HALF_NS")) fp.stagger_half_ns = (uint32_t)atoi(e);
-    if (const char* e = getenv("TRS_STAGGER_STEP_NS")) fp.stagger_step_ns = (uint32_t)atoi(e);
-    if (const char* e = getenv("TRS_DBG_OUT_ALIAS")) fp.dbg_out_alias = atoi(e);
     fp.low2 = pat(k.low);
     fp.high2 = pat(k.high);
     int grid = ctx->sm_count * 2;
