@@ -30,6 +30,14 @@ WORKLOADS = {
     "full_house_mask_240x320": (240, 320, 16384, True, False, 230400 + 230400),
 }
 METRIC = "preprocessed frames/sec (120x160), full observation chain"
+METRICS = {"full_chain_120x160": METRIC, "full_house_mask_240x320": "preprocessed frames/sec (240x320), full-house colour + edge mask"}
+KERNELS = {"full_chain_120x160": "trs::k_preprocess_sw<2,24,23>", "full_house_mask_240x320": "trs::k_preprocess_banded<2,true,24,23>"}
+NOTES = {
+    "full_chain_120x160": "bound by the ALU pipe / issue slots and phase barriers, not by HBM: ten compute warps per CTA run strip walk, NMS and "
+                          "hysteresis while two store warps stream the previous frame out (the SM -> L2 write port tops out at 29 B/clk); "
+                          "see DESIGN.md 4.1 and profiles/",
+    "full_house_mask_240x320": "6 algorithmic bytes per pixel: instruction bound by construction (SURVEY.md 8d); banded kernel, DESIGN.md 4.3",
+}
 
 
 def read_peaks():
@@ -42,7 +50,8 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock + throttle reasons sampled every ~5 ms through NVML (nvidia_ml_py) on a background thread while the timed region runs;
+    falls back to `nvidia-smi -lms` when NVML cannot be loaded."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -50,8 +59,40 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.stop_flag = False
+        self.samples = []          # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((float(mhz), int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import threading
+
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].strip().isdigit() else self.gpu
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.nv = nv
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
             os.close(fd)
@@ -62,6 +103,23 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            sm = sorted(m for m, _ in self.samples)
+            mask = 0
+            for _, r in self.samples:
+                mask |= r
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["samples"] = len(sm)
+            out["sm_max_mhz"] = self.max_mhz
+            out["reasons"] = sorted(k for k, bit in names.items() if mask & bit)
+            out["source"] = "nvml, 5 ms period"
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -91,6 +149,7 @@ class ClockSampler:
             out["sm_mhz"] = sm[len(sm) // 2]
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
+        out["source"] = "nvidia-smi -lms 200"
         return out
 
 
@@ -145,12 +204,12 @@ def other_workloads(torch, dev, local, pool120, h, w):
     t = timed(lambda: cam.normalise_device(src240), reps=10)
     out["resize2x_normalise_4096"] = {"frames_per_s": 4096 / t, "GBps_algorithmic": 4096 * 288000 / t / 1e9}
     cam.onShutdown()
-    # configs[2]: full-house colour + edge mask at 240x320 (u8 -> u8): 460,800 algorithmic bytes per frame; generic banded kernel today
+    # configs[2]: full-house colour + edge mask at 240x320 (u8 -> u8): 460,800 algorithmic bytes per frame; banded kernel
     fh = ImgPreprocessing(full_house_config(), device=local)
     o240 = torch.empty_like(src240)
     t = timed(lambda: fh.process_device(src240, out_u8=o240, want_f32=False), reps=3, warm=1)
     out["full_house_mask_240x320"] = {"frames_per_s": 4096 / t, "GBps": 4096 * 460800 / t / 1e9, "hbm_frac": 4096 * 460800 / t / 1e9 / peak,
-                                       "note": "generic banded kernel (frame does not fit the frame-resident fast path yet)"}
+                                       "note": "banded kernel (k_preprocess_banded): 6 B per pixel, instruction bound"}
     fh.onShutdown()
     del src240, o240, pool240
     # configs[3]: nearest waypoint + speed control for 1M car states (FP64-ALU bound, 76 B of HBM traffic per state)
@@ -192,7 +251,7 @@ def run_reference(args):
             ms.append(res["slowest_worker_s"] * 1e3)
     value = sum(vals) / len(vals)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRICS[args.workload], "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": args.workload, "frames_per_step": res["units"], "threads": res["cores"]},
@@ -325,7 +384,7 @@ def main():
         except Exception:
             pass
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRICS[args.workload], "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {frames} frames/GPU/step of {h}x{w}x3 u8 -> "
@@ -334,8 +393,8 @@ def main():
                        "frames_per_gpu": frames, "h": h, "w": w, "sharding": f"env index, contiguous, {world} rank(s), no data-path collective",
                        "l2": f"inputs {frames * h * w * 3 / 1e9:.2f} GB + outputs per step, far larger than the 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "bytes_per_frame": bytes_per_frame, "kernel": "trs::k_preprocess_fast<2,true,24,23>",
-                         "note": "instruction-issue bound, not HBM bound: see DESIGN.md 4.1 and profiles/"},
+                         "peak_source": peak_src, "bytes_per_frame": bytes_per_frame, "kernel": KERNELS[args.workload],
+                         "note": NOTES[args.workload]},
             "clocks": clocks, "gpu_launches": int(launches),
             "stats_sample": dict(zip(nat.STAT_NAMES[:10], st.tolist()[:10])),
         }

@@ -180,7 +180,8 @@ def test_normalise_and_crop_resize():
     assert np.array_equal(u8.cpu().numpy(), u8_want) and np.array_equal(f32.cpu().numpy(), f32_want)
     assert np.array_equal(u8_want, frames[:, ::2, ::2])
     cam.onShutdown()
-    for roi, out_hw in (((40, 119, 0, 320), None), ((10, 230, 17, 301), (77, 131)), ((0, 240, 0, 320), (300, 333))):
+    for roi, out_hw in (((40, 119, 0, 320), None), ((10, 230, 17, 301), (77, 131)), ((0, 240, 0, 320), (300, 333)), ((3, 200, 8, 311), (300, 332)),
+                        ((0, 240, 0, 320), (60, 80))):
         comp = FrameNormalise(device=0, roi=roi, out_hw=out_hw)
         ho, wo = out_hw if out_hw else (roi[1] - roi[0], roi[3] - roi[2])
         u8_want, f32_want = oracle.crop_resize(frames, roi, (ho, wo))

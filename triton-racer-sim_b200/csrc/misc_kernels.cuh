@@ -95,6 +95,46 @@ __global__ void __launch_bounds__(256) k_crop_resize(const __grid_constant__ Res
     }
 }
 
+// K1c: the same, one output WORD per thread (output rows a multiple of 4 bytes, outputs 16-byte aligned): the source
+// column / row of every output pixel comes from two small shared-memory tables built once per CTA (no division per
+// pixel), a thread gathers the 4 source bytes of its word (L1-resident sectors) and writes one 16-byte f32 chunk and one
+// 4-byte u8 word, so a warp's stores are 512 / 128 contiguous bytes.  A CTA walks whole output rows.
+enum { RESIZE_THREADS = 128, RESIZE_MAX_TAB = 8192 };
+
+__global__ void __launch_bounds__(RESIZE_THREADS) k_crop_resize_words(const __grid_constant__ ResizeParams p)
+{
+    extern __shared__ int s_tab[];                 // [w_out] source byte offset of column x, then [h_out] source row of row y
+    int* s_sx = s_tab;
+    int* s_sy = s_tab + p.w_out;
+    for (int x = threadIdx.x; x < p.w_out; x += blockDim.x) s_sx[x] = 3 * (p.x0 + (int)(((long long)x * p.ws) / p.w_out));
+    for (int y = threadIdx.x; y < p.h_out; y += blockDim.x) s_sy[y] = p.y0 + (int)(((long long)y * p.hs) / p.h_out);
+    __syncthreads();
+    const int wpr = (p.w_out * 3) >> 2;            // output words per row
+    const size_t rows = (size_t)p.n * p.h_out;
+    const size_t src_row_bytes = (size_t)p.w_in * 3;
+    const float rcp = 1.0f / 255.0f;
+    for (size_t R = blockIdx.x; R < rows; R += gridDim.x) {
+        const size_t f = R / p.h_out;
+        const int y = (int)(R - f * p.h_out);
+        const uint8_t* __restrict__ src = p.in + (f * p.h_in + s_sy[y]) * src_row_bytes;
+        for (int c = threadIdx.x; c < wpr; c += blockDim.x) {
+            uint32_t word = 0;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = 4 * c + j, px = o / 3, ch = o - 3 * px;
+                const uint32_t b = __ldg(src + s_sx[px] + ch);
+                word |= b << (8 * j);
+                const float xf = __fsub_rn(__uint_as_float(0x4B000000u | b), 8388608.0f);
+                const float q0 = __fmul_rn(xf, rcp);
+                v[j] = __fmaf_rn(__fmaf_rn(-q0, 255.0f, xf), rcp, q0);          // correctly rounded x / 255 (see norm255_fast)
+            }
+            if (p.out_f32) stg_stream(reinterpret_cast<float4*>(p.out_f32) + R * wpr + c, make_float4(v[0], v[1], v[2], v[3]));
+            if (p.out_u8) reinterpret_cast<uint32_t*>(p.out_u8)[R * wpr + c] = word;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // K6: nearest waypoint, L1 distance in float64, first index wins ties, running minimum starts at 100
 // (track_data_process.py:89-107).  The centre line sits in shared memory as (x,y,z,pad) f64 quads; every lane

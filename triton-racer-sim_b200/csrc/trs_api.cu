@@ -463,6 +463,15 @@ int trs_normalise(trs_ctx* ctx, const uint8_t* in_dev, int n, int h_in, int w_in
         return 0;
     }
     trs::ResizeParams p{in_dev, out_f32_dev, out_u8_dev, n, h_in, w_in, roi_y0, roi_x0, roi_y1 - roi_y0, roi_x1 - roi_x0, h_out, w_out};
+    if ((w_out * 3) % 4 == 0 && w_out + h_out <= trs::RESIZE_MAX_TAB && (!out_f32_dev || ((uintptr_t)out_f32_dev & 15) == 0) &&
+        (!out_u8_dev || ((uintptr_t)out_u8_dev & 3) == 0) && !getenv("TRS_RESIZE_SCALAR")) {
+        const size_t rows = (size_t)n * h_out;
+        const size_t cap = (size_t)ctx->sm_count * 16;
+        trs::k_crop_resize_words<<<(int)(rows < cap ? rows : cap), trs::RESIZE_THREADS, sizeof(int) * (size_t)(w_out + h_out), st>>>(p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CU(cudaGetLastError());
+        return 0;
+    }
     const size_t px = total / 3;
     size_t want = (px + 255) / 256;
     const size_t cap = (size_t)ctx->sm_count * 16;
