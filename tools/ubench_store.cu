@@ -169,7 +169,7 @@ int main()
     const int sms = p.multiProcessorCount;
     const int FR = 64;                                   // frames per CTA
     uint8_t *f32out, *u8out; unsigned long long* cyc;
-    cudaMalloc(&f32out, (size_t)sms * 2 * FR * 288000);     // (the bulk-store probe writes 288,000 B per slot) cudaMalloc(&u8out, (size_t)sms * 2 * FR * 57600); cudaMalloc(&cyc, 8 * sms * 2);
+    cudaMalloc(&f32out, (size_t)sms * 2 * FR * 288000 /* the bulk-store probe writes 288,000 B per slot */); cudaMalloc(&u8out, (size_t)sms * 2 * FR * 57600); cudaMalloc(&cyc, 8 * sms * 2);
     printf("device %s, %d SMs\n", p.name, sms);
     run<128, true>("STG.128 x30 + STG.32 x30 (P4 pattern)", sms, 2, 320, FR, FR, f32out, u8out, cyc);
     run<128, true>("STG.128 x30 + STG.32 x30 (P4 pattern)", sms, 2, 320, FR, 1, f32out, u8out, cyc);
