@@ -76,14 +76,14 @@ enum {
     TRS_STAT_CAND = 7,       /* NMS survivors above the low threshold              */
     TRS_STAT_HYST_SWEEPS = 8,/* hysteresis sweeps summed over frames               */
     TRS_STAT_ROI_SUM = 9,    /* sum of all ROI bytes (brightness statistic)        */
-    /* cycle accounting of the warp-specialised kernel (SM clocks, summed over CTAs; one sampling warp per role) */
-    TRS_STAT_T_FRONT_WAIT_FRAME = 10, /* front group: waiting for the TMA frame load           */
-    TRS_STAT_T_FRONT_WAIT_BACK = 11,  /* front group: waiting for the back group to free a buffer */
-    TRS_STAT_T_FRONT_WORK = 12,       /* front group: Sobel strip walk                          */
-    TRS_STAT_T_BACK_WAIT = 13,        /* back group: waiting for frame / magnitude plane        */
-    TRS_STAT_T_BACK_MASKS = 14,       /* back group: HSV colour masks                           */
-    TRS_STAT_T_BACK_EDGE = 15,        /* back group: NMS + hysteresis                           */
-    TRS_STAT_T_BACK_OUT = 16,         /* back group: merge + stores                             */
+    /* cycle accounting of thread 0 of every CTA (SM clocks, summed over CTAs) — only in builds with -DTRS_PHASE_TIMERS
+       (tools/phase_timing.py); the meaning of slots 12..14 depends on the kernel (see preproc_fast.cuh) */
+    TRS_STAT_T_WAIT_FRAME = 10,       /* waiting for the TMA frame load                         */
+    TRS_STAT_T_STRIP_WALK = 11,       /* P1: Sobel strip walk + colour masks                    */
+    TRS_STAT_T_PHASE_A = 12,          /* resident kernel: NMS           | store-warp kernel: waiting for the store warps */
+    TRS_STAT_T_PHASE_B = 13,          /* resident kernel: hysteresis    | store-warp kernel: NMS                         */
+    TRS_STAT_T_PHASE_C = 14,          /* resident kernel: output        | store-warp kernel: hysteresis                  */
+    TRS_STAT_T_TOTAL = 15,            /* whole frame loop                                        */
     TRS_STAT_COUNT = 24
 };
 

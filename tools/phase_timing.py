@@ -14,5 +14,5 @@ comp.process_device(batch, out_u8=out_u8, out_f32=out_f32, want_f32=want_f32)
 st = comp.stats()
 names = (['wait_frame', 'p1_strip_walk', 'p2_nms', 'p3_hysteresis', 'p4_output', 'total'] if os.environ.get('TRS_NO_STORE_WARP') else
          ['wait_frame', 'p1_strip_walk', 'wait_store_warps', 'p2_nms', 'p3_hysteresis', 'total'])
-keys = ["t_front_wait_frame", "t_front_wait_back", "t_front_work", "t_back_wait", "t_back_masks", "t_back_edge"]
+keys = ["t_wait_frame", "t_strip_walk", "t_phase_a", "t_phase_b", "t_phase_c", "t_total"]
 print({nm: round(st[k] / st['frames']) for nm, k in zip(names, keys)}, 'cycles per frame per CTA; sweeps/frame', st['hyst_sweeps'] / st['frames'])

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("TRS_B200_LIB") or os.path.join(HERE, "libtrs_b200.so"
 MAX_HSV = 4
 STAT_COUNT = 24
 STAT_NAMES = ["frames", "mask0", "mask1", "mask2", "mask3", "edge", "strong", "cand", "hyst_sweeps", "roi_sum",
-              "t_front_wait_frame", "t_front_wait_back", "t_front_work", "t_back_wait", "t_back_masks", "t_back_edge", "t_back_out"]
+              "t_wait_frame", "t_strip_walk", "t_phase_a", "t_phase_b", "t_phase_c", "t_total"]
 
 # every symbol include/trs_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
