@@ -112,9 +112,7 @@ struct FastParams {
     FastRange fr[3];
     uint32_t low2, high2;            // edge thresholds as packed patterns
     int need_hue;                    // some range has a hue bound that can fail
-    int use_store_warp;              // launch k_preprocess_sw (one extra warp per CTA takes sw_share/256 of the output phase)
-    int sw_share;
-    int sw_hyst;                     // store-warp kernel: the store warps run the hysteresis as well
+    int use_store_warp;              // launch k_preprocess_sw (two extra warps per CTA own the output phase)
 };
 
 // ---- small PTX helpers --------------------------------------------------------------------------------
@@ -712,10 +710,8 @@ __device__ __forceinline__ int p3_hysteresis(uint32_t a_cand, uint32_t a_edge, i
 // P4: merge + normalise, written once.  pa[c] = shared address of the bit plane (row 0) feeding output channel c,
 // or 0 if that channel keeps the adjusted pixel.
 // =========================================================================================================
-// The all-planes case can be split between thread groups: `part_lo / part_hi` (in 1/256ths of the frame's warp-iterations) select
-// the share this group (threads t0 of tstride) writes; 0 / 256 = the whole frame.
 __device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&pa)[3], uint32_t a_pix, uint8_t* __restrict__ gout,
-                                          float* __restrict__ gf32, int t0, int tstride, int part_lo = 0, int part_hi = 256)
+                                          float* __restrict__ gf32, int t0, int tstride)
 {
     const int npb = P.k.h * (P.k.w >> 3);              // groups of 8 pixels = plane bytes
     if (!P.k.need_pixels) {
@@ -741,9 +737,8 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&
         if (lane < 30) {
             const int nfull = npb / 5;                       // warp-iterations whose five groups all exist
             const int nwi = (npb + 4) / 5;
-            const int r0 = (nwi * part_lo) >> 8, r1 = (nwi * part_hi) >> 8;
-            const int per = (r1 - r0 + nw - 1) / nw;
-            const int w0 = min(r1, r0 + gw * per), w1 = min(r1, w0 + per), wf = min(nfull, w1);
+            const int per = (nwi + nw - 1) / nw;
+            const int w0 = min(nwi, gw * per), w1 = min(nwi, w0 + per), wf = min(nfull, w1);
             auto emit = [&](auto has_f32, auto has_u8) {
                 uint32_t ax = paX + 5 * w0 + gl, ay = paY + 5 * w0 + gl, az = paZ + 5 * w0 + gl;
                 uint4* fp = reinterpret_cast<uint4*>(gf32) + 30 * w0 + lane;
@@ -1088,19 +1083,19 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const
 }
 
 // =========================================================================================================
-// Store-warp kernel: the resident kernel plus ONE extra warp per CTA that takes most of the output phase off the
-// compute warps' critical path.
+// Store-warp kernel: the resident kernel plus TWO extra warps per CTA that own the output phase.
 //
 // Why: the SM -> L2 write port sustains ~29 B/clk (tools/ubench_store.cu: any store flavour, any number of SMs), so the
 // 288,000 output bytes of a frame occupy it for ~10 k cycles.  With the output phase run by all warps the CTA sits in
-// it for 13.6 k of its 56 k cycles per frame with almost nothing to issue.  Here the store warp writes the first
-// `sw_share`/256 of frame j while the ten compute warps write the rest and then go straight on to the strip walk of
-// frame j + 1.  What makes that legal without a second copy of every plane:
-//   * the colour-mask planes (written by the strip walk, P1) are double-buffered by frame parity (+4.9 KB);
-//   * the candidate / edge planes are first written by the NMS (P2), one whole strip walk later: the compute warps wait
-//     for the store warp's "done with frame j" (named barrier 3) only before P2 of frame j + 1.
-// Hand-over: named barrier 2 = "planes of frame j are final" (compute warps arrive, store warp syncs).  Compute-only
-// phases use named barrier 1.
+// it for 13.6 k of its 56 k cycles per frame with almost nothing to issue.  Here the ten compute warps hand the finished
+// planes of frame j to the store warps and start frame j + 1 at once.  What makes that legal:
+//   * the colour-mask planes (written by the strip walk, P1) and the edge plane (written by the NMS, P2, grown by the
+//     hysteresis, P3) are double-buffered by frame parity, so the store warps have a whole frame time;
+//   * the shared memory for the second edge plane comes from the candidate plane, which only lives from P2 to P3 and sits
+//     on the last 2.4 KB of the frame buffer: those bytes of the next frame arrive by a second, later bulk copy.
+// Hand-over: named barrier 2 = "planes of frame j are final" (compute warps arrive, store warps sync),
+//            named barrier 3 = "done with frame j's planes" (store warps arrive, compute warps sync before P1 of frame j + 2).
+// Compute-only phases use named barrier 1.
 // =========================================================================================================
 enum { SW_COMPUTE_THREADS = 320, SW_THREADS = 384, SW_MAXREG = 80 };      // register allocation rounds a CTA up to a multiple of 4 warps
 
@@ -1123,7 +1118,6 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
     const int NC = SW_COMPUTE_THREADS;
     const int nfr = (int)blockIdx.x < p.n ? (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t mask_set_bytes = (uint32_t)(NR * G.plane_bytes);
-    const int share = P.sw_share;
     const uint32_t main_bytes = frame_bytes - (uint32_t)G.tail_bytes;
     const uint32_t bar_main = S.bar, bar_tail = S.bar + 8;
 
@@ -1177,30 +1171,24 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             p2_nms(P, S.mag[0], S.cand, a_edge, S, M, G.seg_rows_front);
             bar_sync(1, NC);
             TRS_TICK(tk5);
-            if (!P.sw_hyst) {
-                const int sw = p3_hysteresis(S.cand, a_edge, h, ww, tid, NC, [NC](int c) { return bar_or(1, NC, c); });
-                if (p.stats) {                                           // (the candidate plane is counted before the tail copy lands on it)
-                    if (tid == 0) stat_add_one(S, 8, (unsigned long long)sw);
-                    count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid, NC);
-                    bar_sync(1, NC);
-                }
-                if (tid == 0 && G.tail_bytes && j + 1 < nfr)             // the candidate plane is dead: fetch the tail it was sitting in
-                    issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, main_bytes, frame_bytes, bar_tail);
+            const int sw = p3_hysteresis(S.cand, a_edge, h, ww, tid, NC, [NC](int c) { return bar_or(1, NC, c); });
+            if (p.stats) {                                               // (the candidate plane is counted before the tail copy lands on it)
+                if (tid == 0) stat_add_one(S, 8, (unsigned long long)sw);
+                count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid, NC);
+                bar_sync(1, NC);
             }
+            if (tid == 0 && G.tail_bytes && j + 1 < nfr)                 // the candidate plane is dead: fetch the tail it was sitting in
+                issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, main_bytes, frame_bytes, bar_tail);
 #ifdef TRS_PHASE_TIMERS
             if (timing) {
                 const long long tk6 = clock64();
                 tm[0] += tk1 - tk0; tm[1] += tk4 - tk3; tm[2] += tk3 - tk2; tm[3] += tk5 - tk4; tm[4] += tk6 - tk5; tm[5] += tk6 - tk0;
             }
 #endif
-            bar_arrive(2, SW_THREADS);                                   // planes of frame j are final
-            uint32_t pa[3];
-            plane_sources(p, a_edge, a_mask, G.plane_bytes, pa);
-            p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid, NC,
-                      share, 256);
+            bar_arrive(2, SW_THREADS);                                   // planes of frame j are final: the store warps take them from here
             // (no barrier here: the next strip walk writes the other plane set and the magnitude plane only)
         }
-        if (p.stats && !P.sw_hyst) {
+        if (p.stats) {
             bar_sync(1, NC);
             stats_flush(p, S, tid);
         }
@@ -1216,26 +1204,9 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             uint32_t pa[3];
             plane_sources(p, (j & 1) ? S.edge2 : S.edge, S.mask + (j & 1) * mask_set_bytes, G.plane_bytes, pa);
             bar_sync(2, SW_THREADS);
-            if (P.sw_hyst) {
-                // the hysteresis too: the compute warps went on to the next frame right after the NMS
-                const int NS = SW_THREADS - NC;
-                const uint32_t a_edge = (j & 1) ? S.edge2 : S.edge, a_mask = S.mask + (j & 1) * mask_set_bytes;
-                const int sw = p3_hysteresis(S.cand, a_edge, h, ww, tid - NC, NS, [NS](int c) { return bar_or(4, NS, c); });
-                if (p.stats) {
-                    if (tid == NC) stat_add_one(S, 8, (unsigned long long)sw);
-                    count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid - NC, NS);
-                    bar_sync(4, NS);
-                }
-                if (tid == NC && G.tail_bytes && j + 1 < nfr)            // the candidate plane is dead: fetch the tail it was sitting in
-                    issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, main_bytes, frame_bytes, bar_tail);
-            }
             p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid - NC,
-                      SW_THREADS - NC, 0, share);
+                      SW_THREADS - NC);
             if (j + 2 < nfr) bar_arrive(3, SW_THREADS);
-        }
-        if (p.stats && P.sw_hyst) {
-            bar_sync(4, SW_THREADS - NC);
-            stats_flush(p, S, tid - NC);
         }
     }
 }

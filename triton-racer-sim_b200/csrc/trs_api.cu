@@ -276,9 +276,6 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
         if (g2.total <= budget2) {
             fp.g = g2;
             fp.use_store_warp = 1;
-            fp.sw_share = 256;                                           // measured best: the store warps write the whole frame
-            fp.sw_hyst = getenv("TRS_SW_HYST") ? atoi(getenv("TRS_SW_HYST")) : 0;
-            if (const char* e = getenv("TRS_SW_SHARE")) fp.sw_share = atoi(e) < 0 ? 0 : (atoi(e) > 256 ? 256 : atoi(e));
         }
     }
     fp.low2 = pat(k.low);
