@@ -666,41 +666,47 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
 // Two-level schedule: a warp owns a band of rows and relaxes it to a local fixed point with warp-level synchronisation only
 // (no CTA barrier, no waiting for other warps); one CTA-wide OR per round then tells whether any band changed, i.e. whether
 // growth may still cross a band boundary.  The fixed point is unique, so the schedule does not affect the result.
-template <class OrReduce>
-__device__ __forceinline__ int p3_hysteresis(uint32_t a_cand, uint32_t a_edge, int h, int ww, int t0, int tstride, OrReduce group_or)
+// one warp relaxes its band of rows to a local fixed point; returns whether anything changed
+__device__ __forceinline__ int p3_relax_band(uint32_t a_cand, uint32_t a_edge, int h, int ww, int lane, int gw, int nw)
 {
-    const int lane = t0 & 31, gw = t0 >> 5, nw = tstride >> 5;
     const int rows_per = (h + nw - 1) / nw;
     const int y0 = min(h, gw * rows_per), y1 = min(h, y0 + rows_per);
     const int nwords = (y1 - y0) * ww, base = y0 * ww;
     const int rowb = ww * 4;
     const int wi0 = lane % ww, dwi = 32 % ww;             // word column of this lane's first word, and its step (no division per sweep)
+    int band_changed = 0;
+    while (true) {
+        int changed = 0;
+        int wi = wi0;
+        for (int i = lane; i < nwords; i += 32, wi = wi + dwi >= ww ? wi + dwi - ww : wi + dwi) {
+            const int t = base + i;
+            const uint32_t c = lds32(a_cand + 4 * t);
+            const uint32_t ea = a_edge + 4 * t;
+            const uint32_t e = lds32(ea);
+            if (c != e) {
+                const uint32_t mid = e | lds32(ea - rowb) | lds32(ea + rowb);
+                uint32_t lft = 0, rgt = 0;
+                if (wi > 0) lft = lds32(ea - 4) | lds32(ea - rowb - 4) | lds32(ea + rowb - 4);
+                if (wi + 1 < ww) rgt = lds32(ea + 4) | lds32(ea - rowb + 4) | lds32(ea + rowb + 4);
+                const uint32_t spread = mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
+                const uint32_t ne = flood_run((spread & c) | e, c);
+                if (ne != e) { sts32(ea, ne); changed = 1; }
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, changed)) break;
+        band_changed = 1;
+    }
+    return band_changed;
+}
+
+template <class OrReduce>
+__device__ __forceinline__ int p3_hysteresis(uint32_t a_cand, uint32_t a_edge, int h, int ww, int t0, int tstride, OrReduce group_or)
+{
+    const int lane = t0 & 31, gw = t0 >> 5, nw = tstride >> 5;
     int rounds = 0, any;
     do {
-        int round_changed = 0;
-        while (true) {
-            int changed = 0;
-            int wi = wi0;
-            for (int i = lane; i < nwords; i += 32, wi = wi + dwi >= ww ? wi + dwi - ww : wi + dwi) {
-                const int t = base + i;
-                const uint32_t c = lds32(a_cand + 4 * t);
-                const uint32_t ea = a_edge + 4 * t;
-                const uint32_t e = lds32(ea);
-                if (c != e) {
-                    const uint32_t mid = e | lds32(ea - rowb) | lds32(ea + rowb);
-                    uint32_t lft = 0, rgt = 0;
-                    if (wi > 0) lft = lds32(ea - 4) | lds32(ea - rowb - 4) | lds32(ea + rowb - 4);
-                    if (wi + 1 < ww) rgt = lds32(ea + 4) | lds32(ea - rowb + 4) | lds32(ea + rowb + 4);
-                    const uint32_t spread = mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
-                    const uint32_t ne = flood_run((spread & c) | e, c);
-                    if (ne != e) { sts32(ea, ne); changed = 1; }
-                }
-            }
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, changed)) break;
-            round_changed = 1;
-        }
-        any = group_or(round_changed);
+        any = group_or(p3_relax_band(a_cand, a_edge, h, ww, lane, gw, nw));
         ++rounds;
     } while (any);
     return rounds;
@@ -1171,14 +1177,8 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             p2_nms(P, S.mag[0], S.cand, a_edge, S, M, G.seg_rows_front);
             bar_sync(1, NC);
             TRS_TICK(tk5);
-            const int sw = p3_hysteresis(S.cand, a_edge, h, ww, tid, NC, [NC](int c) { return bar_or(1, NC, c); });
-            if (p.stats) {                                               // (the candidate plane is counted before the tail copy lands on it)
-                if (tid == 0) stat_add_one(S, 8, (unsigned long long)sw);
-                count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid, NC);
-                bar_sync(1, NC);
-            }
-            if (tid == 0 && G.tail_bytes && j + 1 < nfr)                 // the candidate plane is dead: fetch the tail it was sitting in
-                issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, main_bytes, frame_bytes, bar_tail);
+            // hysteresis, first level only: every warp relaxes its own band, no CTA-wide round trip; the store warps finish the job
+            p3_relax_band(S.cand, a_edge, h, ww, lane, warp, NC >> 5);
 #ifdef TRS_PHASE_TIMERS
             if (timing) {
                 const long long tk6 = clock64();
@@ -1187,10 +1187,6 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
 #endif
             bar_arrive(2, SW_THREADS);                                   // planes of frame j are final: the store warps take them from here
             // (no barrier here: the next strip walk writes the other plane set and the magnitude plane only)
-        }
-        if (p.stats) {
-            bar_sync(1, NC);
-            stats_flush(p, S, tid);
         }
 #ifdef TRS_PHASE_TIMERS
         if (timing)
@@ -1204,9 +1200,26 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             uint32_t pa[3];
             plane_sources(p, (j & 1) ? S.edge2 : S.edge, S.mask + (j & 1) * mask_set_bytes, G.plane_bytes, pa);
             bar_sync(2, SW_THREADS);
+            {
+                // growth across the compute warps' bands: rounds over the whole plane until nothing changes (usually one checking pass)
+                const int NS = SW_THREADS - NC;
+                const uint32_t a_edge = (j & 1) ? S.edge2 : S.edge, a_mask = S.mask + (j & 1) * mask_set_bytes;
+                const int sw = p3_hysteresis(S.cand, a_edge, h, ww, tid - NC, NS, [NS](int c) { return bar_or(4, NS, c); });
+                if (p.stats) {                                           // (the candidate plane is counted before the tail copy lands on it)
+                    if (tid == NC) stat_add_one(S, 8, (unsigned long long)sw + 1);
+                    count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid - NC, NS);
+                    bar_sync(4, NS);
+                }
+                if (tid == NC && G.tail_bytes && j + 1 < nfr)            // the candidate plane is dead: fetch the tail it was sitting in
+                    issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, main_bytes, frame_bytes, bar_tail);
+            }
             p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid - NC,
                       SW_THREADS - NC);
             if (j + 2 < nfr) bar_arrive(3, SW_THREADS);
+        }
+        if (p.stats) {                                                   // the store warps are the last to touch the counters
+            bar_sync(4, SW_THREADS - NC);
+            stats_flush(p, S, tid - NC);
         }
     }
 }
