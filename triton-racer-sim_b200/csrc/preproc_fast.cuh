@@ -601,25 +601,32 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
     const uint32_t cbase = a_cand + (M.strip >> 1), ebase = a_edge + (M.strip >> 1);
     // one row as packed pairs of magnitudes: P01=(m0,m1) P23=(m2,m3) L01=(m-1,m0) M12=(m1,m2) R23=(m3,m4); raw keeps the codes
     struct Row { uint32_t p01, p23, l01, m12, r23, raw01, raw23; };
-    auto load_row = [&](int y) {
+    struct Raw { uint2 c; uint32_t ml, mr; };                       // a row as loaded: the loads run one step ahead of their use
+    auto fetch_row = [&](int y) {
         const uint32_t rp = mbase + (y + 1) * MS2;
-        const uint2 c = lds64(rp);
-        const uint32_t ml = lds16(rp - 2) & 0x7ffu, mr = lds16(rp + 8) & 0x7ffu;
+        Raw q;
+        q.c = lds64(rp); q.ml = lds16(rp - 2); q.mr = lds16(rp + 8);
+        return q;
+    };
+    auto unpack_row = [&](const Raw& q) {
         Row r;
-        r.raw01 = c.x; r.raw23 = c.y;
-        r.p01 = c.x & 0x07ff07ffu; r.p23 = c.y & 0x07ff07ffu;
-        r.l01 = prmt(ml, r.p01, 0x5410);
+        r.raw01 = q.c.x; r.raw23 = q.c.y;
+        r.p01 = q.c.x & 0x07ff07ffu; r.p23 = q.c.y & 0x07ff07ffu;
+        r.l01 = prmt(q.ml & 0x7ffu, r.p01, 0x5410);
         r.m12 = prmt(r.p01, r.p23, 0x5432);
-        r.r23 = prmt(r.p23, mr, 0x5432);
+        r.r23 = prmt(r.p23, q.mr & 0x7ffu, 0x5432);
         return r;
     };
+    auto load_row = [&](int y) { return unpack_row(fetch_row(y)); };
     const int ya = M.r0;
+    Raw ahead;
     uint32_t cp = cbase + ya * prb, ep = ebase + ya * prb;          // plane bytes of the row being decided
     // rolling three-row window by register renaming (three steps per trip): step k decides row ya + k from rows (up, ce) and loads dn
     auto nms_step = [&](int k, const Row& up, const Row& ce, Row& dn) {
         const int y = ya + k;
         const bool row_in = y < M.r1;
-        dn = load_row(min(y + 1, h));
+        dn = unpack_row(ahead);
+        ahead = fetch_row(min(y + 2, h));
         uint32_t cm[2], sm[2];
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
@@ -650,6 +657,7 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
         cp += prb; ep += prb;
     };
     Row ra = load_row(ya - 1), rb = load_row(ya), rc;
+    ahead = fetch_row(min(ya + 1, h));
 #pragma unroll 1
     for (int k = 0; k < seg_rows; k += 3) {
         nms_step(k, ra, rb, rc);
