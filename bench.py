@@ -229,6 +229,24 @@ def other_workloads(torch, dev, local, pool120, h, w):
                                         "hbm_GBps": n * 76 / t / 1e9, "note": "fp64 L1 argmin over the centre line, not HBM bound"}
     trk.onShutdown()
     spd.onShutdown()
+    # the step after the speed controller: drive-mode select + launch locks + driver assistance, 1M cars
+    from triton_racer_sim_b200 import ControlMultiplexer
+    from triton_racer_sim_b200 import _native as nat2
+    mux = ControlMultiplexer(dict(ai_launch_boost_throttle_enabled=True, ai_launch_lock_steering_enabled=True), device=local)
+    rng = np.random.default_rng(6)
+    d_mode = torch.from_numpy(rng.integers(0, 3, n).astype(np.int32)).to(dev)
+    d_usr = torch.from_numpy(rng.uniform(-1, 1, (3, n))).to(dev)
+    d_ai = torch.from_numpy(rng.uniform(-1, 1, (3, n))).to(dev)
+    prm = nat2.ctl_params_from_cfg(mux.cfg, locks=True, assist=True)
+    clock = [0.0]
+
+    def mux_step():
+        clock[0] += 0.05
+        mux.mux_device(d_mode, d_usr, d_ai, clock[0], speed=d_cur, params=prm)
+    t = timed(mux_step, reps=20)
+    out["control_mux_1M_states"] = {"states_per_s": n / t, "hbm_GBps": n * (4 + 48 + 8 + 24 + 8 + 64) / t / 1e9,
+                                     "note": "156 B of traffic per car (mode, 6 inputs, speed, 3 outputs, state read + written)"}
+    mux.onShutdown()
     return out
 
 

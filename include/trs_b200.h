@@ -148,6 +148,40 @@ int trs_speed_control(trs_ctx* ctx, const double* cur_spd_dev, const float* mode
                       float* spd_feature_dev, void* stream);
 
 /*
+ * Per-car control post-processing, the step after the speed controller:
+ *   ControlMultiplexer.step  TritonRacerSim/components/controlmultiplexer.py:24-43  usr/ai select by drive mode + AI launch locks (48-70)
+ *   DriverAssistance.step    TritonRacerSim/components/driver_assistance.py:13-31    fused when speed_dev is given and assist_mode != 0
+ *   mode_dev (n) int32: TRS_MODE_* (DriveMode.HUMAN / AI_STEERING / AI, components/controller.py:7-10)
+ *   usr_dev, ai_dev, out_dev: (3, n) f64 = steering, throttle, breaking
+ *   now_s: the clock (the reference's locks are ended by sleeping threads; here time is an argument)
+ *   state, updated in place: last_mode_dev (n) int32, initially TRS_MODE_HUMAN; launch_times_dev (TRS_LAUNCH_SLOTS, n) f64,
+ *   initially TRS_NEVER.  A lock is set at the latest launch and cleared at the earliest pending end time after it, as the
+ *   reference's threads do; exact while at most TRS_LAUNCH_SLOTS lock threads would be pending at once.
+ */
+#define TRS_MODE_HUMAN 0
+#define TRS_MODE_AI_STEERING 1
+#define TRS_MODE_AI 2
+#define TRS_LAUNCH_SLOTS 4
+#define TRS_NEVER (-1.0e300)
+typedef struct {
+    int32_t throttle_lock_enabled;   /* ai_launch_boost_throttle_enabled  (core/config.py:57) */
+    int32_t steering_lock_enabled;   /* ai_launch_lock_steering_enabled   (core/config.py:61) */
+    int32_t assist_mode;             /* 0 off, 1 'steering', 2 'speed'    (drive_assist_limit_mode, core/config.py:105) */
+    int32_t reserved;
+    double throttle_lock_value;      /* ai_launch_boost_throttle_value    */
+    double throttle_lock_duration;   /* ai_launch_boost_throttle_duration */
+    double steering_lock_value;      /* ai_launch_lock_steering_value     */
+    double steering_lock_duration;   /* ai_launch_lock_steering_duration  */
+    double assist_k;                 /* drive_assist_limit_k              */
+} trs_ctl_params;
+int trs_control_mux(trs_ctx* ctx, const int32_t* mode_dev, const double* usr_dev, const double* ai_dev, const double* speed_dev,
+                    int n, const trs_ctl_params* p, double now_s, int32_t* last_mode_dev, double* launch_times_dev,
+                    double* out_dev, void* stream);
+/* three_segment_map (TritonRacerSim/utils/mapping.py:9-16): [-1, 1] command -> PWM value around a neutral point. */
+int trs_pwm_map(trs_ctx* ctx, const double* val_dev, int n, double min_map, double mid_map, double max_map, double* out_dev,
+                void* stream);
+
+/*
  * Host-buffer form of trs_preprocess: copies frames host->device in chunks, runs the kernels and
  * copies the requested outputs back, overlapping the three on internal streams; synchronises before
  * returning.  Host buffers may be pageable (slower) or pinned (trs_host_alloc).

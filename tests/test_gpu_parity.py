@@ -319,3 +319,80 @@ def test_other_kernels_still_match(golden_images, monkeypatch, env):
         got, f32 = run_device(cfg, frames)
         assert np.array_equal(got, expected), f"{sname}/{cname}: {describe(got, expected)}"
         assert np.array_equal(f32, oracle.normalise(expected))
+
+
+# ---- per-car control post-processing: bit-exact f64 selects / divisions -----------------------------------
+def _control_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "control.npz"))
+
+
+def test_control_mux_reference_sequences():
+    """The reference's own ControlMultiplexer, run in real time with its lock threads, replayed through the kernel with the recorded
+    clock: every step of every sequence must give the same three floats (N = 1 API with DriveMode-like strings)."""
+    import json
+
+    from triton_racer_sim_b200 import ControlMultiplexer
+    g = _control_golden()
+    names = ['human', 'ai_steering', 'ai']
+    for cname, over in json.loads(bytes(g["mux_cases_json"]).decode()).items():
+        for si in range(3):
+            rows = g[f"mux/{cname}/{si}"]
+            mux = ControlMultiplexer(over, device=0)
+            for r in rows:
+                out = mux.step(names[int(r[1])], *[float(v) for v in r[2:8]], now=float(r[0]))
+                assert isinstance(out[0], float) and list(out) == list(r[8:11]), f"{cname}/{si} at t={r[0]:.3f}"
+            mux.onShutdown()
+
+
+def test_control_mux_batch_against_oracle():
+    from oracle import control as oc
+    from triton_racer_sim_b200 import ControlMultiplexer
+    from triton_racer_sim_b200.config import default_config
+    rng = np.random.default_rng(5)
+    n = 50_000
+    over = dict(ai_launch_boost_throttle_enabled=True, ai_launch_boost_throttle_value=0.9, ai_launch_boost_throttle_duration=0.35,
+                ai_launch_lock_steering_enabled=True, ai_launch_lock_steering_value=0.1, ai_launch_lock_steering_duration=0.12)
+    cfg = default_config(**over)
+    mux = ControlMultiplexer(over, device=0)
+    last, launch = np.zeros(n, np.int32), np.full((oc.LAUNCH_SLOTS, n), oc.NEVER)
+    now = 100.0
+    for step in range(40):
+        now += float(rng.uniform(0.01, 0.09))
+        mode = rng.integers(0, 3, n).astype(np.int32)
+        vals = rng.uniform(-1, 1, (6, n))
+        want = oc.control_mux(mode, vals[0:3], vals[3:6], now, last, launch, cfg)
+        got = mux.step(torch.from_numpy(mode).to(DEV), *[torch.from_numpy(v.copy()).to(DEV) for v in vals], now=now)
+        assert np.array_equal(torch.stack(got).cpu().numpy(), want), f"step {step}"
+    assert np.array_equal(mux.launch_times.cpu().numpy(), launch) and np.array_equal(mux.last_mode.cpu().numpy(), last)
+    mux.onShutdown()
+
+
+def test_driver_assistance_and_pwm_map():
+    from oracle import control as oc
+    from triton_racer_sim_b200 import DriverAssistance, three_segment_map
+    from triton_racer_sim_b200.config import default_config
+    g = _control_golden()
+    st, th, br, sp = g["assist/in"]
+    for mode in ("steering", "speed"):
+        for k in (5, 2.5):
+            da = DriverAssistance(dict(drive_assist_limit_mode=mode, drive_assist_limit_k=k), device=0)
+            got = da.step(*[torch.from_numpy(a.copy()).to(DEV) for a in (st, th, br, sp)])
+            assert np.array_equal(torch.stack(got).cpu().numpy(), g[f"assist/{mode}/{k}"]), f"{mode}/{k}"
+            assert da.step(0.5, None, 0.0, 3.0) == (0.5, None, 0.0)                                  # driver_assistance.py:15
+            one = da.step(float(st[7]), float(th[7]), float(br[7]), float(sp[7]))
+            assert list(one) == list(g[f"assist/{mode}/{k}"][:, 7])
+            da.onShutdown()
+    rng = np.random.default_rng(9)
+    big = [rng.uniform(-2, 2, 200_000), rng.uniform(-1, 1, 200_000), rng.uniform(0, 1, 200_000), rng.uniform(-5, 30, 200_000)]
+    for mode in ("steering", "speed"):
+        cfg = default_config(drive_assist_limit_mode=mode, drive_assist_limit_k=3.7)
+        da = DriverAssistance(cfg, device=0)
+        got = da.step(*[torch.from_numpy(a).to(DEV) for a in big])
+        assert np.array_equal(torch.stack(got).cpu().numpy(), np.stack(oc.driver_assist(*big, cfg)))
+        da.onShutdown()
+    v = g["pwm/in"]
+    for name in ("steering", "throttle", "odd"):
+        a, b, c = g[f"pwm/{name}/map"]
+        assert np.array_equal(three_segment_map(torch.from_numpy(v.copy()).to(DEV), a, b, c).cpu().numpy(), g[f"pwm/{name}"]), name
+    assert three_segment_map(-0.5, 430, 350, 300) == 350 + (350 - 430) * -0.5

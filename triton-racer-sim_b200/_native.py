@@ -18,8 +18,11 @@ STAT_NAMES = ["frames", "mask0", "mask1", "mask2", "mask3", "edge", "strong", "c
 SYMBOLS = [
     "trs_version", "trs_last_error", "trs_kernel_launches", "trs_ctx_create", "trs_ctx_destroy", "trs_ctx_device_info",
     "trs_set_preproc_params", "trs_preprocess", "trs_normalise", "trs_set_track", "trs_locate", "trs_speed_control",
-    "trs_preprocess_host", "trs_host_alloc", "trs_host_free", "trs_debug_canny_stages",
+    "trs_preprocess_host", "trs_host_alloc", "trs_host_free", "trs_debug_canny_stages", "trs_control_mux", "trs_pwm_map",
 ]
+MODE_HUMAN, MODE_AI_STEERING, MODE_AI = 0, 1, 2          # TRS_MODE_*: DriveMode.HUMAN / AI_STEERING / AI (components/controller.py:7-10)
+LAUNCH_SLOTS = 4                                          # TRS_LAUNCH_SLOTS
+NEVER = -1.0e300                                          # TRS_NEVER
 
 
 class PreprocParams(C.Structure):
@@ -37,6 +40,14 @@ class SpdParams(C.Structure):
     _fields_ = [
         ("threshold", C.c_double), ("reverse_multiplier", C.c_double), ("break_multiplier", C.c_double),
         ("use_break", C.c_int32), ("smooth_steering", C.c_int32), ("smooth_threshold", C.c_double),
+    ]
+
+
+class CtlParams(C.Structure):
+    _fields_ = [
+        ("throttle_lock_enabled", C.c_int32), ("steering_lock_enabled", C.c_int32), ("assist_mode", C.c_int32), ("reserved", C.c_int32),
+        ("throttle_lock_value", C.c_double), ("throttle_lock_duration", C.c_double), ("steering_lock_value", C.c_double),
+        ("steering_lock_duration", C.c_double), ("assist_k", C.c_double),
     ]
 
 
@@ -73,6 +84,8 @@ def load():
     lib.trs_host_alloc.argtypes = [C.POINTER(vp), C.c_ulonglong]
     lib.trs_host_free.argtypes = [vp]
     lib.trs_debug_canny_stages.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    lib.trs_control_mux.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(CtlParams), C.c_double, vp, vp, vp, vp]
+    lib.trs_pwm_map.argtypes = [vp, vp, i32, C.c_double, C.c_double, C.c_double, vp, vp]
     for name in SYMBOLS:
         getattr(lib, name)
     _lib = lib
@@ -145,6 +158,23 @@ def preproc_params_from_cfg(cfg: dict) -> PreprocParams:
     p.edge_dest = int(cfg['preprocessing_edge_detection_destination_channel'])
     p.canny_a = float(cfg['preprocessing_edge_detection_threshold_a'])
     p.canny_b = float(cfg['preprocessing_edge_detection_threshold_b'])
+    return p
+
+
+def ctl_params_from_cfg(cfg: dict, locks: bool = True, assist: bool = False) -> CtlParams:
+    """Reference key names (core/config.py:57-63,104-106)."""
+    p = CtlParams()
+    if locks:
+        p.throttle_lock_enabled = int(bool(cfg['ai_launch_boost_throttle_enabled']))
+        p.throttle_lock_value = float(cfg['ai_launch_boost_throttle_value'])
+        p.throttle_lock_duration = float(cfg['ai_launch_boost_throttle_duration'])
+        p.steering_lock_enabled = int(bool(cfg['ai_launch_lock_steering_enabled']))
+        p.steering_lock_value = float(cfg['ai_launch_lock_steering_value'])
+        p.steering_lock_duration = float(cfg['ai_launch_lock_steering_duration'])
+    if assist:
+        mode = cfg['drive_assist_limit_mode']
+        p.assist_mode = {'steering': 1, 'speed': 2}.get(mode, 0)          # any other string: neither branch of driver_assistance.py:16,25
+        p.assist_k = float(cfg['drive_assist_limit_k'])
     return p
 
 

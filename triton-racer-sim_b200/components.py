@@ -9,11 +9,15 @@ can be added to the reference's ``Car`` as they are.  All arithmetic runs in the
   LocationTracker    components/track_data_process.py:68-107     gym/x, gym/y, gym/z -> loc/segment
   SpeedControl       components/keras_pilot.py:80-95,99-118,142-153 + utils/mapping.py:23-35
   FrameNormalise     components/camera.py:36 + keras_pilot.py:49-50 / keras_train.py:41-42
+  ControlMultiplexer components/controlmultiplexer.py:6-70        usr/*, ai/* -> mux/steering, mux/throttle, mux/breaking
+  DriverAssistance   components/driver_assistance.py:4-34         mux/*, gym/speed -> mux/*
+  three_segment_map  utils/mapping.py:9-16                        [-1, 1] command -> PWM value
 """
 from __future__ import annotations
 
 import ctypes as C
 import json
+import time
 
 import numpy as np
 import torch
@@ -313,3 +317,142 @@ class FrameNormalise(Component):
 
     def getName(self):
         return 'Frame Normalise'
+
+
+def _mode_code(m):
+    """DriveMode member (components/controller.py:7-10), its string value, or a TRS_MODE_* integer -> integer code."""
+    v = getattr(m, 'value', m)
+    if isinstance(v, str):
+        return {'human': nat.MODE_HUMAN, 'ai_steering': nat.MODE_AI_STEERING, 'ai': nat.MODE_AI}[v]
+    return int(v)
+
+
+def _as_f64(x, dev, n=None):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float64).reshape(-1).contiguous()
+    return torch.as_tensor(np.asarray(x, np.float64).reshape(-1), device=dev)
+
+
+class ControlMultiplexer(Component):
+    """Batched ``ControlMultiplexer`` (components/controlmultiplexer.py): user / pilot select by drive mode and the AI launch locks.
+
+    ``step(mode, usr_steering, usr_throttle, usr_breaking, ai_steering, ai_throttle, ai_breaking, now=None)``: every argument a
+    scalar (reference types: DriveMode member + python floats -> tuple of floats) or an (N,) array / CUDA tensor (-> CUDA f64
+    tensors).  The reference ends its locks from sleeping threads; here the clock is ``now`` (seconds, default
+    ``time.monotonic()``) and the per-car state (last mode, last launch times) lives in device tensors of this component.
+    """
+
+    def __init__(self, cfg={}, device=None):
+        Component.__init__(self, inputs=['usr/mode', 'usr/steering', 'usr/throttle', 'usr/breaking', 'ai/steering', 'ai/throttle', 'ai/breaking'],
+                           outputs=['mux/steering', 'mux/throttle', 'mux/breaking'])
+        self.cfg = default_config()
+        self.cfg.update(cfg)
+        self.device = _device_index(device)
+        self.ctx = nat.Context(self.device)
+        self.params = nat.ctl_params_from_cfg(self.cfg, locks=True, assist=False)
+        self.last_mode = None
+        self.launch_times = None
+
+    def _state(self, n, dev):
+        if self.last_mode is None or self.last_mode.shape[0] != n:
+            self.last_mode = torch.full((n,), nat.MODE_HUMAN, dtype=torch.int32, device=dev)          # controlmultiplexer.py:10
+            self.launch_times = torch.full((nat.LAUNCH_SLOTS, n), nat.NEVER, dtype=torch.float64, device=dev)
+
+    def mux_device(self, mode: torch.Tensor, usr: torch.Tensor, ai: torch.Tensor, now: float, speed: torch.Tensor = None, params=None):
+        """mode (N,) int32, usr / ai (3, N) f64 on the device -> (3, N) f64 (steering, throttle, breaking)."""
+        n = mode.shape[0]
+        self._state(n, mode.device)
+        out = torch.empty((3, n), dtype=torch.float64, device=mode.device)
+        nat.check(self.ctx.lib.trs_control_mux(self.ctx.handle, _ptr(mode), _ptr(usr), _ptr(ai), _ptr(speed), n,
+                                               C.byref(params if params is not None else self.params), float(now), _ptr(self.last_mode),
+                                               _ptr(self.launch_times), _ptr(out), _stream_ptr(self.device)), "trs_control_mux")
+        return out
+
+    def step(self, *args, now=None):
+        mode = args[0]
+        now = time.monotonic() if now is None else float(now)
+        dev = f"cuda:{self.device}"
+        batched = isinstance(mode, (torch.Tensor, np.ndarray, list, tuple))
+        if batched:
+            if isinstance(mode, torch.Tensor):
+                m = mode.to(device=dev, dtype=torch.int32).contiguous()
+            else:
+                m = torch.as_tensor(np.asarray([_mode_code(x) for x in mode], np.int32), device=dev)
+        else:
+            m = torch.tensor([_mode_code(mode)], dtype=torch.int32, device=dev)
+        vals = [_as_f64(a, dev) for a in args[1:7]]
+        usr, ai = torch.stack(vals[0:3]), torch.stack(vals[3:6])
+        out = self.mux_device(m, usr.contiguous(), ai.contiguous(), now)
+        if batched:
+            return out[0], out[1], out[2]
+        o = out[:, 0].tolist()
+        return o[0], o[1], o[2]
+
+    def onShutdown(self):
+        self.ctx.close()
+
+    def getName(self):
+        return 'Control Multiplexer'
+
+
+class DriverAssistance(Component):
+    """Batched ``DriverAssistance`` (components/driver_assistance.py): steering / speed limiter ``k / x``.  Keys as the reference
+    (``mux/break`` included, driver_assistance.py:8-9); any ``None`` argument passes everything through (driver_assistance.py:15)."""
+
+    def __init__(self, cfg={}, device=None):
+        Component.__init__(self, inputs=['mux/steering', 'mux/throttle', 'mux/break', 'gym/speed'],
+                           outputs=['mux/steering', 'mux/throttle', 'mux/break'], threaded=False)
+        self.cfg = default_config()
+        self.cfg.update(cfg)
+        self.limit_mode = self.cfg['drive_assist_limit_mode']
+        self.k = self.cfg['drive_assist_limit_k']
+        self.device = _device_index(device)
+        self.ctx = nat.Context(self.device)
+        self.params = nat.ctl_params_from_cfg(self.cfg, locks=False, assist=True)
+
+    def assist_device(self, steering, throttle, breaking, speed):
+        n = steering.shape[0]
+        dev = steering.device
+        usr = torch.stack([steering, throttle, breaking]).contiguous()
+        mode = torch.full((n,), nat.MODE_HUMAN, dtype=torch.int32, device=dev)       # "human" selects the first triple unchanged
+        last = torch.full((n,), nat.MODE_HUMAN, dtype=torch.int32, device=dev)
+        launch = torch.full((nat.LAUNCH_SLOTS, n), nat.NEVER, dtype=torch.float64, device=dev)
+        out = torch.empty((3, n), dtype=torch.float64, device=dev)
+        nat.check(self.ctx.lib.trs_control_mux(self.ctx.handle, _ptr(mode), _ptr(usr), _ptr(usr), _ptr(speed), n, C.byref(self.params), 0.0,
+                                               _ptr(last), _ptr(launch), _ptr(out), _stream_ptr(self.device)), "trs_control_mux")
+        return out[0], out[1], out[2]
+
+    def step(self, *args):
+        steering, throttle, breaking, speed = args
+        if any(a is None for a in args):
+            return steering, throttle, breaking
+        dev = f"cuda:{self.device}"
+        batched = isinstance(steering, (torch.Tensor, np.ndarray))
+        s, t, b, v = (_as_f64(a, dev) for a in args)
+        so, to, bo = self.assist_device(s, t, b, v)
+        if batched:
+            return so, to, bo
+        return float(so.item()), float(to.item()), float(bo.item())
+
+    def onShutdown(self):
+        self.ctx.close()
+
+    def getName(self):
+        return 'Driver Assistance'
+
+
+def three_segment_map(val, min_map, mid_map, max_map, device=None):
+    """``utils/mapping.py:9-16`` for N commands: CUDA tensor / array in -> CUDA f64 tensor out; python float in -> float out."""
+    dev_i = _device_index(device)
+    dev = f"cuda:{dev_i}"
+    scalar = not isinstance(val, (torch.Tensor, np.ndarray, list, tuple))
+    v = _as_f64(val, dev)
+    out = torch.empty_like(v)
+    ctx = nat.Context(dev_i)
+    try:
+        nat.check(ctx.lib.trs_pwm_map(ctx.handle, _ptr(v), v.shape[0], float(min_map), float(mid_map), float(max_map), _ptr(out), _stream_ptr(dev_i)),
+                  "trs_pwm_map")
+        torch.cuda.current_stream(dev_i).synchronize()
+    finally:
+        ctx.close()
+    return float(out.item()) if scalar else out

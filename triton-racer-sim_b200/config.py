@@ -1,4 +1,4 @@
-"""Config keys of the hot path with the reference's names and defaults (core/config.py:8-28,65-66,76-80,100-101).
+"""Config keys of the hot path with the reference's names and defaults (core/config.py:8-28,32-37,57-66,76-80,100-106).
 Only these keys are read; any reference `myconfig.json` dict can be passed as-is."""
 
 _DEFAULTS = {
@@ -25,6 +25,22 @@ _DEFAULTS = {
     'spd_ctl_reverse_multiplier': 1.0,
     'spd_ctl_break': False,
     'spd_ctl_break_multiplier': 1.0,
+    # per-car control post-processing (controlmultiplexer.py:11-20, driver_assistance.py:10-11, teensy.py PWM calibration)
+    'calibrate_max_forward_pwm': 400,
+    'calibrate_zero_throttle_pwm': 370,
+    'calibrate_max_reverse_pwm': 330,
+    'calibrate_max_left_pwm': 430,
+    'calibrate_max_right_pwm': 300,
+    'calibrate_neutral_steering_pwm': 350,
+    'ai_launch_boost_throttle_enabled': False,
+    'ai_launch_boost_throttle_value': 1.0,
+    'ai_launch_boost_throttle_duration': 5,
+    'ai_launch_lock_steering_enabled': False,
+    'ai_launch_lock_steering_value': 0.0,
+    'ai_launch_lock_steering_duration': 3,
+    'drive_assist_enabled': False,
+    'drive_assist_limit_mode': 'steering',
+    'drive_assist_limit_k': 5,
     'use_location_tracker': False,
     'track_data_file': 'track_data/generated_track.json',
 }

@@ -229,4 +229,90 @@ __global__ void __launch_bounds__(256) k_speed_control(const double* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// K9: per-car control post-processing, the step after the speed controller:
+//   ControlMultiplexer.step      components/controlmultiplexer.py:24-43 (launch locks: 48-70)
+//   DriverAssistance.step        components/driver_assistance.py:13-31 (fused when a speed vector is given)
+// Launch locks: the reference sets a flag at every AI launch and clears it from a thread that sleeps `duration` seconds,
+// so a re-launch is cut short by an older thread that is still sleeping.  State per car: the last CTL_LAUNCH_SLOTS
+// launch times; the flag is set at the latest launch L and cleared at the earliest t_i + duration that lies after L.
+// ------------------------------------------------------------------------------------------------------
+enum { CTL_LAUNCH_SLOTS = 4, CTL_MODE_HUMAN = 0, CTL_MODE_AI_STEERING = 1, CTL_MODE_AI = 2 };
+#define CTL_NEVER (-1.0e300)
+
+struct CtlKParams {
+    int thr_en, st_en, assist_mode;        // assist_mode: 0 off, 1 'steering', 2 'speed'
+    double thr_val, thr_dur, st_val, st_dur, assist_k;
+};
+
+__device__ __forceinline__ bool ctl_lock_active(const double (&t)[CTL_LAUNCH_SLOTS], double now, double duration)
+{
+    double latest = t[0];
+#pragma unroll
+    for (int i = 1; i < CTL_LAUNCH_SLOTS; ++i) latest = fmax(latest, t[i]);
+    double first_end = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+    for (int i = 0; i < CTL_LAUNCH_SLOTS; ++i) {
+        const double end = __dadd_rn(t[i], duration);
+        if (t[i] > CTL_NEVER && end > latest) first_end = fmin(first_end, end);
+    }
+    return latest > CTL_NEVER && now < first_end;
+}
+
+__global__ void __launch_bounds__(256) k_control_mux(const int* __restrict__ mode, const double* __restrict__ usr, const double* __restrict__ ai,
+                                                    const double* __restrict__ speed, int n, const CtlKParams p, double now,
+                                                    int* __restrict__ last_mode, double* __restrict__ launch, double* __restrict__ out)
+{
+    const int stride = gridDim.x * blockDim.x;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const int m = mode[k];
+        const bool full = m == CTL_MODE_AI;
+        double steering = m == CTL_MODE_HUMAN ? usr[k] : ai[k];                           // :26-31
+        double throttle = full ? ai[n + k] : usr[n + k];
+        double breaking = full ? ai[2 * (size_t)n + k] : usr[2 * (size_t)n + k];
+        double t[CTL_LAUNCH_SLOTS];
+#pragma unroll
+        for (int i = 0; i < CTL_LAUNCH_SLOTS; ++i) t[i] = launch[(size_t)i * n + k];
+        if (last_mode[k] != CTL_MODE_AI && full) {                                        // :33-35: the oldest remembered launch drops out
+            int oldest = 0;
+#pragma unroll
+            for (int i = 1; i < CTL_LAUNCH_SLOTS; ++i)
+                if (t[i] < t[oldest]) oldest = i;
+#pragma unroll
+            for (int i = 0; i < CTL_LAUNCH_SLOTS; ++i)
+                if (i == oldest) { t[i] = now; launch[(size_t)i * n + k] = now; }
+        }
+        if (p.st_en && ctl_lock_active(t, now, p.st_dur)) steering = p.st_val;            // :37-38
+        if (p.thr_en && ctl_lock_active(t, now, p.thr_dur)) throttle = p.thr_val;         // :39-40
+        last_mode[k] = m;                                                                 // :42
+        if (speed && p.assist_mode) {                                                     // driver_assistance.py:15-29
+            const double sp = speed[k];
+            if (p.assist_mode == 1 && sp != 0.0) {
+                const double mx = __ddiv_rn(p.assist_k, sp);
+                if (steering > mx) { steering = mx; throttle = -0.1; }
+                else if (steering < __dmul_rn(mx, -1.0)) { steering = __dmul_rn(mx, -1.0); throttle = -0.1; }
+            } else if (p.assist_mode == 2 && steering != 0.0) {
+                const double mx = __ddiv_rn(p.assist_k, steering);
+                if (sp > mx) { throttle = 0.0; breaking = 0.0; }
+            }
+        }
+        out[k] = steering; out[n + k] = throttle; out[2 * (size_t)n + k] = breaking;
+    }
+}
+
+// three_segment_map (utils/mapping.py:9-16; cap: 18-21): the [-1, 1] command to a PWM value around a neutral point
+__global__ void __launch_bounds__(256) k_pwm_map(const double* __restrict__ val, int n, double min_map, double mid_map, double max_map,
+                                                double* __restrict__ out)
+{
+    const int stride = gridDim.x * blockDim.x;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        double v = val[k];
+        v = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);
+        double r = mid_map;
+        if (v < 0.0) r = __dadd_rn(mid_map, __dmul_rn(__dsub_rn(mid_map, min_map), v));
+        else if (v > 0.0) r = __dadd_rn(mid_map, __dmul_rn(__dsub_rn(max_map, mid_map), v));
+        out[k] = r;
+    }
+}
+
 }  // namespace trs

@@ -532,6 +532,44 @@ int trs_speed_control(trs_ctx* ctx, const double* cur_spd_dev, const float* mode
     return 0;
 }
 
+int trs_control_mux(trs_ctx* ctx, const int32_t* mode_dev, const double* usr_dev, const double* ai_dev, const double* speed_dev, int n,
+                    const trs_ctl_params* p, double now_s, int32_t* last_mode_dev, double* launch_times_dev, double* out_dev, void* stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0 || !p) return fail(TRS_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    if (!mode_dev || !usr_dev || !ai_dev || !last_mode_dev || !launch_times_dev || !out_dev) return fail(TRS_E_ARG, "null pointer");
+    if (p->assist_mode < 0 || p->assist_mode > 2) return fail(TRS_E_ARG, "assist_mode %d (0 off, 1 steering, 2 speed)", p->assist_mode);
+    static_assert(TRS_LAUNCH_SLOTS == trs::CTL_LAUNCH_SLOTS, "header and kernel disagree on the launch slots");
+    trs::CtlKParams k{p->throttle_lock_enabled ? 1 : 0, p->steering_lock_enabled ? 1 : 0, p->assist_mode, p->throttle_lock_value,
+                      p->throttle_lock_duration, p->steering_lock_value, p->steering_lock_duration, p->assist_k};
+    int grid = (n + 255) / 256;
+    const int cap = ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    trs::k_control_mux<<<grid, 256, 0, (cudaStream_t)stream>>>(mode_dev, usr_dev, ai_dev, speed_dev, n, k, now_s, last_mode_dev, launch_times_dev,
+                                                                out_dev);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trs_pwm_map(trs_ctx* ctx, const double* val_dev, int n, double min_map, double mid_map, double max_map, double* out_dev, void* stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0) return fail(TRS_E_ARG, "negative n");
+    if (n == 0) return 0;
+    if (!val_dev || !out_dev) return fail(TRS_E_ARG, "null pointer");
+    int grid = (n + 255) / 256;
+    const int cap = ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    trs::k_pwm_map<<<grid, 256, 0, (cudaStream_t)stream>>>(val_dev, n, min_map, mid_map, max_map, out_dev);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int trs_host_alloc(void** out, unsigned long long bytes)
 {
     if (!out) return fail(TRS_E_ARG, "null out pointer");
