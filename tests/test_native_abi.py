@@ -32,12 +32,13 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "trs_b200.h"\nint main(){printf("%zu %zu\\n", sizeof(trs_preproc_params), sizeof(trs_spd_params));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "trs_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(trs_preproc_params), sizeof(trs_spd_params), sizeof(trs_ctl_params));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
-    a, b = map(int, subprocess.check_output([str(exe)]).split())
+    a, b, c = map(int, subprocess.check_output([str(exe)]).split())
     assert a == C.sizeof(nat.PreprocParams)
     assert b == C.sizeof(nat.SpdParams)
+    assert c == C.sizeof(nat.CtlParams)
 
 
 def test_sass_is_sm100a_only():
