@@ -81,7 +81,9 @@ def test_canny_stage_taps_match_oracle(golden_images):
 
 
 @pytest.mark.parametrize("h,w,n", [(120, 160, 96), (240, 320, 24), (17, 23, 5), (41, 64, 7), (119, 8, 3), (1, 40, 2), (40, 1, 2),
-                                   (480, 640, 3), (130, 2000, 2)])
+                                   (480, 640, 3), (130, 2000, 2),
+                                   # banded kernel: uneven last band, eight segments per band (w = 160), nine warps (w = 96), two bands only
+                                   (241, 320, 5), (480, 160, 5), (300, 96, 5), (150, 320, 5), (3, 320, 2), (1000, 32, 3)])
 def test_fresh_frames_against_oracle(h, w, n):
     frames = synth.frame_pool(n, h, w, seed=1000 + h + w)
     for over in (dict(), dict(preprocessing_dynamic_brightness_enabled=True, preprocessing_contrast_enhancement_ratio=1.6,
