@@ -297,6 +297,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # NCCL's version / debug lines must not share stdout with the JSON line
     import torch
     import torch.distributed as dist
 
