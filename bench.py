@@ -28,15 +28,22 @@ WORKLOADS = {
     # name: (h, w, frames per GPU, want_u8, want_f32, algorithmic bytes per frame)
     "full_chain_120x160": (120, 160, 65536, True, True, 57600 + 57600 + 230400),
     "full_house_mask_240x320": (240, 320, 16384, True, False, 230400 + 230400),
+    # BASELINE.json configs[4]: 1M frames + 1M car states per step over 8 GPUs = 131,072 of each per GPU; a step also runs the
+    # nearest-waypoint lookup, the speed controller and the control multiplexer for the shard's cars (three more launches)
+    "full_pipeline_1M_over_8": (120, 160, 131072, True, True, 57600 + 57600 + 230400),
 }
 METRIC = "preprocessed frames/sec (120x160), full observation chain"
-METRICS = {"full_chain_120x160": METRIC, "full_house_mask_240x320": "preprocessed frames/sec (240x320), full-house colour + edge mask"}
-KERNELS = {"full_chain_120x160": "trs::k_preprocess_sw<2,24,23>", "full_house_mask_240x320": "trs::k_preprocess_banded<2,true,24,23>"}
+METRICS = {"full_chain_120x160": METRIC, "full_house_mask_240x320": "preprocessed frames/sec (240x320), full-house colour + edge mask",
+           "full_pipeline_1M_over_8": "preprocessed frames/sec (120x160), full observation pipeline incl. per-car lookup and control"}
+KERNELS = {"full_chain_120x160": "trs::k_preprocess_sw<2,24,23>", "full_house_mask_240x320": "trs::k_preprocess_banded<2,true,24,23>",
+           "full_pipeline_1M_over_8": "trs::k_preprocess_sw<2,24,23>"}
 NOTES = {
     "full_chain_120x160": "bound by the ALU pipe / issue slots and phase barriers, not by HBM: ten compute warps per CTA run strip walk, NMS and "
                           "hysteresis while two store warps stream the previous frame out (the SM -> L2 write port tops out at 29 B/clk); "
                           "see DESIGN.md 4.1 and profiles/",
     "full_house_mask_240x320": "6 algorithmic bytes per pixel: instruction bound by construction (SURVEY.md 8d); banded kernel, DESIGN.md 4.3",
+    "full_pipeline_1M_over_8": "frames as full_chain_120x160; the per-car kernels (FP64 argmin over 1,185 waypoints, speed control, multiplexer) "
+                               "add three launches per step and are counted in the step time but not in the algorithmic bytes",
 }
 
 
@@ -187,6 +194,15 @@ def other_workloads(torch, dev, local, pool120, h, w):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps * 1e-3
 
+    # configs[0]: the 7,000-record tub (120x160) through the full chain and through the trainer's /255 (keras_train.py:41-42)
+    tub = synth.expand_torch(pool120, 7000)
+    fh0 = ImgPreprocessing(full_house_config(), device=local)
+    tu8, tf32 = torch.empty_like(tub), torch.empty(tub.shape, dtype=torch.float32, device=dev)
+    t = timed(lambda: fh0.process_device(tub, out_u8=tu8, out_f32=tf32, want_f32=True), reps=20)
+    out["tub_7000x120x160_full_chain"] = {"frames_per_s": 7000 / t, "ms": t * 1e3, "hbm_frac": 7000 * 345600 / t / 1e9 / peak,
+                                          "note": "one launch, 24 frames per CTA: pipeline fill / drain visible; outputs (2 GB) near L2 size"}
+    fh0.onShutdown()
+    del tub, tu8, tf32
     # configs[1]: crop + resize + normalise for 4,096 cars x 120x160 (u8 in, f32 out): 288,000 algorithmic bytes per frame
     cars = synth.expand_torch(pool120, 4096)
     norm = FrameNormalise(device=local)
@@ -329,8 +345,32 @@ def main():
     out_u8 = torch.empty_like(batch) if want_u8 else None
     out_f32 = torch.empty(batch.shape, dtype=torch.float32, device=dev) if want_f32 else None
 
+    cars = None
+    if args.workload == "full_pipeline_1M_over_8":
+        import numpy as np
+
+        from triton_racer_sim_b200 import ControlMultiplexer, LocationTracker, SpeedControl
+        from triton_racer_sim_b200 import _native as nat3
+        ncar = end - start
+        wp = synth.synthetic_track(1185)
+        xyz, cur, ms, st = synth.car_states(wp, ncar, seed=4 + rank)
+        rng = np.random.default_rng(40 + rank)
+        cars = {
+            "trk": LocationTracker(wp, device=local), "spd": SpeedControl(dict(spd_ctl_break=True), device=local),
+            "mux": ControlMultiplexer(dict(ai_launch_boost_throttle_enabled=True, ai_launch_lock_steering_enabled=True), device=local),
+            "xyz": torch.from_numpy(xyz).to(dev), "cur": torch.from_numpy(cur).to(dev), "ms": torch.from_numpy(ms).to(dev),
+            "st": torch.from_numpy(st).to(dev), "mode": torch.from_numpy(rng.integers(0, 3, ncar).astype(np.int32)).to(dev),
+            "usr": torch.from_numpy(rng.uniform(-1, 1, (3, ncar))).to(dev), "clock": 0.0,
+        }
+        cars["prm"] = nat3.ctl_params_from_cfg(cars["mux"].cfg, locks=True, assist=True)
+
     def step():
         comp.process_device(batch, out_u8=out_u8, out_f32=out_f32, want_u8=want_u8, want_f32=want_f32)
+        if cars is not None:
+            cars["trk"].locate_device(cars["xyz"])
+            s_, t_, b_, _ = cars["spd"].control_device(cars["cur"], cars["st"], cars["ms"])
+            cars["clock"] += 0.05
+            cars["mux"].mux_device(cars["mode"], cars["usr"], torch.stack([s_, t_, b_]), cars["clock"], speed=cars["cur"], params=cars["prm"])
 
     def barrier():
         if world > 1:

@@ -595,7 +595,9 @@ int trs_preprocess_host(trs_ctx* ctx, const uint8_t* in_host, int n, int h, int 
     if (!out_u8_host && !out_f32_host && !keep_f32_dev && !stats_host) return fail(TRS_E_ARG, "no output requested");
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t fb = (size_t)h * w * 3;
-    size_t chunk = (size_t)(24u << 20) / fb;                   // ~24 MB of frames per chunk
+    size_t chunk_bytes = (size_t)48 << 20;                     // ~48 MB of frames per chunk (the link saturates from ~16 MB up)
+    if (const char* e = getenv("TRS_HOST_CHUNK_MB")) { const int mb = atoi(e); if (mb > 0) chunk_bytes = (size_t)mb << 20; }
+    size_t chunk = chunk_bytes / fb;
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)n) chunk = n;
     chunk = (chunk + 3) & ~(size_t)3;                          // keeps every chunk base 16-byte aligned when fb % 4 == 0
