@@ -182,6 +182,21 @@ int trs_pwm_map(trs_ctx* ctx, const double* val_dev, int n, double min_map, doub
                 void* stream);
 
 /*
+ * Tub ingestion: batched decode of the records' JPEG files, replacing
+ *   np.asarray(Image.open(img_path))      TritonRacerSim/components/keras_train.py:41,309
+ * for the files the reference's recorder writes (Image.fromarray(img).save(path), components/datastorage.py:78: baseline, 8 bit,
+ * YCbCr 4:2:0, one scan, no restart intervals).  Bit-exact with Pillow / libjpeg(-turbo) defaults (integer IDCT, fancy upsampling).
+ *   blob_host     the N files back to back (pageable or pinned host memory)
+ *   offsets_host  N + 1 byte offsets into blob_host (file k = [offsets[k], offsets[k+1]))
+ *   out_u8_dev    (N, h, w, 3) uint8 RGB on the device; every file must be h x w
+ * Parses on the host, uploads the files (about 5 KB per 120x160 record instead of 57.6 KB of pixels), decodes on the GPU;
+ * synchronises `stream` before returning (the staging buffers are reused by the next call).
+ * TRS_E_RANGE: a file is not a baseline 4:2:0 JPEG of the stated size (the message names the record).
+ */
+int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned long long* offsets_host, int n, int h, int w,
+                         uint8_t* out_u8_dev, void* stream);
+
+/*
  * Host-buffer form of trs_preprocess: copies frames host->device in chunks, runs the kernels and
  * copies the requested outputs back, overlapping the three on internal streams; synchronises before
  * returning.  Host buffers may be pageable (slower) or pinned (trs_host_alloc).

@@ -1,0 +1,85 @@
+"""Tub ingestion: the CUDA JPEG decoder against Pillow (the decoder the reference's loaders call, keras_train.py:41), bit for bit."""
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from triton_racer_sim_b200 import synth, tub
+
+pytestmark = pytest.mark.gpu
+
+
+def encode(frames, **kw):
+    files = []
+    for f in frames:
+        buf = io.BytesIO()
+        Image.fromarray(f).save(buf, format="JPEG", **kw)            # datastorage.py:78 (defaults: quality 75, 4:2:0)
+        files.append(buf.getvalue())
+    return files
+
+
+def pil_decode(files):
+    return np.stack([np.asarray(Image.open(io.BytesIO(b))) for b in files])
+
+
+@pytest.mark.parametrize("h,w,n,kw", [(120, 160, 300, {}), (240, 320, 40, {}), (120, 160, 60, dict(quality=95)), (120, 160, 60, dict(quality=20)),
+                                     (121, 163, 9, {}), (7, 9, 5, {}), (64, 96, 7, dict(quality=100)), (2, 3, 4, {}), (1, 1, 3, {})])
+def test_decoder_matches_pillow(h, w, n, kw):
+    frames = synth.frame_pool(n, h, w, seed=7 * h + w)
+    files = encode(frames, **kw)
+    got = tub.decode_jpeg_batch(files, device=0)
+    assert got.shape == (n, h, w, 3) and got.dtype == torch.uint8
+    want = pil_decode(files)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_mixed_table_sets_and_golden_fixture():
+    frames = synth.frame_pool(30, 120, 160, seed=3)
+    files = [encode(frames[k:k + 1], quality=q)[0] for k, q in enumerate([75, 50, 90] * 10)]      # three table sets in one batch
+    assert np.array_equal(tub.decode_jpeg_batch(files, device=0).cpu().numpy(), pil_decode(files))
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg.npz"))
+    blob, offsets = g["blob"], g["offsets"]
+    got = tub.decode_jpeg_batch((blob, offsets), hw=(120, 160), device=0)
+    assert np.array_equal(got.cpu().numpy(), g["decoded"])                                         # Pillow 12.2 / libjpeg-turbo 3.x in the build container
+
+
+def test_unsupported_and_corrupt_files_raise():
+    frames = synth.frame_pool(2, 120, 160, seed=5)
+    with pytest.raises(ValueError):
+        tub.decode_jpeg_batch(encode(frames, progressive=True), device=0)
+    with pytest.raises(ValueError):
+        tub.decode_jpeg_batch(encode(frames, subsampling=0), device=0)                              # 4:4:4
+    ok = encode(frames)
+    with pytest.raises(ValueError):
+        tub.decode_jpeg_batch([ok[0], ok[1][:200]], device=0)                                       # truncated header
+    with pytest.raises(ValueError):
+        tub.decode_jpeg_batch(ok, hw=(240, 320), device=0)                                          # wrong stated size
+
+
+def test_tub_reader_round_trip(tmp_path):
+    """A tub written the way the reference's recorder writes it (datastorage.py:67-79), read back through the GPU decoder and through
+    the full chain: the same as the reference loader's `Image.open` followed by the oracle chain."""
+    import oracle
+    from triton_racer_sim_b200 import ImgPreprocessing
+    from triton_racer_sim_b200.config import full_house_config
+    frames = synth.frame_pool(12, 120, 160, seed=11)
+    for i, f in enumerate(frames, start=1):
+        Image.fromarray(f).save(os.path.join(tmp_path, f"img_{i}.jpg"))
+        with open(os.path.join(tmp_path, f"record_{i}.json"), "w") as fp:
+            json.dump({"cam/img": f"img_{i}.jpg", "mux/steering": 0.1 * i, "gym/speed": 2.0 * i}, fp)
+    rd = tub.TubReader(str(tmp_path), device=0)
+    assert rd.count() == 12
+    dev_frames, records = rd.load(range(1, 13))
+    want = np.stack([np.asarray(Image.open(os.path.join(tmp_path, f"img_{i}.jpg"))) for i in range(1, 13)])
+    assert np.array_equal(dev_frames.cpu().numpy(), want)
+    assert [r["gym/speed"] for r in records] == [2.0 * i for i in range(1, 13)]
+    cfg = full_house_config()
+    comp = ImgPreprocessing(cfg, device=0)
+    u8, _ = comp.process_device(dev_frames)
+    assert np.array_equal(u8.cpu().numpy(), oracle.process_batch(want, cfg))
+    comp.onShutdown()
+    rd.close()

@@ -14,8 +14,11 @@
 #include <atomic>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "../../include/trs_b200.h"
+#include "jpeg_host.h"
+#include "jpeg_kernels.cuh"
 #include "misc_kernels.cuh"
 #include "preproc_kernel.cuh"
 #include "preproc_fast.cuh"
@@ -78,6 +81,10 @@ struct trs_ctx {
     float* st_f32[HOST_STREAMS] = {nullptr, nullptr, nullptr};
     size_t st_in_cap = 0, st_u8_cap = 0, st_f32_cap = 0;
     unsigned long long* stats_dev = nullptr;
+    // tub ingestion staging (grown on demand)
+    uint8_t* jpg_blob = nullptr;   size_t jpg_blob_cap = 0;
+    uint8_t* jpg_planes = nullptr; size_t jpg_planes_cap = 0;
+    void* jpg_meta = nullptr;      size_t jpg_meta_cap = 0;
 };
 
 namespace {
@@ -387,6 +394,7 @@ int trs_ctx_destroy(trs_ctx* ctx)
     }
     cudaFree(ctx->wp_dev);
     cudaFree(ctx->stats_dev);
+    cudaFree(ctx->jpg_blob); cudaFree(ctx->jpg_planes); cudaFree(ctx->jpg_meta);
     delete ctx;
     return 0;
 }
@@ -567,6 +575,70 @@ int trs_pwm_map(trs_ctx* ctx, const double* val_dev, int n, double min_map, doub
     trs::k_pwm_map<<<grid, 256, 0, (cudaStream_t)stream>>>(val_dev, n, min_map, mid_map, max_map, out_dev);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CU(cudaGetLastError());
+    return 0;
+}
+
+int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned long long* offsets_host, int n, int h, int w,
+                         uint8_t* out_u8_dev, void* stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0 || h <= 0 || w <= 0) return fail(TRS_E_ARG, "bad size n=%d h=%d w=%d", n, h, w);
+    if (n == 0) return 0;
+    if (!blob_host || !offsets_host || !out_u8_dev) return fail(TRS_E_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    // ---- host: parse every file, deduplicate the table sets ------------------------------------------------------------------
+    std::vector<trs::JpegRecord> recs((size_t)n);
+    std::vector<trs::JpegTables> sets;
+    for (int k = 0; k < n; ++k) {
+        const unsigned long long a = offsets_host[k], b = offsets_host[k + 1];
+        if (b < a) return fail(TRS_E_ARG, "offsets not ascending at record %d", k);
+        trs::JpegTables T;
+        trs::JpegScan S;
+        memset(&T, 0, sizeof T);
+        const int pr = trs::jpg_parse(blob_host + a, (size_t)(b - a), &T, &S);
+        if (pr) return fail(TRS_E_RANGE, "record %d: %s", k, pr == trs::JPG_E_UNSUPPORTED ? "not a baseline 8-bit YCbCr 4:2:0 single-scan JPEG" : "malformed JPEG");
+        if (S.h != h || S.w != w) return fail(TRS_E_RANGE, "record %d is %dx%d, expected %dx%d", k, S.h, S.w, h, w);
+        size_t si = 0;
+        for (; si < sets.size(); ++si)
+            if (memcmp(&sets[si], &T, sizeof T) == 0) break;
+        if (si == sets.size()) {
+            if (sets.size() >= 64) return fail(TRS_E_RANGE, "more than 64 distinct quantisation / Huffman table sets in one batch");
+            sets.push_back(T);
+        }
+        recs[(size_t)k] = trs::JpegRecord{a + S.data_off, S.data_len, (uint32_t)si};
+    }
+    // ---- device staging ----------------------------------------------------------------------------------------------------------
+    const size_t blob_bytes = (size_t)offsets_host[n];
+    const int mw = (w + 15) / 16, mh = (h + 15) / 16;
+    const size_t ybytes = (size_t)mw * 16 * mh * 16, cbytes = (size_t)mw * 8 * mh * 8;
+    const size_t planes_bytes = (size_t)n * (ybytes + 2 * cbytes);
+    const size_t meta_bytes = sets.size() * sizeof(trs::JpegTables) + (size_t)n * sizeof(trs::JpegRecord) + 16;
+    if (ctx->jpg_blob_cap < blob_bytes + 16) { cudaFree(ctx->jpg_blob); ctx->jpg_blob = nullptr; ctx->jpg_blob_cap = 0; CU(cudaMalloc(&ctx->jpg_blob, blob_bytes + 16)); ctx->jpg_blob_cap = blob_bytes + 16; }
+    if (ctx->jpg_planes_cap < planes_bytes) { cudaFree(ctx->jpg_planes); ctx->jpg_planes = nullptr; ctx->jpg_planes_cap = 0; CU(cudaMalloc(&ctx->jpg_planes, planes_bytes)); ctx->jpg_planes_cap = planes_bytes; }
+    if (ctx->jpg_meta_cap < meta_bytes) { cudaFree(ctx->jpg_meta); ctx->jpg_meta = nullptr; ctx->jpg_meta_cap = 0; CU(cudaMalloc(&ctx->jpg_meta, meta_bytes)); ctx->jpg_meta_cap = meta_bytes; }
+    trs::JpegTables* d_sets = reinterpret_cast<trs::JpegTables*>(ctx->jpg_meta);
+    trs::JpegRecord* d_recs = reinterpret_cast<trs::JpegRecord*>(reinterpret_cast<uint8_t*>(ctx->jpg_meta) + sets.size() * sizeof(trs::JpegTables));
+    int* d_status = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(d_recs) + (size_t)n * sizeof(trs::JpegRecord));
+    CU(cudaMemcpyAsync(ctx->jpg_blob, blob_host, blob_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_sets, sets.data(), sets.size() * sizeof(trs::JpegTables), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_recs, recs.data(), (size_t)n * sizeof(trs::JpegRecord), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    trs::JpegPlanes P{ctx->jpg_planes, ctx->jpg_planes + (size_t)n * ybytes, ctx->jpg_planes + (size_t)n * (ybytes + cbytes), mw, mh};
+    trs::k_jpeg_entropy_idct<<<(n + trs::JPG_THREADS - 1) / trs::JPG_THREADS, trs::JPG_THREADS, 0, st>>>(ctx->jpg_blob, d_recs, d_sets, n, P, d_status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    const size_t groups = (size_t)n * h * ((w + 3) / 4);
+    size_t want = (groups + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 32;
+    trs::k_jpeg_upsample_rgb<<<(int)(want < cap ? want : cap), 256, 0, st>>>(P, n, h, w, out_u8_dev);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaGetLastError());
+    int status = 0;
+    CU(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));                              // recs / sets (host vectors) and the staging buffers are reused
+    if (status) return fail(TRS_E_RANGE, "corrupt entropy-coded data in at least one record (decoder status %d)", status);
     return 0;
 }
 
