@@ -12,7 +12,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # Blackwell B200 only: no multi-arch fatbin, no PTX fallback
     "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",                                   # parity: one rounding per float op
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
 ]
 
 

@@ -185,11 +185,18 @@ TRS_JHD void jpg_idct_islow(const int16_t (&coef)[64], const uint16_t* quant, ui
         const int sh = CB + P1 + 3;
         const int v[8] = {tmp10 + tmp3, tmp11 + tmp2, tmp12 + tmp1, tmp13 + tmp0, tmp13 - tmp0, tmp12 - tmp1, tmp11 - tmp2, tmp10 - tmp3};
         uint8_t* o = out + r * out_stride;
+        uint32_t px[8];
         for (int k = 0; k < 8; ++k) {
             int x = jpg_descale(v[k], sh) + 128;                                    // range_limit: centred clamp to 0..255
-            x = x < 0 ? 0 : (x > 255 ? 255 : x);
-            o[k] = (uint8_t)x;
+            px[k] = (uint32_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
         }
+#if defined(__CUDA_ARCH__)
+        if ((reinterpret_cast<uintptr_t>(o) & 7) == 0) {                             // one 8-byte store per row
+            *reinterpret_cast<uint2*>(o) = make_uint2(px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24), px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24));
+            continue;
+        }
+#endif
+        for (int k = 0; k < 8; ++k) o[k] = (uint8_t)px[k];
     }
 }
 

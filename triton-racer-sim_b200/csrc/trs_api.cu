@@ -14,6 +14,7 @@
 #include <atomic>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/trs_b200.h"
@@ -588,53 +589,106 @@ int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned 
     if (!blob_host || !offsets_host || !out_u8_dev) return fail(TRS_E_ARG, "null pointer");
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaStream_t st = (cudaStream_t)stream;
-    // ---- host: parse every file, deduplicate the table sets ------------------------------------------------------------------
+    // ---- host: parse every file (threads; a file whose header bytes equal the previous file's reuses its tables) -----------------
     std::vector<trs::JpegRecord> recs((size_t)n);
     std::vector<trs::JpegTables> sets;
-    for (int k = 0; k < n; ++k) {
-        const unsigned long long a = offsets_host[k], b = offsets_host[k + 1];
-        if (b < a) return fail(TRS_E_ARG, "offsets not ascending at record %d", k);
-        trs::JpegTables T;
-        trs::JpegScan S;
-        memset(&T, 0, sizeof T);
-        const int pr = trs::jpg_parse(blob_host + a, (size_t)(b - a), &T, &S);
-        if (pr) return fail(TRS_E_RANGE, "record %d: %s", k, pr == trs::JPG_E_UNSUPPORTED ? "not a baseline 8-bit YCbCr 4:2:0 single-scan JPEG" : "malformed JPEG");
-        if (S.h != h || S.w != w) return fail(TRS_E_RANGE, "record %d is %dx%d, expected %dx%d", k, S.h, S.w, h, w);
-        size_t si = 0;
-        for (; si < sets.size(); ++si)
-            if (memcmp(&sets[si], &T, sizeof T) == 0) break;
-        if (si == sets.size()) {
-            if (sets.size() >= 64) return fail(TRS_E_RANGE, "more than 64 distinct quantisation / Huffman table sets in one batch");
-            sets.push_back(T);
+    std::mutex sets_mu;
+    std::atomic<int> first_bad{n};
+    std::vector<int> bad_code((size_t)n, 0);
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 16) nthreads = 16;
+    if ((unsigned)n < 64 * nthreads) nthreads = 1;
+    auto work = [&](int k0, int k1) {
+        const uint8_t* prev = nullptr;
+        uint32_t prev_hdr = 0, prev_set = 0;
+        for (int k = k0; k < k1; ++k) {
+            const unsigned long long a = offsets_host[k], b = offsets_host[k + 1];
+            if (b < a) { bad_code[(size_t)k] = -1; int cur = first_bad.load(); while (k < cur && !first_bad.compare_exchange_weak(cur, k)) {} continue; }
+            const uint8_t* f = blob_host + a;
+            const size_t len = (size_t)(b - a);
+            if (prev && len > prev_hdr && memcmp(prev, f, prev_hdr) == 0) {          // same header bytes: same size, tables and scan parameters
+                recs[(size_t)k] = trs::JpegRecord{a + prev_hdr, (uint32_t)(len - prev_hdr), prev_set};
+                continue;
+            }
+            trs::JpegTables T;
+            trs::JpegScan S;
+            memset(&T, 0, sizeof T);
+            int pr = trs::jpg_parse(f, len, &T, &S);
+            if (!pr && (S.h != h || S.w != w)) pr = -2;
+            if (pr) { bad_code[(size_t)k] = pr; int cur = first_bad.load(); while (k < cur && !first_bad.compare_exchange_weak(cur, k)) {} continue; }
+            size_t si = 0;
+            {
+                std::lock_guard<std::mutex> g(sets_mu);
+                for (; si < sets.size(); ++si)
+                    if (memcmp(&sets[si], &T, sizeof T) == 0) break;
+                if (si == sets.size()) {
+                    if (sets.size() >= 64) { bad_code[(size_t)k] = -3; int cur = first_bad.load(); while (k < cur && !first_bad.compare_exchange_weak(cur, k)) {} continue; }
+                    sets.push_back(T);
+                }
+            }
+            recs[(size_t)k] = trs::JpegRecord{a + S.data_off, S.data_len, (uint32_t)si};
+            prev = f; prev_hdr = S.data_off; prev_set = (uint32_t)si;
         }
-        recs[(size_t)k] = trs::JpegRecord{a + S.data_off, S.data_len, (uint32_t)si};
+    };
+    if (nthreads == 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> pool;
+        const int per = (n + (int)nthreads - 1) / (int)nthreads;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            const int k0 = (int)t * per, k1 = k0 + per < n ? k0 + per : n;
+            if (k0 < k1) pool.emplace_back(work, k0, k1);
+        }
+        for (auto& th : pool) th.join();
     }
-    // ---- device staging ----------------------------------------------------------------------------------------------------------
+    if (first_bad.load() < n) {
+        const int k = first_bad.load(), c = bad_code[(size_t)k];
+        if (c == -1) return fail(TRS_E_ARG, "offsets not ascending at record %d", k);
+        if (c == -2) return fail(TRS_E_RANGE, "record %d does not have the stated size %dx%d", k, h, w);
+        if (c == -3) return fail(TRS_E_RANGE, "more than 64 distinct quantisation / Huffman table sets in one batch");
+        return fail(TRS_E_RANGE, "record %d: %s", k, c == trs::JPG_E_UNSUPPORTED ? "not a baseline 8-bit YCbCr 4:2:0 single-scan JPEG" : "malformed JPEG");
+    }
+    // ---- device staging: the files once, then chunks of records through coefficient and plane buffers ---------------------------
     const size_t blob_bytes = (size_t)offsets_host[n];
-    const int mw = (w + 15) / 16, mh = (h + 15) / 16;
+    const int mw = (w + 15) / 16, mh = (h + 15) / 16, n_mcu = mw * mh;
     const size_t ybytes = (size_t)mw * 16 * mh * 16, cbytes = (size_t)mw * 8 * mh * 8;
-    const size_t planes_bytes = (size_t)n * (ybytes + 2 * cbytes);
+    const size_t coef_per = (size_t)n_mcu * 6 * 64 * sizeof(int16_t);
+    // Entropy decoding is one thread per record and latency bound: the more records in flight the better, so chunks are as large as
+    // ~8 GB of staging allows (87 k records of 120x160)
+    size_t chunk = ((size_t)8 << 30) / (coef_per + ybytes + 2 * cbytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)n) chunk = (size_t)n;
+    const size_t planes_bytes = chunk * (ybytes + 2 * cbytes), coefs_bytes = chunk * coef_per;
     const size_t meta_bytes = sets.size() * sizeof(trs::JpegTables) + (size_t)n * sizeof(trs::JpegRecord) + 16;
-    if (ctx->jpg_blob_cap < blob_bytes + 16) { cudaFree(ctx->jpg_blob); ctx->jpg_blob = nullptr; ctx->jpg_blob_cap = 0; CU(cudaMalloc(&ctx->jpg_blob, blob_bytes + 16)); ctx->jpg_blob_cap = blob_bytes + 16; }
-    if (ctx->jpg_planes_cap < planes_bytes) { cudaFree(ctx->jpg_planes); ctx->jpg_planes = nullptr; ctx->jpg_planes_cap = 0; CU(cudaMalloc(&ctx->jpg_planes, planes_bytes)); ctx->jpg_planes_cap = planes_bytes; }
+    if (ctx->jpg_blob_cap < blob_bytes + 32) { cudaFree(ctx->jpg_blob); ctx->jpg_blob = nullptr; ctx->jpg_blob_cap = 0; CU(cudaMalloc(&ctx->jpg_blob, blob_bytes + 32)); ctx->jpg_blob_cap = blob_bytes + 32; }
+    if (ctx->jpg_planes_cap < planes_bytes + coefs_bytes) { cudaFree(ctx->jpg_planes); ctx->jpg_planes = nullptr; ctx->jpg_planes_cap = 0; CU(cudaMalloc(&ctx->jpg_planes, planes_bytes + coefs_bytes)); ctx->jpg_planes_cap = planes_bytes + coefs_bytes; }
     if (ctx->jpg_meta_cap < meta_bytes) { cudaFree(ctx->jpg_meta); ctx->jpg_meta = nullptr; ctx->jpg_meta_cap = 0; CU(cudaMalloc(&ctx->jpg_meta, meta_bytes)); ctx->jpg_meta_cap = meta_bytes; }
     trs::JpegTables* d_sets = reinterpret_cast<trs::JpegTables*>(ctx->jpg_meta);
     trs::JpegRecord* d_recs = reinterpret_cast<trs::JpegRecord*>(reinterpret_cast<uint8_t*>(ctx->jpg_meta) + sets.size() * sizeof(trs::JpegTables));
     int* d_status = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(d_recs) + (size_t)n * sizeof(trs::JpegRecord));
+    int16_t* d_coefs = reinterpret_cast<int16_t*>(ctx->jpg_planes);
+    uint8_t* d_planes = ctx->jpg_planes + coefs_bytes;
     CU(cudaMemcpyAsync(ctx->jpg_blob, blob_host, blob_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ctx->jpg_blob + blob_bytes, 0, 32, st));                   // the bit reader loads one 8-byte chunk ahead
     CU(cudaMemcpyAsync(d_sets, sets.data(), sets.size() * sizeof(trs::JpegTables), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_recs, recs.data(), (size_t)n * sizeof(trs::JpegRecord), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(d_status, 0, sizeof(int), st));
-    trs::JpegPlanes P{ctx->jpg_planes, ctx->jpg_planes + (size_t)n * ybytes, ctx->jpg_planes + (size_t)n * (ybytes + cbytes), mw, mh};
-    trs::k_jpeg_entropy_idct<<<(n + trs::JPG_THREADS - 1) / trs::JPG_THREADS, trs::JPG_THREADS, 0, st>>>(ctx->jpg_blob, d_recs, d_sets, n, P, d_status);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CU(cudaGetLastError());
-    const size_t groups = (size_t)n * h * ((w + 3) / 4);
-    size_t want = (groups + 255) / 256;
-    const size_t cap = (size_t)ctx->sm_count * 32;
-    trs::k_jpeg_upsample_rgb<<<(int)(want < cap ? want : cap), 256, 0, st>>>(P, n, h, w, out_u8_dev);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CU(cudaGetLastError());
+    for (size_t c0 = 0; c0 < (size_t)n; c0 += chunk) {
+        const int cn = (int)((size_t)n - c0 < chunk ? (size_t)n - c0 : chunk);
+        CU(cudaMemsetAsync(d_coefs, 0, (size_t)cn * coef_per, st));
+        trs::k_jpeg_entropy<<<(cn + trs::JPG_THREADS - 1) / trs::JPG_THREADS, trs::JPG_THREADS, 0, st>>>(ctx->jpg_blob, d_recs + c0, d_sets, cn, n_mcu, d_coefs,
+                                                                                                      d_status);
+        trs::JpegPlanes P{d_planes, d_planes + (size_t)cn * ybytes, d_planes + (size_t)cn * (ybytes + cbytes), mw, mh};
+        const size_t blocks = (size_t)cn * n_mcu * 6;
+        trs::k_jpeg_idct<<<(unsigned)((blocks + trs::JPG_IDCT_THREADS - 1) / trs::JPG_IDCT_THREADS), trs::JPG_IDCT_THREADS, 0, st>>>(d_coefs, d_recs + c0, d_sets, cn, P);
+        const size_t groups = (size_t)cn * h * ((w + 3) / 4);
+        size_t want = (groups + 255) / 256;
+        const size_t cap = (size_t)ctx->sm_count * 32;
+        trs::k_jpeg_upsample_rgb<<<(int)(want < cap ? want : cap), 256, 0, st>>>(P, cn, h, w, out_u8_dev + c0 * (size_t)h * w * 3);
+        g_launches.fetch_add(3, std::memory_order_relaxed);
+        CU(cudaGetLastError());
+    }
     int status = 0;
     CU(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));                              // recs / sets (host vectors) and the staging buffers are reused
