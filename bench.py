@@ -263,6 +263,44 @@ def other_workloads(torch, dev, local, pool120, h, w):
     out["control_mux_1M_states"] = {"states_per_s": n / t, "hbm_GBps": n * (4 + 48 + 8 + 24 + 8 + 64) / t / 1e9,
                                      "note": "156 B of traffic per car (mode, 6 inputs, speed, 3 outputs, state read + written)"}
     mux.onShutdown()
+    # tub ingestion: JPEG files (packed, pinned host memory) -> GPU decode -> (N,H,W,3) u8 on the device;
+    # host parsing and the H2D copy of the files are inside the timed region (wall clock: the call synchronises)
+    try:
+        import io
+
+        from PIL import Image
+
+        from triton_racer_sim_b200 import tub
+        pool_np = pool120[:256].cpu().numpy()
+        files = []
+        for f in pool_np:
+            b = io.BytesIO()
+            Image.fromarray(f).save(b, format='JPEG')                    # datastorage.py:78
+            files.append(b.getvalue())
+        nrec = 32768
+        blob, offsets = tub.pack_files([files[i % 256] for i in range(nrec)])
+        pinned = torch.empty(len(blob), dtype=torch.uint8, pin_memory=True)
+        pinned.numpy()[:] = blob
+        dec = torch.empty((nrec, h, w, 3), dtype=torch.uint8, device=dev)
+        ctx = nat2.Context(local)
+        for _ in range(2):
+            tub.decode_jpeg_batch((pinned.numpy(), offsets), hw=(h, w), ctx=ctx, out=dec)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            tub.decode_jpeg_batch((pinned.numpy(), offsets), hw=(h, w), ctx=ctx, out=dec)
+        torch.cuda.synchronize()
+        t = (time.perf_counter() - t0) / 3
+        t0 = time.perf_counter()
+        for b in files[:256]:
+            np.asarray(Image.open(io.BytesIO(b)))
+        t_pil = (time.perf_counter() - t0) / 256
+        out["tub_jpeg_ingest_32768x120x160"] = {"records_per_s": nrec / t, "h2d_bytes_per_record": len(blob) / nrec,
+                                                 "pillow_1_thread_records_per_s": 1.0 / t_pil,
+                                                 "note": "baseline 4:2:0 JPEG as the recorder writes it; bit-exact with Pillow; parse + H2D + 3 kernels"}
+        ctx.close()
+    except Exception as e:                                               # Pillow missing on the box: report, do not fail the bench
+        out["tub_jpeg_ingest_32768x120x160"] = {"skipped": repr(e)}
     return out
 
 
