@@ -47,6 +47,17 @@ NOTES = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the real stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def read_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -331,7 +342,7 @@ def run_reference(args):
                          "sample": f"{res['units']} frames of {h}x{w} per step, one process per core, cv2.setNumThreads(1); CPU: {cpu_bench.cpu_model()}"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -348,6 +359,12 @@ def main():
     ap.add_argument("--no-others", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly ONE line, the JSON: everything any library prints meanwhile (NCCL's version banner, torchrun warnings)
+    # is sent to stderr at the file-descriptor level; the descriptor is restored for the final print
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -501,7 +518,7 @@ def main():
             line["e2e"] = e2e
         if others is not None:
             line["other_workloads"] = others
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
