@@ -7,11 +7,11 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import ncu_lines
 
 def phase_table(src_path):
-    names = {'hsv_masks_of': 'hsv', 'p1_strip_walk': 'p1', 'p1b_colour_masks': 'p1b', 'p2_nms': 'p2', 'p3_hysteresis': 'p3', 'p4_output': 'p4',
-             'init_tables': 'prolog', 'k_preprocess_fast': 'main', 'k_preprocess_ws': 'main'}
+    names = {'hsv_masks_of': 'hsv', 'p1_strip_walk': 'p1', 'p1b_colour_masks': 'p1b', 'p2_nms': 'p2', 'p3_hysteresis': 'p3', 'p3_relax_band': 'p3', 'p4_output': 'p4',
+             'init_tables': 'prolog', 'k_preprocess_fast': 'main', 'k_preprocess_sw': 'main', 'k_preprocess_banded': 'main'}
     marks = []
     for i, ln in enumerate(open(src_path), 1):
-        m = re.match(r'(__device__ __forceinline__ \w+ |__global__ void __launch_bounds__\([^)]*\) )(\w+)\(', ln)
+        m = re.match(r'(__device__ __forceinline__ \w+ |__global__ void __launch_bounds__\([^)]*\) |__global__ void __maxnreg__\([^)]*\) )(\w+)\(', ln)
         if m and m.group(2) in names:
             marks.append((i, names[m.group(2)]))
     return marks
