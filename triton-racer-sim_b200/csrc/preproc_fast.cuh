@@ -674,38 +674,57 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
 // Two-level schedule: a warp owns a band of rows and relaxes it to a local fixed point with warp-level synchronisation only
 // (no CTA barrier, no waiting for other warps); one CTA-wide OR per round then tells whether any band changed, i.e. whether
 // growth may still cross a band boundary.  The fixed point is unique, so the schedule does not affect the result.
+// grow the edge bits of plane word t (column wi) from its 3x3 word neighbourhood through its candidates; returns whether it changed
+__device__ __forceinline__ int p3_update_word(uint32_t a_cand, uint32_t a_edge, int t, int wi, int ww)
+{
+    const int rowb = ww * 4;
+    const uint32_t c = lds32(a_cand + 4 * t);
+    const uint32_t ea = a_edge + 4 * t;
+    const uint32_t e = lds32(ea);
+    if (c == e) return 0;
+    const uint32_t mid = e | lds32(ea - rowb) | lds32(ea + rowb);
+    uint32_t lft = 0, rgt = 0;
+    if (wi > 0) lft = lds32(ea - 4) | lds32(ea - rowb - 4) | lds32(ea + rowb - 4);
+    if (wi + 1 < ww) rgt = lds32(ea + 4) | lds32(ea - rowb + 4) | lds32(ea + rowb + 4);
+    const uint32_t spread = mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
+    const uint32_t ne = flood_run((spread & c) | e, c);
+    if (ne == e) return 0;
+    sts32(ea, ne);
+    return 1;
+}
+
 // one warp relaxes its band of rows to a local fixed point; returns whether anything changed
 __device__ __forceinline__ int p3_relax_band(uint32_t a_cand, uint32_t a_edge, int h, int ww, int lane, int gw, int nw)
 {
     const int rows_per = (h + nw - 1) / nw;
     const int y0 = min(h, gw * rows_per), y1 = min(h, y0 + rows_per);
     const int nwords = (y1 - y0) * ww, base = y0 * ww;
-    const int rowb = ww * 4;
     const int wi0 = lane % ww, dwi = 32 % ww;             // word column of this lane's first word, and its step (no division per sweep)
     int band_changed = 0;
     while (true) {
         int changed = 0;
         int wi = wi0;
-        for (int i = lane; i < nwords; i += 32, wi = wi + dwi >= ww ? wi + dwi - ww : wi + dwi) {
-            const int t = base + i;
-            const uint32_t c = lds32(a_cand + 4 * t);
-            const uint32_t ea = a_edge + 4 * t;
-            const uint32_t e = lds32(ea);
-            if (c != e) {
-                const uint32_t mid = e | lds32(ea - rowb) | lds32(ea + rowb);
-                uint32_t lft = 0, rgt = 0;
-                if (wi > 0) lft = lds32(ea - 4) | lds32(ea - rowb - 4) | lds32(ea + rowb - 4);
-                if (wi + 1 < ww) rgt = lds32(ea + 4) | lds32(ea - rowb + 4) | lds32(ea + rowb + 4);
-                const uint32_t spread = mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
-                const uint32_t ne = flood_run((spread & c) | e, c);
-                if (ne != e) { sts32(ea, ne); changed = 1; }
-            }
-        }
+        for (int i = lane; i < nwords; i += 32, wi = wi + dwi >= ww ? wi + dwi - ww : wi + dwi) changed |= p3_update_word(a_cand, a_edge, base + i, wi, ww);
         __syncwarp();
         if (!__any_sync(0xffffffffu, changed)) break;
         band_changed = 1;
     }
     return band_changed;
+}
+
+// After every band of `rows_per` rows has been relaxed on its own (p3_relax_band by nb warps), the only words that can still be short
+// of the global fixed point are those in the rows on either side of a band boundary: one pass over them.  Returns whether any changed
+// (then the growth has to be carried on with full rounds).
+__device__ __forceinline__ int p3_check_band_boundaries(uint32_t a_cand, uint32_t a_edge, int h, int ww, int rows_per, int t0, int tstride)
+{
+    const int nb = (h + rows_per - 1) / rows_per - 1;     // boundaries
+    int changed = 0;
+    for (int i = t0; i < nb * 2 * ww; i += tstride) {
+        const int b = i / (2 * ww), rem = i - b * 2 * ww, rr = rem / ww, wi = rem - rr * ww;
+        const int y = (b + 1) * rows_per - 1 + rr;
+        if (y < h) changed |= p3_update_word(a_cand, a_edge, y * ww + wi, wi, ww);
+    }
+    return changed;
 }
 
 template <class OrReduce>
@@ -1212,7 +1231,10 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
                 // growth across the compute warps' bands: rounds over the whole plane until nothing changes (usually one checking pass)
                 const int NS = SW_THREADS - NC;
                 const uint32_t a_edge = (j & 1) ? S.edge2 : S.edge, a_mask = S.mask + (j & 1) * mask_set_bytes;
-                const int sw = p3_hysteresis(S.cand, a_edge, h, ww, tid - NC, NS, [NS](int c) { return bar_or(4, NS, c); });
+                // the bands' interiors are at their fixed points: only rows next to a band boundary can still change
+                int sw = 0;
+                if (bar_or(4, NS, p3_check_band_boundaries(S.cand, a_edge, h, ww, (h + (NC >> 5) - 1) / (NC >> 5), tid - NC, NS)))
+                    sw = p3_hysteresis(S.cand, a_edge, h, ww, tid - NC, NS, [NS](int c) { return bar_or(4, NS, c); });
                 if (p.stats) {                                           // (the candidate plane is counted before the tail copy lands on it)
                     if (tid == NC) stat_add_one(S, 8, (unsigned long long)sw + 1);
                     count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid - NC, NS);
