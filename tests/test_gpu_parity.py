@@ -213,6 +213,24 @@ def test_locate_golden_tracks(golden_tracks):
         trk2.onShutdown()
 
 
+@pytest.mark.parametrize("which", ["warp", "thread"])
+def test_locate_both_kernels_on_the_golden_states(golden_tracks, monkeypatch, which):
+    """The warp-per-car kernel (shuffle reduction on (distance, index); default for small batches) and the thread-per-car kernel on the
+    reference's own outputs, ties and > 100 sentinel cases included."""
+    monkeypatch.setenv("TRS_LOCATE", which)
+    for name in ("generated_track", "mountain_track"):
+        wp, xyz = golden_tracks[f"wp/{name}"], golden_tracks[f"xyz/{name}"]
+        trk = LocationTracker(wp, 0, 10, device=0)
+        idx, seg = trk.locate_device(torch.from_numpy(xyz).to(DEV))
+        assert np.array_equal(idx.cpu().numpy(), golden_tracks[f"idx/{name}"]), which
+        assert np.array_equal(seg.cpu().numpy(), golden_tracks[f"seg/{name}/0_10"]), which
+        xyz2, _, _, _ = synth.car_states(wp, 30_000, seed=23)
+        idx2, seg2 = trk.locate_device(torch.from_numpy(xyz2).to(DEV))
+        iw, sw_ = oracle.locate(wp, xyz2)
+        assert np.array_equal(idx2.cpu().numpy(), iw) and np.array_equal(seg2.cpu().numpy(), sw_), which
+        trk.onShutdown()
+
+
 def test_locate_large_batch_against_oracle(golden_tracks):
     for name, n in (("generated_track", 200_000), ("mountain_track", 100_000)):
         wp = golden_tracks[f"wp/{name}"]

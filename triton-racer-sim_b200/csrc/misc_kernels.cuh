@@ -186,6 +186,44 @@ __global__ void __launch_bounds__(LOC_THREADS) k_locate(const double* __restrict
     }
 }
 
+// K6b: the same for SMALL batches (N = 1 drop-in, a few thousand cars): one WARP per car, the lanes split the centre line
+// (lane l takes waypoints l, l + 32, ...: ascending, so a lane keeps the first index of its own minimum) and a warp-shuffle
+// reduction on the pair (distance, index) — smaller distance, then smaller index — yields the reference's first-index argmin.
+// A thread per car would leave the GPU empty at these sizes.
+enum { LOCW_THREADS = 256 };
+
+__global__ void __launch_bounds__(LOCW_THREADS) k_locate_warp(const double* __restrict__ wp, int n_wp, double min_map, double max_map,
+                                                              const double* __restrict__ xyz, int n, int32_t* __restrict__ idx_out,
+                                                              double* __restrict__ seg_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps_per_grid) {
+        const double px = xyz[3 * (size_t)k], py = xyz[3 * (size_t)k + 1], pz = xyz[3 * (size_t)k + 2];
+        double best = 100.0;                                     // track_data_process.py:93: the running minimum starts at 100
+        int sel = 0x7fffffff;                                    // "nothing closer than 100 yet"
+        for (int i = lane; i < n_wp; i += 32) {
+            const double d = __dadd_rn(__dadd_rn(fabs(__dsub_rn(px, __ldg(wp + 3 * (size_t)i))), fabs(__dsub_rn(py, __ldg(wp + 3 * (size_t)i + 1)))),
+                                       fabs(__dsub_rn(pz, __ldg(wp + 3 * (size_t)i + 2))));
+            if (d < best) { best = d; sel = i; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int os = __shfl_xor_sync(0xffffffffu, sel, o);
+            if (ob < best || (ob == best && os < sel)) { best = ob; sel = os; }
+        }
+        if (lane == 0) {
+            const int idx = sel == 0x7fffffff ? 0 : sel;        // nothing closer than 100: index 0 (:91-92)
+            if (idx_out) idx_out[k] = idx;
+            if (seg_out) {
+                const double q = __ddiv_rn((double)idx, (double)n_wp);
+                seg_out[k] = __dadd_rn(__dmul_rn(q, __dsub_rn(max_map, min_map)), min_map);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // K7: speed-control tail of the pilots (keras_pilot.py:80-95 == 99-118, 142-153; utils/mapping.py:23-35).
 // Types follow numpy >= 2 promotion with np.float32 model outputs: the products and the speed difference are

@@ -511,6 +511,20 @@ int trs_locate(trs_ctx* ctx, const double* xyz_dev, int n, int32_t* idx_dev, dou
     if (n < 0) return fail(TRS_E_ARG, "negative n");
     if (n == 0) return 0;
     if (!xyz_dev || (!idx_dev && !segment_dev)) return fail(TRS_E_ARG, "null pointer");
+    // small batches: a warp per car with a shuffle reduction (a thread per car would not fill the GPU); TRS_LOCATE=warp|thread forces one
+    const char* force = getenv("TRS_LOCATE");
+    const bool warp_per_car = force ? force[0] == 'w' : n < ctx->sm_count * 256;      // measured crossover ~50 k cars (15 us vs 55 us below it)
+    if (warp_per_car) {
+        const int warps_per_block = trs::LOCW_THREADS / 32;
+        int grid = (n + warps_per_block - 1) / warps_per_block;
+        const int cap = ctx->sm_count * 8;
+        if (grid > cap) grid = cap;
+        trs::k_locate_warp<<<grid, trs::LOCW_THREADS, 0, (cudaStream_t)stream>>>(ctx->wp_dev, ctx->n_wp, ctx->min_map, ctx->max_map, xyz_dev, n, idx_dev,
+                                                                                 segment_dev);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CU(cudaGetLastError());
+        return 0;
+    }
     const int per_block = trs::LOC_THREADS * trs::LOC_CARS;
     const int grid = (n + per_block - 1) / per_block;
     trs::k_locate<<<grid, trs::LOC_THREADS, 0, (cudaStream_t)stream>>>(ctx->wp_dev, ctx->n_wp, ctx->min_map, ctx->max_map, xyz_dev, n, idx_dev, segment_dev);
