@@ -184,7 +184,7 @@ def cpu_reference_leg(cfg, h, w, per_worker):
     }
 
 
-def other_workloads(torch, dev, local, pool120, h, w):
+def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
     """Short runs of the remaining BASELINE.json configurations (device-resident inputs, CUDA events)."""
     import numpy as np
 
@@ -256,6 +256,14 @@ def other_workloads(torch, dev, local, pool120, h, w):
                                         "hbm_GBps": n * 76 / t / 1e9, "note": "fp64 L1 argmin over the centre line, not HBM bound"}
     trk.onShutdown()
     spd.onShutdown()
+    if cpu_legs:                      # the reference's pure-Python loop + math.atan laws on the host cores (bounded sample)
+        try:
+            from oracle import cpu_bench
+            res = cpu_bench.run("cars", 1500, h, w, dict(spd_ctl_break=True))
+            out["waypoint_speed_1M_states"].update({"cpu_states_per_s": res["value"], "cpu_cores": res["cores"],
+                                                    "cpu_sample": f"{res['units']} states ({1500} per worker process), LocationTracker loop + pilot tail"})
+        except Exception as e:
+            out["waypoint_speed_1M_states"]["cpu_skipped"] = repr(e)
     # the step after the speed controller: drive-mode select + launch locks + driver assistance, 1M cars
     from triton_racer_sim_b200 import ControlMultiplexer
     from triton_racer_sim_b200 import _native as nat2
@@ -484,7 +492,7 @@ def main():
     # ---- the other BASELINE.json configurations, short runs on rank 0's GPU (reported, not the headline) -----------
     others = None
     if rank == 0 and not args.no_others:
-        others = other_workloads(torch, dev, local, pool, h, w)
+        others = other_workloads(torch, dev, local, pool, h, w, cpu_legs=not args.no_cpu_baseline)
 
     if rank == 0:
         peak, peak_src = read_peaks()
