@@ -37,6 +37,13 @@ def test_decoder_matches_pillow(h, w, n, kw):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("sub,h,w", [(0, 120, 160), (1, 120, 160), (0, 121, 163), (1, 121, 163), (1, 7, 9), (0, 3, 5), (2, 33, 70)])
+def test_other_chroma_subsamplings(sub, h, w):
+    frames = synth.frame_pool(20, h, w, seed=sub + h + w)
+    files = encode(frames, quality=85, subsampling=sub)                # 0: 4:4:4, 1: 4:2:2, 2: 4:2:0
+    assert np.array_equal(tub.decode_jpeg_batch(files, device=0).cpu().numpy(), pil_decode(files))
+
+
 def test_mixed_table_sets_and_golden_fixture():
     frames = synth.frame_pool(30, 120, 160, seed=3)
     files = [encode(frames[k:k + 1], quality=q)[0] for k, q in enumerate([75, 50, 90] * 10)]      # three table sets in one batch
@@ -52,7 +59,11 @@ def test_unsupported_and_corrupt_files_raise():
     with pytest.raises(ValueError):
         tub.decode_jpeg_batch(encode(frames, progressive=True), device=0)
     with pytest.raises(ValueError):
-        tub.decode_jpeg_batch(encode(frames, subsampling=0), device=0)                              # 4:4:4
+        tub.decode_jpeg_batch(encode(frames[:1], subsampling=0) + encode(frames[1:], subsampling=2), device=0)   # two samplings in one batch
+    grey = io.BytesIO()
+    Image.fromarray(frames[0][..., 0]).save(grey, format="JPEG")
+    with pytest.raises(ValueError):
+        tub.decode_jpeg_batch([grey.getvalue()], hw=(120, 160), device=0)
     ok = encode(frames)
     with pytest.raises(ValueError):
         tub.decode_jpeg_batch([ok[0], ok[1][:200]], device=0)                                       # truncated header

@@ -3,10 +3,10 @@
 // Replaces `np.asarray(Image.open(img_path))` in the reference's tub loaders (TritonRacerSim/components/keras_train.py:41,309),
 // i.e. Pillow -> libjpeg(-turbo) with its default decompression settings, for the files the reference's recorder writes
 // (`Image.fromarray(img).save(path)`, components/datastorage.py:78: baseline sequential, 8 bit, YCbCr 4:2:0, one interleaved
-// scan, no restart intervals).  Every stage restates the published libjpeg algorithm the default path runs, bit for bit:
+// scan, no restart intervals) and for the 4:2:2 / 4:4:4 variants of the same.  Every stage restates the published libjpeg algorithm the default path runs, bit for bit:
 //   entropy decoding          jdhuff.c decode_mcu (canonical Huffman codes, HUFF_EXTEND, zigzag order)
 //   dequantisation + IDCT     jidctint.c jpeg_idct_islow (JDCT_ISLOW, CONST_BITS 13, PASS1_BITS 2)
-//   chroma upsampling         jdsample.c h2v2_fancy_upsample (triangle filter, 3/4 + 1/4 in both directions, edge replication)
+//   chroma upsampling         jdsample.c h2v2_fancy_upsample / h2v1_fancy_upsample (triangle filters, edge replication)
 //   colour conversion         jdcolor.c ycc_rgb_convert (16-bit fixed-point tables)
 // The functions are pure (memory in, memory out, no threads), so the same source is compiled by nvcc into the kernels and by
 // g++ into a host-side check against Pillow (tests/test_jpeg_host.py).
@@ -218,6 +218,24 @@ TRS_JHD int jpg_upsample_h2v2(const uint8_t* c, int cs, int cw, int ch, int x, i
     if (cx == 0) return (thiscol * 4 + 8) >> 4;
     const int lastcol = 3 * r0[cx - 1] + r1[cx - 1];
     return (thiscol * 3 + lastcol + 8) >> 4;
+}
+
+// jdsample.c h2v1_fancy_upsample (4:2:2): horizontal triangle filter only, (3 * this + neighbour + 1 or 2) >> 2, edges replicated
+TRS_JHD int jpg_upsample_h2v1(const uint8_t* c, int cs, int cw, int x, int y)
+{
+    const uint8_t* r0 = c + y * cs;
+    const int cx = x >> 1;
+    if (cw <= 2) return r0[cx];
+    if (x & 1) return (3 * r0[cx] + r0[cx + 1 < cw ? cx + 1 : cx] + 2) >> 2;
+    return (3 * r0[cx] + r0[cx > 0 ? cx - 1 : 0] + 1) >> 2;
+}
+
+// chroma sample for output pixel (x, y) under luma sampling (hs, vs) in {(2,2), (2,1), (1,1)}
+TRS_JHD int jpg_chroma_at(const uint8_t* c, int cs, int cw, int ch, int hs, int vs, int x, int y)
+{
+    if (hs == 2 && vs == 2) return jpg_upsample_h2v2(c, cs, cw, ch, x, y);
+    if (hs == 2) return jpg_upsample_h2v1(c, cs, cw, x, y);
+    return c[y * cs + x];
 }
 
 TRS_JHD void jpg_ycc_to_rgb(int y, int cb, int cr, uint8_t& r, uint8_t& g, uint8_t& b)

@@ -1,7 +1,8 @@
 // jpeg_host.h — host-side parsing of a tub record's JPEG file into the tables and the entropy-coded segment the kernels need.
-// Accepts what the reference's recorder writes (components/datastorage.py:78, Pillow defaults): baseline sequential DCT (SOF0),
-// 8-bit samples, three components sampled 2x2 / 1x1 / 1x1, one interleaved scan, no restart intervals.  Anything else is
-// reported as unsupported (the caller raises; there is no CPU decoder to fall back to).
+// Accepts what the reference's recorder writes (components/datastorage.py:78, Pillow defaults) and its close relatives: baseline
+// sequential DCT (SOF0), 8-bit samples, three components (ids 1, 2, 3 = Y, Cb, Cr) with luma sampled 2x2 (4:2:0), 2x1 (4:2:2) or
+// 1x1 (4:4:4) and chroma 1x1, one interleaved scan, no restart intervals.  Anything else is reported as unsupported (the caller
+// raises; there is no CPU decoder to fall back to).
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -14,6 +15,7 @@ enum { JPG_E_FORMAT = 10, JPG_E_UNSUPPORTED = 11 };
 
 struct JpegScan {
     int h, w;
+    int hs, vs;                       // luma sampling factors: (2,2), (2,1) or (1,1)
     uint32_t data_off, data_len;      // entropy-coded segment: from the byte after the SOS header to the end of the file
 };
 
@@ -107,9 +109,12 @@ inline int jpg_parse(const uint8_t* f, size_t len, JpegTables* T, JpegScan* S)
             if (sl < 15 || seg[0] != 8 || seg[5] != 3) return JPG_E_UNSUPPORTED;
             S->h = (seg[1] << 8) | seg[2];
             S->w = (seg[3] << 8) | seg[4];
-            const int want_hv[3] = {0x22, 0x11, 0x11};
+            const int hv0 = seg[7];
+            if (hv0 != 0x22 && hv0 != 0x21 && hv0 != 0x11) return JPG_E_UNSUPPORTED;
+            S->hs = hv0 >> 4;
+            S->vs = hv0 & 15;
             for (int c = 0; c < 3; ++c) {
-                if (seg[6 + 3 * c] != c + 1 || seg[7 + 3 * c] != want_hv[c] || seg[8 + 3 * c] > 3) return JPG_E_UNSUPPORTED;
+                if (seg[6 + 3 * c] != c + 1 || (c > 0 && seg[7 + 3 * c] != 0x11) || seg[8 + 3 * c] > 3) return JPG_E_UNSUPPORTED;
                 comp_tq[c] = seg[8 + 3 * c];
             }
             if (comp_tq[1] != comp_tq[2]) return JPG_E_UNSUPPORTED;

@@ -22,10 +22,11 @@ struct JpegRecord {
 };
 
 struct JpegPlanes {
-    uint8_t* y;             // per record: (mh*16) x (mw*16)
+    uint8_t* y;             // per record: (mh*8*vs) x (mw*8*hs)
     uint8_t* cb;            // per record: (mh*8) x (mw*8)
     uint8_t* cr;
-    int mw, mh;
+    int mw, mh;             // MCUs per row / column
+    int hs, vs;             // luma sampling factors of the batch: (2,2) 4:2:0, (2,1) 4:2:2, (1,1) 4:4:4
 };
 
 enum { JPG_THREADS = 64, JPG_IDCT_THREADS = 128 };
@@ -117,9 +118,9 @@ __device__ __forceinline__ int jpg_dev_extend(JpegStream& s, int nb)
 }
 
 // Entropy decoding: one thread per record; the non-zero quantised coefficients go to a pre-zeroed (record, block, 64) int16 buffer
-// in natural order.  Block order inside a record: MCU-major, then the six blocks of the MCU (Y00 Y01 Y10 Y11 Cb Cr).
+// in natural order.  Block order inside a record: MCU-major, then the blocks of the MCU (luma in raster order, Cb, Cr).
 __global__ void __launch_bounds__(JPG_THREADS) k_jpeg_entropy(const uint8_t* __restrict__ blob, const JpegRecord* __restrict__ recs,
-                                                             const JpegTables* __restrict__ tables, int n, int n_mcu, int16_t* __restrict__ coefs,
+                                                             const JpegTables* __restrict__ tables, int n, int n_mcu, int luma_blocks, int16_t* __restrict__ coefs,
                                                              int* __restrict__ status)
 {
     __shared__ JpegSmemTables T;
@@ -153,11 +154,12 @@ __global__ void __launch_bounds__(JPG_THREADS) k_jpeg_entropy(const uint8_t* __r
             JpegStream s;
             jpg_stream_open(s, blob + rec.data_off, rec.data_len);
             int dc[3] = {0, 0, 0};
-            int16_t* out = coefs + (size_t)r * n_mcu * 6 * 64;
+            const int bpm = luma_blocks + 2;                       // blocks per MCU: the luma blocks in raster order, then Cb, Cr
+            int16_t* out = coefs + (size_t)r * n_mcu * bpm * 64;
+            int sub = 0;
 #pragma unroll 1
-            for (int blk = 0; blk < n_mcu * 6; ++blk, out += 64) {
-                const int sub = blk % 6;
-                const int comp = sub < 4 ? 0 : sub - 3;
+            for (int blk = 0; blk < n_mcu * bpm; ++blk, out += 64, sub = sub + 1 == bpm ? 0 : sub + 1) {
+                const int comp = sub < luma_blocks ? 0 : sub - luma_blocks + 1;
                 const int td = comp ? 2 : 0, ta = td + 1;
                 int sym = jpg_dev_symbol(s, T, td, err);
                 if (sym) dc[comp] += jpg_dev_extend(s, sym);
@@ -188,13 +190,13 @@ __global__ void __launch_bounds__(JPG_THREADS) k_jpeg_entropy(const uint8_t* __r
 __global__ void __launch_bounds__(JPG_IDCT_THREADS) k_jpeg_idct(const int16_t* __restrict__ coefs, const JpegRecord* __restrict__ recs,
                                                                const JpegTables* __restrict__ tables, int n, JpegPlanes P)
 {
-    const int n_mcu = P.mw * P.mh;
-    const size_t total = (size_t)n * n_mcu * 6;
+    const int n_mcu = P.mw * P.mh, lb = P.hs * P.vs, bpm = lb + 2;
+    const size_t total = (size_t)n * n_mcu * bpm;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int r = (int)(i / ((size_t)n_mcu * 6));
-    const int blk = (int)(i - (size_t)r * n_mcu * 6);
-    const int mcu = blk / 6, sub = blk - 6 * mcu, my = mcu / P.mw, mx = mcu - my * P.mw;
+    const int r = (int)(i / ((size_t)n_mcu * bpm));
+    const int blk = (int)(i - (size_t)r * n_mcu * bpm);
+    const int mcu = blk / bpm, sub = blk - bpm * mcu, my = mcu / P.mw, mx = mcu - my * P.mw;
     const JpegTables& G = tables[recs[r].table_set];
     int16_t coef[64];
     const uint4* src = reinterpret_cast<const uint4*>(coefs + i * 64);
@@ -205,20 +207,22 @@ __global__ void __launch_bounds__(JPG_IDCT_THREADS) k_jpeg_idct(const int16_t* _
 #pragma unroll
         for (int q = 0; q < 4; ++q) { coef[8 * k + 2 * q] = (int16_t)(w[q] & 0xffffu); coef[8 * k + 2 * q + 1] = (int16_t)(w[q] >> 16); }
     }
-    const int ys = P.mw * 16, cs = P.mw * 8;
-    if (sub < 4) {
-        uint8_t* Y = P.y + (size_t)r * ys * P.mh * 16;
-        jpg_idct_islow(coef, G.quant[0], Y + (my * 16 + (sub >> 1) * 8) * ys + mx * 16 + (sub & 1) * 8, ys);
+    const int ys = P.mw * 8 * P.hs, cs = P.mw * 8;
+    if (sub < lb) {
+        uint8_t* Y = P.y + (size_t)r * ys * P.mh * 8 * P.vs;
+        const int by = sub / P.hs, bx = sub - by * P.hs;
+        jpg_idct_islow(coef, G.quant[0], Y + ((my * P.vs + by) * 8) * ys + (mx * P.hs + bx) * 8, ys);
     } else {
-        uint8_t* C = (sub == 4 ? P.cb : P.cr) + (size_t)r * cs * P.mh * 8;
+        uint8_t* C = (sub == lb ? P.cb : P.cr) + (size_t)r * cs * P.mh * 8;
         jpg_idct_islow(coef, G.quant[1], C + my * 8 * cs + mx * 8, cs);
     }
 }
 
 __global__ void __launch_bounds__(256) k_jpeg_upsample_rgb(JpegPlanes P, int n, int h, int w, uint8_t* __restrict__ out)
 {
-    const int ys = P.mw * 16, cs = P.mw * 8;
-    const int cw = (w + 1) / 2, ch = (h + 1) / 2;
+    const int ys = P.mw * 8 * P.hs, cs = P.mw * 8;
+    const int cw = (w + P.hs - 1) / P.hs, ch = (h + P.vs - 1) / P.vs;
+    const bool h2v2 = P.hs == 2 && P.vs == 2;
     const int gpr = (w + 3) / 4;                                   // groups of 4 pixels per row
     const size_t total = (size_t)n * h * gpr;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -228,12 +232,12 @@ __global__ void __launch_bounds__(256) k_jpeg_upsample_rgb(JpegPlanes P, int n, 
         const size_t t = i / gpr;
         const int y = (int)(t % h);
         const size_t r = t / h;
-        const uint8_t* Y = P.y + r * (size_t)ys * P.mh * 16 + (size_t)y * ys;
+        const uint8_t* Y = P.y + r * (size_t)ys * P.mh * 8 * P.vs + (size_t)y * ys;
         const uint8_t* Cb = P.cb + r * (size_t)cs * P.mh * 8;
         const uint8_t* Cr = P.cr + r * (size_t)cs * P.mh * 8;
         uint8_t px[12];
         const int x0 = 4 * g;
-        if (words && cw > 2) {
+        if (words && cw > 2 && h2v2) {
             // four pixels share four chroma columns: column sums 3 * near row + far row once, then the horizontal triangle filter
             // (jdsample.c h2v2_fancy_upsample; the edge formulas equal the general one with the edge column replicated)
             const int cy = y >> 1, cx0 = x0 >> 1;
@@ -258,7 +262,8 @@ __global__ void __launch_bounds__(256) k_jpeg_upsample_rgb(JpegPlanes P, int n, 
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int x = min(x0 + q, w - 1);
-                jpg_ycc_to_rgb(Y[x], jpg_upsample_h2v2(Cb, cs, cw, ch, x, y), jpg_upsample_h2v2(Cr, cs, cw, ch, x, y), px[3 * q], px[3 * q + 1], px[3 * q + 2]);
+                jpg_ycc_to_rgb(Y[x], jpg_chroma_at(Cb, cs, cw, ch, P.hs, P.vs, x, y), jpg_chroma_at(Cr, cs, cw, ch, P.hs, P.vs, x, y), px[3 * q], px[3 * q + 1],
+                               px[3 * q + 2]);
             }
         }
         uint8_t* o = out + ((r * h + y) * (size_t)w + x0) * 3;

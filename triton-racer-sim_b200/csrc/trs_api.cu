@@ -608,6 +608,7 @@ int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned 
     std::vector<trs::JpegTables> sets;
     std::mutex sets_mu;
     std::atomic<int> first_bad{n};
+    std::atomic<int> sampling{0};                                // (hs << 4 | vs) of the batch: every record must agree
     std::vector<int> bad_code((size_t)n, 0);
     unsigned nthreads = std::thread::hardware_concurrency();
     if (nthreads < 1) nthreads = 1;
@@ -630,6 +631,11 @@ int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned 
             memset(&T, 0, sizeof T);
             int pr = trs::jpg_parse(f, len, &T, &S);
             if (!pr && (S.h != h || S.w != w)) pr = -2;
+            if (!pr) {
+                int expect = 0;
+                const int mine = (S.hs << 4) | S.vs;
+                if (!sampling.compare_exchange_strong(expect, mine) && expect != mine) pr = -4;
+            }
             if (pr) { bad_code[(size_t)k] = pr; int cur = first_bad.load(); while (k < cur && !first_bad.compare_exchange_weak(cur, k)) {} continue; }
             size_t si = 0;
             {
@@ -661,13 +667,15 @@ int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned 
         if (c == -1) return fail(TRS_E_ARG, "offsets not ascending at record %d", k);
         if (c == -2) return fail(TRS_E_RANGE, "record %d does not have the stated size %dx%d", k, h, w);
         if (c == -3) return fail(TRS_E_RANGE, "more than 64 distinct quantisation / Huffman table sets in one batch");
-        return fail(TRS_E_RANGE, "record %d: %s", k, c == trs::JPG_E_UNSUPPORTED ? "not a baseline 8-bit YCbCr 4:2:0 single-scan JPEG" : "malformed JPEG");
+        if (c == -4) return fail(TRS_E_RANGE, "record %d has another chroma subsampling than the records before it (one per batch)", k);
+        return fail(TRS_E_RANGE, "record %d: %s", k, c == trs::JPG_E_UNSUPPORTED ? "not a baseline 8-bit YCbCr (4:2:0 / 4:2:2 / 4:4:4) single-scan JPEG" : "malformed JPEG");
     }
     // ---- device staging: the files once, then chunks of records through coefficient and plane buffers ---------------------------
     const size_t blob_bytes = (size_t)offsets_host[n];
-    const int mw = (w + 15) / 16, mh = (h + 15) / 16, n_mcu = mw * mh;
-    const size_t ybytes = (size_t)mw * 16 * mh * 16, cbytes = (size_t)mw * 8 * mh * 8;
-    const size_t coef_per = (size_t)n_mcu * 6 * 64 * sizeof(int16_t);
+    const int hs = sampling.load() >> 4, vs = sampling.load() & 15, lb = hs * vs;
+    const int mw = (w + 8 * hs - 1) / (8 * hs), mh = (h + 8 * vs - 1) / (8 * vs), n_mcu = mw * mh;
+    const size_t ybytes = (size_t)mw * 8 * hs * mh * 8 * vs, cbytes = (size_t)mw * 8 * mh * 8;
+    const size_t coef_per = (size_t)n_mcu * (lb + 2) * 64 * sizeof(int16_t);
     // Entropy decoding is one thread per record and latency bound: the more records in flight the better, so chunks are as large as
     // ~8 GB of staging allows (87 k records of 120x160)
     size_t chunk = ((size_t)8 << 30) / (coef_per + ybytes + 2 * cbytes);
@@ -691,10 +699,10 @@ int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned 
     for (size_t c0 = 0; c0 < (size_t)n; c0 += chunk) {
         const int cn = (int)((size_t)n - c0 < chunk ? (size_t)n - c0 : chunk);
         CU(cudaMemsetAsync(d_coefs, 0, (size_t)cn * coef_per, st));
-        trs::k_jpeg_entropy<<<(cn + trs::JPG_THREADS - 1) / trs::JPG_THREADS, trs::JPG_THREADS, 0, st>>>(ctx->jpg_blob, d_recs + c0, d_sets, cn, n_mcu, d_coefs,
+        trs::k_jpeg_entropy<<<(cn + trs::JPG_THREADS - 1) / trs::JPG_THREADS, trs::JPG_THREADS, 0, st>>>(ctx->jpg_blob, d_recs + c0, d_sets, cn, n_mcu, lb, d_coefs,
                                                                                                       d_status);
-        trs::JpegPlanes P{d_planes, d_planes + (size_t)cn * ybytes, d_planes + (size_t)cn * (ybytes + cbytes), mw, mh};
-        const size_t blocks = (size_t)cn * n_mcu * 6;
+        trs::JpegPlanes P{d_planes, d_planes + (size_t)cn * ybytes, d_planes + (size_t)cn * (ybytes + cbytes), mw, mh, hs, vs};
+        const size_t blocks = (size_t)cn * n_mcu * (lb + 2);
         trs::k_jpeg_idct<<<(unsigned)((blocks + trs::JPG_IDCT_THREADS - 1) / trs::JPG_IDCT_THREADS), trs::JPG_IDCT_THREADS, 0, st>>>(d_coefs, d_recs + c0, d_sets, cn, P);
         const size_t groups = (size_t)cn * h * ((w + 3) / 4);
         size_t want = (groups + 255) / 256;
