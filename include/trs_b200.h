@@ -197,6 +197,16 @@ int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned 
                          uint8_t* out_u8_dev, void* stream);
 
 /*
+ * Gym telemetry ingestion: the camera images of N simulator clients, replacing
+ *   Image.open(BytesIO(base64.b64decode(json_packet["image"])))     TritonRacerSim/components/gyminterface.py:96-99
+ * text_host holds the N base64 strings back to back (standard alphabet, '=' padding optional, white space ignored),
+ * offsets_host N + 1 byte offsets into it.  The strings are decoded on the host (threads) and the JPEG files go through the same
+ * path as trs_jpeg_decode_host.  TRS_E_RANGE: a string is not valid base64 or not a supported JPEG of the stated size.
+ */
+int trs_telemetry_decode_host(trs_ctx* ctx, const char* text_host, const unsigned long long* offsets_host, int n, int h, int w,
+                              uint8_t* out_u8_dev, void* stream);
+
+/*
  * Host-buffer form of trs_preprocess: copies frames host->device in chunks, runs the kernels and
  * copies the requested outputs back, overlapping the three on internal streams; synchronises before
  * returning.  Host buffers may be pageable (slower) or pinned (trs_host_alloc).

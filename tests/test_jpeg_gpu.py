@@ -94,3 +94,28 @@ def test_tub_reader_round_trip(tmp_path):
     assert np.array_equal(u8.cpu().numpy(), oracle.process_batch(want, cfg))
     comp.onShutdown()
     rd.close()
+
+
+def test_telemetry_packets_like_the_gym_interface():
+    """gyminterface.py:95-104: Image.open(BytesIO(base64.b64decode(packet["image"]))) and five floats per packet."""
+    import base64
+    frames = synth.frame_pool(150, 120, 160, seed=17)
+    files = encode(frames)
+    rng = np.random.default_rng(3)
+    packets = []
+    for k, f in enumerate(files):
+        txt = base64.b64encode(f).decode()
+        if k % 7 == 0:
+            txt = "\n".join(txt[i:i + 76] for i in range(0, len(txt), 76))            # MIME-style line breaks are ignored
+        if k % 5 == 0:
+            txt = txt.rstrip("=")                                                       # padding is optional
+        packets.append({"msg_type": "telemetry", "image": txt, "pos_x": str(rng.normal()), "pos_y": float(rng.normal()), "pos_z": 1.5 + k,
+                        "speed": rng.uniform(0, 20), "cte": "0.25"})
+    got = tub.decode_telemetry_batch(packets, device=0)
+    want = np.stack([np.asarray(Image.open(io.BytesIO(f))) for f in files])           # == b64decode of the (re-padded) strings
+    assert np.array_equal(got["cam/img"].cpu().numpy(), want)
+    assert np.array_equal(got["gym/x"].cpu().numpy(), np.asarray([float(p["pos_x"]) for p in packets]))
+    assert np.array_equal(got["gym/cte"].cpu().numpy(), np.full(150, 0.25)) and got["gym/speed"].dtype == torch.float64
+    packets[3]["image"] = packets[3]["image"][:50] + "!" + packets[3]["image"][51:]
+    with pytest.raises(ValueError):
+        tub.decode_telemetry_batch(packets, hw=(120, 160), device=0)

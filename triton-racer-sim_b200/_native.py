@@ -19,7 +19,7 @@ SYMBOLS = [
     "trs_version", "trs_last_error", "trs_kernel_launches", "trs_ctx_create", "trs_ctx_destroy", "trs_ctx_device_info",
     "trs_set_preproc_params", "trs_preprocess", "trs_normalise", "trs_set_track", "trs_locate", "trs_speed_control",
     "trs_preprocess_host", "trs_host_alloc", "trs_host_free", "trs_debug_canny_stages", "trs_control_mux", "trs_pwm_map",
-    "trs_jpeg_decode_host",
+    "trs_jpeg_decode_host", "trs_telemetry_decode_host",
 ]
 MODE_HUMAN, MODE_AI_STEERING, MODE_AI = 0, 1, 2          # TRS_MODE_*: DriveMode.HUMAN / AI_STEERING / AI (components/controller.py:7-10)
 LAUNCH_SLOTS = 4                                          # TRS_LAUNCH_SLOTS
@@ -88,6 +88,7 @@ def load():
     lib.trs_control_mux.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(CtlParams), C.c_double, vp, vp, vp, vp]
     lib.trs_pwm_map.argtypes = [vp, vp, i32, C.c_double, C.c_double, C.c_double, vp, vp]
     lib.trs_jpeg_decode_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.trs_telemetry_decode_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     for name in SYMBOLS:
         getattr(lib, name)
     _lib = lib

@@ -718,6 +718,87 @@ int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned 
     return 0;
 }
 
+int trs_telemetry_decode_host(trs_ctx* ctx, const char* text_host, const unsigned long long* offsets_host, int n, int h, int w,
+                              uint8_t* out_u8_dev, void* stream)
+{
+    if (!ctx) return fail(TRS_E_ARG, "null context");
+    if (n < 0 || h <= 0 || w <= 0) return fail(TRS_E_ARG, "bad size n=%d h=%d w=%d", n, h, w);
+    if (n == 0) return 0;
+    if (!text_host || !offsets_host || !out_u8_dev) return fail(TRS_E_ARG, "null pointer");
+    // base64 -> bytes on the host: output offsets from the text lengths (an upper bound per string), decoded by up to 16 threads
+    std::vector<unsigned long long> offs((size_t)n + 1);
+    offs[0] = 0;
+    for (int k = 0; k < n; ++k) {
+        if (offsets_host[k + 1] < offsets_host[k]) return fail(TRS_E_ARG, "offsets not ascending at packet %d", k);
+        offs[(size_t)k + 1] = offs[(size_t)k] + ((offsets_host[k + 1] - offsets_host[k]) / 4 + 1) * 3;
+    }
+    std::vector<uint8_t> blob((size_t)offs[(size_t)n] + 16);
+    std::vector<unsigned long long> lens((size_t)n, 0);
+    std::atomic<int> first_bad{n};
+    static const struct B64Table {
+        int8_t v[256];
+        B64Table() {
+            for (int i = 0; i < 256; ++i) v[i] = -1;
+            const char* a = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+            for (int i = 0; i < 64; ++i) v[(unsigned char)a[i]] = (int8_t)i;
+            v[(unsigned char)'='] = -2;
+            v[(unsigned char)' '] = v[(unsigned char)'\n'] = v[(unsigned char)'\r'] = v[(unsigned char)'\t'] = -3;
+        }
+    } B64;
+    auto work = [&](int k0, int k1) {
+        for (int k = k0; k < k1; ++k) {
+            const unsigned char* s = reinterpret_cast<const unsigned char*>(text_host) + offsets_host[k];
+            const size_t len = (size_t)(offsets_host[k + 1] - offsets_host[k]);
+            uint8_t* o = blob.data() + offs[(size_t)k];
+            uint32_t acc = 0;
+            int nb = 0;
+            size_t out = 0;
+            bool bad = false;
+            for (size_t i = 0; i < len; ++i) {
+                const int v = B64.v[s[i]];
+                if (v >= 0) {
+                    acc = (acc << 6) | (uint32_t)v;
+                    if (++nb == 4) { o[out++] = (uint8_t)(acc >> 16); o[out++] = (uint8_t)(acc >> 8); o[out++] = (uint8_t)acc; nb = 0; acc = 0; }
+                } else if (v == -2) {
+                    break;                                           // padding: the rest is '='
+                } else if (v != -3) {
+                    bad = true;
+                    break;
+                }
+            }
+            if (nb == 3) { o[out++] = (uint8_t)(acc >> 10); o[out++] = (uint8_t)(acc >> 2); }
+            else if (nb == 2) { o[out++] = (uint8_t)(acc >> 4); }
+            else if (nb == 1) bad = true;
+            if (bad) { int cur = first_bad.load(); while (k < cur && !first_bad.compare_exchange_weak(cur, k)) {} }
+            lens[(size_t)k] = out;
+        }
+    };
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 16) nthreads = 16;
+    if ((unsigned)n < 64 * nthreads) nthreads = 1;
+    if (nthreads == 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> pool;
+        const int per = (n + (int)nthreads - 1) / (int)nthreads;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            const int k0 = (int)t * per, k1 = k0 + per < n ? k0 + per : n;
+            if (k0 < k1) pool.emplace_back(work, k0, k1);
+        }
+        for (auto& th : pool) th.join();
+    }
+    if (first_bad.load() < n) return fail(TRS_E_RANGE, "packet %d: the image string is not valid base64", first_bad.load());
+    // compact the files (the slots were sized by the upper bound) and hand them to the JPEG path
+    std::vector<unsigned long long> foffs((size_t)n + 1);
+    foffs[0] = 0;
+    for (int k = 0; k < n; ++k) {
+        if (foffs[(size_t)k] != offs[(size_t)k]) memmove(blob.data() + foffs[(size_t)k], blob.data() + offs[(size_t)k], (size_t)lens[(size_t)k]);
+        foffs[(size_t)k + 1] = foffs[(size_t)k] + lens[(size_t)k];
+    }
+    return trs_jpeg_decode_host(ctx, blob.data(), foffs.data(), n, h, w, out_u8_dev, stream);
+}
+
 int trs_host_alloc(void** out, unsigned long long bytes)
 {
     if (!out) return fail(TRS_E_ARG, "null out pointer");

@@ -98,3 +98,36 @@ class TubReader:
 
     def close(self):
         self.ctx.close()
+
+
+def decode_telemetry_batch(packets, hw=None, device=None, ctx=None):
+    """N simulator telemetry packets (the dicts ``GymInterface.on_msg_recv`` receives, components/gyminterface.py:95-104) ->
+    ``{'cam/img': (N,H,W,3) uint8 CUDA tensor, 'gym/x', 'gym/y', 'gym/z', 'gym/speed', 'gym/cte': (N,) float64 CUDA tensors}``
+    (the keys GymInterface publishes, gyminterface.py:52).  The base64 image strings are decoded and the JPEGs decompressed behind
+    ``trs_telemetry_decode_host``."""
+    n = len(packets)
+    texts = [p["image"].encode("ascii") if isinstance(p["image"], str) else bytes(p["image"]) for p in packets]
+    text, offsets = pack_files(texts)
+    if hw is None:
+        import base64
+        head = b"".join(texts[0].split())[:2048]                       # the frame header sits in the first few hundred bytes
+        head = head[:len(head) // 4 * 4]
+        hw = jpeg_size(base64.b64decode(head + b"=" * (-len(head) % 4)))
+    h, w = int(hw[0]), int(hw[1])
+    own = ctx is None
+    dev = torch.cuda.current_device() if device is None else int(device if not isinstance(device, torch.device) else device.index)
+    ctx = nat.Context(dev) if own else ctx
+    try:
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=f"cuda:{ctx.device}")
+        text = np.ascontiguousarray(text, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        nat.check(ctx.lib.trs_telemetry_decode_host(ctx.handle, C.c_void_p(text.ctypes.data), C.c_void_p(offsets.ctypes.data), n, h, w,
+                                                    C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(ctx.device).cuda_stream)),
+                  "trs_telemetry_decode_host")
+    finally:
+        if own:
+            ctx.close()
+    res = {"cam/img": out}
+    for key, field in (("gym/x", "pos_x"), ("gym/y", "pos_y"), ("gym/z", "pos_z"), ("gym/speed", "speed"), ("gym/cte", "cte")):
+        res[key] = torch.as_tensor(np.asarray([float(p[field]) for p in packets], np.float64), device=out.device)      # gyminterface.py:100-104
+    return res
