@@ -207,6 +207,49 @@ int trs_telemetry_decode_host(trs_ctx* ctx, const char* text_host, const unsigne
                               uint8_t* out_u8_dev, void* stream);
 
 /*
+ * Forward pass of the pilots' networks, replacing for N frames
+ *   self.model(img_arr) / self.model((img_arr, spd)) / self.model((img_arr, spd, features))
+ *                                           TritonRacerSim/components/keras_pilot.py:59,71,81,104
+ * on the models built by
+ *   Keras_2D_CNN.get_model                  TritonRacerSim/components/keras_train.py:127-174
+ *   Keras_2D_FULL_HOUSE.get_model           TritonRacerSim/components/keras_train.py:184-245
+ * together with the `np.asarray(img, float32) / 255` in front of them (keras_pilot.py:49-50).  Dropout is the identity at inference.
+ * Arithmetic: tcgen05 tensor cores, fp16 operands (10-bit mantissa, as TensorFlow's TF32 convolutions on a GPU), fp32 accumulation,
+ * fp16 activations between layers, fp32 in the Dense heads; not bit-exact with any CPU evaluation (tolerance: tests/test_pilot_gpu.py).
+ *
+ * Weights are host fp32 arrays in Keras layout, named "<layer>/kernel" (Conv2D: (kh, kw, in, out); Dense: (in, out)) and
+ * "<layer>/bias" with the reference's layer names (conv1..conv7, dense1..dense3, output_layer, feature1..feature3; full house:
+ * output_speed, current_spd_1..current_spd_3, dense4..dense6, out_steering).
+ */
+#define TRS_PILOT_CNN_2D 0             /* ModelType.CNN_2D          (utils/types.py): image -> (steering, throttle)          */
+#define TRS_PILOT_CNN_2D_SPD_FTR 1     /* ModelType.CNN_2D_SPD_FTR : image + speed/20 -> (steering, throttle)                 */
+#define TRS_PILOT_CNN_2D_SPD_CTL 2     /* ModelType.CNN_2D_SPD_CTL : image -> (steering, speed/20); same network as CNN_2D    */
+#define TRS_PILOT_CNN_2D_FULL_HOUSE 3  /* ModelType.CNN_2D_FULL_HOUSE: image + speed/20 + loc/segment -> (steering, speed/20) */
+typedef struct trs_pilot trs_pilot;
+typedef struct trs_tensor {
+    const char* name;
+    const float* data;      /* host, C-contiguous */
+    int32_t ndim;
+    int32_t shape[4];
+} trs_tensor;
+/* h, w: frame size (w even, at least 93 x 93 so that every VALID convolution has an output); max_batch: frames per internal chunk
+ * (sizes the activation workspace: about 0.6 MB per 120x160 frame). */
+int trs_pilot_create(trs_ctx* ctx, int model_type, int h, int w, const trs_tensor* weights, int n_weights, int max_batch,
+                     trs_pilot** out);
+int trs_pilot_destroy(trs_pilot* p);
+/*   frames_dev      (N,h,w,3) u8 `cam/img` / `cam/processed_img`
+ *   spd_feature_dev (N) f32 gym/speed / 20   (SPD_FTR, FULL_HOUSE; keras_pilot.py:68,100-101)
+ *   loc_feature_dev (N) f32 loc/segment      (FULL_HOUSE; keras_pilot.py:102-103)
+ *   out_dev         (N,2) f32: the model's output row per frame */
+int trs_pilot_forward(trs_pilot* p, const uint8_t* frames_dev, int n, const float* spd_feature_dev, const float* loc_feature_dev,
+                      float* out_dev, void* stream);
+/* Debug tap for the parity tests: activations of the most recent chunk.  layer 0: the fp16 (h,w,4) input; 1..7: conv outputs, fp16
+ * NHWC; 8: the fp32 partial sums of the first Dense layers.  Copies `bytes` bytes to host_out after synchronising `stream`. */
+int trs_pilot_debug_activation(trs_pilot* p, int layer, void* host_out, unsigned long long bytes, void* stream);
+/* Shape of a layer's output for one frame: (rows, cols, channels). */
+int trs_pilot_layer_shape(trs_pilot* p, int layer, int* ho, int* wo, int* c);
+
+/*
  * Host-buffer form of trs_preprocess: copies frames host->device in chunks, runs the kernels and
  * copies the requested outputs back, overlapping the three on internal streams; synchronises before
  * returning.  Host buffers may be pageable (slower) or pinned (trs_host_alloc).

@@ -1,0 +1,132 @@
+"""The pilots' networks on the tensor cores against the fp32 CPU restatement of the reference's models
+(oracle/pilot_ref.py <- keras_train.py:127-245, keras_pilot.py:49-117).
+
+A floating-point kernel, so a tolerance instead of bit equality: operands are fp16 (10-bit mantissa, what TensorFlow's TF32 convolutions
+keep on a GPU), accumulation fp32.  Two levels:
+  * layer by layer, each layer's fp32 reference fed with the GPU's own fp16 input of that layer: only this layer's rounding remains
+    -> |err| <= 2e-3 * max|activation| (LAYER_TOL);
+  * end to end against the all-fp32 network -> |err| <= 1e-2 on outputs of order 0.1..1 (E2E_TOL).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pilot_ref as ref
+from triton_racer_sim_b200 import synth
+from triton_racer_sim_b200.pilot import KerasPilot, ModelType, PilotNet
+
+pytestmark = pytest.mark.gpu
+
+LAYER_TOL = 2e-3
+E2E_TOL = 1e-2
+KINDS = {ModelType.CNN_2D: ref.CNN_2D, ModelType.CNN_2D_SPD_FTR: ref.CNN_2D_SPD_FTR, ModelType.CNN_2D_SPD_CTL: ref.CNN_2D_SPD_CTL,
+         ModelType.CNN_2D_FULL_HOUSE: ref.CNN_2D_FULL_HOUSE}
+
+
+def features(n, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.uniform(0, 1, n).astype(np.float32), rng.uniform(0, 10, n).astype(np.float32))
+
+
+def test_layer_by_layer():
+    n, h, w = 9, 120, 160
+    frames = synth.frame_pool(n, h, w, seed=11)
+    wts = ref.random_weights(ref.CNN_2D_FULL_HOUSE, h, w, seed=3)
+    spd, loc = features(n, 1)
+    net = PilotNet(ModelType.CNN_2D_FULL_HOUSE, wts, h, w, device=0, max_batch=16)
+    out = net.forward_device(torch.from_numpy(frames).cuda(), torch.from_numpy(spd).cuda(), torch.from_numpy(loc).cuda()).cpu().numpy()
+    # layer 0: x / 255 in fp16, padded to four channels
+    a0 = net.activation(0, n)
+    want0 = (frames.astype(np.float32) / np.float32(255)).astype(np.float16)
+    assert np.array_equal(a0[..., :3], want0) and not a0[..., 3].any()
+    prev = a0[..., :3].astype(np.float32)
+    report = []
+    for layer in range(1, 8):
+        got = net.activation(layer, n).astype(np.float32)
+        want = ref.conv_stack(wts, torch.from_numpy(prev), layer - 1, layer)[0].numpy()
+        assert got.shape == want.shape, (layer, got.shape, want.shape)
+        err = np.abs(got - want).max()
+        report.append((layer, float(err), float(np.abs(want).max())))
+        assert err <= LAYER_TOL * max(1.0, np.abs(want).max()), f"conv{layer}: max|err| {err} (max|act| {np.abs(want).max()}); so far {report}"
+        prev = got
+    flat = torch.from_numpy(prev.reshape(n, -1))
+    want_out = ref.heads(wts, ref.CNN_2D_FULL_HOUSE, flat, spd, loc).numpy()
+    assert np.abs(out - want_out).max() <= 2e-3, f"heads: {np.abs(out - want_out).max()}"
+    e2e = ref.forward(wts, ref.CNN_2D_FULL_HOUSE, frames, spd, loc)
+    assert np.abs(out - e2e).max() <= E2E_TOL, f"end to end: {np.abs(out - e2e).max()}"
+    net.close()
+
+
+@pytest.mark.parametrize("mt", list(KINDS))
+@pytest.mark.parametrize("n,cap", [(1, 8), (37, 64), (130, 48)])
+def test_models_end_to_end(mt, n, cap):
+    h, w = 120, 160
+    frames = synth.frame_pool(n, h, w, seed=5 + n)
+    wts = ref.random_weights(KINDS[mt], h, w, seed=n)
+    spd, loc = features(n, n)
+    net = PilotNet(mt, wts, h, w, device=0, max_batch=cap)
+    out = net.forward_device(torch.from_numpy(frames).cuda(), torch.from_numpy(spd).cuda(), torch.from_numpy(loc).cuda()).cpu().numpy()
+    want = ref.forward(wts, KINDS[mt], frames, spd, loc)
+    assert out.shape == want.shape == (n, 2)
+    assert np.abs(out - want).max() <= E2E_TOL, np.abs(out - want).max()
+    net.close()
+
+
+@pytest.mark.parametrize("h,w", [(240, 320), (122, 166), (96, 94)])
+def test_other_frame_sizes(h, w):
+    n = 5
+    frames = synth.frame_pool(n, h, w, seed=h)
+    wts = ref.random_weights(ref.CNN_2D, h, w, seed=h + w)
+    net = PilotNet(ModelType.CNN_2D, wts, h, w, device=0, max_batch=4)
+    out = net.forward_device(torch.from_numpy(frames).cuda()).cpu().numpy()
+    want = ref.forward(wts, ref.CNN_2D, frames)
+    assert np.abs(out - want).max() <= E2E_TOL, np.abs(out - want).max()
+    net.close()
+
+
+def test_keras_pilot_component_matches_the_reference_glue():
+    """KerasPilot.step: model -> cap / speed control exactly as keras_pilot.py:56-117, given the model outputs."""
+    import oracle
+    n, h, w = 64, 120, 160
+    frames = synth.frame_pool(n, h, w, seed=2)
+    rng = np.random.default_rng(0)
+    speed = rng.uniform(0, 20, n)
+    seg = rng.uniform(0, 10, n)
+    for mt in KINDS:
+        wts = ref.random_weights(KINDS[mt], h, w, seed=1)
+        cfg = dict(spd_ctl_break=True)
+        pilot = KerasPilot(cfg, wts, mt, device=0, max_batch=64)
+        assert pilot.step_inputs == ['cam/img', 'gym/speed', 'loc/segment', 'gym/cte', 'usr/mode']
+        assert pilot.step_outputs == ['ai/steering', 'ai/throttle', 'ai/breaking']
+        assert pilot.step(None, 0, 0, 0, 'ai') == (0.0, 0.0, 0.0)
+        assert pilot.step(frames[0], 1.0, 1.0, 0.0, 'user') == (0.0, 0.0, 0.0)
+        fr = torch.from_numpy(frames).cuda()
+        s, t, b = pilot.step(fr, torch.from_numpy(speed).cuda(), torch.from_numpy(seg).cuda(), None, 'ai')
+        spd_feat = (speed / 20).astype(np.float32)
+        raw = pilot.model.forward_device(fr, torch.from_numpy(spd_feat).cuda(), torch.from_numpy(seg.astype(np.float32)).cuda()).cpu().numpy()
+        if mt in (ModelType.CNN_2D, ModelType.CNN_2D_SPD_FTR):
+            assert np.array_equal(s.cpu().numpy(), np.clip(raw[:, 0].astype(np.float64), -1, 1))
+            assert np.array_equal(t.cpu().numpy(), np.clip(raw[:, 1].astype(np.float64), -1, 1))
+            assert not b.cpu().numpy().any()
+        else:
+            so, th, br, _ = oracle.speed_control(speed, raw[:, 1], raw[:, 0], pilot.cfg)
+            assert np.array_equal(s.cpu().numpy(), so)
+            assert np.allclose(t.cpu().numpy(), th, rtol=1e-5, atol=0) and np.allclose(b.cpu().numpy(), br, rtol=1e-5, atol=0)
+        one = pilot.step(frames[3], float(speed[3]), float(seg[3]), 0.0, 'ai')
+        assert all(isinstance(v, float) for v in one)
+        assert abs(one[0] - float(s[3])) <= 1e-6
+        pilot.onShutdown()
+
+
+def test_missing_or_misshapen_weights_are_refused():
+    wts = ref.random_weights(ref.CNN_2D, 120, 160, seed=0)
+    bad = dict(wts)
+    del bad["conv3/bias"]
+    with pytest.raises(ValueError, match="conv3/bias"):
+        PilotNet(ModelType.CNN_2D, bad, 120, 160, device=0, max_batch=4)
+    bad = dict(wts)
+    bad["dense1/kernel"] = bad["dense1/kernel"][:-1]
+    with pytest.raises(ValueError, match="dense1/kernel"):
+        PilotNet(ModelType.CNN_2D, bad, 120, 160, device=0, max_batch=4)
+    with pytest.raises(ValueError):
+        PilotNet(ModelType.CNN_2D, wts, 120, 161, device=0, max_batch=4)

@@ -20,6 +20,7 @@ SYMBOLS = [
     "trs_set_preproc_params", "trs_preprocess", "trs_normalise", "trs_set_track", "trs_locate", "trs_speed_control",
     "trs_preprocess_host", "trs_host_alloc", "trs_host_free", "trs_debug_canny_stages", "trs_control_mux", "trs_pwm_map",
     "trs_jpeg_decode_host", "trs_telemetry_decode_host",
+    "trs_pilot_create", "trs_pilot_destroy", "trs_pilot_forward", "trs_pilot_debug_activation", "trs_pilot_layer_shape",
 ]
 MODE_HUMAN, MODE_AI_STEERING, MODE_AI = 0, 1, 2          # TRS_MODE_*: DriveMode.HUMAN / AI_STEERING / AI (components/controller.py:7-10)
 LAUNCH_SLOTS = 4                                          # TRS_LAUNCH_SLOTS
@@ -50,6 +51,11 @@ class CtlParams(C.Structure):
         ("throttle_lock_value", C.c_double), ("throttle_lock_duration", C.c_double), ("steering_lock_value", C.c_double),
         ("steering_lock_duration", C.c_double), ("assist_k", C.c_double),
     ]
+
+
+class Tensor(C.Structure):
+    """trs_tensor: one named host weight array in Keras layout."""
+    _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("ndim", C.c_int32), ("shape", C.c_int32 * 4)]
 
 
 class NativeError(RuntimeError):
@@ -89,6 +95,11 @@ def load():
     lib.trs_pwm_map.argtypes = [vp, vp, i32, C.c_double, C.c_double, C.c_double, vp, vp]
     lib.trs_jpeg_decode_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.trs_telemetry_decode_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.trs_pilot_create.argtypes = [vp, i32, i32, i32, C.POINTER(Tensor), i32, i32, C.POINTER(vp)]
+    lib.trs_pilot_destroy.argtypes = [vp]
+    lib.trs_pilot_forward.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    lib.trs_pilot_debug_activation.argtypes = [vp, i32, vp, C.c_ulonglong, vp]
+    lib.trs_pilot_layer_shape.argtypes = [vp, i32] + [C.POINTER(C.c_int)] * 3
     for name in SYMBOLS:
         getattr(lib, name)
     _lib = lib

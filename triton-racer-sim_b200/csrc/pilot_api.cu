@@ -1,0 +1,456 @@
+// pilot_api.cu — host side of the pilots' forward pass (include/trs_b200.h: trs_pilot_*): weight repacking from Keras layout, the
+// tiling of every layer, TMA tensor maps, launch sequence.  Kernels: pilot_kernels.cuh.  No CPU evaluation of the network lives here.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pilot_kernels.cuh"
+#include "trs_internal.h"
+
+using namespace trs::pilot;
+
+#define CU(call)                                                       \
+    do {                                                               \
+        cudaError_t _e = (call);                                       \
+        if (_e != cudaSuccess) return trs_i_cuda_fail(_e, #call);      \
+    } while (0)
+
+namespace {
+
+constexpr int N_CONV = 7;
+// keras_train.py:135-152 / 197-211: (kernel, stride, filters)
+const int CONV_K[N_CONV] = {5, 5, 5, 3, 3, 3, 3};
+const int CONV_S[N_CONV] = {2, 2, 2, 1, 1, 1, 1};
+const int CONV_F[N_CONV] = {24, 32, 64, 64, 64, 128, 128};
+
+struct Layer {
+    int kh = 0, kw = 0, stride = 1, cin = 0, cin_mem = 0, cout = 0, npad = 0, stages = 0;
+    int hi = 0, wi = 0, ho = 0, wo = 0;
+    GemmGeom g{};
+    alignas(64) CUtensorMap map_a;
+    alignas(64) CUtensorMap map_b;
+    __half* w_dev = nullptr;      // [npad][nkb * 64]
+    float* b_dev = nullptr;       // [npad]
+    void* in = nullptr;           // activation read
+    void* out = nullptr;          // activation written
+    size_t out_bytes_per_frame = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+
+// Tile of the M dimension: a box of bx output columns x by output rows x bn frames with at most 128 rows that wastes the fewest
+// accumulator rows (frames only stack when a box holds whole rows).
+void choose_box(int wo, int ho, int* bx, int* by, int* bn)
+{
+    double best = -1;
+    for (int x = 1; x <= std::min(wo, BLOCK_M); ++x)
+        for (int y = 1; y <= ho && x * y <= BLOCK_M; ++y) {
+            const int nmax = (x == wo) ? BLOCK_M / (x * y) : 1;
+            for (int n = 1; n <= nmax; ++n) {
+                const double tiles = (double)((wo + x - 1) / x) * ((ho + y - 1) / y) / n;
+                const double eff = (double)wo * ho / (tiles * BLOCK_M);
+                if (eff > best + 1e-9) { best = eff; *bx = x; *by = y; *bn = n; }
+            }
+        }
+}
+
+const trs_tensor* find(const trs_tensor* w, int n, const std::string& name)
+{
+    for (int i = 0; i < n; ++i)
+        if (w[i].name && name == w[i].name) return &w[i];
+    return nullptr;
+}
+
+int need(const trs_tensor* w, int n, const std::string& name, std::initializer_list<int> shape, const trs_tensor** out)
+{
+    const trs_tensor* t = find(w, n, name);
+    if (!t || !t->data) return trs_i_fail(TRS_E_ARG, "weight '%s' is missing", name.c_str());
+    bool ok = t->ndim == (int)shape.size();
+    int i = 0;
+    for (int s : shape) { if (ok && t->shape[i] != s) ok = false; ++i; }
+    if (!ok) {
+        char have[64] = "", want[64] = "";
+        for (int k = 0; k < t->ndim && k < 4; ++k) snprintf(have + strlen(have), sizeof have - strlen(have), "%d,", t->shape[k]);
+        for (int s : shape) snprintf(want + strlen(want), sizeof want - strlen(want), "%d,", s);
+        return trs_i_fail(TRS_E_ARG, "weight '%s' has shape (%s), the model needs (%s)", name.c_str(), have, want);
+    }
+    *out = t;
+    return 0;
+}
+
+template <int NPAD, int STAGES, bool F32>
+int launch_gemm(const Layer& L, int nf, cudaStream_t st)
+{
+    constexpr int smem = gemm_smem_bytes(NPAD, STAGES);
+    GemmGeom g = L.g;
+    g.nf = nf;
+    const long long tiles = (long long)g.x_tiles * g.y_tiles * ((nf + g.bn - 1) / g.bn);
+    k_pilot_gemm<NPAD, STAGES, F32><<<(unsigned)tiles, GEMM_THREADS, smem, st>>>(L.map_a, L.map_b, g, L.b_dev, L.out);
+    CU(cudaGetLastError());
+    trs_i_count_launches(1);
+    return 0;
+}
+
+template <int NPAD, int STAGES, bool F32>
+cudaError_t allow_smem()
+{
+    return cudaFuncSetAttribute(k_pilot_gemm<NPAD, STAGES, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(NPAD, STAGES));
+}
+
+}  // namespace
+
+struct trs_pilot {
+    trs_ctx* ctx = nullptr;
+    int device = 0, sm_count = 0;
+    int kind = 0, h = 0, w = 0, cap = 0;
+    Layer L[N_CONV + 1];              // seven convolutions + the first Dense layers of the heads as one GEMM
+    __half* in16 = nullptr;           // (cap,h,w,4) fp16
+    float* partial = nullptr;         // (cap, ldp) fp32
+    float* blob_dev = nullptr;
+    HeadsArgs heads{};
+    int heads_smem = 0;
+    int last_n = 0;
+};
+
+namespace {
+
+int encode_maps(trs_pilot* p, Layer& L)
+{
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return trs_i_fail(TRS_E_STATE, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t es = 2;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)L.kw * L.cin_mem, (cuuint64_t)L.wo, (cuuint64_t)L.kh, (cuuint64_t)L.ho, (cuuint64_t)p->cap};
+        const cuuint64_t strides[4] = {(cuuint64_t)L.stride * L.cin_mem * es, (cuuint64_t)L.wi * L.cin_mem * es,
+                                       (cuuint64_t)L.stride * L.wi * L.cin_mem * es, (cuuint64_t)L.hi * L.wi * L.cin_mem * es};
+        const cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)L.g.bx, 1u, (cuuint32_t)L.g.by, (cuuint32_t)L.g.bn};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        for (int i = 0; i < 4; ++i)
+            if (strides[i] % 16) return trs_i_fail(TRS_E_ARG, "activation stride %llu of a %dx%dx%d layer is not a multiple of 16 bytes (frame width must be even)",
+                                                   (unsigned long long)strides[i], L.hi, L.wi, L.cin_mem);
+        CUresult r = enc(&L.map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, L.in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return trs_i_fail(TRS_E_STATE, "cuTensorMapEncodeTiled (activations %dx%dx%d) failed: CUresult %d", L.hi, L.wi, L.cin_mem, (int)r);
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)L.g.nkb * BLOCK_K, (cuuint64_t)L.npad};
+        const cuuint64_t strides[1] = {(cuuint64_t)L.g.nkb * BLOCK_K * es};
+        const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)L.npad};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&L.map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L.w_dev, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return trs_i_fail(TRS_E_STATE, "cuTensorMapEncodeTiled (weights) failed: CUresult %d", (int)r);
+    }
+    return 0;
+}
+
+// B operand of a layer: [npad][kernel rows][kchunks * 64] fp16, zero where a (kw, channel) run is shorter than its chunks or a
+// channel / filter is padding.  `rows` picks the filters: rows[j] = (source tensor, column) or nullptr.
+struct FilterSrc { const float* data; int col; int n_cols; };
+
+int upload_weights(Layer& L, const std::vector<FilterSrc>& filt, const std::vector<float>& bias)
+{
+    const size_t ktot = (size_t)L.g.nkb * BLOCK_K;
+    std::vector<__half> hb((size_t)L.npad * ktot, __float2half(0.0f));
+    const int run = L.kw * L.cin_mem;
+    for (int j = 0; j < (int)filt.size(); ++j) {
+        if (!filt[j].data) continue;
+        for (int r = 0; r < L.kh; ++r)
+            for (int e = 0; e < run; ++e) {
+                const int kw = e / L.cin_mem, c = e % L.cin_mem;
+                if (c >= L.cin) continue;
+                // Keras (kh, kw, in, out): ((r * KW + kw) * Cin + c) * n_cols + col;  Dense (in, out) is the kh = kw = 1 case
+                const float v = filt[j].data[(((size_t)r * L.kw + kw) * L.cin + c) * filt[j].n_cols + filt[j].col];
+                hb[(size_t)j * ktot + (size_t)r * L.g.kchunks * BLOCK_K + e] = __float2half_rn(v);
+            }
+    }
+    CU(cudaMalloc(&L.w_dev, hb.size() * sizeof(__half)));
+    CU(cudaMemcpy(L.w_dev, hb.data(), hb.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    std::vector<float> b(L.npad, 0.0f);
+    for (size_t j = 0; j < bias.size() && j < b.size(); ++j) b[j] = bias[j];
+    CU(cudaMalloc(&L.b_dev, b.size() * sizeof(float)));
+    CU(cudaMemcpy(L.b_dev, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int append(std::vector<float>& blob, const trs_tensor* t)
+{
+    size_t n = 1;
+    for (int i = 0; i < t->ndim; ++i) n *= (size_t)t->shape[i];
+    const int off = (int)blob.size();
+    blob.insert(blob.end(), t->data, t->data + n);
+    return off;
+}
+
+void destroy(trs_pilot* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (Layer& L : p->L) {
+        cudaFree(L.w_dev);
+        cudaFree(L.b_dev);
+        if (&L != &p->L[N_CONV]) cudaFree(L.out);
+    }
+    cudaFree(p->in16);
+    cudaFree(p->partial);
+    cudaFree(p->blob_dev);
+    delete p;
+}
+
+int build(trs_pilot* p, const trs_tensor* w, int nw)
+{
+    // geometry of the convolutions (VALID padding: keras_train.py:135-152)
+    int hi = p->h, wi = p->w, cin = 3, cin_mem = 4;
+    for (int i = 0; i < N_CONV; ++i) {
+        Layer& L = p->L[i];
+        L.kh = L.kw = CONV_K[i];
+        L.stride = CONV_S[i];
+        L.cin = cin; L.cin_mem = cin_mem; L.cout = CONV_F[i];
+        L.npad = L.cout <= 32 ? 32 : (L.cout <= 64 ? 64 : 128);
+        L.stages = L.npad == 128 ? 3 : 4;
+        L.hi = hi; L.wi = wi;
+        L.ho = (hi - L.kh) / L.stride + 1;
+        L.wo = (wi - L.kw) / L.stride + 1;
+        if (hi < L.kh || wi < L.kw || L.ho < 1 || L.wo < 1)
+            return trs_i_fail(TRS_E_RANGE, "a %dx%d frame is too small: conv%d would have no output", p->h, p->w, i + 1);
+        GemmGeom& g = L.g;
+        choose_box(L.wo, L.ho, &g.bx, &g.by, &g.bn);
+        g.wo = L.wo; g.ho = L.ho; g.nf = 0;
+        g.x_tiles = (L.wo + g.bx - 1) / g.bx;
+        g.y_tiles = (L.ho + g.by - 1) / g.by;
+        g.kchunks = (L.kw * L.cin_mem + BLOCK_K - 1) / BLOCK_K;
+        g.nkb = L.kh * g.kchunks;
+        g.n_valid = L.cout;
+        g.ldc = L.cout;
+        L.out_bytes_per_frame = (size_t)L.ho * L.wo * L.cout * sizeof(__half);
+        hi = L.ho; wi = L.wo; cin = cin_mem = L.cout;
+    }
+    const int flat = hi * wi * cin;                       // Flatten of the NHWC tensor (keras_train.py:153)
+    const bool full = p->kind == TRS_PILOT_CNN_2D_FULL_HOUSE;
+    const int nfeat = p->kind == TRS_PILOT_CNN_2D_SPD_FTR ? 1 : 0;
+
+    // workspace
+    CU(cudaMalloc(&p->in16, (size_t)p->cap * p->h * p->w * 4 * sizeof(__half)));
+    for (int i = 0; i < N_CONV; ++i) {
+        CU(cudaMalloc(&p->L[i].out, (size_t)p->cap * p->L[i].out_bytes_per_frame));
+        p->L[i].in = i == 0 ? (void*)p->in16 : p->L[i - 1].out;
+    }
+
+    // convolution weights
+    for (int i = 0; i < N_CONV; ++i) {
+        Layer& L = p->L[i];
+        const std::string name = "conv" + std::to_string(i + 1);
+        const trs_tensor *k, *b;
+        int rc;
+        if ((rc = need(w, nw, name + "/kernel", {L.kh, L.kw, L.cin, L.cout}, &k))) return rc;
+        if ((rc = need(w, nw, name + "/bias", {L.cout}, &b))) return rc;
+        std::vector<FilterSrc> filt(L.cout);
+        for (int j = 0; j < L.cout; ++j) filt[j] = {k->data, j, L.cout};
+        if ((rc = upload_weights(L, filt, std::vector<float>(b->data, b->data + L.cout)))) return rc;
+        if ((rc = encode_maps(p, L))) return rc;
+    }
+
+    // heads (keras_train.py:155-166 | 213-241)
+    std::vector<float> blob;
+    HeadsArgs& H = p->heads;
+    H.n_heads = full ? 2 : 1;
+    const char* d_names[2][4] = {{"dense1", "dense2", "dense3", full ? "output_speed" : "output_layer"},
+                                 {"dense4", "dense5", "dense6", "out_steering"}};
+    const char* f_names[2][3] = {{"feature1", "feature2", "feature3"}, {"current_spd_1", "current_spd_2", "current_spd_3"}};
+    Layer& D = p->L[N_CONV];
+    D.kh = D.kw = 1; D.stride = 1; D.cin = D.cin_mem = flat; D.hi = D.wi = D.ho = D.wo = 1;
+    D.npad = full ? 256 : 128;
+    D.stages = 3;
+    D.cout = full ? 228 : 100;
+    {
+        GemmGeom& g = D.g;
+        g.bx = 1; g.by = 1; g.bn = BLOCK_M;
+        g.wo = 1; g.ho = 1; g.x_tiles = 1; g.y_tiles = 1;
+        g.kchunks = (flat + BLOCK_K - 1) / BLOCK_K;
+        g.nkb = g.kchunks;
+        g.n_valid = D.cout;
+        g.ldc = D.npad;
+    }
+    H.ldp = D.npad;
+    std::vector<FilterSrc> filt(D.cout, FilterSrc{nullptr, 0, 0});
+    for (int h = 0; h < H.n_heads; ++h) {
+        HeadDesc& d = H.head[h];
+        int rc;
+        const int widths[3] = {full ? 16 : 4 * nfeat, full ? 32 : 8 * nfeat, full ? 64 : 16 * nfeat};
+        int prev = 1;
+        for (int i = 0; i < 3; ++i) {
+            d.fw[i] = widths[i];
+            if (!widths[i]) continue;
+            const trs_tensor *k, *b;
+            if ((rc = need(w, nw, std::string(f_names[h][i]) + "/kernel", {prev, widths[i]}, &k))) return rc;
+            if ((rc = need(w, nw, std::string(f_names[h][i]) + "/bias", {widths[i]}, &b))) return rc;
+            d.f_w[i] = append(blob, k);
+            d.f_b[i] = append(blob, b);
+            prev = widths[i];
+        }
+        d.n_prev = (full && h == 1) ? widths[2] : 0;        // keras_train.py:215,231: x = [image, y]; s = Concatenate([x, s])
+        const int ny = widths[2] + d.n_prev;
+        const trs_tensor *k1, *b1, *k2, *b2, *k3, *b3, *ko, *bo;
+        d.n_out = full ? 1 : 2;
+        d.out_slot = full ? (h == 0 ? 1 : 0) : 0;          // keras_train.py:239: Concatenate([out_steering, out_speed])
+        d.part_col = h * 128;
+        if ((rc = need(w, nw, std::string(d_names[h][0]) + "/kernel", {flat + ny, 100}, &k1))) return rc;
+        if ((rc = need(w, nw, std::string(d_names[h][0]) + "/bias", {100}, &b1))) return rc;
+        if ((rc = need(w, nw, std::string(d_names[h][1]) + "/kernel", {100, 50}, &k2))) return rc;
+        if ((rc = need(w, nw, std::string(d_names[h][1]) + "/bias", {50}, &b2))) return rc;
+        if ((rc = need(w, nw, std::string(d_names[h][2]) + "/kernel", {50, 25}, &k3))) return rc;
+        if ((rc = need(w, nw, std::string(d_names[h][2]) + "/bias", {25}, &b3))) return rc;
+        if ((rc = need(w, nw, std::string(d_names[h][3]) + "/kernel", {25, d.n_out}, &ko))) return rc;
+        if ((rc = need(w, nw, std::string(d_names[h][3]) + "/bias", {d.n_out}, &bo))) return rc;
+        for (int j = 0; j < 100; ++j) filt[d.part_col + j] = {k1->data, j, 100};      // image rows of the kernel go to the GEMM
+        d.d1y_w = (int)blob.size();
+        blob.insert(blob.end(), k1->data + (size_t)flat * 100, k1->data + (size_t)(flat + ny) * 100);
+        d.d1_b = append(blob, b1);
+        d.d2_w = append(blob, k2); d.d2_b = append(blob, b2);
+        d.d3_w = append(blob, k3); d.d3_b = append(blob, b3);
+        d.o_w = append(blob, ko);  d.o_b = append(blob, bo);
+    }
+    {
+        int rc;
+        if ((rc = upload_weights(D, filt, std::vector<float>()))) return rc;
+        D.in = p->L[N_CONV - 1].out;
+        // the flattened features of one frame are one "kernel row": dims (flat, 1, 1, 1, cap)
+        D.kw = 1; D.cin_mem = flat; D.wi = 1; D.hi = 1;
+        CU(cudaMalloc(&p->partial, (size_t)p->cap * H.ldp * sizeof(float)));
+        D.out = p->partial;
+        if ((rc = encode_maps(p, D))) return rc;
+    }
+    H.blob_floats = (int)blob.size();
+    CU(cudaMalloc(&p->blob_dev, blob.size() * sizeof(float)));
+    CU(cudaMemcpy(p->blob_dev, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+    p->heads_smem = (H.blob_floats + HEADS_WARPS * HEADS_SCRATCH) * (int)sizeof(float);
+    if (p->heads_smem > 200 * 1024) return trs_i_fail(TRS_E_RANGE, "head weights (%d bytes) do not fit shared memory", p->heads_smem);
+    CU(cudaFuncSetAttribute(k_pilot_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, p->heads_smem));
+    CU((allow_smem<32, 4, false>()));
+    CU((allow_smem<64, 4, false>()));
+    CU((allow_smem<128, 3, false>()));
+    CU((allow_smem<128, 3, true>()));
+    CU((allow_smem<256, 3, true>()));
+    return 0;
+}
+
+int run_layer(const Layer& L, int nf, bool f32, cudaStream_t st)
+{
+    if (f32) return L.npad == 256 ? launch_gemm<256, 3, true>(L, nf, st) : launch_gemm<128, 3, true>(L, nf, st);
+    switch (L.npad) {
+        case 32: return launch_gemm<32, 4, false>(L, nf, st);
+        case 64: return launch_gemm<64, 4, false>(L, nf, st);
+        default: return launch_gemm<128, 3, false>(L, nf, st);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int trs_pilot_create(trs_ctx* ctx, int model_type, int h, int w, const trs_tensor* weights, int n_weights, int max_batch, trs_pilot** out)
+{
+    if (!ctx || !out || !weights || n_weights <= 0) return trs_i_fail(TRS_E_ARG, "null argument");
+    *out = nullptr;
+    if (model_type < TRS_PILOT_CNN_2D || model_type > TRS_PILOT_CNN_2D_FULL_HOUSE) return trs_i_fail(TRS_E_ARG, "unknown model type %d", model_type);
+    if (h < 1 || w < 1 || (w & 1) || ((long long)h * w) % 4) return trs_i_fail(TRS_E_ARG, "frame %dx%d: the width must be even and h*w a multiple of 4", h, w);
+    if (max_batch < 1) return trs_i_fail(TRS_E_ARG, "max_batch=%d", max_batch);
+    trs_pilot* p = new (std::nothrow) trs_pilot();
+    if (!p) return trs_i_fail(TRS_E_ARG, "out of host memory");
+    p->ctx = ctx;
+    p->device = trs_i_ctx_device(ctx);
+    p->sm_count = trs_i_ctx_sm_count(ctx);
+    p->kind = model_type; p->h = h; p->w = w; p->cap = max_batch;
+    cudaError_t e = cudaSetDevice(p->device);
+    if (e != cudaSuccess) { delete p; return trs_i_cuda_fail(e, "cudaSetDevice"); }
+    const int rc = build(p, weights, n_weights);
+    if (rc) { destroy(p); return rc; }
+    *out = p;
+    return 0;
+}
+
+int trs_pilot_destroy(trs_pilot* p)
+{
+    destroy(p);
+    return 0;
+}
+
+int trs_pilot_forward(trs_pilot* p, const uint8_t* frames_dev, int n, const float* spd_feature_dev, const float* loc_feature_dev,
+                      float* out_dev, void* stream)
+{
+    if (!p || !frames_dev || !out_dev) return trs_i_fail(TRS_E_ARG, "null argument");
+    if (n < 0) return trs_i_fail(TRS_E_ARG, "n=%d", n);
+    const bool full = p->kind == TRS_PILOT_CNN_2D_FULL_HOUSE;
+    if ((full || p->kind == TRS_PILOT_CNN_2D_SPD_FTR) && !spd_feature_dev) return trs_i_fail(TRS_E_ARG, "this model needs the speed feature");
+    if (full && !loc_feature_dev) return trs_i_fail(TRS_E_ARG, "the full-house model needs the loc/segment feature");
+    if (((uintptr_t)frames_dev & 3) != 0) return trs_i_fail(TRS_E_ARG, "frames must be 4-byte aligned");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t frame_bytes = (size_t)p->h * p->w * 3;
+    // head 0 reads feature_vec_input, head 1 current_spd_input (keras_train.py:213,226; keras_pilot.py:104)
+    const float* feat0 = full ? loc_feature_dev : spd_feature_dev;
+    const float* feat1 = spd_feature_dev;
+    for (int done = 0; done < n; done += p->cap) {
+        const int m = std::min(p->cap, n - done);
+        const size_t quads = (size_t)m * p->h * p->w / 4;
+        const unsigned grid = (unsigned)std::min<size_t>((quads + 255) / 256, (size_t)p->sm_count * 16);
+        k_pilot_input<<<grid, 256, 0, st>>>(frames_dev + (size_t)done * frame_bytes, p->in16, quads);
+        CU(cudaGetLastError());
+        trs_i_count_launches(1);
+        for (int i = 0; i <= N_CONV; ++i) {
+            const int rc = run_layer(p->L[i], m, i == N_CONV, st);
+            if (rc) return rc;
+        }
+        const unsigned hgrid = (unsigned)std::min((m + HEADS_WARPS - 1) / HEADS_WARPS, p->sm_count);
+        k_pilot_heads<<<hgrid, HEADS_WARPS * 32, p->heads_smem, st>>>(p->heads, p->blob_dev, p->partial, feat0 ? feat0 + done : nullptr,
+                                                                       feat1 ? feat1 + done : nullptr, out_dev + (size_t)done * 2, m);
+        CU(cudaGetLastError());
+        trs_i_count_launches(1);
+        p->last_n = m;
+    }
+    return 0;
+}
+
+int trs_pilot_layer_shape(trs_pilot* p, int layer, int* ho, int* wo, int* c)
+{
+    if (!p || layer < 0 || layer > N_CONV + 1 || !ho || !wo || !c) return trs_i_fail(TRS_E_ARG, "bad layer %d", layer);
+    if (layer == 0) { *ho = p->h; *wo = p->w; *c = 4; }
+    else if (layer <= N_CONV) { *ho = p->L[layer - 1].ho; *wo = p->L[layer - 1].wo; *c = p->L[layer - 1].cout; }
+    else { *ho = 1; *wo = 1; *c = p->heads.ldp; }
+    return 0;
+}
+
+int trs_pilot_debug_activation(trs_pilot* p, int layer, void* host_out, unsigned long long bytes, void* stream)
+{
+    if (!p || layer < 0 || layer > N_CONV + 1 || !host_out) return trs_i_fail(TRS_E_ARG, "bad layer %d", layer);
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    const void* src = layer == 0 ? (const void*)p->in16 : (layer <= N_CONV ? p->L[layer - 1].out : (const void*)p->partial);
+    CU(cudaMemcpy(host_out, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -23,6 +23,7 @@
 #include "misc_kernels.cuh"
 #include "preproc_kernel.cuh"
 #include "preproc_fast.cuh"
+#include "trs_internal.h"
 
 namespace {
 
@@ -87,6 +88,19 @@ struct trs_ctx {
     uint8_t* jpg_planes = nullptr; size_t jpg_planes_cap = 0;
     void* jpg_meta = nullptr;      size_t jpg_meta_cap = 0;
 };
+
+int trs_i_fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+int trs_i_cuda_fail(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+void trs_i_count_launches(int k) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
+int trs_i_ctx_device(const trs_ctx* ctx) { return ctx->device; }
+int trs_i_ctx_sm_count(const trs_ctx* ctx) { return ctx->sm_count; }
 
 namespace {
 
