@@ -243,7 +243,7 @@ int trs_pilot_destroy(trs_pilot* p);
  *   out_dev         (N,2) f32: the model's output row per frame */
 int trs_pilot_forward(trs_pilot* p, const uint8_t* frames_dev, int n, const float* spd_feature_dev, const float* loc_feature_dev,
                       float* out_dev, void* stream);
-/* Debug tap for the parity tests: activations of the most recent chunk.  layer 0: the fp16 (h,w,4) input; 1..7: conv outputs, fp16
+/* Debug tap for the parity tests: activations of the most recent chunk.  layer 1..7: conv outputs, fp16
  * NHWC; 8: the fp32 partial sums of the first Dense layers.  Copies `bytes` bytes to host_out after synchronising `stream`. */
 int trs_pilot_debug_activation(trs_pilot* p, int layer, void* host_out, unsigned long long bytes, void* stream);
 /* Shape of a layer's output for one frame: (rows, cols, channels). */

@@ -63,12 +63,15 @@ EncodeTiledFn encode_fn()
 
 // Tile of the M dimension: a box of bx output columns x by output rows x bn frames with at most 128 rows that wastes the fewest
 // accumulator rows (frames only stack when a box holds whole rows).
-void choose_box(int wo, int ho, int* bx, int* by, int* bn)
+int conv1_pitch_words(int bx) { return (6 * bx + 20 + 3) / 4 + 1; }      // a patch row: 2 bx + 3 pixels, misalignment, one spare word
+
+void choose_box(int wo, int ho, int* bx, int* by, int* bn, bool conv1 = false)
 {
     double best = -1;
     for (int x = 1; x <= std::min(wo, BLOCK_M); ++x)
         for (int y = 1; y <= ho && x * y <= BLOCK_M; ++y) {
-            const int nmax = (x == wo) ? BLOCK_M / (x * y) : 1;
+            if (conv1 && conv1_pitch_words(x) * (2 * y + 3) > C1_PATCH_WORDS) continue;   // the input patch is staged through registers
+            const int nmax = (x == wo && !conv1) ? BLOCK_M / (x * y) : 1;
             for (int n = 1; n <= nmax; ++n) {
                 const double tiles = (double)((wo + x - 1) / x) * ((ho + y - 1) / y) / n;
                 const double eff = (double)wo * ho / (tiles * BLOCK_M);
@@ -102,13 +105,17 @@ int need(const trs_tensor* w, int n, const std::string& name, std::initializer_l
 }
 
 template <int NPAD, int STAGES, bool F32>
-int launch_gemm(const Layer& L, int nf, cudaStream_t st)
+int launch_gemm(const Layer& L, int nf, int sm_count, cudaStream_t st)
 {
     constexpr int smem = gemm_smem_bytes(NPAD, STAGES);
     GemmGeom g = L.g;
     g.nf = nf;
     const long long tiles = (long long)g.x_tiles * g.y_tiles * ((nf + g.bn - 1) / g.bn);
-    k_pilot_gemm<NPAD, STAGES, F32><<<(unsigned)tiles, GEMM_THREADS, smem, st>>>(L.map_a, L.map_b, g, L.b_dev, L.out);
+    if (tiles > 0x7fffffffLL) return trs_i_fail(TRS_E_RANGE, "too many tiles in one launch: lower max_batch");
+    g.tiles = (int)tiles;
+    const int per_sm = NPAD <= 128 ? 2 : 1;                                   // shared memory and 2 x NPAD TMEM columns per CTA
+    const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)sm_count * per_sm);
+    k_pilot_gemm<NPAD, STAGES, F32><<<grid, GEMM_THREADS, smem, st>>>(L.map_a, L.map_b, g, L.b_dev, L.out);
     CU(cudaGetLastError());
     trs_i_count_launches(1);
     return 0;
@@ -127,7 +134,7 @@ struct trs_pilot {
     int device = 0, sm_count = 0;
     int kind = 0, h = 0, w = 0, cap = 0;
     Layer L[N_CONV + 1];              // seven convolutions + the first Dense layers of the heads as one GEMM
-    __half* in16 = nullptr;           // (cap,h,w,4) fp16
+    Conv1Geom c1{};
     float* partial = nullptr;         // (cap, ldp) fp32
     float* blob_dev = nullptr;
     HeadsArgs heads{};
@@ -137,12 +144,12 @@ struct trs_pilot {
 
 namespace {
 
-int encode_maps(trs_pilot* p, Layer& L)
+int encode_maps(trs_pilot* p, Layer& L, bool weights_only = false)
 {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return trs_i_fail(TRS_E_STATE, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t es = 2;
-    {
+    if (!weights_only) {
         const cuuint64_t dims[5] = {(cuuint64_t)L.kw * L.cin_mem, (cuuint64_t)L.wo, (cuuint64_t)L.kh, (cuuint64_t)L.ho, (cuuint64_t)p->cap};
         const cuuint64_t strides[4] = {(cuuint64_t)L.stride * L.cin_mem * es, (cuuint64_t)L.wi * L.cin_mem * es,
                                        (cuuint64_t)L.stride * L.wi * L.cin_mem * es, (cuuint64_t)L.hi * L.wi * L.cin_mem * es};
@@ -171,13 +178,21 @@ int encode_maps(trs_pilot* p, Layer& L)
 // channel / filter is padding.  `rows` picks the filters: rows[j] = (source tensor, column) or nullptr.
 struct FilterSrc { const float* data; int col; int n_cols; };
 
-int upload_weights(Layer& L, const std::vector<FilterSrc>& filt, const std::vector<float>& bias)
+int upload_weights(Layer& L, const std::vector<FilterSrc>& filt, const std::vector<float>& bias, bool conv1 = false)
 {
     const size_t ktot = (size_t)L.g.nkb * BLOCK_K;
     std::vector<__half> hb((size_t)L.npad * ktot, __float2half(0.0f));
     const int run = L.kw * L.cin_mem;
     for (int j = 0; j < (int)filt.size(); ++j) {
         if (!filt[j].data) continue;
+        if (conv1) {
+            // k = kernel row * 16 + (kw * 3 + c); the kernel feeds the raw bytes 0..255, so the 1 / 255 of keras_pilot.py:50 is here
+            for (int r = 0; r < L.kh; ++r)
+                for (int e = 0; e < run; ++e)
+                    hb[(size_t)j * ktot + (size_t)r * 16 + e] =
+                        __float2half_rn(filt[j].data[((size_t)r * run + e) * filt[j].n_cols + filt[j].col] / 255.0f);
+            continue;
+        }
         for (int r = 0; r < L.kh; ++r)
             for (int e = 0; e < run; ++e) {
                 const int kw = e / L.cin_mem, c = e % L.cin_mem;
@@ -214,7 +229,6 @@ void destroy(trs_pilot* p)
         cudaFree(L.b_dev);
         if (&L != &p->L[N_CONV]) cudaFree(L.out);
     }
-    cudaFree(p->in16);
     cudaFree(p->partial);
     cudaFree(p->blob_dev);
     delete p;
@@ -223,7 +237,7 @@ void destroy(trs_pilot* p)
 int build(trs_pilot* p, const trs_tensor* w, int nw)
 {
     // geometry of the convolutions (VALID padding: keras_train.py:135-152)
-    int hi = p->h, wi = p->w, cin = 3, cin_mem = 4;
+    int hi = p->h, wi = p->w, cin = 3, cin_mem = 3;
     for (int i = 0; i < N_CONV; ++i) {
         Layer& L = p->L[i];
         L.kh = L.kw = CONV_K[i];
@@ -237,12 +251,12 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
         if (hi < L.kh || wi < L.kw || L.ho < 1 || L.wo < 1)
             return trs_i_fail(TRS_E_RANGE, "a %dx%d frame is too small: conv%d would have no output", p->h, p->w, i + 1);
         GemmGeom& g = L.g;
-        choose_box(L.wo, L.ho, &g.bx, &g.by, &g.bn);
+        choose_box(L.wo, L.ho, &g.bx, &g.by, &g.bn, i == 0);
         g.wo = L.wo; g.ho = L.ho; g.nf = 0;
         g.x_tiles = (L.wo + g.bx - 1) / g.bx;
         g.y_tiles = (L.ho + g.by - 1) / g.by;
         g.kchunks = (L.kw * L.cin_mem + BLOCK_K - 1) / BLOCK_K;
-        g.nkb = L.kh * g.kchunks;
+        g.nkb = i == 0 ? 2 : L.kh * g.kchunks;             // conv1: K = 5 x 16 in two atoms (k_pilot_conv1)
         g.n_valid = L.cout;
         g.ldc = L.cout;
         L.out_bytes_per_frame = (size_t)L.ho * L.wo * L.cout * sizeof(__half);
@@ -253,11 +267,13 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
     const int nfeat = p->kind == TRS_PILOT_CNN_2D_SPD_FTR ? 1 : 0;
 
     // workspace
-    CU(cudaMalloc(&p->in16, (size_t)p->cap * p->h * p->w * 4 * sizeof(__half)));
     for (int i = 0; i < N_CONV; ++i) {
         CU(cudaMalloc(&p->L[i].out, (size_t)p->cap * p->L[i].out_bytes_per_frame));
-        p->L[i].in = i == 0 ? (void*)p->in16 : p->L[i - 1].out;
+        p->L[i].in = i == 0 ? nullptr : p->L[i - 1].out;     // conv1 reads the caller's u8 frames
     }
+    p->c1.h = p->h; p->c1.w = p->w;
+    p->c1.pitch_words = conv1_pitch_words(p->L[0].g.bx);
+    p->c1.patch_rows = 2 * p->L[0].g.by + 3;
 
     // convolution weights
     for (int i = 0; i < N_CONV; ++i) {
@@ -269,8 +285,8 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
         if ((rc = need(w, nw, name + "/bias", {L.cout}, &b))) return rc;
         std::vector<FilterSrc> filt(L.cout);
         for (int j = 0; j < L.cout; ++j) filt[j] = {k->data, j, L.cout};
-        if ((rc = upload_weights(L, filt, std::vector<float>(b->data, b->data + L.cout)))) return rc;
-        if ((rc = encode_maps(p, L))) return rc;
+        if ((rc = upload_weights(L, filt, std::vector<float>(b->data, b->data + L.cout), i == 0))) return rc;
+        if ((rc = encode_maps(p, L, i == 0))) return rc;
     }
 
     // heads (keras_train.py:155-166 | 213-241)
@@ -349,21 +365,22 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
     p->heads_smem = (H.blob_floats + HEADS_WARPS * HEADS_SCRATCH) * (int)sizeof(float);
     if (p->heads_smem > 200 * 1024) return trs_i_fail(TRS_E_RANGE, "head weights (%d bytes) do not fit shared memory", p->heads_smem);
     CU(cudaFuncSetAttribute(k_pilot_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, p->heads_smem));
-    CU((allow_smem<32, 4, false>()));
+    CU(cudaFuncSetAttribute(k_pilot_conv1, cudaFuncAttributeMaxDynamicSharedMemorySize, c1_smem_bytes()));
+    CU((allow_smem<32, 5, false>()));
     CU((allow_smem<64, 4, false>()));
     CU((allow_smem<128, 3, false>()));
     CU((allow_smem<128, 3, true>()));
-    CU((allow_smem<256, 3, true>()));
+    CU((allow_smem<256, 4, true>()));
     return 0;
 }
 
-int run_layer(const Layer& L, int nf, bool f32, cudaStream_t st)
+int run_layer(const Layer& L, int nf, bool f32, int sms, cudaStream_t st)
 {
-    if (f32) return L.npad == 256 ? launch_gemm<256, 3, true>(L, nf, st) : launch_gemm<128, 3, true>(L, nf, st);
+    if (f32) return L.npad == 256 ? launch_gemm<256, 4, true>(L, nf, sms, st) : launch_gemm<128, 3, true>(L, nf, sms, st);
     switch (L.npad) {
-        case 32: return launch_gemm<32, 4, false>(L, nf, st);
-        case 64: return launch_gemm<64, 4, false>(L, nf, st);
-        default: return launch_gemm<128, 3, false>(L, nf, st);
+        case 32: return launch_gemm<32, 5, false>(L, nf, sms, st);
+        case 64: return launch_gemm<64, 4, false>(L, nf, sms, st);
+        default: return launch_gemm<128, 3, false>(L, nf, sms, st);
     }
 }
 
@@ -415,13 +432,23 @@ int trs_pilot_forward(trs_pilot* p, const uint8_t* frames_dev, int n, const floa
     const float* feat1 = spd_feature_dev;
     for (int done = 0; done < n; done += p->cap) {
         const int m = std::min(p->cap, n - done);
-        const size_t quads = (size_t)m * p->h * p->w / 4;
-        const unsigned grid = (unsigned)std::min<size_t>((quads + 255) / 256, (size_t)p->sm_count * 16);
-        k_pilot_input<<<grid, 256, 0, st>>>(frames_dev + (size_t)done * frame_bytes, p->in16, quads);
-        CU(cudaGetLastError());
-        trs_i_count_launches(1);
-        for (int i = 0; i <= N_CONV; ++i) {
-            const int rc = run_layer(p->L[i], m, i == N_CONV, st);
+        {
+            const Layer& L = p->L[0];
+            GemmGeom g = L.g;
+            g.nf = m;
+            const long long tiles = (long long)g.x_tiles * g.y_tiles * m;
+            if (tiles > 0x7fffffffLL) return trs_i_fail(TRS_E_RANGE, "too many tiles in one launch: lower max_batch");
+            g.tiles = (int)tiles;
+            Conv1Geom c = p->c1;
+            c.total_bytes = (unsigned long long)m * frame_bytes;
+            const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)p->sm_count * 2);
+            k_pilot_conv1<<<grid, C1_THREADS, c1_smem_bytes(), st>>>(L.map_b, g, c, frames_dev + (size_t)done * frame_bytes, L.b_dev,
+                                                                     static_cast<__half*>(L.out));
+            CU(cudaGetLastError());
+            trs_i_count_launches(1);
+        }
+        for (int i = 1; i <= N_CONV; ++i) {
+            const int rc = run_layer(p->L[i], m, i == N_CONV, p->sm_count, st);
             if (rc) return rc;
         }
         const unsigned hgrid = (unsigned)std::min((m + HEADS_WARPS - 1) / HEADS_WARPS, p->sm_count);
@@ -437,8 +464,8 @@ int trs_pilot_forward(trs_pilot* p, const uint8_t* frames_dev, int n, const floa
 int trs_pilot_layer_shape(trs_pilot* p, int layer, int* ho, int* wo, int* c)
 {
     if (!p || layer < 0 || layer > N_CONV + 1 || !ho || !wo || !c) return trs_i_fail(TRS_E_ARG, "bad layer %d", layer);
-    if (layer == 0) { *ho = p->h; *wo = p->w; *c = 4; }
-    else if (layer <= N_CONV) { *ho = p->L[layer - 1].ho; *wo = p->L[layer - 1].wo; *c = p->L[layer - 1].cout; }
+    if (layer == 0) return trs_i_fail(TRS_E_ARG, "layer 0 is the caller's u8 frame: conv1 reads it directly");
+    if (layer <= N_CONV) { *ho = p->L[layer - 1].ho; *wo = p->L[layer - 1].wo; *c = p->L[layer - 1].cout; }
     else { *ho = 1; *wo = 1; *c = p->heads.ldp; }
     return 0;
 }
@@ -448,7 +475,8 @@ int trs_pilot_debug_activation(trs_pilot* p, int layer, void* host_out, unsigned
     if (!p || layer < 0 || layer > N_CONV + 1 || !host_out) return trs_i_fail(TRS_E_ARG, "bad layer %d", layer);
     CU(cudaSetDevice(p->device));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    const void* src = layer == 0 ? (const void*)p->in16 : (layer <= N_CONV ? p->L[layer - 1].out : (const void*)p->partial);
+    if (layer == 0) return trs_i_fail(TRS_E_ARG, "layer 0 is the caller's u8 frame: conv1 reads it directly");
+    const void* src = layer <= N_CONV ? p->L[layer - 1].out : (const void*)p->partial;
     CU(cudaMemcpy(host_out, src, bytes, cudaMemcpyDeviceToHost));
     return 0;
 }

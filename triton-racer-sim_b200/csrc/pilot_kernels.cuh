@@ -37,6 +37,7 @@ struct GemmGeom {
     int nkb;                 // K blocks = kernel rows * kchunks
     int n_valid;             // output columns that exist (<= NPAD)
     int ldc;                 // output row pitch in elements
+    int tiles;               // x_tiles * y_tiles * ceil(nf / bn)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,8 +128,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 
 constexpr int gemm_smem_bytes(int npad, int stages) { return stages * (A_STAGE_BYTES + npad * BLOCK_K * 2) + 1024; }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // C[tile rows, NPAD] = A-box . B^T (+ bias, ReLU, fp16) or raw fp32 partial sums (OUT_F32: the flattened features times the first
 // Dense layers of the heads; bias and activation are applied by k_pilot_heads together with the feature branches).
+// Persistent: CTA c takes tiles c, c + gridDim.x, ...; the producer runs ahead across tile boundaries through the stage ring, and
+// the accumulator is double-buffered in TMEM (2 x NPAD columns) so the epilogue of one tile overlaps the MMAs of the next.
 template <int NPAD, int STAGES, bool OUT_F32>
 __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_constant__ CUtensorMap map_a,
                                                              const __grid_constant__ CUtensorMap map_b, const GemmGeom g,
@@ -136,23 +144,21 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
 {
     constexpr int B_STAGE_BYTES = NPAD * BLOCK_K * 2;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    constexpr int TMEM_COLS = NPAD < 32 ? 32 : NPAD;
+    constexpr int TMEM_COLS = 2 * NPAD;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[STAGES];
     __shared__ __align__(8) uint64_t bar_empty[STAGES];
-    __shared__ __align__(8) uint64_t bar_acc;
+    __shared__ __align__(8) uint64_t bar_acc_full[2];
+    __shared__ __align__(8) uint64_t bar_acc_empty[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ float bias_s[NPAD];
 
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle atoms are 1024-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // tile -> box origin
-    int t = blockIdx.x;
-    const int xt = t % g.x_tiles;  t /= g.x_tiles;
-    const int yt = t % g.y_tiles;  t /= g.y_tiles;
-    const int x0 = xt * g.bx, y0 = yt * g.by, n0 = t * g.bn;
     const uint32_t rows_box = (uint32_t)(g.bx * g.by * g.bn);
 
+    if (!OUT_F32)
+        for (int i = threadIdx.x; i < NPAD; i += GEMM_THREADS) bias_s[i] = __ldg(bias + i);
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
@@ -163,7 +169,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
                 mbar_init(smem_u32(&bar_full[s]), 1);
                 mbar_init(smem_u32(&bar_empty[s]), 1);
             }
-            mbar_init(smem_u32(&bar_acc), 1);
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(smem_u32(&bar_acc_full[a]), 1);
+                mbar_init(smem_u32(&bar_acc_empty[a]), 4);      // one arrival per epilogue warp
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -178,78 +187,102 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < g.nkb; ++kb) {
-                const int s = kb % STAGES, round = kb / STAGES;
-                if (round > 0) mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(round - 1) & 1u);
-                const uint32_t full = smem_u32(&bar_full[s]);
-                mbar_expect_tx(full, rows_box * (BLOCK_K * 2) + B_STAGE_BYTES);
-                const int kr = kb / g.kchunks, ch = kb - kr * g.kchunks;
-                const uint32_t a_dst = tiles + (uint32_t)s * STAGE_BYTES;
-                tma_load_5d(a_dst, &map_a, full, ch * BLOCK_K, x0, kr, y0, n0);
-                tma_load_2d(a_dst + A_STAGE_BYTES, &map_b, full, kb * BLOCK_K, 0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+                int t = tile;
+                const int xt = t % g.x_tiles;  t /= g.x_tiles;
+                const int yt = t % g.y_tiles;  t /= g.y_tiles;
+                const int x0 = xt * g.bx, y0 = yt * g.by, n0 = t * g.bn;
+                for (int kb = 0; kb < g.nkb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, round = it / STAGES;
+                    if (round > 0) mbar_wait(smem_u32(&bar_empty[s]), (round - 1) & 1u);
+                    const uint32_t full = smem_u32(&bar_full[s]);
+                    mbar_expect_tx(full, rows_box * (BLOCK_K * 2) + B_STAGE_BYTES);
+                    const int kr = kb / g.kchunks, ch = kb - kr * g.kchunks;
+                    const uint32_t a_dst = tiles + s * STAGE_BYTES;
+                    tma_load_5d(a_dst, &map_a, full, ch * BLOCK_K, x0, kr, y0, n0);
+                    tma_load_2d(a_dst + A_STAGE_BYTES, &map_b, full, kb * BLOCK_K, 0);
+                }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(NPAD);
-            for (int kb = 0; kb < g.nkb; ++kb) {
-                const int s = kb % STAGES, round = kb / STAGES;
-                mbar_wait(smem_u32(&bar_full[s]), (uint32_t)round & 1u);
+            uint32_t it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++ti) {
+                const uint32_t acc = ti & 1u, use = ti >> 1;
+                if (use > 0) mbar_wait(smem_u32(&bar_acc_empty[acc]), (use - 1) & 1u);     // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_src = tiles + (uint32_t)s * STAGE_BYTES;
-                const uint64_t da = umma_desc_sw128(a_src), db = umma_desc_sw128(a_src + A_STAGE_BYTES);
+                const uint32_t d_tmem = tmem_base + acc * NPAD;
+                for (int kb = 0; kb < g.nkb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, round = it / STAGES;
+                    mbar_wait(smem_u32(&bar_full[s]), round & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_src = tiles + s * STAGE_BYTES;
+                    const uint64_t da = umma_desc_sw128(a_src), db = umma_desc_sw128(a_src + A_STAGE_BYTES);
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)      // +32 bytes inside the swizzle atom per K step
-                    umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
-                umma_commit(smem_u32(&bar_empty[s]));           // stage free once these MMAs have read it
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)      // +32 bytes inside the swizzle atom per K step
+                        umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+                    umma_commit(smem_u32(&bar_empty[s]));           // stage free once these MMAs have read it
+                }
+                umma_commit(smem_u32(&bar_acc_full[acc]));          // accumulator complete
             }
-            umma_commit(smem_u32(&bar_acc));                    // accumulator complete
         }
         __syncwarp();
     } else {
         // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread = one accumulator row = one output pixel
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        const int x = x0 + r % g.bx;
-        const int t2 = r / g.bx;
-        const int y = y0 + t2 % g.by;
-        const int n = n0 + t2 / g.by;
-        const bool live = (uint32_t)r < rows_box && x < g.wo && y < g.ho && n < g.nf;
-        const size_t row = ((size_t)n * g.ho + y) * g.wo + x;
-        mbar_wait(smem_u32(&bar_acc), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int rx = r % g.bx, t2 = r / g.bx;
+        const int ry = t2 % g.by, rn = t2 / g.by;
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++ti) {
+            int t = tile;
+            const int xt = t % g.x_tiles;  t /= g.x_tiles;
+            const int yt = t % g.y_tiles;  t /= g.y_tiles;
+            const int x = xt * g.bx + rx, y = yt * g.by + ry, n = t * g.bn + rn;
+            const bool live = (uint32_t)r < rows_box && x < g.wo && y < g.ho && n < g.nf;
+            const size_t row = ((size_t)n * g.ho + y) * g.wo + x;
+            const uint32_t acc = ti & 1u, use = ti >> 1;
+            mbar_wait(smem_u32(&bar_acc_full[acc]), use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + acc * NPAD + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < NPAD; c += 16) {
-            if (c >= g.n_valid) break;                          // warp-uniform
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (!live) continue;
-            if (OUT_F32) {
-                float4* dst = reinterpret_cast<float4*>(static_cast<float*>(out) + row * g.ldc + c);
+            for (int c = 0; c < NPAD; c += 16) {
+                if (c >= g.n_valid) break;                          // warp-uniform
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (!live) continue;
+                if (OUT_F32) {
+                    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(out) + row * g.ldc + c);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (c + 4 * j < g.n_valid)
-                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                             __uint_as_float(v[4 * j + 3]));
-            } else {
-                uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(out) + row * g.ldc + c);
+                    for (int j = 0; j < 4; ++j)
+                        if (c + 4 * j < g.n_valid)
+                            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                                 __uint_as_float(v[4 * j + 3]));
+                } else {
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(out) + row * g.ldc + c);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (c + 8 * j >= g.n_valid) break;
-                    uint32_t p[4];
+                    for (int j = 0; j < 2; ++j) {
+                        if (c + 8 * j >= g.n_valid) break;
+                        uint32_t p[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int col = c + 8 * j + 2 * e;
-                        const float a = fmaxf(__uint_as_float(v[8 * j + 2 * e]) + __ldg(bias + col), 0.0f);
-                        const float b = fmaxf(__uint_as_float(v[8 * j + 2 * e + 1]) + __ldg(bias + col + 1), 0.0f);
-                        const __half2 h = __floats2half2_rn(a, b);
-                        p[e] = *reinterpret_cast<const uint32_t*>(&h);
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = c + 8 * j + 2 * e;
+                            const float a = fmaxf(__uint_as_float(v[8 * j + 2 * e]) + bias_s[col], 0.0f);
+                            const float b = fmaxf(__uint_as_float(v[8 * j + 2 * e + 1]) + bias_s[col + 1], 0.0f);
+                            const __half2 h = __floats2half2_rn(a, b);
+                            p[e] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        dst[j] = make_uint4(p[0], p[1], p[2], p[3]);
                     }
-                    dst[j] = make_uint4(p[0], p[1], p[2], p[3]);
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -260,30 +293,233 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
     }
 }
 
-// (N,H,W,3) u8 -> (N,H,W,4) fp16 = x / 255 (keras_pilot.py:49-50), fourth channel zero: 8 bytes per pixel, so a pixel step of the
-// stride-2 first convolution is 16 bytes, the granularity a TMA stride needs.  Four pixels (12 bytes in, 32 bytes out) per thread.
-__global__ void __launch_bounds__(256) k_pilot_input(const uint8_t* __restrict__ in, __half* __restrict__ out, size_t n_quads)
+// First convolution (5x5 / 2 on the 3-channel u8 frame, keras_train.py:135 | 197) straight from the camera bytes.
+//
+// Through the TMA path above this layer costs more than the other six together: a kernel row is only 15 values, so 5 of every 8
+// 16-byte chunks TMA moves are padding, and every input byte is fetched 6 times from L2.  Here the CTA stages the tile's input patch
+// (a few KB of u8) in shared memory once, and four builder warps write the im2col rows themselves, already in the 128-byte-swizzled
+// K-major layout tcgen05.mma reads: K = 5 kernel rows x 16 (15 bytes of a row = 5 pixels x RGB, + 1 whose weight is zero).  Bytes
+// become fp16 by bit tricks (0x6400 | b is the half 1024 + b; one HSUB2 gives b exactly), and the 1 / 255 of
+// `np.asarray(img, float32) / 255` (keras_pilot.py:49-50) is folded into the fp16 weights.  The weights (32 x 80) stay resident in
+// shared memory for the CTA's lifetime.  Warps: 0..3 builders, 4 TMEM + MMA issue, 5..8 epilogue.
+constexpr int C1_THREADS = 288;
+constexpr int C1_STAGES = 2;
+constexpr int C1_NPAD = 32;
+constexpr int C1_PATCH_REGS = 6;                          // patch words a builder thread carries for the next tile
+constexpr int C1_PATCH_WORDS = 128 * C1_PATCH_REGS;
+constexpr int C1_A_STAGE = 2 * A_STAGE_BYTES;             // two 64-wide swizzle atoms (k 0..63, k 64..79)
+constexpr int C1_B_BYTES = 2 * C1_NPAD * BLOCK_K * 2;
+constexpr int c1_smem_bytes() { return C1_STAGES * C1_A_STAGE + C1_B_BYTES + 2 * C1_PATCH_WORDS * 4 + 1024; }
+
+struct Conv1Geom {
+    int h, w;                // input frame
+    int pitch_words;         // patch row pitch in 32-bit words
+    int patch_rows;          // 2 * by + 3
+    unsigned long long total_bytes;   // bytes of the frames buffer of this launch
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads)
 {
-    __shared__ __half lut[256];
-    lut[threadIdx.x] = __float2half_rn(__fdiv_rn((float)threadIdx.x, 255.0f));
-    __syncthreads();
-    const uint32_t* in32 = reinterpret_cast<const uint32_t*>(in);
-    uint4* out16 = reinterpret_cast<uint4*>(out);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t w0 = __ldg(in32 + 3 * i), w1 = __ldg(in32 + 3 * i + 1), w2 = __ldg(in32 + 3 * i + 2);
-        const uint8_t b[12] = {(uint8_t)w0, (uint8_t)(w0 >> 8), (uint8_t)(w0 >> 16), (uint8_t)(w0 >> 24),
-                               (uint8_t)w1, (uint8_t)(w1 >> 8), (uint8_t)(w1 >> 16), (uint8_t)(w1 >> 24),
-                               (uint8_t)w2, (uint8_t)(w2 >> 8), (uint8_t)(w2 >> 16), (uint8_t)(w2 >> 24)};
-        uint32_t o[8];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const uint32_t r = __half_as_ushort(lut[b[3 * p]]), gch = __half_as_ushort(lut[b[3 * p + 1]]);
-            const uint32_t bl = __half_as_ushort(lut[b[3 * p + 2]]);
-            o[2 * p] = r | (gch << 16);
-            o[2 * p + 1] = bl;
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constant__ CUtensorMap map_b, const GemmGeom g, const Conv1Geom c,
+                                                            const uint8_t* __restrict__ frames, const float* __restrict__ bias,
+                                                            __half* __restrict__ out)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[C1_STAGES];
+    __shared__ __align__(8) uint64_t bar_empty[C1_STAGES];
+    __shared__ __align__(8) uint64_t bar_acc_full[2];
+    __shared__ __align__(8) uint64_t bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_w;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float bias_s[C1_NPAD];
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_smem = base + C1_STAGES * C1_A_STAGE;
+    uint8_t* const gen_base = smem_raw + (base - smem_u32(smem_raw));
+    uint32_t* const patch = reinterpret_cast<uint32_t*>(gen_base + C1_STAGES * C1_A_STAGE + C1_B_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rows_box = (uint32_t)(g.bx * g.by);
+
+    for (int i = threadIdx.x; i < C1_NPAD; i += C1_THREADS) bias_s[i] = __ldg(bias + i);
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int s = 0; s < C1_STAGES; ++s) {
+                mbar_init(smem_u32(&bar_full[s]), 4);            // one arrival per builder warp
+                mbar_init(smem_u32(&bar_empty[s]), 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(smem_u32(&bar_acc_full[a]), 1);
+                mbar_init(smem_u32(&bar_acc_empty[a]), 4);
+            }
+            mbar_init(smem_u32(&bar_w), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+            // the weights: two 64-wide atoms of 32 rows, once per CTA
+            mbar_expect_tx(smem_u32(&bar_w), C1_B_BYTES);
+            tma_load_2d(b_smem, &map_b, smem_u32(&bar_w), 0, 0);
+            tma_load_2d(b_smem + C1_NPAD * BLOCK_K * 2, &map_b, smem_u32(&bar_w), BLOCK_K, 0);
         }
-        out16[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
-        out16[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2 * C1_NPAD)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp < 4) {
+        // ---- builders: thread r owns accumulator row r = output pixel (ry, rx) of the tile ----
+        const int r = threadIdx.x;
+        const int rx = r % g.bx, ry = r / g.bx;
+        const int words = c.pitch_words * c.patch_rows;
+        const size_t frame_bytes = (size_t)c.h * c.w * 3;
+        const uint32_t* const in32 = reinterpret_cast<const uint32_t*>(frames);
+        uint32_t pre[C1_PATCH_REGS];
+        auto fetch = [&](int tile) {                                 // patch words of `tile` -> registers
+            int t = tile;
+            const int xt = t % g.x_tiles;  t /= g.x_tiles;
+            const int yt = t % g.y_tiles;  t /= g.y_tiles;
+            const size_t origin = (size_t)t * frame_bytes + ((size_t)(2 * yt * g.by) * c.w + 2 * xt * g.bx) * 3;
+#pragma unroll
+            for (int i = 0; i < C1_PATCH_REGS; ++i) {
+                const int wi = r + i * 128;
+                pre[i] = 0;
+                if (wi < words) {
+                    const int j = wi / c.pitch_words, k = wi - j * c.pitch_words;
+                    const size_t src = ((origin + (size_t)j * c.w * 3) & ~(size_t)3) + (size_t)k * 4;
+                    if (2 * yt * g.by + j < c.h && src < c.total_bytes) pre[i] = __ldg(in32 + (src >> 2));
+                }
+            }
+        };
+        uint32_t it = 0;
+        if ((int)blockIdx.x < g.tiles) fetch(blockIdx.x);
+        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++it) {
+            uint32_t* const pbuf = patch + (it & 1u) * C1_PATCH_WORDS;
+#pragma unroll
+            for (int i = 0; i < C1_PATCH_REGS; ++i)
+                if (r + i * 128 < words) pbuf[r + i * 128] = pre[i];
+            named_bar_sync(1, 128);                                  // patch of this tile complete (the other buffer is free: see below)
+            int t = tile;
+            const int xt = t % g.x_tiles;  t /= g.x_tiles;
+            const int yt = t % g.y_tiles;  t /= g.y_tiles;
+            const size_t origin = (size_t)t * frame_bytes + ((size_t)(2 * yt * g.by) * c.w + 2 * xt * g.bx) * 3;
+            if (tile + (int)gridDim.x < g.tiles) fetch(tile + gridDim.x);
+            const uint32_t s = it % C1_STAGES, round = it / C1_STAGES;
+            if (round > 0) mbar_wait(smem_u32(&bar_empty[s]), (round - 1) & 1u);
+            const bool live = (uint32_t)r < rows_box && xt * g.bx + rx < g.wo && yt * g.by + ry < g.ho;
+            if (live) {
+                uint8_t* const a_row = gen_base + s * C1_A_STAGE + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+                for (int kr = 0; kr < 5; ++kr) {
+                    const int j = 2 * ry + kr;
+                    const uint32_t d = (uint32_t)((origin + (size_t)j * c.w * 3) & 3);     // misalignment of this patch row
+                    const uint32_t o = d + 6u * (uint32_t)rx;
+                    const uint32_t* wsrc = pbuf + j * c.pitch_words + (o >> 2);
+                    const uint32_t sel = 0x3210u + 0x1111u * (o & 3u);
+                    const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3], w4 = wsrc[4];
+                    const uint32_t b0 = __byte_perm(w0, w1, sel), b1 = __byte_perm(w1, w2, sel);
+                    const uint32_t b2 = __byte_perm(w2, w3, sel), b3 = __byte_perm(w3, w4, sel);
+                    const uint32_t bw[4] = {b0, b1, b2, b3};
+                    uint32_t hv[8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        // bytes (x0 x1 x2 x3) -> halves 1024 + x (0x64xx), minus 1024 -> the integers 0..255, exact in fp16
+                        const uint32_t lo = __byte_perm(bw[q], 0x64646464u, 0x4140), hi = __byte_perm(bw[q], 0x64646464u, 0x4342);
+                        const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
+                        const __half2 hl = __hsub2(*reinterpret_cast<const __half2*>(&lo), k1024);
+                        const __half2 hh = __hsub2(*reinterpret_cast<const __half2*>(&hi), k1024);
+                        hv[2 * q] = *reinterpret_cast<const uint32_t*>(&hl);
+                        hv[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    // k = kr * 16 .. +15 -> 16-byte chunks 2 kr and 2 kr + 1 of the row; chunks 0..7 in atom 0, 8..9 in atom 1
+                    const int c0 = 2 * kr, c1 = 2 * kr + 1;
+                    uint8_t* const dst0 = a_row + (c0 >> 3) * A_STAGE_BYTES + (((c0 & 7) ^ (r & 7)) << 4);
+                    uint8_t* const dst1 = a_row + (c1 >> 3) * A_STAGE_BYTES + (((c1 & 7) ^ (r & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst0) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+                    *reinterpret_cast<uint4*>(dst1) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+            // The patch buffer written next iteration is the one read two barriers ago: every builder has passed this tile's
+            // named barrier after finishing the reads of the previous tile, so no second barrier is needed.
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(C1_NPAD);
+            mbar_wait(smem_u32(&bar_w), 0);
+            const uint64_t db0 = umma_desc_sw128(b_smem), db1 = umma_desc_sw128(b_smem + C1_NPAD * BLOCK_K * 2);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = it & 1u, use = it >> 1;
+                if (use > 0) mbar_wait(smem_u32(&bar_acc_empty[acc]), (use - 1) & 1u);
+                const uint32_t s = it % C1_STAGES, round = it / C1_STAGES;
+                mbar_wait(smem_u32(&bar_full[s]), round & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + acc * C1_NPAD;
+                const uint64_t da0 = umma_desc_sw128(base + s * C1_A_STAGE), da1 = umma_desc_sw128(base + s * C1_A_STAGE + A_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0));
+                umma_f16(d_tmem, da1, db1, idesc, 1u);              // k = 64..79
+                umma_commit(smem_u32(&bar_empty[s]));
+                umma_commit(smem_u32(&bar_acc_full[acc]));
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int rx = r % g.bx, ry = r / g.bx;
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++ti) {
+            int t = tile;
+            const int xt = t % g.x_tiles;  t /= g.x_tiles;
+            const int yt = t % g.y_tiles;  t /= g.y_tiles;
+            const int x = xt * g.bx + rx, y = yt * g.by + ry;
+            const bool live = (uint32_t)r < rows_box && x < g.wo && y < g.ho;
+            const size_t row = ((size_t)t * g.ho + y) * g.wo + x;
+            const uint32_t acc = ti & 1u, use = ti >> 1;
+            mbar_wait(smem_u32(&bar_acc_full[acc]), use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + acc * C1_NPAD + ((uint32_t)(q * 32) << 16);
+            uint32_t v[16], u[16];
+            tmem_ld16(taddr, v);
+            tmem_ld16(taddr + 16, u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));      // values are in registers: the accumulator is free
+            if (live) {
+                uint4* dst = reinterpret_cast<uint4*>(out + row * g.ldc);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (8 * j >= g.n_valid) break;
+                    uint32_t p[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = 8 * j + 2 * e;
+                        const uint32_t xa = col < 16 ? v[col & 15] : u[col & 15], xb = col < 16 ? v[(col + 1) & 15] : u[(col + 1) & 15];
+                        const float a = fmaxf(__uint_as_float(xa) + bias_s[col], 0.0f);
+                        const float b = fmaxf(__uint_as_float(xb) + bias_s[col + 1], 0.0f);
+                        const __half2 h = __floats2half2_rn(a, b);
+                        p[e] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    dst[j] = make_uint4(p[0], p[1], p[2], p[3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * C1_NPAD) : "memory");
     }
 }
 

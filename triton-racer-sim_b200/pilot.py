@@ -64,7 +64,7 @@ def load_weights(path) -> dict:
 class PilotNet:
     """Batched forward pass: (N,H,W,3) u8 frames [+ speed / 20, + loc/segment] -> (N,2) float32 model outputs."""
 
-    LAYERS = 9          # debug taps: 0 input fp16x4, 1..7 conv outputs, 8 first-Dense partial sums
+    LAYERS = 8          # debug taps: 1..7 conv outputs, 8 first-Dense partial sums
 
     def __init__(self, model_type, weights, h=120, w=160, device=None, max_batch=4096):
         self.model_type = _model_type(model_type)
