@@ -395,6 +395,8 @@ int trs_pilot_create(trs_ctx* ctx, int model_type, int h, int w, const trs_tenso
     if (model_type < TRS_PILOT_CNN_2D || model_type > TRS_PILOT_CNN_2D_FULL_HOUSE) return trs_i_fail(TRS_E_ARG, "unknown model type %d", model_type);
     if (h < 1 || w < 1 || (w & 1) || ((long long)h * w) % 4) return trs_i_fail(TRS_E_ARG, "frame %dx%d: the width must be even and h*w a multiple of 4", h, w);
     if (max_batch < 1) return trs_i_fail(TRS_E_ARG, "max_batch=%d", max_batch);
+    if ((unsigned long long)max_batch * h * w * 3 >= (1ull << 32))
+        return trs_i_fail(TRS_E_RANGE, "max_batch=%d frames of %dx%d exceed 4 GiB per chunk (the first layer addresses a chunk with 32 bits)", max_batch, h, w);
     trs_pilot* p = new (std::nothrow) trs_pilot();
     if (!p) return trs_i_fail(TRS_E_ARG, "out of host memory");
     p->ctx = ctx;

@@ -40,6 +40,31 @@ struct GemmGeom {
     int tiles;               // x_tiles * y_tiles * ceil(nf / bn)
 };
 
+// Walks the tiles c, c + G, c + 2G, ... of a persistent CTA without dividing per tile: (x tile, y tile, frame tile) with carries.
+struct TileWalk {
+    int tile, xt, yt, nt;
+    int gx, gy, gn, stride;
+    __device__ __forceinline__ void init(const GemmGeom& g, int first, int step)
+    {
+        tile = first; stride = step;
+        int t = first;
+        xt = t % g.x_tiles;  t /= g.x_tiles;
+        yt = t % g.y_tiles;  nt = t / g.y_tiles;
+        t = step;
+        gx = t % g.x_tiles;  t /= g.x_tiles;
+        gy = t % g.y_tiles;  gn = t / g.y_tiles;
+    }
+    __device__ __forceinline__ void next(const GemmGeom& g)
+    {
+        tile += stride;
+        xt += gx;
+        if (xt >= g.x_tiles) { xt -= g.x_tiles; ++yt; }
+        yt += gy;
+        if (yt >= g.y_tiles) { yt -= g.y_tiles; ++nt; }
+        nt += gn;
+    }
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -62,13 +87,13 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-// A wait that cannot hang the GPU: a barrier that does not flip within ~2 s of SM clocks is a protocol bug -> trap.
+// A wait that cannot hang the GPU: a barrier that has not flipped after 2^22 polls (each poll already blocks for the hardware's
+// try_wait time limit) is a protocol bug -> trap instead of spinning forever.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    if (mbar_try(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try(bar, parity))
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (++spins == (1u << 22)) __trap();
 }
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4)
@@ -188,20 +213,19 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
-                int t = tile;
-                const int xt = t % g.x_tiles;  t /= g.x_tiles;
-                const int yt = t % g.y_tiles;  t /= g.y_tiles;
-                const int x0 = xt * g.bx, y0 = yt * g.by, n0 = t * g.bn;
+            TileWalk tw;
+            for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g)) {
+                const int x0 = tw.xt * g.bx, y0 = tw.yt * g.by, n0 = tw.nt * g.bn;
+                int kr = 0, ch = 0;
                 for (int kb = 0; kb < g.nkb; ++kb, ++it) {
                     const uint32_t s = it % STAGES, round = it / STAGES;
                     if (round > 0) mbar_wait(smem_u32(&bar_empty[s]), (round - 1) & 1u);
                     const uint32_t full = smem_u32(&bar_full[s]);
                     mbar_expect_tx(full, rows_box * (BLOCK_K * 2) + B_STAGE_BYTES);
-                    const int kr = kb / g.kchunks, ch = kb - kr * g.kchunks;
                     const uint32_t a_dst = tiles + s * STAGE_BYTES;
                     tma_load_5d(a_dst, &map_a, full, ch * BLOCK_K, x0, kr, y0, n0);
                     tma_load_2d(a_dst + A_STAGE_BYTES, &map_b, full, kb * BLOCK_K, 0);
+                    if (++ch == g.kchunks) { ch = 0; ++kr; }
                 }
             }
         }
@@ -237,11 +261,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
         const int rx = r % g.bx, t2 = r / g.bx;
         const int ry = t2 % g.by, rn = t2 / g.by;
         uint32_t ti = 0;
-        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++ti) {
-            int t = tile;
-            const int xt = t % g.x_tiles;  t /= g.x_tiles;
-            const int yt = t % g.y_tiles;  t /= g.y_tiles;
-            const int x = xt * g.bx + rx, y = yt * g.by + ry, n = t * g.bn + rn;
+        TileWalk tw;
+        for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g), ++ti) {
+            const int x = tw.xt * g.bx + rx, y = tw.yt * g.by + ry, n = tw.nt * g.bn + rn;
             const bool live = (uint32_t)r < rows_box && x < g.wo && y < g.ho && n < g.nf;
             const size_t row = ((size_t)n * g.ho + y) * g.wo + x;
             const uint32_t acc = ti & 1u, use = ti >> 1;
@@ -377,60 +399,63 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
         const int r = threadIdx.x;
         const int rx = r % g.bx, ry = r / g.bx;
         const int words = c.pitch_words * c.patch_rows;
-        const size_t frame_bytes = (size_t)c.h * c.w * 3;
+        const uint32_t row_bytes = (uint32_t)c.w * 3u, frame_bytes = (uint32_t)c.h * row_bytes;
+        const uint32_t total = (uint32_t)c.total_bytes;
         const uint32_t* const in32 = reinterpret_cast<const uint32_t*>(frames);
+        // the patch words this thread carries: (patch row, word in row), fixed for the whole launch
+        int pj[C1_PATCH_REGS], pk[C1_PATCH_REGS];
+#pragma unroll
+        for (int i = 0; i < C1_PATCH_REGS; ++i) {
+            const int wi = r + i * 128;
+            pj[i] = wi < words ? wi / c.pitch_words : -1;
+            pk[i] = wi - pj[i] * c.pitch_words;
+        }
         uint32_t pre[C1_PATCH_REGS];
-        auto fetch = [&](int tile) {                                 // patch words of `tile` -> registers
-            int t = tile;
-            const int xt = t % g.x_tiles;  t /= g.x_tiles;
-            const int yt = t % g.y_tiles;  t /= g.y_tiles;
-            const size_t origin = (size_t)t * frame_bytes + ((size_t)(2 * yt * g.by) * c.w + 2 * xt * g.bx) * 3;
+        auto origin_of = [&](const TileWalk& t) { return (uint32_t)t.nt * frame_bytes + ((uint32_t)(2 * t.yt * g.by) * (uint32_t)c.w + 2u * t.xt * g.bx) * 3u; };
+        auto fetch = [&](const TileWalk& t) {                        // patch words of tile t -> registers
+            const uint32_t origin = origin_of(t);
+            const int row0 = 2 * t.yt * g.by;
 #pragma unroll
             for (int i = 0; i < C1_PATCH_REGS; ++i) {
-                const int wi = r + i * 128;
                 pre[i] = 0;
-                if (wi < words) {
-                    const int j = wi / c.pitch_words, k = wi - j * c.pitch_words;
-                    const size_t src = ((origin + (size_t)j * c.w * 3) & ~(size_t)3) + (size_t)k * 4;
-                    if (2 * yt * g.by + j < c.h && src < c.total_bytes) pre[i] = __ldg(in32 + (src >> 2));
-                }
+                const uint32_t src = ((origin + (uint32_t)pj[i] * row_bytes) & ~3u) + 4u * (uint32_t)pk[i];
+                if (pj[i] >= 0 && row0 + pj[i] < c.h && src < total) pre[i] = __ldg(in32 + (src >> 2));
             }
         };
         uint32_t it = 0;
-        if ((int)blockIdx.x < g.tiles) fetch(blockIdx.x);
-        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++it) {
+        TileWalk cur, nxt;
+        cur.init(g, blockIdx.x, gridDim.x);
+        nxt = cur;
+        if (cur.tile < g.tiles) fetch(cur);
+        for (; cur.tile < g.tiles; cur = nxt, ++it) {
             uint32_t* const pbuf = patch + (it & 1u) * C1_PATCH_WORDS;
 #pragma unroll
             for (int i = 0; i < C1_PATCH_REGS; ++i)
-                if (r + i * 128 < words) pbuf[r + i * 128] = pre[i];
+                if (pj[i] >= 0) pbuf[r + i * 128] = pre[i];
             named_bar_sync(1, 128);                                  // patch of this tile complete (the other buffer is free: see below)
-            int t = tile;
-            const int xt = t % g.x_tiles;  t /= g.x_tiles;
-            const int yt = t % g.y_tiles;  t /= g.y_tiles;
-            const size_t origin = (size_t)t * frame_bytes + ((size_t)(2 * yt * g.by) * c.w + 2 * xt * g.bx) * 3;
-            if (tile + (int)gridDim.x < g.tiles) fetch(tile + gridDim.x);
+            nxt.next(g);
+            if (nxt.tile < g.tiles) fetch(nxt);
+            const uint32_t origin = origin_of(cur);
             const uint32_t s = it % C1_STAGES, round = it / C1_STAGES;
             if (round > 0) mbar_wait(smem_u32(&bar_empty[s]), (round - 1) & 1u);
-            const bool live = (uint32_t)r < rows_box && xt * g.bx + rx < g.wo && yt * g.by + ry < g.ho;
+            const bool live = (uint32_t)r < rows_box && cur.xt * g.bx + rx < g.wo && cur.yt * g.by + ry < g.ho;
             if (live) {
                 uint8_t* const a_row = gen_base + s * C1_A_STAGE + (r >> 3) * 1024 + (r & 7) * 128;
+                const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
 #pragma unroll
                 for (int kr = 0; kr < 5; ++kr) {
                     const int j = 2 * ry + kr;
-                    const uint32_t d = (uint32_t)((origin + (size_t)j * c.w * 3) & 3);     // misalignment of this patch row
-                    const uint32_t o = d + 6u * (uint32_t)rx;
+                    const uint32_t o = ((origin + (uint32_t)j * row_bytes) & 3u) + 6u * (uint32_t)rx;   // row misalignment + pixel offset
                     const uint32_t* wsrc = pbuf + j * c.pitch_words + (o >> 2);
                     const uint32_t sel = 0x3210u + 0x1111u * (o & 3u);
                     const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3], w4 = wsrc[4];
-                    const uint32_t b0 = __byte_perm(w0, w1, sel), b1 = __byte_perm(w1, w2, sel);
-                    const uint32_t b2 = __byte_perm(w2, w3, sel), b3 = __byte_perm(w3, w4, sel);
-                    const uint32_t bw[4] = {b0, b1, b2, b3};
+                    const uint32_t bw[4] = {__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel),
+                                            __byte_perm(w3, w4, sel)};
                     uint32_t hv[8];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         // bytes (x0 x1 x2 x3) -> halves 1024 + x (0x64xx), minus 1024 -> the integers 0..255, exact in fp16
                         const uint32_t lo = __byte_perm(bw[q], 0x64646464u, 0x4140), hi = __byte_perm(bw[q], 0x64646464u, 0x4342);
-                        const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
                         const __half2 hl = __hsub2(*reinterpret_cast<const __half2*>(&lo), k1024);
                         const __half2 hh = __hsub2(*reinterpret_cast<const __half2*>(&hi), k1024);
                         hv[2 * q] = *reinterpret_cast<const uint32_t*>(&hl);
@@ -477,13 +502,11 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
         const int r = q * 32 + lane;
         const int rx = r % g.bx, ry = r / g.bx;
         uint32_t ti = 0;
-        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++ti) {
-            int t = tile;
-            const int xt = t % g.x_tiles;  t /= g.x_tiles;
-            const int yt = t % g.y_tiles;  t /= g.y_tiles;
-            const int x = xt * g.bx + rx, y = yt * g.by + ry;
+        TileWalk tw;
+        for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g), ++ti) {
+            const int x = tw.xt * g.bx + rx, y = tw.yt * g.by + ry;
             const bool live = (uint32_t)r < rows_box && x < g.wo && y < g.ho;
-            const size_t row = ((size_t)t * g.ho + y) * g.wo + x;
+            const size_t row = ((size_t)tw.nt * g.ho + y) * g.wo + x;
             const uint32_t acc = ti & 1u, use = ti >> 1;
             mbar_wait(smem_u32(&bar_acc_full[acc]), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
