@@ -58,6 +58,16 @@ def emit(line: dict):
     print(json.dumps(line), flush=True)
 
 
+def read_tensor_peak():
+    """Dense bf16/fp16 tensor-core peak (TFLOP/s) for the pilots' forward pass: the sustained cuBLAS figure of MEASURED_PEAKS.json."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            j = json.load(f)
+        return float(j.get("bf16_tflops_sustained") or j["bf16_tflops"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    except Exception:
+        return 2250.0, "fallback (nominal dense bf16, B200_PROFILING.md)"
+
+
 def read_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -282,6 +292,54 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
     out["control_mux_1M_states"] = {"states_per_s": n / t, "hbm_GBps": n * (4 + 48 + 8 + 24 + 8 + 64) / t / 1e9,
                                      "note": "156 B of traffic per car (mode, 6 inputs, speed, 3 outputs, state read + written)"}
     mux.onShutdown()
+    # the pilots' networks: full-house forward pass on the tensor cores, alone and behind the fused chain
+    try:
+        from oracle import pilot_ref
+        from triton_racer_sim_b200.pilot import KerasPilot, ModelType
+        npil = 16384
+        wts = pilot_ref.random_weights(pilot_ref.CNN_2D_FULL_HOUSE, h, w, seed=1)
+        pilot = KerasPilot(dict(spd_ctl_break=True), wts, ModelType.CNN_2D_FULL_HOUSE, device=local, max_batch=8192)
+        pf = synth.expand_torch(pool120, npil)
+        p_spd = torch.rand(npil, device=dev, dtype=torch.float64) * 20
+        p_seg = torch.rand(npil, device=dev) * 10
+        t = timed(lambda: pilot.pilot_device(pf, p_spd, p_seg), reps=5)
+        macs, hh, ww, cc = 0, h, w, 3
+        for k, s_, f_ in pilot_ref.CONVS:
+            hh, ww = (hh - k) // s_ + 1, (ww - k) // s_ + 1
+            macs += hh * ww * f_ * k * k * cc
+            cc = f_
+        macs += hh * ww * cc * 200 + 2 * (100 * 50 + 50 * 25 + 25 + 16 + 16 * 32 + 32 * 64 + 64 * 100) + 64 * 100
+        tpeak, tsrc = read_tensor_peak()
+        entry = {"frames_per_s": npil / t, "ms": t * 1e3, "mflop_per_frame": 2 * macs / 1e6,
+                 "roofline": {"bound": "tensor", "achieved": 2 * macs * npil / t / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                              "frac": 2 * macs * npil / t / 1e12 / tpeak, "peak_source": tsrc,
+                              "note": "algorithmic flops of the reference's layers (no padding counted); fp16 operands, fp32 accumulate; "
+                                      "the convolutions are L2-bandwidth bound (TMA im2col re-reads every input kh*kw/s^2 times), not MMA bound"},
+                 "launches_per_8192_frames": 10,
+                 "note": "u8 frames + gym/speed + loc/segment -> model -> speed control (ai/steering, ai/throttle, ai/breaking)"}
+        fh1 = ImgPreprocessing(full_house_config(), device=local)
+        pu8 = torch.empty_like(pf)
+
+        def obs_to_control():
+            fh1.process_device(pf, out_u8=pu8, want_f32=False)
+            pilot.pilot_device(pu8, p_spd, p_seg)
+        t2 = timed(obs_to_control, reps=5)
+        entry["with_preprocessing_frames_per_s"] = npil / t2
+        fh1.onShutdown()
+        if cpu_legs:
+            import time as _t
+            ncpu = 256
+            fr = pool120[:ncpu].cpu().numpy()
+            pilot_ref.forward(wts, pilot_ref.CNN_2D_FULL_HOUSE, fr[:32], np.zeros(32, np.float32), np.zeros(32, np.float32))
+            t0 = _t.perf_counter()
+            pilot_ref.forward(wts, pilot_ref.CNN_2D_FULL_HOUSE, fr, np.zeros(ncpu, np.float32), np.zeros(ncpu, np.float32))
+            entry["cpu_frames_per_s"] = ncpu / (_t.perf_counter() - t0)
+            entry["cpu_sample"] = f"{ncpu} frames, torch fp32 on {torch.get_num_threads()} host threads (oracle/pilot_ref.py)"
+        out["pilot_full_house_16384x120x160"] = entry
+        pilot.onShutdown()
+        del pf, pu8
+    except Exception as e:
+        out["pilot_full_house_16384x120x160"] = {"skipped": repr(e)}
     # tub ingestion: JPEG files (packed, pinned host memory) -> GPU decode -> (N,H,W,3) u8 on the device;
     # host parsing and the H2D copy of the files are inside the timed region (wall clock: the call synchronises)
     try:

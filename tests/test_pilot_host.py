@@ -1,0 +1,70 @@
+"""CPU-side checks of the pilots' path: the fp32 reference used as the checker (oracle/pilot_ref.py) against a naive restatement of
+Conv2D / Dense, the weight container, and the loud failure without a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pilot_ref as ref
+
+
+def naive_conv_valid(x, k, b, s):
+    """x (H,W,Ci), k (kh,kw,Ci,Co) Keras layout, VALID padding, ReLU."""
+    kh, kw, ci, co = k.shape
+    ho, wo = (x.shape[0] - kh) // s + 1, (x.shape[1] - kw) // s + 1
+    out = np.zeros((ho, wo, co), np.float64)
+    for y in range(ho):
+        for xx in range(wo):
+            patch = x[y * s:y * s + kh, xx * s:xx * s + kw, :].astype(np.float64)
+            out[y, xx] = np.tensordot(patch, k.astype(np.float64), axes=([0, 1, 2], [0, 1, 2])) + b
+    return np.maximum(out, 0)
+
+
+def test_reference_convolutions_follow_keras_layout():
+    rng = np.random.default_rng(0)
+    wts = ref.random_weights(ref.CNN_2D, 120, 160, seed=4)
+    x = rng.uniform(0, 1, (1, 31, 37, 3)).astype(np.float32)
+    a = ref.conv_stack(wts, torch.from_numpy(x), 0, 2)
+    want1 = naive_conv_valid(x[0], wts["conv1/kernel"], wts["conv1/bias"], 2)
+    assert a[0].shape[1:] == want1.shape and np.allclose(a[0][0].numpy(), want1, atol=1e-5)
+    want2 = naive_conv_valid(want1, wts["conv2/kernel"], wts["conv2/bias"], 2)
+    assert np.allclose(a[1][0].numpy(), want2, atol=1e-4)
+
+
+def test_reference_shapes_and_head_wiring():
+    assert ref.conv_out_hw(120, 160) == (4, 9)                       # Flatten -> 4 * 9 * 128 = 4608
+    sh = ref.weight_shapes(ref.CNN_2D_FULL_HOUSE)
+    assert sh["dense1/kernel"] == (4608 + 64, 100)                   # keras_train.py:215  x = Concatenate([x, y])
+    assert sh["dense4/kernel"] == (4608 + 128, 100)                  # keras_train.py:231  s = Concatenate([x, s]) with that x
+    assert ref.weight_shapes(ref.CNN_2D_SPD_FTR)["dense1/kernel"] == (4608 + 16, 100)
+    assert ref.weight_shapes(ref.CNN_2D)["output_layer/kernel"] == (25, 2)
+    # the full-house output row is (steering, speed): keras_train.py:239 Concatenate([out_steering, out_speed])
+    wts = ref.random_weights(ref.CNN_2D_FULL_HOUSE, seed=2)
+    frames = np.random.default_rng(1).integers(0, 256, (3, 120, 160, 3), dtype=np.uint8)
+    spd, loc = np.array([.1, .5, .9], np.float32), np.array([1., 5., 9.], np.float32)
+    base = ref.forward(wts, ref.CNN_2D_FULL_HOUSE, frames, spd, loc)
+    w2 = dict(wts)
+    w2["out_steering/bias"] = wts["out_steering/bias"] + 1
+    assert np.allclose(ref.forward(w2, ref.CNN_2D_FULL_HOUSE, frames, spd, loc) - base, [[1, 0]] * 3, atol=1e-6)
+    # the speed feature reaches only the steering head, the loc/segment feature both (it is part of x)
+    d_spd = ref.forward(wts, ref.CNN_2D_FULL_HOUSE, frames, spd + 0.3, loc) - base
+    assert np.abs(d_spd[:, 0]).max() > 0 and not d_spd[:, 1].any()
+    d_loc = ref.forward(wts, ref.CNN_2D_FULL_HOUSE, frames, spd, loc + 2) - base
+    assert np.abs(d_loc[:, 0]).max() > 0 and np.abs(d_loc[:, 1]).max() > 0
+
+
+def test_weight_file_round_trip(tmp_path):
+    from triton_racer_sim_b200.pilot import load_weights
+    wts = ref.random_weights(ref.CNN_2D_SPD_FTR, seed=5)
+    path = tmp_path / "model.npz"
+    np.savez(path, **wts)
+    back = load_weights(path)
+    assert sorted(back) == sorted(wts) and all(np.array_equal(back[k], wts[k]) for k in wts)
+
+
+def test_pilot_without_a_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    from triton_racer_sim_b200 import _native as nat
+    from triton_racer_sim_b200.pilot import ModelType, PilotNet
+    with pytest.raises((nat.NativeError, RuntimeError)):
+        PilotNet(ModelType.CNN_2D, ref.random_weights(ref.CNN_2D), device=0)
