@@ -314,7 +314,7 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
                  "roofline": {"bound": "tensor", "achieved": 2 * macs * npil / t / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                               "frac": 2 * macs * npil / t / 1e12 / tpeak, "peak_source": tsrc,
                               "note": "algorithmic flops of the reference's layers (no padding counted); fp16 operands, fp32 accumulate; "
-                                      "the convolutions are L2-bandwidth bound (TMA im2col re-reads every input kh*kw/s^2 times), not MMA bound"},
+                                      "bound by the operand fetch of small-N MMAs (N = 24..128 filters: ~64 B/clk shared memory -> tensor core), see DESIGN.md 4.8"},
                  "launches_per_8192_frames": 10,
                  "note": "u8 frames + gym/speed + loc/segment -> model -> speed control (ai/steering, ai/throttle, ai/breaking)"}
         fh1 = ImgPreprocessing(full_house_config(), device=local)

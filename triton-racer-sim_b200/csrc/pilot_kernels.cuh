@@ -96,6 +96,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         if (++spins == (1u << 22)) __trap();
 }
 
+// The same for warps that are not on the critical path (epilogue warps waiting for an accumulator, the MMA thread of conv1 waiting
+// for the builders): back off between polls so that the spin does not take issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity)) {
+        __nanosleep(40);
+        if (++spins == (1u << 22)) __trap();
+    }
+}
+
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4)
 {
     asm volatile(
@@ -267,7 +278,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
             const bool live = (uint32_t)r < rows_box && x < g.wo && y < g.ho && n < g.nf;
             const size_t row = ((size_t)n * g.ho + y) * g.wo + x;
             const uint32_t acc = ti & 1u, use = ti >> 1;
-            mbar_wait(smem_u32(&bar_acc_full[acc]), use & 1u);
+            mbar_wait_relaxed(smem_u32(&bar_acc_full[acc]), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + acc * NPAD + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -412,14 +423,21 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
         }
         uint32_t pre[C1_PATCH_REGS];
         auto origin_of = [&](const TileWalk& t) { return (uint32_t)t.nt * frame_bytes + ((uint32_t)(2 * t.yt * g.by) * (uint32_t)c.w + 2u * t.xt * g.bx) * 3u; };
+        // Rows below the frame (last y tile) belong to the next frame or lie past the buffer: only dead output rows read them, so
+        // the one guard needed is the end of the buffer.  When a frame row is a whole number of words every patch row has the
+        // origin's misalignment and a word's source is origin + a per-thread constant.
+        const bool word_rows = (row_bytes & 3u) == 0;
+        uint32_t poff[C1_PATCH_REGS];
+#pragma unroll
+        for (int i = 0; i < C1_PATCH_REGS; ++i) poff[i] = (uint32_t)pj[i] * row_bytes + 4u * (uint32_t)pk[i];
         auto fetch = [&](const TileWalk& t) {                        // patch words of tile t -> registers
             const uint32_t origin = origin_of(t);
-            const int row0 = 2 * t.yt * g.by;
 #pragma unroll
             for (int i = 0; i < C1_PATCH_REGS; ++i) {
                 pre[i] = 0;
-                const uint32_t src = ((origin + (uint32_t)pj[i] * row_bytes) & ~3u) + 4u * (uint32_t)pk[i];
-                if (pj[i] >= 0 && row0 + pj[i] < c.h && src < total) pre[i] = __ldg(in32 + (src >> 2));
+                const uint32_t src = word_rows ? (origin & ~3u) + poff[i]
+                                               : ((origin + (uint32_t)pj[i] * row_bytes) & ~3u) + 4u * (uint32_t)pk[i];
+                if (pj[i] >= 0 && src < total) pre[i] = __ldg(in32 + (src >> 2));
             }
         };
         uint32_t it = 0;
@@ -485,7 +503,7 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
                 const uint32_t acc = it & 1u, use = it >> 1;
                 if (use > 0) mbar_wait(smem_u32(&bar_acc_empty[acc]), (use - 1) & 1u);
                 const uint32_t s = it % C1_STAGES, round = it / C1_STAGES;
-                mbar_wait(smem_u32(&bar_full[s]), round & 1u);
+                mbar_wait_relaxed(smem_u32(&bar_full[s]), round & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + acc * C1_NPAD;
                 const uint64_t da0 = umma_desc_sw128(base + s * C1_A_STAGE), da1 = umma_desc_sw128(base + s * C1_A_STAGE + A_STAGE_BYTES);
@@ -508,7 +526,7 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
             const bool live = (uint32_t)r < rows_box && x < g.wo && y < g.ho;
             const size_t row = ((size_t)tw.nt * g.ho + y) * g.wo + x;
             const uint32_t acc = ti & 1u, use = ti >> 1;
-            mbar_wait(smem_u32(&bar_acc_full[acc]), use & 1u);
+            mbar_wait_relaxed(smem_u32(&bar_acc_full[acc]), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + acc * C1_NPAD + ((uint32_t)(q * 32) << 16);
             uint32_t v[16], u[16];
