@@ -105,3 +105,24 @@ def test_two_rank_gloo_sharding_and_stats():
         assert p.exitcode == 0
     frames, sum_ok, equal, slowest = q.get(timeout=10)
     assert frames == 37 and sum_ok and equal and slowest == 2.0
+
+
+def test_tub_labels_and_features_follow_the_reference_loaders():
+    """keras_train.py:113-119,264-299: what each DataLoader subclass keeps of a record; float32 as at keras_train.py:48-49."""
+    import numpy as np
+
+    from triton_racer_sim_b200 import tub
+    recs = [{'mux/steering': 0.25, 'mux/throttle': 0.5, 'gym/speed': 7.0, 'loc/segment': 3.5},
+            {'mux/steering': -1.0, 'mux/throttle': 0.1, 'gym/speed': 20.0, 'loc/segment': 0.0}]
+    lab, ft = tub.labels_and_features(recs, "DataLoader")
+    assert lab.dtype == np.float32 and ft is None and np.array_equal(lab, np.float32([[0.25, 0.5], [-1.0, 0.1]]))
+    lab, ft = tub.labels_and_features(recs, "cnn_2d_speed_as_feature")
+    assert np.array_equal(ft, np.float32([[7.0 / 20], [1.0]])) and np.array_equal(lab[:, 1], np.float32([0.5, 0.1]))
+    lab, ft = tub.labels_and_features(recs, "SpeedCtlDataLoader")
+    assert ft is None and np.array_equal(lab, np.float32([[0.25, 7.0 / 20], [-1.0, 1.0]]))
+    lab, ft = tub.labels_and_features(recs, "cnn_2d_full_house")
+    assert np.array_equal(ft, np.float32([[7.0 / 20, 3.5], [1.0, 0.0]])) and np.array_equal(lab, np.float32([[0.25, 7.0 / 20], [-1.0, 1.0]]))
+    # the same values the reference's classes produce (np.asarray(..., dtype=float32) of its tuples)
+    for r in recs:
+        assert np.array_equal(tub.labels_and_features([r], "FullHouseDataLoader")[1][0],
+                              np.asarray(np.asarray((r['gym/speed'] / 20, r['loc/segment'])), dtype=np.float32))

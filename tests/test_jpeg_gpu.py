@@ -93,6 +93,10 @@ def test_tub_reader_round_trip(tmp_path):
     u8, _ = comp.process_device(dev_frames)
     assert np.array_equal(u8.cpu().numpy(), oracle.process_batch(want, cfg))
     comp.onShutdown()
+    # the trainer's view of the same batch (keras_train.py:33-57 with SpeedCtlDataLoader, :271-276): labels (steering, speed / 20)
+    fr2, labels, feats = rd.load_examples(range(1, 13), "cnn_2d_speed_control")
+    assert torch.equal(fr2, dev_frames) and feats is None
+    assert np.array_equal(labels.cpu().numpy(), np.float32([[0.1 * i, 2.0 * i / 20] for i in range(1, 13)]))
     rd.close()
 
 

@@ -71,6 +71,31 @@ def decode_jpeg_batch(files, hw=None, device=None, ctx=None, out=None) -> torch.
     return out
 
 
+# The reference's loader classes differ only in what they take from a record (keras_train.py:113-119, 264-299):
+#   name -> (labels(record), features(record) or None); values become float32 as in keras_train.py:48-49.
+LOADERS = {
+    "DataLoader": (lambda r: (r['mux/steering'], r['mux/throttle']), None),                                   # :113-119
+    "SpeedFeatureDataLoader": (lambda r: (r['mux/steering'], r['mux/throttle']), lambda r: (r['gym/speed'] / 20,)),   # :264-269
+    "SpeedCtlDataLoader": (lambda r: (r['mux/steering'], r['gym/speed'] / 20), None),                         # :271-276
+    "FullHouseDataLoader": (lambda r: (r['mux/steering'], r['gym/speed'] / 20),                                # :292-299
+                            lambda r: (r['gym/speed'] / 20, r['loc/segment'])),
+}
+# the loader train() picks for each model type (keras_train.py:384-395)
+LOADER_OF_MODEL = {"cnn_2d": "DataLoader", "cnn_2d_speed_as_feature": "SpeedFeatureDataLoader",
+                   "cnn_2d_speed_control": "SpeedCtlDataLoader", "cnn_2d_full_house": "FullHouseDataLoader"}
+
+
+def labels_and_features(records, loader="DataLoader"):
+    """What the reference's ``DataLoader.load`` keeps of each record, gathered for a batch:
+    labels (N, 2) float32 and features (N, k) float32 or None (keras_train.py:48-52)."""
+    get_labels, get_features = LOADERS[LOADER_OF_MODEL.get(loader, loader)]
+    labels = np.asarray([get_labels(r) for r in records], dtype=np.float32).reshape(len(records), -1)
+    feats = None
+    if get_features is not None:
+        feats = np.asarray([get_features(r) for r in records], dtype=np.float32).reshape(len(records), -1)
+    return labels, feats
+
+
 class TubReader:
     """A tub folder as the reference's loaders see it: records 1..N, ``img_{i}.jpg`` + ``record_{i}.json`` (keras_train.py:36-46)."""
 
@@ -95,6 +120,14 @@ class TubReader:
             with open(os.path.join(self.path, f"record_{i}.json")) as f:
                 records.append(json.load(f))
         return decode_jpeg_batch(files, device=self.device, ctx=self.ctx), records
+
+    def load_examples(self, indices, loader="DataLoader"):
+        """One batch the way ``DataLoader.load`` builds its examples (keras_train.py:33-57): frames stay uint8 on the GPU (the `/255`
+        is fused into the consumers), labels and feature vectors come back as float32 CUDA tensors."""
+        frames, records = self.load(indices)
+        labels, feats = labels_and_features(records, loader)
+        dev = frames.device
+        return frames, torch.from_numpy(labels).to(dev), None if feats is None else torch.from_numpy(feats).to(dev)
 
     def close(self):
         self.ctx.close()
