@@ -336,6 +336,21 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
             entry["cpu_frames_per_s"] = ncpu / (_t.perf_counter() - t0)
             entry["cpu_sample"] = f"{ncpu} frames, torch fp32 on {torch.get_num_threads()} host threads (oracle/pilot_ref.py)"
         out["pilot_full_house_16384x120x160"] = entry
+        # the reference's own call, one car: numpy frame + python floats in, python floats out (H2D, kernels, D2H, synchronise)
+        import time as _t2
+        one = pool120[0].cpu().numpy()
+        fh2 = ImgPreprocessing(full_house_config(), device=local)
+        lat = {}
+        for name, fn in (("img_preprocessing_step", lambda: fh2.step(one)),
+                         ("keras_pilot_step", lambda: pilot.step(one, 7.5, 3.2, 0.0, 'ai'))):
+            for _ in range(20):
+                fn()
+            t0 = _t2.perf_counter()
+            for _ in range(200):
+                fn()
+            lat[name] = (_t2.perf_counter() - t0) / 200 * 1e6
+        fh2.onShutdown()
+        out["single_car_latency_us"] = dict(lat, note="N = 1 through Component.step with the reference's argument types, wall clock per call")
         pilot.onShutdown()
         del pf, pu8
     except Exception as e:

@@ -201,9 +201,10 @@ class KerasPilot(Component):
         frames = torch.from_numpy(img.reshape((-1,) + img.shape[-3:])).to(dev)
         as_t = lambda v: None if v is None else torch.as_tensor(np.atleast_1d(np.asarray(v, np.float64)), device=dev)
         s, t, b = self.pilot_device(frames, as_t(speed), as_t(segment))
+        res = torch.stack([s, t, b]).cpu().numpy()                      # one device -> host copy for the three outputs
         if single:
-            return float(s[0].item()), float(t[0].item()), float(b[0].item())
-        return s.cpu().numpy(), t.cpu().numpy(), b.cpu().numpy()
+            return float(res[0, 0]), float(res[1, 0]), float(res[2, 0])
+        return res[0], res[1], res[2]
 
     def onStart(self):
         if self.cfg.get('preprocessing_enabled'):
