@@ -243,6 +243,11 @@ int trs_pilot_destroy(trs_pilot* p);
  *   out_dev         (N,2) f32: the model's output row per frame */
 int trs_pilot_forward(trs_pilot* p, const uint8_t* frames_dev, int n, const float* spd_feature_dev, const float* loc_feature_dev,
                       float* out_dev, void* stream);
+/* The glue behind the model for ModelType.CNN_2D / CNN_2D_SPD_FTR (keras_pilot.py:59-63, 71-76): __cap on both outputs
+ * (keras_pilot.py:142-145), __smooth_steering on the first (147-153), breaking = 0.0.  model_out_dev (N,2) f32; outputs (N) f64.
+ * (CNN_2D_SPD_CTL / CNN_2D_FULL_HOUSE continue with trs_speed_control.) */
+int trs_pilot_cap(trs_ctx* ctx, const float* model_out_dev, int n, int smooth_steering, double smooth_threshold, double* steering_dev,
+                  double* throttle_dev, double* breaking_dev, void* stream);
 /* Debug tap for the parity tests: activations of the most recent chunk.  layer 1..7: conv outputs, fp16
  * NHWC; 8: the fp32 partial sums of the first Dense layers.  Copies `bytes` bytes to host_out after synchronising `stream`. */
 int trs_pilot_debug_activation(trs_pilot* p, int layer, void* host_out, unsigned long long bytes, void* stream);

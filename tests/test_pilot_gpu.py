@@ -114,6 +114,22 @@ def test_keras_pilot_component_matches_the_reference_glue():
         pilot.onShutdown()
 
 
+def test_cap_and_smooth_steering_like_the_reference():
+    """keras_pilot.py:142-153 on the model outputs of ModelType.CNN_2D: cap to [-1, 1], snap beyond the threshold, breaking 0."""
+    n, h, w = 96, 120, 160
+    frames = torch.from_numpy(synth.frame_pool(n, h, w, seed=4)).cuda()
+    wts = ref.random_weights(ref.CNN_2D, h, w, seed=8)
+    wts["output_layer/kernel"] = wts["output_layer/kernel"] * 6          # push outputs beyond +-1 so the cap matters
+    pilot = KerasPilot(dict(smooth_steering_enabled=True, smooth_steering_threshold=0.3), wts, ModelType.CNN_2D, device=0, max_batch=128)
+    s, t, b = (v.cpu().numpy() for v in pilot.step(frames, None, None, None, 'ai_steering'))
+    raw = pilot.model.forward_device(frames).cpu().numpy().astype(np.float64)
+    cap = np.clip(raw, -1.0, 1.0)
+    want_s = np.where(cap[:, 0] > 0.3, 1.0, np.where(cap[:, 0] < -0.3, -1.0, cap[:, 0]))
+    assert (np.abs(raw) > 1).any() and (np.abs(cap[:, 0]) <= 0.3).any()
+    assert np.array_equal(s, want_s) and np.array_equal(t, cap[:, 1]) and not b.any()
+    pilot.onShutdown()
+
+
 def test_missing_or_misshapen_weights_are_refused():
     wts = ref.random_weights(ref.CNN_2D, 120, 160, seed=0)
     bad = dict(wts)

@@ -21,6 +21,7 @@ SYMBOLS = [
     "trs_preprocess_host", "trs_host_alloc", "trs_host_free", "trs_debug_canny_stages", "trs_control_mux", "trs_pwm_map",
     "trs_jpeg_decode_host", "trs_telemetry_decode_host",
     "trs_pilot_create", "trs_pilot_destroy", "trs_pilot_forward", "trs_pilot_debug_activation", "trs_pilot_layer_shape",
+    "trs_pilot_cap",
 ]
 MODE_HUMAN, MODE_AI_STEERING, MODE_AI = 0, 1, 2          # TRS_MODE_*: DriveMode.HUMAN / AI_STEERING / AI (components/controller.py:7-10)
 LAUNCH_SLOTS = 4                                          # TRS_LAUNCH_SLOTS
@@ -100,6 +101,7 @@ def load():
     lib.trs_pilot_forward.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     lib.trs_pilot_debug_activation.argtypes = [vp, i32, vp, C.c_ulonglong, vp]
     lib.trs_pilot_layer_shape.argtypes = [vp, i32] + [C.POINTER(C.c_int)] * 3
+    lib.trs_pilot_cap.argtypes = [vp, vp, i32, i32, C.c_double, vp, vp, vp, vp]
     for name in SYMBOLS:
         getattr(lib, name)
     _lib = lib

@@ -463,6 +463,20 @@ int trs_pilot_forward(trs_pilot* p, const uint8_t* frames_dev, int n, const floa
     return 0;
 }
 
+int trs_pilot_cap(trs_ctx* ctx, const float* model_out_dev, int n, int smooth_steering, double smooth_threshold, double* steering_dev,
+                  double* throttle_dev, double* breaking_dev, void* stream)
+{
+    if (!ctx || !model_out_dev || !steering_dev || !throttle_dev || !breaking_dev) return trs_i_fail(TRS_E_ARG, "null argument");
+    if (n < 0) return trs_i_fail(TRS_E_ARG, "n=%d", n);
+    if (n == 0) return 0;
+    CU(cudaSetDevice(trs_i_ctx_device(ctx)));
+    k_pilot_cap<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(model_out_dev, n, smooth_steering, smooth_threshold, steering_dev,
+                                                                   throttle_dev, breaking_dev);
+    CU(cudaGetLastError());
+    trs_i_count_launches(1);
+    return 0;
+}
+
 int trs_pilot_layer_shape(trs_pilot* p, int layer, int* ho, int* wo, int* c)
 {
     if (!p || layer < 0 || layer > N_CONV + 1 || !ho || !wo || !c) return trs_i_fail(TRS_E_ARG, "bad layer %d", layer);

@@ -648,5 +648,25 @@ __global__ void __launch_bounds__(HEADS_WARPS * 32) k_pilot_heads(const HeadsArg
     }
 }
 
+// The glue behind the model for ModelType.CNN_2D / CNN_2D_SPD_FTR (keras_pilot.py:59-63 | 71-76): __cap on both outputs
+// (keras_pilot.py:142-145), __smooth_steering on the first (147-153), breaking 0.0; results as float64 like the reference's floats.
+__global__ void __launch_bounds__(256) k_pilot_cap(const float* __restrict__ model_out, int n, int smooth, double threshold,
+                                                   double* __restrict__ steering, double* __restrict__ throttle,
+                                                   double* __restrict__ breaking)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = (double)model_out[2 * i], t = (double)model_out[2 * i + 1];
+    s = s < -1.0 ? -1.0 : (s > 1.0 ? 1.0 : s);
+    t = t < -1.0 ? -1.0 : (t > 1.0 ? 1.0 : t);
+    if (smooth) {
+        if (s > threshold) s = 1.0;
+        else if (s < -threshold) s = -1.0;
+    }
+    steering[i] = s;
+    throttle[i] = t;
+    breaking[i] = 0.0;
+}
+
 }  // namespace pilot
 }  // namespace trs

@@ -172,17 +172,14 @@ class KerasPilot(Component):
             # spd = np.asarray(real_spd / 20, float32): float64 division, then one rounding (keras_pilot.py:68,100)
             spd_feat = (speed.to(device=dev, dtype=torch.float64) / 20).to(torch.float32)
         out = self.model.forward_device(frames, spd_feat, segment if mt == ModelType.CNN_2D_FULL_HOUSE else None)
-        if mt in (ModelType.CNN_2D, ModelType.CNN_2D_SPD_FTR):
-            o = out.to(torch.float64).clamp_(-1.0, 1.0)                                           # __cap on both outputs (keras_pilot.py:60,72)
-            steering, throttle = o[:, 0], o[:, 1]
-            if self.smooth_steering:                                                              # keras_pilot.py:147-153
-                t = self.smooth_steering_threshold
-                steering = torch.where(steering > t, torch.ones_like(steering), torch.where(steering < -t, -torch.ones_like(steering), steering))
-            return steering, throttle, torch.zeros(n, dtype=torch.float64, device=dev)
         res = torch.empty((3, n), dtype=torch.float64, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        if mt in (ModelType.CNN_2D, ModelType.CNN_2D_SPD_FTR):                                     # keras_pilot.py:59-63, 71-76
+            nat.check(lib.trs_pilot_cap(ctx, p(out), n, int(self.smooth_steering), self.smooth_steering_threshold, p(res[0]), p(res[1]),
+                                        p(res[2]), stream), "trs_pilot_cap")
+            return res[0], res[1], res[2]
         cur = speed.to(device=dev, dtype=torch.float64).contiguous()
         steer, mspd = out[:, 0].contiguous(), out[:, 1].contiguous()
-        p = lambda t: C.c_void_p(t.data_ptr())
         nat.check(lib.trs_speed_control(ctx, p(cur), p(mspd), p(steer), n, C.byref(self.spd_params), p(res[0]), p(res[1]), p(res[2]),
                                         None, stream), "trs_speed_control")
         return res[0], res[1], res[2]
