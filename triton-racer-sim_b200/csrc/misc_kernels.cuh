@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_crop_resize(const __grid_constant__ Res
 // column / row of every output pixel comes from two small shared-memory tables built once per CTA (no division per
 // pixel), a thread gathers the 4 source bytes of its word (L1-resident sectors) and writes one 16-byte f32 chunk and one
 // 4-byte u8 word, so a warp's stores are 512 / 128 contiguous bytes.  A CTA walks whole output rows.
-enum { RESIZE_THREADS = 128, RESIZE_MAX_TAB = 8192 };
+enum { RESIZE_THREADS = 128, RESIZE_MAX_TAB = 8192, RESIZE_DEPTH = 8 };
 
 __global__ void __launch_bounds__(RESIZE_THREADS) k_crop_resize_words(const __grid_constant__ ResizeParams p)
 {
@@ -132,6 +132,81 @@ __global__ void __launch_bounds__(RESIZE_THREADS) k_crop_resize_words(const __gr
             if (p.out_f32) stg_stream(reinterpret_cast<float4*>(p.out_f32) + R * wpr + c, make_float4(v[0], v[1], v[2], v[3]));
             if (p.out_u8) reinterpret_cast<uint32_t*>(p.out_u8)[R * wpr + c] = word;
         }
+    }
+}
+
+// K1d: the same with the source row staged in shared memory.  K1c gathers its bytes with one byte load each; here the part of the
+// source row the window needs arrives by 16-byte asynchronous copies (LDGSTS), double-buffered across the rows a CTA walks, and
+// the gather runs on shared memory with the four source offsets of an output word in one 16-byte table entry.  No division per
+// row either: (frame, output row) advance by the grid stride with a carry.  Needs 16-byte aligned source rows.
+__global__ void __launch_bounds__(RESIZE_THREADS) k_crop_resize_rows(const __grid_constant__ ResizeParams p, int col_lo, int span)
+{
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const int wpr = (p.w_out * 3) >> 2;            // output words per row
+    int4* s_off = reinterpret_cast<int4*>(s_dyn);                                   // [wpr] source offsets (within the staged span) of a word's bytes
+    int* s_sy = reinterpret_cast<int*>(s_dyn + sizeof(int4) * wpr);                 // [h_out] source row of row y
+    uint8_t* s_row = s_dyn + ((sizeof(int4) * wpr + sizeof(int) * p.h_out + 15) & ~(size_t)15);   // 2 x span
+    for (int c = threadIdx.x; c < wpr; c += blockDim.x) {
+        int o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = 4 * c + j, px = b / 3, ch = b - 3 * px;
+            o[j] = 3 * (p.x0 + (int)(((long long)px * p.ws) / p.w_out)) + ch - col_lo;
+        }
+        s_off[c] = make_int4(o[0], o[1], o[2], o[3]);
+    }
+    for (int y = threadIdx.x; y < p.h_out; y += blockDim.x) s_sy[y] = p.y0 + (int)(((long long)y * p.hs) / p.h_out);
+    __syncthreads();
+    const size_t rows = (size_t)p.n * p.h_out;
+    const size_t src_row_bytes = (size_t)p.w_in * 3;
+    const int chunks = span >> 4;
+    const float rcp = 1.0f / 255.0f;
+    const int gq = (int)(gridDim.x / p.h_out), gr = (int)(gridDim.x % p.h_out);
+    size_t f = blockIdx.x / p.h_out;
+    int y = (int)(blockIdx.x - f * p.h_out);
+    auto stage = [&](size_t ff, int yy, int buf) {
+        const uint8_t* src = p.in + (ff * p.h_in + s_sy[yy]) * src_row_bytes + col_lo;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_row + (size_t)buf * span);
+        for (int i = threadIdx.x; i < chunks; i += blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // RESIZE_DEPTH rows in flight per CTA: the row being gathered and the next RESIZE_DEPTH - 1 being staged (one commit group per
+    // row, empty past the end, so that "all but the newest RESIZE_DEPTH - 1 groups" always means "this row has landed")
+    auto advance = [&](size_t& ff, int& yy) {
+        ff += gq; yy += gr;
+        if (yy >= p.h_out) { yy -= p.h_out; ++ff; }
+    };
+    size_t fs = f;                                                          // (frame, row) of the next row to stage
+    int ys = y;
+    size_t Rs = blockIdx.x;
+    for (int d = 0; d < RESIZE_DEPTH - 1; ++d) {
+        if (Rs < rows) stage(fs, ys, d);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        Rs += gridDim.x; advance(fs, ys);
+    }
+    size_t R = blockIdx.x;
+    for (uint32_t it = 0; R < rows; R += gridDim.x, ++it) {
+        if (Rs < rows) stage(fs, ys, (it + RESIZE_DEPTH - 1) % RESIZE_DEPTH);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        Rs += gridDim.x; advance(fs, ys);
+        asm volatile("cp.async.wait_group %0;" ::"n"(RESIZE_DEPTH - 1) : "memory");
+        __syncthreads();
+        const uint8_t* row = s_row + (size_t)(it % RESIZE_DEPTH) * span;
+        for (int c = threadIdx.x; c < wpr; c += blockDim.x) {
+            const int4 o = s_off[c];
+            const uint32_t b[4] = {row[o.x], row[o.y], row[o.z], row[o.w]};
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xf = __fsub_rn(__uint_as_float(0x4B000000u | b[j]), 8388608.0f);
+                const float q0 = __fmul_rn(xf, rcp);
+                v[j] = __fmaf_rn(__fmaf_rn(-q0, 255.0f, xf), rcp, q0);          // correctly rounded x / 255 (see norm255_fast)
+            }
+            if (p.out_f32) stg_stream(reinterpret_cast<float4*>(p.out_f32) + R * wpr + c, make_float4(v[0], v[1], v[2], v[3]));
+            if (p.out_u8) reinterpret_cast<uint32_t*>(p.out_u8)[R * wpr + c] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        }
+        __syncthreads();                                                    // this buffer is restaged in the next iteration
     }
 }
 

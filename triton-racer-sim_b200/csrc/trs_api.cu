@@ -487,6 +487,17 @@ int trs_normalise(trs_ctx* ctx, const uint8_t* in_dev, int n, int h_in, int w_in
         (!out_u8_dev || ((uintptr_t)out_u8_dev & 3) == 0) && !getenv("TRS_RESIZE_SCALAR")) {
         const size_t rows = (size_t)n * h_out;
         const size_t cap = (size_t)ctx->sm_count * 16;
+        // source rows staged in shared memory when they are 16-byte aligned (camera.py:36: 320x240 -> 160x120 is)
+        const int col_lo = (3 * roi_x0) & ~15, col_hi = (3 * roi_x1 + 15) & ~15;
+        const int span = (col_hi < w_in * 3 ? col_hi : w_in * 3) - col_lo;
+        const size_t tab = ((sizeof(int) * 4 * (size_t)((w_out * 3) >> 2) + sizeof(int) * (size_t)h_out + 15) & ~(size_t)15);
+        if ((w_in * 3) % 16 == 0 && ((uintptr_t)in_dev & 15) == 0 && span % 16 == 0 && tab + trs::RESIZE_DEPTH * (size_t)span <= 48 * 1024 &&
+            !getenv("TRS_RESIZE_GATHER")) {
+            trs::k_crop_resize_rows<<<(int)(rows < cap ? rows : cap), trs::RESIZE_THREADS, tab + trs::RESIZE_DEPTH * (size_t)span, st>>>(p, col_lo, span);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            CU(cudaGetLastError());
+            return 0;
+        }
         trs::k_crop_resize_words<<<(int)(rows < cap ? rows : cap), trs::RESIZE_THREADS, sizeof(int) * (size_t)(w_out + h_out), st>>>(p);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CU(cudaGetLastError());
