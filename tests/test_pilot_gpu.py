@@ -114,6 +114,21 @@ def test_keras_pilot_component_matches_the_reference_glue():
         pilot.onShutdown()
 
 
+def test_workspace_grows_with_the_batch():
+    h, w = 120, 160
+    wts = ref.random_weights(ref.CNN_2D, h, w, seed=12)
+    net = PilotNet(ModelType.CNN_2D, wts, h, w, device=0, max_batch=64, initial_batch=2)
+    assert net.capacity == 2
+    expect = 2
+    for n in (1, 3, 40, 5, 100):
+        frames = synth.frame_pool(n, h, w, seed=n)
+        out = net.forward_device(torch.from_numpy(frames).cuda()).cpu().numpy()
+        expect = max(expect, min(n, 64))                                  # grows to the largest batch seen, never past max_batch
+        assert net.capacity == expect
+        assert np.abs(out - ref.forward(wts, ref.CNN_2D, frames)).max() <= E2E_TOL
+    net.close()
+
+
 def test_cap_and_smooth_steering_like_the_reference():
     """keras_pilot.py:142-153 on the model outputs of ModelType.CNN_2D: cap to [-1, 1], snap beyond the threshold, breaking 0."""
     n, h, w = 96, 120, 160

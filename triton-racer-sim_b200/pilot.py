@@ -66,35 +66,53 @@ class PilotNet:
 
     LAYERS = 8          # debug taps: 1..7 conv outputs, 8 first-Dense partial sums
 
-    def __init__(self, model_type, weights, h=120, w=160, device=None, max_batch=4096):
+    def __init__(self, model_type, weights, h=120, w=160, device=None, max_batch=8192, initial_batch=64):
+        """max_batch: largest internal chunk (frames per launch sequence); the activation workspace (~0.6 MB per 120x160 frame) starts
+        at `initial_batch` frames and grows to the largest batch seen, up to max_batch, so a single-car pilot stays small."""
         self.model_type = _model_type(model_type)
         self.device = torch.cuda.current_device() if device is None else torch.device(device).index if not isinstance(device, int) else device
         self.ctx = nat.Context(self.device)
         self.h, self.w = int(h), int(w)
         if not isinstance(weights, dict):
             weights = load_weights(weights)
-        self._keep = [np.ascontiguousarray(v, np.float32) for v in weights.values()]
-        names = [k.encode() for k in weights.keys()]
-        arr = (nat.Tensor * len(names))()
-        for i, (nm, v) in enumerate(zip(names, self._keep)):
+        self._weights = {k: np.ascontiguousarray(v, np.float32) for k, v in weights.items()}      # kept for workspace growth
+        for nm, v in self._weights.items():
             if v.ndim > 4:
                 raise ValueError(f"weight {nm!r} has {v.ndim} dimensions")
+        self.max_batch = int(max_batch)
+        self.handle = None
+        self.capacity = 0
+        self._create(min(self.max_batch, max(1, int(initial_batch))))
+
+    def _create(self, capacity):
+        names = [k.encode() for k in self._weights]
+        arr = (nat.Tensor * len(names))()
+        for i, (nm, v) in enumerate(zip(names, self._weights.values())):
             arr[i].name = nm
             arr[i].data = v.ctypes.data_as(C.POINTER(C.c_float))
             arr[i].ndim = v.ndim
             for d in range(v.ndim):
                 arr[i].shape[d] = v.shape[d]
         h_ = C.c_void_p()
-        nat.check(self.ctx.lib.trs_pilot_create(self.ctx.handle, _KIND[self.model_type], self.h, self.w, arr, len(names), int(max_batch),
+        nat.check(self.ctx.lib.trs_pilot_create(self.ctx.handle, _KIND[self.model_type], self.h, self.w, arr, len(names), int(capacity),
                                                 C.byref(h_)), "trs_pilot_create")
-        self.handle = h_
-        self._keep = None                                # the library has repacked and uploaded everything
+        if self.handle:
+            torch.cuda.synchronize(self.device)          # work queued on the old workspace
+            self.ctx.lib.trs_pilot_destroy(self.handle)
+        self.handle, self.capacity = h_, int(capacity)
+
+    def reserve(self, n):
+        """Make the workspace hold chunks of min(n, max_batch) frames."""
+        want = min(int(n), self.max_batch)
+        if want > self.capacity:
+            self._create(want)
 
     def forward_device(self, frames: torch.Tensor, spd_feature: torch.Tensor = None, loc_feature: torch.Tensor = None, out=None):
         assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and tuple(frames.shape[1:]) == (self.h, self.w, 3), \
             f"frames must be (N,{self.h},{self.w},3) uint8 on the GPU"
         frames = frames.contiguous()
         n = frames.shape[0]
+        self.reserve(n)
         if out is None:
             out = torch.empty((n, 2), dtype=torch.float32, device=frames.device)
         f32 = lambda t: None if t is None else t.to(device=frames.device, dtype=torch.float32).contiguous()
@@ -145,7 +163,7 @@ class KerasPilot(Component):
     call), Python floats out.  ``usr/mode`` is one mode for the whole batch, as one pilot serves it.
     """
 
-    def __init__(self, cfg, model_path, model_type, device=None, max_batch=4096):
+    def __init__(self, cfg, model_path, model_type, device=None, max_batch=8192):
         inputs = ['cam/img', 'gym/speed', 'loc/segment', 'gym/cte', 'usr/mode']                   # keras_pilot.py:18-19
         outputs = ['ai/steering', 'ai/throttle', 'ai/breaking']
         Component.__init__(self, inputs=inputs, outputs=outputs, threaded=False)
