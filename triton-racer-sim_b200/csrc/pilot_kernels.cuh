@@ -162,6 +162,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
         : "r"(taddr));
 }
 
+// A operand from tensor memory (row m = TMEM lane m, two fp16 k-values per 32-bit column): no shared-memory read for A.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
 constexpr int gemm_smem_bytes(int npad, int stages) { return stages * (A_STAGE_BYTES + npad * BLOCK_K * 2) + 1024; }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
@@ -340,9 +357,12 @@ constexpr int C1_STAGES = 2;
 constexpr int C1_NPAD = 32;
 constexpr int C1_PATCH_REGS = 6;                          // patch words a builder thread carries for the next tile
 constexpr int C1_PATCH_WORDS = 128 * C1_PATCH_REGS;
-constexpr int C1_A_STAGE = 2 * A_STAGE_BYTES;             // two 64-wide swizzle atoms (k 0..63, k 64..79)
+constexpr int C1_K = 80;                                  // 5 kernel rows x 16
+constexpr int C1_A_COLS = C1_K / 2;                       // TMEM columns of one A stage (two fp16 per column)
+constexpr int C1_TMEM_A0 = 2 * C1_NPAD;                   // accumulators first, then the A stages
+constexpr int C1_TMEM_COLS = 256;                         // 2 x 32 + 2 x 40 = 144 -> next power of two
 constexpr int C1_B_BYTES = 2 * C1_NPAD * BLOCK_K * 2;
-constexpr int c1_smem_bytes() { return C1_STAGES * C1_A_STAGE + C1_B_BYTES + 2 * C1_PATCH_WORDS * 4 + 1024; }
+constexpr int c1_smem_bytes() { return C1_B_BYTES + 2 * C1_PATCH_WORDS * 4 + 1024; }
 
 struct Conv1Geom {
     int h, w;                // input frame
@@ -370,9 +390,9 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
     __shared__ float bias_s[C1_NPAD];
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_smem = base + C1_STAGES * C1_A_STAGE;
+    const uint32_t b_smem = base;
     uint8_t* const gen_base = smem_raw + (base - smem_u32(smem_raw));
-    uint32_t* const patch = reinterpret_cast<uint32_t*>(gen_base + C1_STAGES * C1_A_STAGE + C1_B_BYTES);
+    uint32_t* const patch = reinterpret_cast<uint32_t*>(gen_base + C1_B_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rows_box = (uint32_t)(g.bx * g.by);
 
@@ -396,7 +416,7 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
             tma_load_2d(b_smem + C1_NPAD * BLOCK_K * 2, &map_b, smem_u32(&bar_w), BLOCK_K, 0);
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2 * C1_NPAD)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(C1_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -456,38 +476,34 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
             const uint32_t origin = origin_of(cur);
             const uint32_t s = it % C1_STAGES, round = it / C1_STAGES;
             if (round > 0) mbar_wait(smem_u32(&bar_empty[s]), (round - 1) & 1u);
-            const bool live = (uint32_t)r < rows_box && cur.xt * g.bx + rx < g.wo && cur.yt * g.by + ry < g.ho;
-            if (live) {
-                uint8_t* const a_row = gen_base + s * C1_A_STAGE + (r >> 3) * 1024 + (r & 7) * 128;
-                const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
+            // rows of the tile that do not exist still take part in the warp-wide TMEM stores: they build from the patch origin
+            const bool live = (uint32_t)r < rows_box;
+            const int bx_ = live ? rx : 0, by_ = live ? ry : 0;
+            const uint32_t a_tmem = tmem_base + ((uint32_t)(warp * 32) << 16) + C1_TMEM_A0 + s * C1_A_COLS;
+            const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
 #pragma unroll
-                for (int kr = 0; kr < 5; ++kr) {
-                    const int j = 2 * ry + kr;
-                    const uint32_t o = ((origin + (uint32_t)j * row_bytes) & 3u) + 6u * (uint32_t)rx;   // row misalignment + pixel offset
-                    const uint32_t* wsrc = pbuf + j * c.pitch_words + (o >> 2);
-                    const uint32_t sel = 0x3210u + 0x1111u * (o & 3u);
-                    const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3], w4 = wsrc[4];
-                    const uint32_t bw[4] = {__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel),
-                                            __byte_perm(w3, w4, sel)};
-                    uint32_t hv[8];
+            for (int kr = 0; kr < 5; ++kr) {
+                const int j = 2 * by_ + kr;
+                const uint32_t o = ((origin + (uint32_t)j * row_bytes) & 3u) + 6u * (uint32_t)bx_;   // row misalignment + pixel offset
+                const uint32_t* wsrc = pbuf + j * c.pitch_words + (o >> 2);
+                const uint32_t sel = 0x3210u + 0x1111u * (o & 3u);
+                const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3], w4 = wsrc[4];
+                const uint32_t bw[4] = {__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel),
+                                        __byte_perm(w3, w4, sel)};
+                uint32_t hv[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        // bytes (x0 x1 x2 x3) -> halves 1024 + x (0x64xx), minus 1024 -> the integers 0..255, exact in fp16
-                        const uint32_t lo = __byte_perm(bw[q], 0x64646464u, 0x4140), hi = __byte_perm(bw[q], 0x64646464u, 0x4342);
-                        const __half2 hl = __hsub2(*reinterpret_cast<const __half2*>(&lo), k1024);
-                        const __half2 hh = __hsub2(*reinterpret_cast<const __half2*>(&hi), k1024);
-                        hv[2 * q] = *reinterpret_cast<const uint32_t*>(&hl);
-                        hv[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&hh);
-                    }
-                    // k = kr * 16 .. +15 -> 16-byte chunks 2 kr and 2 kr + 1 of the row; chunks 0..7 in atom 0, 8..9 in atom 1
-                    const int c0 = 2 * kr, c1 = 2 * kr + 1;
-                    uint8_t* const dst0 = a_row + (c0 >> 3) * A_STAGE_BYTES + (((c0 & 7) ^ (r & 7)) << 4);
-                    uint8_t* const dst1 = a_row + (c1 >> 3) * A_STAGE_BYTES + (((c1 & 7) ^ (r & 7)) << 4);
-                    *reinterpret_cast<uint4*>(dst0) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
-                    *reinterpret_cast<uint4*>(dst1) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
+                for (int q = 0; q < 4; ++q) {
+                    // bytes (x0 x1 x2 x3) -> halves 1024 + x (0x64xx), minus 1024 -> the integers 0..255, exact in fp16
+                    const uint32_t lo = __byte_perm(bw[q], 0x64646464u, 0x4140), hi = __byte_perm(bw[q], 0x64646464u, 0x4342);
+                    const __half2 hl = __hsub2(*reinterpret_cast<const __half2*>(&lo), k1024);
+                    const __half2 hh = __hsub2(*reinterpret_cast<const __half2*>(&hi), k1024);
+                    hv[2 * q] = *reinterpret_cast<const uint32_t*>(&hl);
+                    hv[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&hh);
                 }
+                tmem_st8(a_tmem + 8u * kr, hv);                     // k = 16 kr .. +15 of this thread's row = 8 columns of its lane
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's reads
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
             // The patch buffer written next iteration is the one read two barriers ago: every builder has passed this tile's
@@ -506,10 +522,10 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
                 mbar_wait_relaxed(smem_u32(&bar_full[s]), round & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + acc * C1_NPAD;
-                const uint64_t da0 = umma_desc_sw128(base + s * C1_A_STAGE), da1 = umma_desc_sw128(base + s * C1_A_STAGE + A_STAGE_BYTES);
+                const uint32_t a_tmem = tmem_base + C1_TMEM_A0 + s * C1_A_COLS;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0));
-                umma_f16(d_tmem, da1, db1, idesc, 1u);              // k = 64..79
+                for (int k = 0; k < 4; ++k) umma_f16_ts(d_tmem, a_tmem + 8u * k, db0 + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0));
+                umma_f16_ts(d_tmem, a_tmem + 32u, db1, idesc, 1u);   // k = 64..79
                 umma_commit(smem_u32(&bar_empty[s]));
                 umma_commit(smem_u32(&bar_acc_full[acc]));
             }
@@ -560,7 +576,7 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
     __syncthreads();
     if (warp == 4) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * C1_NPAD) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C1_TMEM_COLS) : "memory");
     }
 }
 
