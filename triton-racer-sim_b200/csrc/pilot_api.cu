@@ -259,6 +259,7 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
         g.nkb = i == 0 ? 2 : L.kh * g.kchunks;             // conv1: K = 5 x 16 in two atoms (k_pilot_conv1)
         g.n_valid = L.cout;
         g.ldc = L.cout;
+        g.last_steps = ((L.kw * L.cin_mem - (g.kchunks - 1) * BLOCK_K) + UMMA_K - 1) / UMMA_K;
         L.out_bytes_per_frame = (size_t)L.ho * L.wo * L.cout * sizeof(__half);
         hi = L.ho; wi = L.wo; cin = cin_mem = L.cout;
     }
@@ -309,6 +310,7 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
         g.nkb = g.kchunks;
         g.n_valid = D.cout;
         g.ldc = D.npad;
+        g.last_steps = ((flat - (g.kchunks - 1) * BLOCK_K) + UMMA_K - 1) / UMMA_K;
     }
     H.ldp = D.npad;
     std::vector<FilterSrc> filt(D.cout, FilterSrc{nullptr, 0, 0});

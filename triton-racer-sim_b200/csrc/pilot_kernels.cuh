@@ -38,6 +38,7 @@ struct GemmGeom {
     int n_valid;             // output columns that exist (<= NPAD)
     int ldc;                 // output row pitch in elements
     int tiles;               // x_tiles * y_tiles * ceil(nf / bn)
+    int last_steps;          // MMAs (K = 16 each) the last chunk of a kernel row needs: the rest of its 64 columns is padding
 };
 
 // Walks the tiles c, c + G, c + 2G, ... of a persistent CTA without dividing per tile: (x tile, y tile, frame tile) with carries.
@@ -267,15 +268,19 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
                 if (use > 0) mbar_wait(smem_u32(&bar_acc_empty[acc]), (use - 1) & 1u);     // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + acc * NPAD;
+                int ch = 0;
                 for (int kb = 0; kb < g.nkb; ++kb, ++it) {
                     const uint32_t s = it % STAGES, round = it / STAGES;
                     mbar_wait(smem_u32(&bar_full[s]), round & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_src = tiles + s * STAGE_BYTES;
                     const uint64_t da = umma_desc_sw128(a_src), db = umma_desc_sw128(a_src + A_STAGE_BYTES);
+                    const bool last = ++ch == g.kchunks;            // the last chunk of a kernel row may be mostly padding
+                    if (last) ch = 0;
+                    const int steps = last ? g.last_steps : BLOCK_K / UMMA_K;
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k)      // +32 bytes inside the swizzle atom per K step
-                        umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+                        if (k < steps) umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
                     umma_commit(smem_u32(&bar_empty[s]));           // stage free once these MMAs have read it
                 }
                 umma_commit(smem_u32(&bar_acc_full[acc]));          // accumulator complete
