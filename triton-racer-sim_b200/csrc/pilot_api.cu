@@ -68,6 +68,7 @@ int conv1_pitch_words(int bx) { return (6 * bx + 20 + 3) / 4 + 1; }      // a pa
 void choose_box(int wo, int ho, int* bx, int* by, int* bn, bool conv1 = false)
 {
     double best = -1;
+    *bx = *by = *bn = 1;
     for (int x = 1; x <= std::min(wo, BLOCK_M); ++x)
         for (int y = 1; y <= ho && x * y <= BLOCK_M; ++y) {
             if (conv1 && conv1_pitch_words(x) * (2 * y + 3) > C1_PATCH_WORDS) continue;   // the input patch is staged through registers
@@ -75,7 +76,9 @@ void choose_box(int wo, int ho, int* bx, int* by, int* bn, bool conv1 = false)
             for (int n = 1; n <= nmax; ++n) {
                 const double tiles = (double)((wo + x - 1) / x) * ((ho + y - 1) / y) / n;
                 const double eff = (double)wo * ho / (tiles * BLOCK_M);
-                if (eff > best + 1e-9) { best = eff; *bx = x; *by = y; *bn = n; }
+                // on ties the widest box wins: a warp's 32 rows then span the fewest image rows (fewer bank conflicts in conv1's
+                // patch reads, longer contiguous runs in every epilogue)
+                if (eff > best + 1e-9 || (eff > best - 1e-9 && x > *bx)) { best = eff; *bx = x; *by = y; *bn = n; }
             }
         }
 }
