@@ -233,7 +233,9 @@ typedef struct trs_tensor {
     int32_t shape[4];
 } trs_tensor;
 /* h, w: frame size (w even, at least 93 x 93 so that every VALID convolution has an output); max_batch: frames per internal chunk
- * (sizes the activation workspace: about 0.6 MB per 120x160 frame). */
+ * (sizes the activation workspace: about 0.6 MB per 120x160 frame; max_batch * h * w * 3 must stay below 4 GiB).
+ * A trs_pilot owns one workspace: calls on the same pilot must be ordered (same stream, or synchronised by the caller); use one
+ * pilot per stream for concurrent work.  trs_pilot_forward splits N into chunks of max_batch frames on the caller's stream. */
 int trs_pilot_create(trs_ctx* ctx, int model_type, int h, int w, const trs_tensor* weights, int n_weights, int max_batch,
                      trs_pilot** out);
 int trs_pilot_destroy(trs_pilot* p);
