@@ -114,6 +114,41 @@ def test_keras_pilot_component_matches_the_reference_glue():
         pilot.onShutdown()
 
 
+def test_components_chain_like_the_readme(tmp_path):
+    """ImgPreprocessing -> LocationTracker -> KerasPilot with CUDA tensors, weights from an .npz file, against the oracles end to end."""
+    import oracle
+    from triton_racer_sim_b200 import ImgPreprocessing, LocationTracker
+    from triton_racer_sim_b200.config import full_house_config
+    n, h, w = 48, 120, 160
+    cfg = full_house_config()
+    cfg['spd_ctl_break'] = True
+    frames = synth.frame_pool(n, h, w, seed=21)
+    wp = synth.synthetic_track(300)
+    xyz, cur, _, _ = synth.car_states(wp, n, seed=3)
+    wts = ref.random_weights(ref.CNN_2D_FULL_HOUSE, h, w, seed=6)
+    np.savez(tmp_path / "model.npz", **wts)
+    pre, trk = ImgPreprocessing(cfg, device=0), LocationTracker(wp, device=0)
+    pilot = KerasPilot(cfg, str(tmp_path / "model.npz"), 'cnn_2d_full_house', device=0)
+    pilot.step_inputs[0] = 'cam/processed_img'                                       # manage.py:49-50
+    processed, = pre.step(torch.from_numpy(frames).cuda())
+    t_xyz = torch.from_numpy(xyz).cuda()
+    segment, = trk.step(t_xyz[:, 0], t_xyz[:, 1], t_xyz[:, 2])
+    s, t, b = pilot.step(processed, torch.from_numpy(cur).cuda(), segment, None, 'ai')
+    # the same through the CPU checkers
+    want_img = oracle.process_batch(frames, cfg)
+    assert np.array_equal(processed.cpu().numpy(), want_img)
+    _, want_seg = oracle.locate(wp, xyz)
+    assert np.array_equal(segment.cpu().numpy(), want_seg)
+    model = ref.forward(wts, ref.CNN_2D_FULL_HOUSE, want_img, (cur / 20).astype(np.float32), want_seg.astype(np.float32))
+    got_model = pilot.model.forward_device(processed, torch.from_numpy((cur / 20).astype(np.float32)).cuda(), segment).cpu().numpy()
+    assert np.abs(got_model - model).max() <= E2E_TOL
+    so, th, br, _ = oracle.speed_control(cur, got_model[:, 1], got_model[:, 0], pilot.cfg)
+    assert np.array_equal(s.cpu().numpy(), so) and np.allclose(t.cpu().numpy(), th, rtol=1e-5, atol=0)
+    assert np.allclose(b.cpu().numpy(), br, rtol=1e-5, atol=0)
+    for c in (pre, trk, pilot):
+        c.onShutdown()
+
+
 def test_workspace_grows_with_the_batch():
     h, w = 120, 160
     wts = ref.random_weights(ref.CNN_2D, h, w, seed=12)
