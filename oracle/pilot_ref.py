@@ -6,7 +6,8 @@ Restates Keras_2D_CNN.get_model (TritonRacerSim/components/keras_train.py:127-17
 names ("conv1/kernel" (kh,kw,in,out), "dense1/kernel" (in,out), "…/bias").
 
 PARITY UNPINNED: TensorFlow is not installed in this image, so this restatement cannot be checked against the reference's own
-model objects; it follows the layer list line by line (VALID padding, ReLU, NHWC Flatten order, Concatenate order).  A floating-point
+model objects; it follows the layer list line by line (VALID padding, ReLU, NHWC Flatten order, Concatenate order) and is itself
+checked against an independent explicit-loop numpy restatement of the same layer list (tests/test_pilot_host.py).  A floating-point
 kernel is compared with it within a stated tolerance (tests/test_pilot_gpu.py), not bit for bit.
 """
 import numpy as np

@@ -52,6 +52,57 @@ def test_reference_shapes_and_head_wiring():
     assert np.abs(d_loc[:, 0]).max() > 0 and np.abs(d_loc[:, 1]).max() > 0
 
 
+def naive_forward(wts, model_type, frame_u8, spd=None, loc=None):
+    """One frame through the reference's layer list (keras_train.py:131-174 | 191-243) in float64 numpy, written independently of
+    oracle/pilot_ref.py: explicit loops for Conv2D, C-order Flatten of the (H,W,C) tensor, np.concatenate in the reference's order."""
+    relu = lambda v: np.maximum(v, 0)
+    dense = lambda name, v, act=True: (relu if act else (lambda t: t))(v @ wts[f"{name}/kernel"].astype(np.float64) + wts[f"{name}/bias"])
+    x = frame_u8.astype(np.float32) / np.float32(255)                    # keras_pilot.py:49-50
+    for i, (k, s_, _) in enumerate(ref.CONVS):
+        x = naive_conv_valid(x, wts[f"conv{i + 1}/kernel"], wts[f"conv{i + 1}/bias"], s_)
+    x = x.reshape(-1)                                                     # Flatten (keras_train.py:153 | 211)
+    if model_type == ref.CNN_2D_FULL_HOUSE:
+        y = np.array([loc], np.float64)                                   # feature_vec_input <- loc/segment (keras_pilot.py:102-104)
+        for n in ("feature1", "feature2", "feature3"):
+            y = dense(n, y)
+        x = np.concatenate([x, y])                                        # keras_train.py:215
+        z = x
+        for n in ("dense1", "dense2", "dense3"):
+            z = dense(n, z)
+        out_speed = dense("output_speed", z, act=False)
+        s = np.array([spd], np.float64)                                   # current_spd_input <- speed / 20 (keras_pilot.py:100-101)
+        for n in ("current_spd_1", "current_spd_2", "current_spd_3"):
+            s = dense(n, s)
+        s = np.concatenate([x, s])                                        # keras_train.py:231
+        for n in ("dense4", "dense5", "dense6"):
+            s = dense(n, s)
+        out_steering = dense("out_steering", s, act=False)
+        return np.concatenate([out_steering, out_speed])                  # keras_train.py:239
+    z = x
+    if model_type == ref.CNN_2D_SPD_FTR:
+        y = np.array([spd], np.float64)
+        for n in ("feature1", "feature2", "feature3"):
+            y = dense(n, y)
+        z = np.concatenate([x, y])                                        # keras_train.py:160
+    for n in ("dense1", "dense2", "dense3"):
+        z = dense(n, z)
+    return dense("output_layer", z, act=False)
+
+
+@pytest.mark.parametrize("model_type", [ref.CNN_2D, ref.CNN_2D_SPD_FTR, ref.CNN_2D_SPD_CTL, ref.CNN_2D_FULL_HOUSE])
+def test_reference_network_against_an_independent_restatement(model_type):
+    """The checker itself checked: the PyTorch restatement against explicit numpy loops over the reference's layer list."""
+    h, w = 94, 96                                                         # the smallest frames the seven VALID convolutions accept
+    rng = np.random.default_rng(model_type)
+    wts = ref.random_weights(model_type, h, w, seed=20 + model_type)
+    frames = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    spd, loc = np.float32([0.35, 0.8]), np.float32([2.5, 9.0])
+    got = ref.forward(wts, model_type, frames, spd, loc)
+    for i in range(2):
+        want = naive_forward(wts, model_type, frames[i], float(spd[i]), float(loc[i]))
+        assert np.allclose(got[i], want, atol=2e-5), (got[i], want)
+
+
 def test_weight_file_round_trip(tmp_path):
     from triton_racer_sim_b200.pilot import load_weights
     wts = ref.random_weights(ref.CNN_2D_SPD_FTR, seed=5)
