@@ -298,7 +298,7 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
         from triton_racer_sim_b200.pilot import KerasPilot, ModelType
         npil = 16384
         wts = pilot_ref.random_weights(pilot_ref.CNN_2D_FULL_HOUSE, h, w, seed=1)
-        pilot = KerasPilot(dict(spd_ctl_break=True), wts, ModelType.CNN_2D_FULL_HOUSE, device=local, max_batch=8192)
+        pilot = KerasPilot(dict(spd_ctl_break=True), wts, ModelType.CNN_2D_FULL_HOUSE, device=local, max_batch=16384)
         pf = synth.expand_torch(pool120, npil)
         p_spd = torch.rand(npil, device=dev, dtype=torch.float64) * 20
         p_seg = torch.rand(npil, device=dev) * 10
@@ -315,7 +315,7 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
                               "frac": 2 * macs * npil / t / 1e12 / tpeak, "peak_source": tsrc,
                               "note": "algorithmic flops of the reference's layers (no padding counted); fp16 operands, fp32 accumulate; "
                                       "bound by the operand fetch of small-N MMAs (N = 24..128 filters: ~64 B/clk shared memory -> tensor core), see DESIGN.md 4.8"},
-                 "launches_per_8192_frames": 10,
+                 "launches_per_16384_frames": 10,
                  "note": "u8 frames + gym/speed + loc/segment -> model -> speed control (ai/steering, ai/throttle, ai/breaking)"}
         fh1 = ImgPreprocessing(full_house_config(), device=local)
         pu8 = torch.empty_like(pf)

@@ -70,6 +70,20 @@ __device__ __forceinline__ uint32_t jpg_stream_byte(JpegStream& s)          // n
 
 __device__ __forceinline__ void jpg_stream_fill(JpegStream& s)              // top up to more than 32 valid bits
 {
+    // fast path: the next four bytes at once when none of them is 0xff (no stuffed zero to drop, no marker to stop at)
+    if (s.n <= 32 && s.left >= 4) {
+        const int sh = 8 * s.pos;
+        uint32_t w = (uint32_t)(s.cur >> sh);
+        if (s.pos > 4) w |= (uint32_t)(s.nxt << (64 - sh));
+        const uint32_t v = ~w;
+        if (((v - 0x01010101u) & ~v & 0x80808080u) == 0) {                     // ~w has no zero byte <=> w has no 0xff byte
+            s.buf |= (uint64_t)__byte_perm(w, 0, 0x0123) << (32 - s.n);        // stream order is big-endian
+            s.n += 32;
+            s.pos += 4;
+            s.left -= 4;
+            if (s.pos >= 8) { s.pos -= 8; s.cur = s.nxt; s.nxt = jpg_ld8(s.p); ++s.p; }
+        }
+    }
 #pragma unroll 1
     while (s.n <= 32) {
         uint32_t c = 0;

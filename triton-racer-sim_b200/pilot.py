@@ -66,7 +66,7 @@ class PilotNet:
 
     LAYERS = 8          # debug taps: 1..7 conv outputs, 8 first-Dense partial sums
 
-    def __init__(self, model_type, weights, h=120, w=160, device=None, max_batch=8192, initial_batch=64):
+    def __init__(self, model_type, weights, h=120, w=160, device=None, max_batch=16384, initial_batch=64):
         """max_batch: largest internal chunk (frames per launch sequence); the activation workspace (~0.6 MB per 120x160 frame) starts
         at `initial_batch` frames and grows to the largest batch seen, up to max_batch, so a single-car pilot stays small."""
         self.model_type = _model_type(model_type)
@@ -163,7 +163,7 @@ class KerasPilot(Component):
     call), Python floats out.  ``usr/mode`` is one mode for the whole batch, as one pilot serves it.
     """
 
-    def __init__(self, cfg, model_path, model_type, device=None, max_batch=8192):
+    def __init__(self, cfg, model_path, model_type, device=None, max_batch=16384):
         inputs = ['cam/img', 'gym/speed', 'loc/segment', 'gym/cte', 'usr/mode']                   # keras_pilot.py:18-19
         outputs = ['ai/steering', 'ai/throttle', 'ai/breaking']
         Component.__init__(self, inputs=inputs, outputs=outputs, threaded=False)
