@@ -2,9 +2,10 @@
 //
 //   k_jpeg_entropy        one THREAD per record: Huffman decoding is sequential within a scan (no restart markers in the
 //                         recorder's files), so the parallelism is across the N records of the batch.  The bit stream comes in
-//                         8-byte aligned loads one chunk ahead, the decoding tables sit in shared memory, and only the non-zero
-//                         coefficients are written (pre-zeroed int16 buffer, natural order).
-//   k_jpeg_idct           one thread per 8x8 block: dequantisation + integer IDCT, samples into planar Y / Cb / Cr (MCU-padded).
+//                         8-byte aligned loads one chunk ahead, the decoding tables sit in shared memory.  A block's coefficients
+//                         stay in the thread (natural order); at the end of the block - where the lanes of a warp meet again -
+//                         the thread dequantises and runs the integer IDCT itself and writes the 8x8 samples into planar
+//                         Y / Cb / Cr (MCU-padded): no coefficient buffer (61 KB per 120x160 record) is written, zeroed or re-read.
 //   k_jpeg_upsample_rgb   one thread per 4 output pixels: triangle-filter chroma upsampling + YCbCr -> RGB, interleaved u8 out
 //                         (the (N,H,W,3) layout the rest of the path reads).
 #pragma once
@@ -29,7 +30,7 @@ struct JpegPlanes {
     int hs, vs;             // luma sampling factors of the batch: (2,2) 4:2:0, (2,1) 4:2:2, (1,1) 4:4:4
 };
 
-enum { JPG_THREADS = 64, JPG_IDCT_THREADS = 128 };
+enum { JPG_THREADS = 64 };
 
 // ---- device-side bit reader: 8-byte aligned global loads one chunk ahead, bytes handed out from registers ----------------
 struct JpegStream {
@@ -134,8 +135,7 @@ __device__ __forceinline__ int jpg_dev_extend(JpegStream& s, int nb)
 // Entropy decoding: one thread per record; the non-zero quantised coefficients go to a pre-zeroed (record, block, 64) int16 buffer
 // in natural order.  Block order inside a record: MCU-major, then the blocks of the MCU (luma in raster order, Cb, Cr).
 __global__ void __launch_bounds__(JPG_THREADS) k_jpeg_entropy(const uint8_t* __restrict__ blob, const JpegRecord* __restrict__ recs,
-                                                             const JpegTables* __restrict__ tables, int n, int n_mcu, int luma_blocks, int16_t* __restrict__ coefs,
-                                                             int* __restrict__ status)
+                                                             const JpegTables* __restrict__ tables, int n, JpegPlanes P, int* __restrict__ status)
 {
     __shared__ JpegSmemTables T;
     // A CTA whose records disagree on the table set loads the sets one after the other (common case: one set for the whole batch).
@@ -168,16 +168,23 @@ __global__ void __launch_bounds__(JPG_THREADS) k_jpeg_entropy(const uint8_t* __r
             JpegStream s;
             jpg_stream_open(s, blob + rec.data_off, rec.data_len);
             int dc[3] = {0, 0, 0};
+            const int luma_blocks = P.hs * P.vs, n_mcu = P.mw * P.mh;
             const int bpm = luma_blocks + 2;                       // blocks per MCU: the luma blocks in raster order, then Cb, Cr
-            int16_t* out = coefs + (size_t)r * n_mcu * bpm * 64;
-            int sub = 0;
+            const int ys = P.mw * 8 * P.hs, cs = P.mw * 8;
+            uint8_t* const Yp = P.y + (size_t)r * ys * P.mh * 8 * P.vs;
+            uint8_t* const Cbp = P.cb + (size_t)r * cs * P.mh * 8;
+            uint8_t* const Crp = P.cr + (size_t)r * cs * P.mh * 8;
+            int sub = 0, mx = 0, my = 0;
 #pragma unroll 1
-            for (int blk = 0; blk < n_mcu * bpm; ++blk, out += 64, sub = sub + 1 == bpm ? 0 : sub + 1) {
+            for (int blk = 0; blk < n_mcu * bpm; ++blk) {
                 const int comp = sub < luma_blocks ? 0 : sub - luma_blocks + 1;
                 const int td = comp ? 2 : 0, ta = td + 1;
+                int16_t coef[64];
+#pragma unroll
+                for (int k = 0; k < 64; ++k) coef[k] = 0;
                 int sym = jpg_dev_symbol(s, T, td, err);
                 if (sym) dc[comp] += jpg_dev_extend(s, sym);
-                if (dc[comp]) out[0] = (int16_t)dc[comp];
+                coef[0] = (int16_t)dc[comp];
 #pragma unroll 1
                 for (int k = 1; k < 64; ++k) {
                     sym = jpg_dev_symbol(s, T, ta, err);
@@ -186,50 +193,26 @@ __global__ void __launch_bounds__(JPG_THREADS) k_jpeg_entropy(const uint8_t* __r
                     if (sym) {
                         k += run;
                         if (k > 63) { err = JPG_E_BADCODE; break; }
-                        out[T.natural[k]] = (int16_t)jpg_dev_extend(s, sym);
+                        coef[T.natural[k]] = (int16_t)jpg_dev_extend(s, sym);
                     } else {
                         if (run != 15) break;
                         k += 15;
                     }
                 }
+                // the lanes of the warp are together again here: dequantisation + IDCT of this block with all of them active
+                if (comp == 0) {
+                    const int by = sub / P.hs, bx = sub - by * P.hs;
+                    jpg_idct_islow(coef, G.quant[0], Yp + ((my * P.vs + by) * 8) * ys + (mx * P.hs + bx) * 8, ys);
+                } else {
+                    jpg_idct_islow(coef, G.quant[1], (comp == 1 ? Cbp : Crp) + my * 8 * cs + mx * 8, cs);
+                }
+                if (++sub == bpm) { sub = 0; if (++mx == P.mw) { mx = 0; ++my; } }
             }
             mine_done = true;
         }
         __syncthreads();
     }
     if (err) atomicMax(status, err);
-}
-
-// Dequantisation + integer IDCT: one thread per 8x8 block, coefficients from the buffer above, samples into the planar buffers
-__global__ void __launch_bounds__(JPG_IDCT_THREADS) k_jpeg_idct(const int16_t* __restrict__ coefs, const JpegRecord* __restrict__ recs,
-                                                               const JpegTables* __restrict__ tables, int n, JpegPlanes P)
-{
-    const int n_mcu = P.mw * P.mh, lb = P.hs * P.vs, bpm = lb + 2;
-    const size_t total = (size_t)n * n_mcu * bpm;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int r = (int)(i / ((size_t)n_mcu * bpm));
-    const int blk = (int)(i - (size_t)r * n_mcu * bpm);
-    const int mcu = blk / bpm, sub = blk - bpm * mcu, my = mcu / P.mw, mx = mcu - my * P.mw;
-    const JpegTables& G = tables[recs[r].table_set];
-    int16_t coef[64];
-    const uint4* src = reinterpret_cast<const uint4*>(coefs + i * 64);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint4 v = __ldg(src + k);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { coef[8 * k + 2 * q] = (int16_t)(w[q] & 0xffffu); coef[8 * k + 2 * q + 1] = (int16_t)(w[q] >> 16); }
-    }
-    const int ys = P.mw * 8 * P.hs, cs = P.mw * 8;
-    if (sub < lb) {
-        uint8_t* Y = P.y + (size_t)r * ys * P.mh * 8 * P.vs;
-        const int by = sub / P.hs, bx = sub - by * P.hs;
-        jpg_idct_islow(coef, G.quant[0], Y + ((my * P.vs + by) * 8) * ys + (mx * P.hs + bx) * 8, ys);
-    } else {
-        uint8_t* C = (sub == lb ? P.cb : P.cr) + (size_t)r * cs * P.mh * 8;
-        jpg_idct_islow(coef, G.quant[1], C + my * 8 * cs + mx * 8, cs);
-    }
 }
 
 __global__ void __launch_bounds__(256) k_jpeg_upsample_rgb(JpegPlanes P, int n, int h, int w, uint8_t* __restrict__ out)
@@ -241,11 +224,15 @@ __global__ void __launch_bounds__(256) k_jpeg_upsample_rgb(JpegPlanes P, int n, 
     const size_t total = (size_t)n * h * gpr;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const bool words = (w & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int g = (int)(i % gpr);
-        const size_t t = i / gpr;
-        const int y = (int)(t % h);
-        const size_t r = t / h;
+    // (record, row, group of four pixels) of this thread's items: one division at the start, then the grid stride with carries
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int g = (int)(i0 % gpr), y = (int)((i0 / gpr) % h);
+    size_t r = i0 / gpr / h;
+    const int sg = (int)(stride % gpr), sy = (int)((stride / gpr) % h);
+    const size_t sr = stride / gpr / h;
+    for (size_t i = i0; i < total; i += stride, g += sg, y += sy, r += sr) {
+        if (g >= gpr) { g -= gpr; ++y; }
+        if (y >= h) { y -= h; ++r; }
         const uint8_t* Y = P.y + r * (size_t)ys * P.mh * 8 * P.vs + (size_t)y * ys;
         const uint8_t* Cb = P.cb + r * (size_t)cs * P.mh * 8;
         const uint8_t* Cr = P.cr + r * (size_t)cs * P.mh * 8;

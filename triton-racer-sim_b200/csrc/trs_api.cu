@@ -707,37 +707,31 @@ int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned 
     const int hs = sampling.load() >> 4, vs = sampling.load() & 15, lb = hs * vs;
     const int mw = (w + 8 * hs - 1) / (8 * hs), mh = (h + 8 * vs - 1) / (8 * vs), n_mcu = mw * mh;
     const size_t ybytes = (size_t)mw * 8 * hs * mh * 8 * vs, cbytes = (size_t)mw * 8 * mh * 8;
-    const size_t coef_per = (size_t)n_mcu * (lb + 2) * 64 * sizeof(int16_t);
     // Entropy decoding is one thread per record and latency bound: the more records in flight the better, so chunks are as large as
-    // ~8 GB of staging allows (87 k records of 120x160)
-    size_t chunk = ((size_t)8 << 30) / (coef_per + ybytes + 2 * cbytes);
+    // ~8 GB of plane staging allows (290 k records of 120x160)
+    size_t chunk = ((size_t)8 << 30) / (ybytes + 2 * cbytes);
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)n) chunk = (size_t)n;
-    const size_t planes_bytes = chunk * (ybytes + 2 * cbytes), coefs_bytes = chunk * coef_per;
+    const size_t planes_bytes = chunk * (ybytes + 2 * cbytes);
     const size_t meta_bytes = sets.size() * sizeof(trs::JpegTables) + (size_t)n * sizeof(trs::JpegRecord) + 16;
-    if (ctx->jpg_planes_cap < planes_bytes + coefs_bytes) { cudaFree(ctx->jpg_planes); ctx->jpg_planes = nullptr; ctx->jpg_planes_cap = 0; CU(cudaMalloc(&ctx->jpg_planes, planes_bytes + coefs_bytes)); ctx->jpg_planes_cap = planes_bytes + coefs_bytes; }
+    if (ctx->jpg_planes_cap < planes_bytes) { cudaFree(ctx->jpg_planes); ctx->jpg_planes = nullptr; ctx->jpg_planes_cap = 0; CU(cudaMalloc(&ctx->jpg_planes, planes_bytes)); ctx->jpg_planes_cap = planes_bytes; }
     if (ctx->jpg_meta_cap < meta_bytes) { cudaFree(ctx->jpg_meta); ctx->jpg_meta = nullptr; ctx->jpg_meta_cap = 0; CU(cudaMalloc(&ctx->jpg_meta, meta_bytes)); ctx->jpg_meta_cap = meta_bytes; }
     trs::JpegTables* d_sets = reinterpret_cast<trs::JpegTables*>(ctx->jpg_meta);
     trs::JpegRecord* d_recs = reinterpret_cast<trs::JpegRecord*>(reinterpret_cast<uint8_t*>(ctx->jpg_meta) + sets.size() * sizeof(trs::JpegTables));
     int* d_status = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(d_recs) + (size_t)n * sizeof(trs::JpegRecord));
-    int16_t* d_coefs = reinterpret_cast<int16_t*>(ctx->jpg_planes);
-    uint8_t* d_planes = ctx->jpg_planes + coefs_bytes;
+    uint8_t* d_planes = ctx->jpg_planes;
     CU(cudaMemcpyAsync(d_sets, sets.data(), sets.size() * sizeof(trs::JpegTables), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_recs, recs.data(), (size_t)n * sizeof(trs::JpegRecord), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(d_status, 0, sizeof(int), st));
     for (size_t c0 = 0; c0 < (size_t)n; c0 += chunk) {
         const int cn = (int)((size_t)n - c0 < chunk ? (size_t)n - c0 : chunk);
-        CU(cudaMemsetAsync(d_coefs, 0, (size_t)cn * coef_per, st));
-        trs::k_jpeg_entropy<<<(cn + trs::JPG_THREADS - 1) / trs::JPG_THREADS, trs::JPG_THREADS, 0, st>>>(ctx->jpg_blob, d_recs + c0, d_sets, cn, n_mcu, lb, d_coefs,
-                                                                                                      d_status);
         trs::JpegPlanes P{d_planes, d_planes + (size_t)cn * ybytes, d_planes + (size_t)cn * (ybytes + cbytes), mw, mh, hs, vs};
-        const size_t blocks = (size_t)cn * n_mcu * (lb + 2);
-        trs::k_jpeg_idct<<<(unsigned)((blocks + trs::JPG_IDCT_THREADS - 1) / trs::JPG_IDCT_THREADS), trs::JPG_IDCT_THREADS, 0, st>>>(d_coefs, d_recs + c0, d_sets, cn, P);
+        trs::k_jpeg_entropy<<<(cn + trs::JPG_THREADS - 1) / trs::JPG_THREADS, trs::JPG_THREADS, 0, st>>>(ctx->jpg_blob, d_recs + c0, d_sets, cn, P, d_status);
         const size_t groups = (size_t)cn * h * ((w + 3) / 4);
         size_t want = (groups + 255) / 256;
         const size_t cap = (size_t)ctx->sm_count * 32;
         trs::k_jpeg_upsample_rgb<<<(int)(want < cap ? want : cap), 256, 0, st>>>(P, cn, h, w, out_u8_dev + c0 * (size_t)h * w * 3);
-        g_launches.fetch_add(3, std::memory_order_relaxed);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
         CU(cudaGetLastError());
     }
     int status = 0;
