@@ -149,6 +149,30 @@ def test_components_chain_like_the_readme(tmp_path):
         c.onShutdown()
 
 
+def test_outputs_do_not_depend_on_batch_or_shard():
+    """Size-independent property at a larger size: a frame's outputs are bit-identical whatever batch, chunk or shard it sits in
+    (rows of an MMA tile are independent; tiles stack frames in conv3..conv7 and in the Dense GEMM)."""
+    h, w, n = 120, 160, 5000
+    pool = torch.from_numpy(synth.frame_pool(64, h, w, seed=31)).cuda()
+    frames = synth.expand_torch(pool, n)
+    wts = ref.random_weights(ref.CNN_2D_FULL_HOUSE, h, w, seed=13)
+    g = torch.Generator(device='cuda').manual_seed(5)
+    spd = torch.rand(n, device='cuda', generator=g)
+    loc = torch.rand(n, device='cuda', generator=g) * 10
+    big = PilotNet(ModelType.CNN_2D_FULL_HOUSE, wts, h, w, device=0, max_batch=2048)           # three chunks, the last one ragged
+    whole = big.forward_device(frames, spd, loc).clone()
+    small = PilotNet(ModelType.CNN_2D_FULL_HOUSE, wts, h, w, device=0, max_batch=64)
+    for lo, hi in ((0, 1), (7, 20), (2040, 2060), (4990, 5000), (1234, 1234 + 333)):             # shards, incl. across chunk borders
+        part = small.forward_device(frames[lo:hi], spd[lo:hi], loc[lo:hi])
+        assert torch.equal(part, whole[lo:hi]), (lo, hi)
+    # and against the fp32 reference on a sample
+    idx = [0, 63, 2047, 2048, 4999]
+    want = ref.forward(wts, ref.CNN_2D_FULL_HOUSE, frames[idx].cpu().numpy(), spd[idx].cpu().numpy(), loc[idx].cpu().numpy())
+    assert np.abs(whole[idx].cpu().numpy() - want).max() <= E2E_TOL
+    big.close()
+    small.close()
+
+
 def test_workspace_grows_with_the_batch():
     h, w = 120, 160
     wts = ref.random_weights(ref.CNN_2D, h, w, seed=12)
