@@ -71,6 +71,20 @@ def test_unsupported_and_corrupt_files_raise():
         tub.decode_jpeg_batch(ok, hw=(240, 320), device=0)                                          # wrong stated size
 
 
+def test_large_batch_of_mixed_records():
+    """20,003 records of very different sizes and two table sets in random order: every copy of a file decodes to Pillow's pixels."""
+    uniq = synth.frame_pool(96, 120, 160, seed=23)
+    files = encode(uniq[:48]) + encode(uniq[48:], quality=92)                 # two table sets, sizes from ~3 KB to ~25 KB
+    want_u = pil_decode(files)
+    n = 20003
+    order = np.random.default_rng(2).integers(0, len(files), n)
+    got = tub.decode_jpeg_batch([files[i] for i in order], device=0).cpu().numpy()
+    assert got.shape == (n, 120, 160, 3)
+    for k in range(len(files)):
+        sel = np.nonzero(order == k)[0]
+        assert (got[sel] == want_u[k][None]).all(), k
+
+
 def test_tub_reader_round_trip(tmp_path):
     """A tub written the way the reference's recorder writes it (datastorage.py:67-79), read back through the GPU decoder and through
     the full chain: the same as the reference loader's `Image.open` followed by the oracle chain."""

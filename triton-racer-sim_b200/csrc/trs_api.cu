@@ -704,8 +704,8 @@ int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned 
         return fail(TRS_E_RANGE, "record %d: %s", k, c == trs::JPG_E_UNSUPPORTED ? "not a baseline 8-bit YCbCr (4:2:0 / 4:2:2 / 4:4:4) single-scan JPEG" : "malformed JPEG");
     }
     // ---- device staging: chunks of records through coefficient and plane buffers ----------------------------------------------
-    const int hs = sampling.load() >> 4, vs = sampling.load() & 15, lb = hs * vs;
-    const int mw = (w + 8 * hs - 1) / (8 * hs), mh = (h + 8 * vs - 1) / (8 * vs), n_mcu = mw * mh;
+    const int hs = sampling.load() >> 4, vs = sampling.load() & 15;
+    const int mw = (w + 8 * hs - 1) / (8 * hs), mh = (h + 8 * vs - 1) / (8 * vs);
     const size_t ybytes = (size_t)mw * 8 * hs * mh * 8 * vs, cbytes = (size_t)mw * 8 * mh * 8;
     // Entropy decoding is one thread per record and latency bound: the more records in flight the better, so chunks are as large as
     // ~8 GB of plane staging allows (290 k records of 120x160)
