@@ -190,6 +190,14 @@ def test_normalise_and_crop_resize():
         f32, u8 = comp.normalise_device(d, want_u8=True)
         assert np.array_equal(u8.cpu().numpy(), u8_want) and np.array_equal(f32.cpu().numpy(), f32_want)
         comp.onShutdown()
+    # source rows that are not a multiple of 16 bytes (322 x 3 = 966): the byte-gather kernel instead of the row-staged one
+    wide = synth.frame_pool(4, 100, 322, seed=5)
+    for roi, out_hw in (((0, 100, 0, 322), (50, 160)), ((5, 90, 3, 300), (64, 100))):
+        comp = FrameNormalise(device=0, roi=roi, out_hw=out_hw)
+        u8_want, f32_want = oracle.crop_resize(wide, roi, out_hw)
+        f32, u8 = comp.normalise_device(torch.from_numpy(wide).to(DEV), want_u8=True)
+        assert np.array_equal(u8.cpu().numpy(), u8_want) and np.array_equal(f32.cpu().numpy(), f32_want)
+        comp.onShutdown()
     odd = synth.frame_pool(3, 7, 9, seed=1)                                              # 189 bytes per frame: unaligned tail path
     comp = FrameNormalise(device=0)
     assert np.array_equal(comp.step(odd)[0], oracle.normalise(odd))
