@@ -32,13 +32,14 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "trs_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(trs_preproc_params), sizeof(trs_spd_params), sizeof(trs_ctl_params));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "trs_b200.h"\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(trs_preproc_params), sizeof(trs_spd_params), sizeof(trs_ctl_params), sizeof(trs_tensor), offsetof(trs_tensor, ndim), offsetof(trs_tensor, shape));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
-    a, b, c = map(int, subprocess.check_output([str(exe)]).split())
+    a, b, c, t, t_ndim, t_shape = map(int, subprocess.check_output([str(exe)]).split())
     assert a == C.sizeof(nat.PreprocParams)
     assert b == C.sizeof(nat.SpdParams)
     assert c == C.sizeof(nat.CtlParams)
+    assert t == C.sizeof(nat.Tensor) and t_ndim == nat.Tensor.ndim.offset and t_shape == nat.Tensor.shape.offset
 
 
 def test_sass_is_sm100a_only():
