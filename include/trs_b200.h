@@ -46,8 +46,8 @@ typedef struct trs_preproc_params {
     int32_t color_filter_enabled; /* preprocessing_color_filter_enabled         (config.py:22) */
     int32_t n_hsv;                /* len(preprocessing_color_filter_hsvs)       (config.py:23) */
     int32_t edge_enabled;         /* preprocessing_edge_detection_enabled       (config.py:25) */
-    double hsv_lo[TRS_MAX_HSV][3];/* lower (H,S,V) bound of each range, compared as reals      */
-    double hsv_hi[TRS_MAX_HSV][3];/* upper (H,S,V) bound, inclusive                              */
+    double hsv_lo[TRS_MAX_HSV][3];/* lower (H,S,V) bound of each range; rounded to int32 half-to-even (out of range -> INT_MIN) before the compare, as cv2.inRange does */
+    double hsv_hi[TRS_MAX_HSV][3];/* upper (H,S,V) bound, inclusive, same rounding */
     int32_t color_dest[TRS_MAX_HSV]; /* preprocessing_color_filter_destination_channels (config.py:24) */
     int32_t edge_dest;            /* preprocessing_edge_detection_destination_channel (config.py:28) */
     double canny_a;               /* preprocessing_edge_detection_threshold_a   (config.py:26) */
@@ -62,6 +62,10 @@ typedef struct trs_spd_params {
     int32_t use_break;            /* spd_ctl_break                */
     int32_t smooth_steering;      /* smooth_steering_enabled      */
     double smooth_threshold;      /* smooth_steering_threshold    */
+    int32_t numpy_legacy_promotion; /* 0: NumPy >= 2 scalar promotion (NEP 50): np.float32 model output * 20, * threshold and the speed gap stay
+                                     *    float32 (what the reference computes under the numpy this image pins);
+                                     * 1: NumPy 1.x promotion: the same expressions are float64 (the TF2-era stacks the reference was written for) */
+    int32_t reserved;
 } trs_spd_params;
 
 /* Per-call statistics written by trs_preprocess (all counters are sums over the N frames). */
@@ -262,10 +266,21 @@ int trs_pilot_layer_shape(trs_pilot* p, int layer, int* ho, int* wo, int* c);
  * returning.  Host buffers may be pageable (slower) or pinned (trs_host_alloc).
  *   keep_f32_dev: optional device buffer (N,H,W,3) f32 that receives the normalised tensor and
  *   stays on the GPU for the pilot's model — nullable.
+ *   stream: the caller's stream (cudaStream_t, NULL = the legacy default stream).  Work already queued on it
+ *   (e.g. a pilot still reading keep_f32_dev from the previous step) is waited for before the internal
+ *   streams touch any device buffer; everything is complete when the call returns, so the caller's stream
+ *   may read keep_f32_dev right after it.
  */
 int trs_preprocess_host(trs_ctx* ctx, const uint8_t* in_host, int n, int h, int w,
                         uint8_t* out_u8_host, float* out_f32_host, float* keep_f32_dev,
-                        unsigned long long* stats_host);
+                        unsigned long long* stats_host, void* stream);
+
+/*
+ * Measurement aid (bench.py): the FP64 pipe rate of the context's GPU, the denominator of the nearest-waypoint kernel's roofline
+ * (trs_locate is FP64-ALU bound).  dfma_tflops: dense DFMA chains, 2 flops per lane-instruction; dadd_tinst_per_s:
+ * 10^12 DADD lane-instructions per second.  Synchronises.
+ */
+int trs_probe_fp64(trs_ctx* ctx, double* dfma_tflops, double* dadd_tinst_per_s);
 
 /* Pinned host allocations for the *_host entry points. */
 int trs_host_alloc(void** out, unsigned long long bytes);

@@ -44,6 +44,7 @@ class SpdParams(C.Structure):
     _fields_ = [
         ("threshold", C.c_double), ("reverse_multiplier", C.c_double), ("break_multiplier", C.c_double),
         ("use_break", C.c_int32), ("smooth_steering", C.c_int32), ("smooth_threshold", C.c_double),
+        ("numpy_legacy_promotion", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -197,6 +198,7 @@ def spd_params_from_cfg(cfg: dict) -> SpdParams:
     p.use_break = int(bool(cfg.get("spd_ctl_break", False)))
     p.smooth_steering = int(bool(cfg.get("smooth_steering_enabled", False)))
     p.smooth_threshold = float(cfg.get("smooth_steering_threshold", 0.9))
+    p.numpy_legacy_promotion = int(bool(cfg.get("spd_ctl_numpy_legacy_promotion", False)))
     return p
 
 

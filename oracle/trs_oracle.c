@@ -347,6 +347,7 @@ typedef struct orc_spd_params {
     double threshold, reverse_multiplier, break_multiplier;
     int32_t use_break, smooth_steering;
     double smooth_threshold;
+    int32_t numpy_legacy_promotion, reserved;   /* 1: NumPy 1.x promotion, np.float32 * 20 is float64 and so is everything after it */
 } orc_spd_params;
 
 void orc_speed_control(const double* cur, const float* model_spd, const float* model_steer, int n,
@@ -359,17 +360,29 @@ void orc_speed_control(const double* cur, const float* model_spd, const float* m
         volatile float steer_f = model_steer[k];
         double steering = steer_f;
         if (steer_f < -1.0f) steering = -1.0; else if (steer_f > 1.0f) steering = 1.0;
-        volatile float predicted = model_spd[k] * 20.0f;                 /* np.float32 * int */
-        volatile float target_f = predicted * (float)p->threshold;      /* np.float32 * python float -> float32 */
-        volatile float real_f = (float)real_spd;
-        volatile float delta_f = target_f - real_f;
-        volatile float delta2_f = delta_f * 2.0f;
-        double delta = delta_f;
-        double throttle = p->reverse_multiplier * atan((double)delta2_f) / half_pi;
+        double delta, delta2;
+        int faster;
+        if (p->numpy_legacy_promotion) {
+            volatile double predicted = (double)model_spd[k] * 20.0;    /* NumPy 1.x: np.float32 scalar * python int -> float64 */
+            volatile double target = predicted * p->threshold;
+            volatile double d = target - real_spd;
+            volatile double d2 = d * 2;
+            volatile double gap = predicted - real_spd;
+            delta = d; delta2 = d2; faster = gap > 0.0;
+        } else {
+            volatile float predicted = model_spd[k] * 20.0f;             /* np.float32 * int */
+            volatile float target_f = predicted * (float)p->threshold;  /* np.float32 * python float -> float32 */
+            volatile float real_f = (float)real_spd;
+            volatile float delta_f = target_f - real_f;
+            volatile float delta2_f = delta_f * 2.0f;
+            volatile float gap = predicted - real_f;
+            delta = delta_f; delta2 = delta2_f; faster = gap > 0.0f;
+        }
+        double throttle = p->reverse_multiplier * atan(delta2) / half_pi;
         if (-0.2 < throttle && throttle < 0.0) throttle = 0.0;
         double breaking = 0.0;
         if (p->use_break) {
-            { volatile float gap = predicted - real_f; throttle = (gap > 0.0f) ? 1.0 : 0.0; }
+            throttle = faster ? 1.0 : 0.0;
             breaking = -1.0 * p->break_multiplier * atan(delta * 1.0) / half_pi;
             if (breaking < 0.4) breaking = 0.0;
         }

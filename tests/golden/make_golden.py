@@ -190,11 +190,14 @@ SPD_CASES = {
 }
 
 
-def pilot_tail(cfg, real_spd, model_steer, model_spd):
-    """keras_pilot.py:80-95 replayed with the reference's own calcThrottle/calcBreak."""
+def pilot_tail(cfg, real_spd, model_steer, model_spd, numpy1=False):
+    """keras_pilot.py:80-95 replayed with the reference's own calcThrottle/calcBreak.  numpy1: what NumPy 1.x scalar promotion makes of
+    line 83 (`np.float32 * 20` is float64 there, so everything after it is float64 too); NumPy >= 2 keeps float32 (NEP 50)."""
     steering = model_steer                                           # numpy()[0][0] -> np.float32
     if steering < -1.0: steering = -1.0                              # __cap, :142-145
     elif steering > 1.0: steering = 1.0
+    if numpy1:
+        model_spd = np.float64(model_spd)
     predicted_speed = model_spd * 20                                 # :83
     breaking = 0.0
     throttle = calcThrottle(real_spd, predicted_speed * cfg['spd_ctl_threshold'], cfg['spd_ctl_reverse_multiplier'])
@@ -215,6 +218,7 @@ def run_speed():
         cfg = ref_cfg(**over)
         res = np.array([pilot_tail(cfg, float(c), s, m) for c, s, m in zip(cur, steer, model_spd)], np.float64)
         arrays[f"out/{cname}"] = res
+        arrays[f"out_numpy1/{cname}"] = np.array([pilot_tail(cfg, float(c), s, m, numpy1=True) for c, s, m in zip(cur, steer, model_spd)], np.float64)
     arrays["feature"] = np.array([np.asarray(float(c) / 20, dtype=np.float32) for c in cur], np.float32)   # keras_pilot.py:100
     arrays["cases_json"] = np.frombuffer(json.dumps(SPD_CASES).encode(), np.uint8)
     np.savez_compressed(os.path.join(HERE, "speed.npz"), **arrays)

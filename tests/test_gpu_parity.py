@@ -278,6 +278,14 @@ def test_speed_control_golden(golden_speed):
         assert all(isinstance(v, float) for v in out) and abs(out[1] - want[3, 1]) <= RTOL * abs(want[3, 1])
         assert comp.step(None, None, None) == (0.0, 0.0, 0.0)
         comp.onShutdown()
+        # the same states under NumPy 1.x scalar promotion (float64 speed gap): its own golden set
+        comp1 = SpeedControl(dict(cfg, spd_ctl_numpy_legacy_promotion=True), device=0)
+        s1, t1, b1, _ = comp1.control_device(torch.from_numpy(cur).to(DEV), torch.from_numpy(st).to(DEV), torch.from_numpy(ms).to(DEV))
+        want1 = golden_speed[f"out_numpy1/{cname}"]
+        assert np.array_equal(s1.cpu().numpy(), want1[:, 0]), cname
+        for got, ref in ((t1.cpu().numpy(), want1[:, 1]), (b1.cpu().numpy(), want1[:, 2])):
+            assert (~(np.abs(got - ref) <= RTOL * np.abs(ref))).sum() == 0, f"{cname} (numpy 1 promotion)"
+        comp1.onShutdown()
 
 
 def test_full_size_properties():

@@ -117,3 +117,9 @@ def test_speed_control_matches_reference(golden_speed):
         for k in range(0, 200):
             got = cv2_chain.pilot_tail(float(cur[k]), st[k], ms[k], cfg)
             assert got == tuple(want[k]), (cname, k)
+        # NumPy 1.x scalar promotion (np.float32 * 20 -> float64): the reference functions fed float64, see make_golden.py
+        so, th, br, _ = oracle.speed_control(cur, ms, st, dict(cfg, spd_ctl_numpy_legacy_promotion=True))
+        want1 = golden_speed[f"out_numpy1/{cname}"]
+        assert np.array_equal(so, want1[:, 0]), cname
+        assert np.allclose(th, want1[:, 1], rtol=1e-12, atol=0) and np.allclose(br, want1[:, 2], rtol=1e-12, atol=0), cname
+        assert np.array_equal(th == 0, want1[:, 1] == 0) and np.array_equal(br == 0, want1[:, 2] == 0), cname

@@ -21,7 +21,7 @@ SYMBOLS = [
     "trs_preprocess_host", "trs_host_alloc", "trs_host_free", "trs_debug_canny_stages", "trs_control_mux", "trs_pwm_map",
     "trs_jpeg_decode_host", "trs_telemetry_decode_host",
     "trs_pilot_create", "trs_pilot_destroy", "trs_pilot_forward", "trs_pilot_debug_activation", "trs_pilot_layer_shape",
-    "trs_pilot_cap",
+    "trs_pilot_cap", "trs_probe_fp64",
 ]
 MODE_HUMAN, MODE_AI_STEERING, MODE_AI = 0, 1, 2          # TRS_MODE_*: DriveMode.HUMAN / AI_STEERING / AI (components/controller.py:7-10)
 LAUNCH_SLOTS = 4                                          # TRS_LAUNCH_SLOTS
@@ -43,6 +43,7 @@ class SpdParams(C.Structure):
     _fields_ = [
         ("threshold", C.c_double), ("reverse_multiplier", C.c_double), ("break_multiplier", C.c_double),
         ("use_break", C.c_int32), ("smooth_steering", C.c_int32), ("smooth_threshold", C.c_double),
+        ("numpy_legacy_promotion", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -88,7 +89,7 @@ def load():
     lib.trs_set_track.argtypes = [vp, vp, i32, C.c_double, C.c_double]
     lib.trs_locate.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.trs_speed_control.argtypes = [vp, vp, vp, vp, i32, C.POINTER(SpdParams), vp, vp, vp, vp, vp]
-    lib.trs_preprocess_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.trs_preprocess_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.trs_host_alloc.argtypes = [C.POINTER(vp), C.c_ulonglong]
     lib.trs_host_free.argtypes = [vp]
     lib.trs_debug_canny_stages.argtypes = [vp, vp, i32, i32, vp, vp, vp]
@@ -102,6 +103,7 @@ def load():
     lib.trs_pilot_debug_activation.argtypes = [vp, i32, vp, C.c_ulonglong, vp]
     lib.trs_pilot_layer_shape.argtypes = [vp, i32] + [C.POINTER(C.c_int)] * 3
     lib.trs_pilot_cap.argtypes = [vp, vp, i32, i32, C.c_double, vp, vp, vp, vp]
+    lib.trs_probe_fp64.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in SYMBOLS:
         getattr(lib, name)
     _lib = lib
@@ -143,6 +145,17 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def probe_fp64(device: int = 0):
+    """(DFMA TFLOP/s, 10^12 DADD lane-instructions/s) measured on `device` (bench.py: denominator of the waypoint lookup's roofline)."""
+    ctx = Context(device)
+    try:
+        a, b = C.c_double(), C.c_double()
+        check(ctx.lib.trs_probe_fp64(ctx.handle, C.byref(a), C.byref(b)), "trs_probe_fp64")
+        return a.value, b.value
+    finally:
+        ctx.close()
 
 
 def kernel_launches() -> int:
@@ -202,4 +215,6 @@ def spd_params_from_cfg(cfg: dict) -> SpdParams:
     p.use_break = int(bool(cfg['spd_ctl_break']))
     p.smooth_steering = int(bool(cfg['smooth_steering_enabled']))
     p.smooth_threshold = float(cfg['smooth_steering_threshold'])
+    # not a reference key: which NumPy scalar promotion the caller's stack has ("NumPy promotion"); default NumPy >= 2
+    p.numpy_legacy_promotion = int(bool(cfg.get('spd_ctl_numpy_legacy_promotion', False)))
     return p

@@ -43,6 +43,21 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _check_device_tensor(t, dev: int, dtype, name: str):
+    """Every pointer handed to the library must be a contiguous tensor of the stated dtype on the context's GPU: a CPU or other-GPU
+    tensor would otherwise become an illegal-address fault that poisons the CUDA context."""
+    if t is None:
+        return
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch tensor, got {type(t).__name__}")
+    if not t.is_cuda or t.device.index != dev:
+        raise ValueError(f"{name} must live on cuda:{dev}, got {t.device}")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
 def _np_ptr(a):
     return C.c_void_p(a.ctypes.data) if a is not None else None
 
@@ -95,6 +110,10 @@ class ImgPreprocessing(Component):
             out_u8 = torch.empty_like(frames)
         if want_f32 and out_f32 is None:
             out_f32 = torch.empty(frames.shape, dtype=torch.float32, device=frames.device)
+        for t, dt, name in ((out_u8, torch.uint8, "out_u8"), (out_f32, torch.float32, "out_f32")):
+            _check_device_tensor(t, self.device, dt, name)
+            if t is not None and tuple(t.shape) != tuple(frames.shape):
+                raise ValueError(f"{name} must have the frames' shape {tuple(frames.shape)}, got {tuple(t.shape)}")
         stats = None
         if self.collect_stats:
             if self._stats_dev is None:
@@ -122,8 +141,11 @@ class ImgPreprocessing(Component):
         if want_u8 and out_u8 is None:
             out_u8 = np.empty_like(frames)
         stats = (C.c_ulonglong * nat.STAT_COUNT)() if self.collect_stats else None
+        if keep_f32_dev is not None:
+            _check_device_tensor(keep_f32_dev, self.device, torch.float32, "keep_f32_dev")
+        # the caller's stream is handed over so that work queued on it (a pilot still reading keep_f32_dev) is waited for first
         nat.check(self.ctx.lib.trs_preprocess_host(self.ctx.handle, _np_ptr(frames), n, h, w, _np_ptr(out_u8), _np_ptr(out_f32),
-                                                   _ptr(keep_f32_dev), stats), "trs_preprocess_host")
+                                                   _ptr(keep_f32_dev), stats, _stream_ptr(self.device)), "trs_preprocess_host")
         if stats is not None:
             self.last_stats = dict(zip(nat.STAT_NAMES, list(stats)))
         return out_u8, out_f32
@@ -190,6 +212,7 @@ class LocationTracker(Component):
         if xyz.dtype != torch.float64 or xyz.dim() != 2 or xyz.shape[1] != 3:
             raise ValueError(f"expected (N,3) float64, got {tuple(xyz.shape)} {xyz.dtype}")
         xyz = xyz.contiguous()
+        _check_device_tensor(xyz, self.device, torch.float64, "xyz")
         n = xyz.shape[0]
         idx = torch.empty(n, dtype=torch.int32, device=xyz.device) if want_idx else None
         seg = torch.empty(n, dtype=torch.float64, device=xyz.device) if want_segment else None
@@ -240,6 +263,10 @@ class SpeedControl(Component):
         cur = cur.to(torch.float64).contiguous()
         steer = steer.to(torch.float32).contiguous()
         spd = spd.to(torch.float32).contiguous()
+        for t, name in ((cur, "gym/speed"), (steer, "pilot/steering"), (spd, "pilot/speed")):
+            _check_device_tensor(t, self.device, None, name)
+            if t.dim() != 1 or t.shape[0] != n:
+                raise ValueError(f"{name} must have shape ({n},), got {tuple(t.shape)}")
         out = torch.empty((3, n), dtype=torch.float64, device=cur.device)
         feat = torch.empty(n, dtype=torch.float32, device=cur.device) if want_feature else None
         nat.check(self.ctx.lib.trs_speed_control(self.ctx.handle, _ptr(cur), _ptr(spd), _ptr(steer), n, C.byref(self.params),
@@ -289,6 +316,7 @@ class FrameNormalise(Component):
         if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
             raise ValueError(f"expected (N,H,W,3) uint8 frames, got {tuple(frames.shape)} {frames.dtype}")
         frames = frames.contiguous()
+        _check_device_tensor(frames, self.device, torch.uint8, "frames")
         n, h, w, _ = frames.shape
         y0, y1, x0, x1 = self.roi if self.roi is not None else (0, h, 0, w)
         ho, wo = self.out_hw if self.out_hw is not None else (y1 - y0, x1 - x0)
@@ -361,6 +389,12 @@ class ControlMultiplexer(Component):
     def mux_device(self, mode: torch.Tensor, usr: torch.Tensor, ai: torch.Tensor, now: float, speed: torch.Tensor = None, params=None):
         """mode (N,) int32, usr / ai (3, N) f64 on the device -> (3, N) f64 (steering, throttle, breaking)."""
         n = mode.shape[0]
+        _check_device_tensor(mode, self.device, torch.int32, "mode")
+        for t, name in ((usr, "usr"), (ai, "ai")):
+            _check_device_tensor(t, self.device, torch.float64, name)
+            if tuple(t.shape) != (3, n):
+                raise ValueError(f"{name} must have shape (3, {n}), got {tuple(t.shape)}")
+        _check_device_tensor(speed, self.device, torch.float64, "speed")
         self._state(n, mode.device)
         out = torch.empty((3, n), dtype=torch.float64, device=mode.device)
         nat.check(self.ctx.lib.trs_control_mux(self.ctx.handle, _ptr(mode), _ptr(usr), _ptr(ai), _ptr(speed), n,
@@ -413,6 +447,8 @@ class DriverAssistance(Component):
     def assist_device(self, steering, throttle, breaking, speed):
         n = steering.shape[0]
         dev = steering.device
+        for t, name in ((steering, "mux/steering"), (throttle, "mux/throttle"), (breaking, "mux/break"), (speed, "gym/speed")):
+            _check_device_tensor(t, self.device, torch.float64, name)
         usr = torch.stack([steering, throttle, breaking]).contiguous()
         mode = torch.full((n,), nat.MODE_HUMAN, dtype=torch.int32, device=dev)       # "human" selects the first triple unchanged
         last = torch.full((n,), nat.MODE_HUMAN, dtype=torch.int32, device=dev)

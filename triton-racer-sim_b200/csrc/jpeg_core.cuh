@@ -113,6 +113,7 @@ TRS_JHD void jpg_decode_block(JpegBits& b, const JpegHuff& dc, const JpegHuff& a
 {
     for (int i = 0; i < 64; ++i) coef[i] = 0;
     int s = jpg_symbol(b, dc, err);
+    if (s > 11) { err = JPG_E_BADCODE; return; }          // DC categories of 8-bit baseline data are 0..11
     if (s) last_dc += jpg_receive_extend(b, s);
     coef[0] = (int16_t)last_dc;
     for (int k = 1; k < 64; ++k) {

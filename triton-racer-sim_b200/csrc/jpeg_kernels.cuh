@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(JPG_THREADS) k_jpeg_entropy(const uint8_t* __r
 #pragma unroll
                 for (int k = 0; k < 64; ++k) coef[k] = 0;
                 int sym = jpg_dev_symbol(s, T, td, err);
+                if (sym > 11) { err = JPG_E_BADCODE; sym = 0; }     // a DC category above 11 cannot occur in 8-bit baseline data (malformed DHT)
                 if (sym) dc[comp] += jpg_dev_extend(s, sym);
                 coef[0] = (int16_t)dc[comp];
 #pragma unroll 1

@@ -261,6 +261,26 @@ __global__ void __launch_bounds__(LOC_THREADS) k_locate(const double* __restrict
     }
 }
 
+// Measurement aid for K6's roofline (bench.py): the box's FP64 pipe rate.  ILP independent chains per thread of one fp64 instruction
+// each (FMA = true: DFMA, 2 flops; false: DADD, 1 flop), 256 threads per CTA, enough CTAs to fill every SM.
+enum { PROBE64_ILP = 8, PROBE64_THREADS = 256 };
+template <bool FMA>
+__global__ void __launch_bounds__(PROBE64_THREADS) k_probe_fp64(double* __restrict__ out, int iters, double a, double b)
+{
+    double r[PROBE64_ILP];
+#pragma unroll
+    for (int i = 0; i < PROBE64_ILP; ++i) r[i] = (double)(threadIdx.x + 1) * 1e-3 + i;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < PROBE64_ILP; ++i) r[i] = FMA ? __fma_rn(r[i], a, b) : __dadd_rn(r[i], b);
+    }
+    double acc = 0;
+#pragma unroll
+    for (int i = 0; i < PROBE64_ILP; ++i) acc = __dadd_rn(acc, r[i]);
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 // K6b: the same for SMALL batches (N = 1 drop-in, a few thousand cars): one WARP per car, the lanes split the centre line
 // (lane l takes waypoints l, l + 32, ...: ascending, so a lane keeps the first index of its own minimum) and a warp-shuffle
 // reduction on the pair (distance, index) — smaller distance, then smaller index — yields the reference's first-index argmin.
@@ -301,12 +321,14 @@ __global__ void __launch_bounds__(LOCW_THREADS) k_locate_warp(const double* __re
 
 // ------------------------------------------------------------------------------------------------------
 // K7: speed-control tail of the pilots (keras_pilot.py:80-95 == 99-118, 142-153; utils/mapping.py:23-35).
-// Types follow numpy >= 2 promotion with np.float32 model outputs: the products and the speed difference are
-// float32, atan and everything after it float64.
+// Types follow numpy >= 2 promotion with np.float32 model outputs by default: the products and the speed difference are
+// float32, atan and everything after it float64.  legacy_f64 selects NumPy 1.x promotion instead (np.float32 * 20 is already
+// float64 there), which moves results only at the dead-band cut-offs (-0.2, 0, 0.4) and at the `predicted - real > 0` test.
 // ------------------------------------------------------------------------------------------------------
 struct SpdKParams {
     double threshold, reverse_multiplier, break_multiplier, smooth_threshold;
     int use_break, smooth_steering;
+    int legacy_f64;               // NumPy 1.x scalar promotion: the model's float32 speed is widened before the first multiply
 };
 
 __global__ void __launch_bounds__(256) k_speed_control(const double* __restrict__ cur, const float* __restrict__ model_spd,
@@ -321,16 +343,28 @@ __global__ void __launch_bounds__(256) k_speed_control(const double* __restrict_
         const float steer_f = model_steer[k];
         double steering = (double)steer_f;
         if (steer_f < -1.0f) steering = -1.0; else if (steer_f > 1.0f) steering = 1.0;
-        const float predicted = __fmul_rn(model_spd[k], 20.0f);
-        const float target = __fmul_rn(predicted, (float)p.threshold);
-        const float real_f = (float)real_spd;
-        const float delta = __fsub_rn(target, real_f);
-        double throttle = __ddiv_rn(__dmul_rn(p.reverse_multiplier, atan((double)__fmul_rn(delta, 2.0f))), half_pi);
+        double delta, delta2;          // predicted * threshold - current, and twice that, in the promotion the caller asked for
+        bool faster;                    // predicted - current > 0
+        if (p.legacy_f64) {
+            const double predicted = __dmul_rn((double)model_spd[k], 20.0);
+            delta = __dsub_rn(__dmul_rn(predicted, p.threshold), real_spd);
+            delta2 = __dmul_rn(delta, 2.0);
+            faster = __dsub_rn(predicted, real_spd) > 0.0;
+        } else {
+            const float predicted = __fmul_rn(model_spd[k], 20.0f);
+            const float target = __fmul_rn(predicted, (float)p.threshold);
+            const float real_f = (float)real_spd;
+            const float delta_f = __fsub_rn(target, real_f);
+            delta = (double)delta_f;
+            delta2 = (double)__fmul_rn(delta_f, 2.0f);
+            faster = __fsub_rn(predicted, real_f) > 0.0f;
+        }
+        double throttle = __ddiv_rn(__dmul_rn(p.reverse_multiplier, atan(delta2)), half_pi);
         if (-0.2 < throttle && throttle < 0.0) throttle = 0.0;
         double breaking = 0.0;
         if (p.use_break) {
-            throttle = (__fsub_rn(predicted, real_f) > 0.0f) ? 1.0 : 0.0;
-            breaking = __ddiv_rn(__dmul_rn(__dmul_rn(-1.0, p.break_multiplier), atan((double)delta)), half_pi);
+            throttle = faster ? 1.0 : 0.0;
+            breaking = __ddiv_rn(__dmul_rn(__dmul_rn(-1.0, p.break_multiplier), atan(delta)), half_pi);
             if (breaking < 0.4) breaking = 0.0;
         }
         if (p.smooth_steering) {

@@ -226,7 +226,7 @@ int append(std::vector<float>& blob, const trs_tensor* t)
 void destroy(trs_pilot* p)
 {
     if (!p) return;
-    cudaSetDevice(p->device);
+    TrsDeviceGuard guard(p->device);
     for (Layer& L : p->L) {
         cudaFree(L.w_dev);
         cudaFree(L.b_dev);
@@ -408,8 +408,8 @@ int trs_pilot_create(trs_ctx* ctx, int model_type, int h, int w, const trs_tenso
     p->device = trs_i_ctx_device(ctx);
     p->sm_count = trs_i_ctx_sm_count(ctx);
     p->kind = model_type; p->h = h; p->w = w; p->cap = max_batch;
-    cudaError_t e = cudaSetDevice(p->device);
-    if (e != cudaSuccess) { delete p; return trs_i_cuda_fail(e, "cudaSetDevice"); }
+    TrsDeviceGuard guard(p->device);
+    if (guard.err != cudaSuccess) { delete p; return trs_i_cuda_fail(guard.err, "cudaSetDevice"); }
     const int rc = build(p, weights, n_weights);
     if (rc) { destroy(p); return rc; }
     *out = p;
@@ -431,7 +431,8 @@ int trs_pilot_forward(trs_pilot* p, const uint8_t* frames_dev, int n, const floa
     if ((full || p->kind == TRS_PILOT_CNN_2D_SPD_FTR) && !spd_feature_dev) return trs_i_fail(TRS_E_ARG, "this model needs the speed feature");
     if (full && !loc_feature_dev) return trs_i_fail(TRS_E_ARG, "the full-house model needs the loc/segment feature");
     if (((uintptr_t)frames_dev & 3) != 0) return trs_i_fail(TRS_E_ARG, "frames must be 4-byte aligned");
-    CU(cudaSetDevice(p->device));
+    TrsDeviceGuard guard(p->device);
+    if (guard.err != cudaSuccess) return trs_i_cuda_fail(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t frame_bytes = (size_t)p->h * p->w * 3;
     // head 0 reads feature_vec_input, head 1 current_spd_input (keras_train.py:213,226; keras_pilot.py:104)
@@ -474,7 +475,8 @@ int trs_pilot_cap(trs_ctx* ctx, const float* model_out_dev, int n, int smooth_st
     if (!ctx || !model_out_dev || !steering_dev || !throttle_dev || !breaking_dev) return trs_i_fail(TRS_E_ARG, "null argument");
     if (n < 0) return trs_i_fail(TRS_E_ARG, "n=%d", n);
     if (n == 0) return 0;
-    CU(cudaSetDevice(trs_i_ctx_device(ctx)));
+    TrsDeviceGuard guard(trs_i_ctx_device(ctx));
+    if (guard.err != cudaSuccess) return trs_i_cuda_fail(guard.err, "cudaSetDevice");
     k_pilot_cap<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(model_out_dev, n, smooth_steering, smooth_threshold, steering_dev,
                                                                    throttle_dev, breaking_dev);
     CU(cudaGetLastError());
@@ -494,7 +496,8 @@ int trs_pilot_layer_shape(trs_pilot* p, int layer, int* ho, int* wo, int* c)
 int trs_pilot_debug_activation(trs_pilot* p, int layer, void* host_out, unsigned long long bytes, void* stream)
 {
     if (!p || layer < 0 || layer > N_CONV + 1 || !host_out) return trs_i_fail(TRS_E_ARG, "bad layer %d", layer);
-    CU(cudaSetDevice(p->device));
+    TrsDeviceGuard guard(p->device);
+    if (guard.err != cudaSuccess) return trs_i_cuda_fail(guard.err, "cudaSetDevice");
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     if (layer == 0) return trs_i_fail(TRS_E_ARG, "layer 0 is the caller's u8 frame: conv1 reads it directly");
     const void* src = layer <= N_CONV ? p->L[layer - 1].out : (const void*)p->partial;

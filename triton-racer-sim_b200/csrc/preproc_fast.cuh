@@ -76,7 +76,7 @@ __host__ __device__ inline FastGeom fast_geometry(int h, int w, int n_ranges, in
     g.plane_bytes = (((h + 2) * g.nsg * 4) + 15) & ~15;
     const int pix = ((pix_rows * w * 3 + 15) & ~15) + 16;
     const int mag = ((((mag_rows + 2) * g.mag_stride + 4) * 2) + 15) & ~15;
-    int o = 0;
+    int o = 16;                                                        // the strip walk reads the word LEFT of every row start unconditionally
     for (int b = 0; b < (ws ? 2 : 1); ++b) { g.off_pix[b] = o; o += pix; }
     for (int b = 0; b < (ws ? 2 : 1); ++b) { g.off_mag[b] = o; o += mag; }
     if (!ws) { g.off_pix[1] = g.off_pix[0]; g.off_mag[1] = g.off_mag[0]; }
@@ -148,6 +148,30 @@ __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+// predicated stores: a lane that does not store costs nothing (an `if` around a store becomes BSSY / BRA / BSYNC around it)
+__device__ __forceinline__ void sts8_if(bool on, uint32_t a, uint32_t v)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.u8 [%0], %1;\n}\n" ::"r"(a), "r"(v), "r"((uint32_t)on) : "memory");
+}
+__device__ __forceinline__ void sts64_if(bool on, uint32_t a, uint2 v)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\n@p st.shared.v2.u32 [%0], {%1,%2};\n}\n" ::"r"(a), "r"(v.x), "r"(v.y), "r"((uint32_t)on) : "memory");
+}
+
+// Frame dimensions as the phase functions see them.  The store-warp kernel is also instantiated with the reference's camera size
+// (120 x 160, core/config.py:8-9) as compile-time constants: every row stride, plane pitch and loop bound of the walks becomes an
+// immediate instead of a constant-bank load plus address arithmetic per row step.
+struct Dims {
+    int h, w, mag_stride, plane_bytes;
+};
+template <int H, int W>
+__device__ __forceinline__ Dims make_dims(const FastParams& P)
+{
+    Dims d;
+    if (H > 0 && W > 0) { d.h = H; d.w = W; d.mag_stride = W + 4; d.plane_bytes = (((H + 2) * (W / 32) * 4) + 15) & ~15; }
+    else { d.h = P.k.h; d.w = P.k.w; d.mag_stride = P.g.mag_stride; d.plane_bytes = P.g.plane_bytes; }
+    return d;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -331,6 +355,17 @@ struct SatThresholds {
     static constexpr bool use = n >= 1 && n <= 2;
 };
 
+// Hue bounds without computing the hue: h = (h0 * hdiv[d] + 2048) >> 12 is monotone in the numerator h0, and the wrapped values (h0 < 0:
+// h + 180 >= 150) can never pass an upper bound <= 149, so "lo <= h <= hi" is "A_lo[d] <= h0 <= A_hi[d]".  Used when the live-bound words
+// are compile-time constants, exactly one of two ranges bounds the hue on both sides and the other does not look at it (the reference's
+// defaults, core/config.py:23); the host only picks such a variant when that upper bound is <= 149.  The table (in the place of hdiv) holds
+// the two thresholds of a delta d, biased by 2048 like the packed numerators, as 16-bit halves.
+template <int NR, int F0, int F1>
+struct HueThresholds {
+    static constexpr bool use = F0 >= 0 && F1 >= 0 && NR == 2 && (((F0 & 3) == 3 && (F1 & 3) == 0) || ((F0 & 3) == 0 && (F1 & 3) == 3));
+    static constexpr int range = (F0 >= 0 && (F0 & 3) == 3) ? 0 : 1;
+};
+
 template <int NR, int F0, int F1>
 __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t (&A)[3], const uint32_t (&B)[3], uint32_t a_sdiv, uint32_t a_hue,
                                              uint32_t (&okm)[NR > 0 ? NR : 1][2])
@@ -387,6 +422,12 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
             const uint32_t rg = X[0] + 0x08000800u - X[1] + (d2[half] << 2);
             const uint32_t eqr = heq_mask(v2[half], X[0]), eqg = heq_mask(v2[half], X[1]);
             const uint32_t h02 = bsel(eqr, gb, bsel(eqg, br, rg));
+            if (HueThresholds<NR, F0, F1>::use) {
+                constexpr int HR = HueThresholds<NR, F0, F1>::range;
+                const uint32_t tl = lds32(mad_u32(d2[half] & 0xffffu, 4u, a_hue)), th = lds32(mad_u32(d2[half] >> 16, 4u, a_hue));
+                okm[HR][half] &= hge_mask(h02, prmt(tl, th, 0x5410)) & hle_mask(h02, prmt(tl, th, 0x7632));
+                continue;
+            }
             // ((h0 + 2048) hd + (2048 - 2048 hd)) >> 12 == (h0 hd + 2048) >> 12
             const int tl = (int)lds32(a_hue + 4 * (d2[half] & 0xffffu)), th = (int)lds32(a_hue + 4 * (d2[half] >> 16));
             int hlo = ((int)(h02 & 0xffffu) * tl + (2048 - 2048 * tl)) >> 12;
@@ -414,25 +455,22 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
 // =========================================================================================================
 // P1: strip walk — Sobel / magnitude / direction -> magnitude plane, colour masks -> bit planes
 // =========================================================================================================
-template <int NR, bool EDGE, int F0, int F1>
 // tail_bar != 0: the last rows of the frame arrive under a second mbarrier; every thread waits for it at the top of trip `tail_k`
 // (a multiple of 3, before any segment loads such a row)
-// Banded use: a_pix / a_mag are VIRTUAL bases (the address image row 0 / magnitude row -1 would have), the segment rows of M lie in the
+// BANDED: a_pix / a_mag are VIRTUAL bases (the address image row 0 / magnitude row -1 would have), the segment rows of M lie in the
 // band's magnitude rows, and colour-mask rows are stored only inside [mask_lo, mask_hi).
-__device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pix, uint32_t a_mag, uint32_t a_mask, const SmemMap& S, const StripMap& M,
-                                              int seg_rows, uint32_t tail_bar = 0, uint32_t tail_parity = 0, int tail_k = 0, int mask_lo = 0,
-                                              int mask_hi = 1 << 30)
+template <int NR, bool EDGE, int F0, int F1, bool BANDED = false>
+__device__ __forceinline__ void p1_strip_walk(const FastParams& P, const Dims& Dm, uint32_t a_pix, uint32_t a_mag, uint32_t a_mask, const SmemMap& S,
+                                              const StripMap& M, int seg_rows, uint32_t tail_bar = 0, uint32_t tail_parity = 0, int tail_k = 0,
+                                              int mask_lo = 0, int mask_hi = 1 << 30)
 {
-    const int h = P.k.h, w = P.k.w;
-    const int row_bytes = w * 3, prb = w >> 3, MS2 = P.g.mag_stride * 2, nstrips = w >> 2;
+    const int h = Dm.h, w = Dm.w;
+    const int row_bytes = w * 3, prb = w >> 3, MS2 = Dm.mag_stride * 2, nstrips = w >> 2;
     const int r0 = M.r0, r1 = M.r1;
-    // per-thread constants of the strip walk
+    // per-thread constants of the strip walk.  The words left and right of the strip are loaded from the same offsets by every lane
+    // and the two edge strips patch them (replicated border: pixel -1 = pixel 0, pixel w = pixel w - 1), so the byte selectors of the
+    // neighbour pairs are compile-time constants (per-lane selectors cost ~14 instructions per row step to rematerialise)
     const bool left_edge = M.strip == 0, right_edge = M.strip == nstrips - 1;
-    const int offL = left_edge ? 0 : -4;                    // word holding the pixel left of the strip (replicated at x = 0)
-    const int offR = right_edge ? 8 : 12;                   // word holding the pixel right of the strip (replicated at x = w-1)
-    const uint32_t selL0 = 0x5450u | (left_edge ? 0u : 1u), selL1 = 0x5450u | (left_edge ? 1u : 2u), selL2 = 0x5450u | (left_edge ? 2u : 3u);
-    const uint32_t selR0 = 0x1012u | ((right_edge ? 5u : 4u) << 8), selR1 = 0x1012u | ((right_edge ? 6u : 5u) << 8),
-                   selR2 = 0x1012u | ((right_edge ? 7u : 6u) << 8);
     const int nsteps = seg_rows + 2;
     const uint32_t strip_base = a_pix + 12 * M.strip;
     const uint32_t mask_base = a_mask + (M.strip >> 1);
@@ -456,11 +494,13 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
         uint32_t A[3], B[3];
         unpack_planar(w0, w1, w2, A, B);
         if (EDGE) {
-            const uint32_t wl = lds32(rp + offL), wr = lds32(rp + offR);
+            uint32_t wl = lds32(rp - 4), wr = lds32(rp + 12);       // bytes 1..3 of wl = pixel -1, bytes 0..2 of wr = pixel 4
+            if (left_edge) wl = w0 << 8;                            // (the 16 spare bytes in front of the frame keep rp - 4 inside the window)
+            if (right_edge) wr = w2 >> 8;
             // neighbours: Lh = pixels (-1,1), Rh = pixels (2,4)
             uint32_t Lh[3], Rh[3];
-            Lh[0] = prmt(wl, B[0], selL0); Lh[1] = prmt(wl, B[1], selL1); Lh[2] = prmt(wl, B[2], selL2);
-            Rh[0] = prmt(A[0], wr, selR0); Rh[1] = prmt(A[1], wr, selR1); Rh[2] = prmt(A[2], wr, selR2);
+            Lh[0] = prmt(wl, B[0], 0x5451); Lh[1] = prmt(wl, B[1], 0x5452); Lh[2] = prmt(wl, B[2], 0x5453);
+            Rh[0] = prmt(A[0], wr, 0x1412); Rh[1] = prmt(A[1], wr, 0x1512); Rh[2] = prmt(A[2], wr, 0x1612);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 Dn[c] = hsub(B[c], Lh[c]);                      // pixels (0,2): p[x+1] - p[x-1]
@@ -471,29 +511,25 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
         }
         // ---- colour masks for the loaded row ---------------------------------------------------------
         if (NR > 0 && k >= 1 && k <= seg_rows) {                 // warp-uniform: the halo rows above and below belong to other segments
-            const bool row_in = y_row < r1 && y_row >= mask_lo && y_row < mask_hi;      // the loaded row belongs to this segment (and band)
+            const bool row_in = M.store_lane && y_row < r1 && (!BANDED || (y_row >= mask_lo && y_row < mask_hi));      // the loaded row belongs to this segment (and band)
             uint32_t okm[NR > 0 ? NR : 1][2];                    // per range: half masks for pixels (0,2) and (1,3)
             hsv_masks_of<NR, F0, F1>(P, A, B, S.sdiv, S.hue, okm);
             if (NR == 2) {
                 // pixels 0..3 of a range sit in (okm[r][0].lo, okm[r][1].lo, okm[r][0].hi, okm[r][1].hi)
                 const uint32_t top = nibble_pair_top(prmt(okm[0][0], okm[0][1], 0x6240), prmt(okm[NR - 1][0], okm[NR - 1][1], 0x6240));
                 const uint32_t other = __shfl_down_sync(0xffffffffu, top, 1);
-                if (M.store_lane && row_in) {
-                    uint32_t b0, b1;
-                    merge_nibble_pairs(top, other, b0, b1);
-                    sts8(mp, b0);
-                    sts8(mp + P.g.plane_bytes, b1);
-                }
+                uint32_t b0, b1;
+                merge_nibble_pairs(top, other, b0, b1);
+                sts8_if(row_in, mp, b0);
+                sts8_if(row_in, mp + Dm.plane_bytes, b1);
             } else {
                 uint32_t v = 0;
 #pragma unroll
                 for (int r = 0; r < NR; ++r) v |= nibble_of(okm[r][0], okm[r][1]) << (8 * r);
                 const uint32_t other = __shfl_down_sync(0xffffffffu, v, 1);
                 v |= other << 4;
-                if (M.store_lane && row_in) {
 #pragma unroll
-                    for (int r = 0; r < NR; ++r) sts8(mp + r * P.g.plane_bytes, v >> (8 * r));
-                }
+                for (int r = 0; r < NR; ++r) sts8_if(row_in, mp + r * Dm.plane_bytes, v >> (8 * r));
             }
         }
         // ---- Sobel combine for output row y = r0 + k - 2 ----------------------------------------------
@@ -536,12 +572,10 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, uint32_t a_pi
                 const uint32_t diag = (SD & 0x00010001u) | 0x00020002u;
                 code[half] = ~H2 & bsel(V2, 0x00010001u, diag);
             }
-            if (M.ok && y < r1) {
-                uint2 v;      // pixel order: (A.lo, B.lo) = pixels (0, 1), (A.hi, B.hi) = pixels (2, 3)
-                v.x = prmt(mg[0], mg[1], 0x5410) | (prmt(code[0], code[1], 0x5410) << 11);
-                v.y = prmt(mg[0], mg[1], 0x7632) | (prmt(code[0], code[1], 0x7632) << 11);
-                sts64(gp, v);
-            }
+            uint2 v;      // pixel order: (A.lo, B.lo) = pixels (0, 1), (A.hi, B.hi) = pixels (2, 3)
+            v.x = prmt(mg[0], mg[1], 0x5410) | (prmt(code[0], code[1], 0x5410) << 11);
+            v.y = prmt(mg[0], mg[1], 0x7632) | (prmt(code[0], code[1], 0x7632) << 11);
+            sts64_if(M.ok && y < r1, gp, v);
             gp += MS2;
         }
         // advance to the next image row: the pixel address stays put while the row index is outside [1, h - 1] (replicated borders)
@@ -593,10 +627,11 @@ __device__ __forceinline__ void stats_flush(const PreKParams& p, const SmemMap& 
 // =========================================================================================================
 // P2: non-maximum suppression, strip walk over the magnitude plane, two pixels per compare
 // =========================================================================================================
-__device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint32_t a_cand, uint32_t a_edge, const SmemMap& S, const StripMap& M, int seg_rows)
+__device__ __forceinline__ void p2_nms(const FastParams& P, const Dims& Dm, uint32_t a_mag, uint32_t a_cand, uint32_t a_edge, const SmemMap& S,
+                                       const StripMap& M, int seg_rows)
 {
     uint32_t n_strong = 0;
-    const int h = P.k.h, prb = P.k.w >> 3, MS2 = P.g.mag_stride * 2;
+    const int h = Dm.h, prb = Dm.w >> 3, MS2 = Dm.mag_stride * 2;
     const uint32_t mbase = a_mag + 2 * (4 + 4 * M.strip);
     const uint32_t cbase = a_cand + (M.strip >> 1), ebase = a_edge + (M.strip >> 1);
     // one row as packed pairs of magnitudes: P01=(m0,m1) P23=(m2,m3) L01=(m-1,m0) M12=(m1,m2) R23=(m3,m4); raw keeps the codes
@@ -647,13 +682,11 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, uint32_t a_mag, uint
         // pixels (0,1) sit in the halves of cm[0], (2,3) in cm[1]: one byte per pixel, then both nibbles by one multiply
         const uint32_t top = nibble_pair_top(prmt(cm[0], cm[1], 0x6420), prmt(sm[0], sm[1], 0x6420));
         const uint32_t other = __shfl_down_sync(0xffffffffu, top, 1);
-        if (M.store_lane && row_in) {
-            uint32_t bc, bs;
-            merge_nibble_pairs(top, other, bc, bs);
-            sts8(cp, bc);
-            sts8(ep, bs);
-            if (P.k.stats) n_strong += __popc(bs & 0xffu);
-        }
+        uint32_t bc, bs;
+        merge_nibble_pairs(top, other, bc, bs);
+        sts8_if(M.store_lane && row_in, cp, bc);
+        sts8_if(M.store_lane && row_in, ep, bs);
+        if (P.k.stats && M.store_lane && row_in) n_strong += __popc(bs & 0xffu);
         cp += prb; ep += prb;
     };
     Row ra = load_row(ya - 1), rb = load_row(ya), rc;
@@ -743,10 +776,10 @@ __device__ __forceinline__ int p3_hysteresis(uint32_t a_cand, uint32_t a_edge, i
 // P4: merge + normalise, written once.  pa[c] = shared address of the bit plane (row 0) feeding output channel c,
 // or 0 if that channel keeps the adjusted pixel.
 // =========================================================================================================
-__device__ __forceinline__ void p4_output(const FastParams& P, const uint32_t (&pa)[3], uint32_t a_pix, uint8_t* __restrict__ gout,
+__device__ __forceinline__ void p4_output(const FastParams& P, const Dims& Dm, const uint32_t (&pa)[3], uint32_t a_pix, uint8_t* __restrict__ gout,
                                           float* __restrict__ gf32, int t0, int tstride)
 {
-    const int npb = P.k.h * (P.k.w >> 3);              // groups of 8 pixels = plane bytes
+    const int npb = Dm.h * (Dm.w >> 3);                // groups of 8 pixels = plane bytes
     if (!P.k.need_pixels) {
         // All three channels are bit planes.  Six lanes share one plane byte (8 pixels = 24 output items = six 4-item chunks):
         // lane (g, s) emits chunk s of group g, i.e. one 16-byte f32 store and one 4-byte u8 store, so that consecutive lanes
@@ -877,7 +910,24 @@ __device__ __forceinline__ void init_tables(const PreKParams& p, const SmemMap& 
             sts32(S.sdiv + 4 * i, (uint32_t)sd);
         }
         const int hd = i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
-        sts32(S.hue + 4 * i, (uint32_t)hd);
+        if (HueThresholds<NR, F0, F1>::use) {
+            // numerators h0 of a delta i that land in [lo, hi]: smallest with h0 hd + 2048 >= 4096 lo, largest with h0 hd + 2048 <= 4096 hi + 4095
+            const long long lo = p.ranges[HueThresholds<NR, F0, F1>::range].lo[0], hi = p.ranges[HueThresholds<NR, F0, F1>::range].hi[0];
+            long long a_lo, a_hi;
+            if (hd == 0) {                                                     // grey pixel: h = 0
+                const bool pass = lo <= 0 && 0 <= hi;
+                a_lo = pass ? -2048 : 1; a_hi = pass ? 4000 : 0;
+            } else {
+                const long long nl = 4096 * lo - 2048, nh = 4096 * hi + 2047;
+                a_lo = nl >= 0 ? (nl + hd - 1) / hd : -((-nl) / hd);           // ceiling
+                a_hi = nh >= 0 ? nh / hd : -((-nh + hd - 1) / hd);             // floor
+            }
+            a_lo = a_lo < -2048 ? -2048 : (a_lo > 20000 ? 20000 : a_lo);
+            a_hi = a_hi < -2048 ? -2048 : (a_hi > 20000 ? 20000 : a_hi);
+            sts32(S.hue + 4 * i, (uint32_t)(a_lo + 2048) | ((uint32_t)(a_hi + 2048) << 16));
+        } else {
+            sts32(S.hue + 4 * i, (uint32_t)hd);
+        }
         sts8(S.lut + i, p.lut[i]);
     }
 }
@@ -978,6 +1028,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
     const uint32_t frame_bytes = (uint32_t)h * w * 3;
     const int plane_words = h * ww;
     const StripMap M = strip_map(warp, lane, ww, G.seg_rows_front, h);
+    const Dims Dm = make_dims<0, 0>(P);
 
     init_tables<NR, F0, F1>(p, S, tid, nthr);
     stats_zero(S, tid);
@@ -1006,21 +1057,21 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
         phase ^= 1u;
         const long long tk1 = timing ? clock64() : 0;
         adjust_in_place(p, S.pix[0], S, s_red, tid, nthr, lane, [] { __syncthreads(); });
-        p1_strip_walk<NR, EDGE, F0, F1>(P, S.pix[0], S.mag[0], S.mask, S, M, G.seg_rows_front);
+        p1_strip_walk<NR, EDGE, F0, F1>(P, Dm, S.pix[0], S.mag[0], S.mask, S, M, G.seg_rows_front);
         __syncthreads();
         const long long tk2 = timing ? clock64() : 0;
         if (!p.need_pixels && tid == 0 && f + (int)gridDim.x < p.n)       // pixels are dead: prefetch the next frame
             issue_frame_load(S.pix[0], p.in + (size_t)(f + gridDim.x) * frame_bytes, frame_bytes, S.bar);
         long long tk3 = tk2, tk4 = tk2;
         if (EDGE) {
-            p2_nms(P, S.mag[0], S.cand, S.edge, S, M, G.seg_rows_front);
+            p2_nms(P, Dm, S.mag[0], S.cand, S.edge, S, M, G.seg_rows_front);
             __syncthreads();
             tk3 = timing ? clock64() : 0;
             const int sw = p3_hysteresis(S.cand, S.edge, h, ww, tid, nthr, [](int c) { return __syncthreads_or(c); });
             if (tid == 0 && p.stats) stat_add_one(S, 8, (unsigned long long)sw);
             tk4 = timing ? clock64() : 0;
         }
-        p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr,
+        p4_output(P, Dm, pa, S.pix[0], p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr,
                   tid, nthr);
         if (p.stats) count_planes<NR, EDGE>(p, S, S.cand, S.edge, S.mask, G.plane_bytes, plane_words, tid, nthr);
         __syncthreads();
@@ -1060,6 +1111,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const
     const uint32_t row_bytes = (uint32_t)w * 3, frame_bytes = (uint32_t)h * row_bytes;
     const int plane_words = h * ww;
     const int BH = G.band_h, NB = G.n_bands, MS = G.mag_stride;
+    const Dims Dm = make_dims<0, 0>(P);
 
     init_tables<NR, F0, F1>(p, S, tid, nthr);
     stats_zero(S, tid);
@@ -1092,7 +1144,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const
                 for (int i = tid; i < MS; i += nthr) sts16(a_mag + 2 * ((h + 1) * MS + i), 0);
             }
             const StripMap M1 = strip_map(warp, lane, ww, G.seg_rows_front, m1, m0);
-            p1_strip_walk<NR, EDGE, F0, F1>(P, a_pix, a_mag, S.mask, S, M1, G.seg_rows_front, 0u, 0u, 0, by0, by1);
+            p1_strip_walk<NR, EDGE, F0, F1, true>(P, Dm, a_pix, a_mag, S.mask, S, M1, G.seg_rows_front, 0u, 0u, 0, by0, by1);
             __syncthreads();
             if (tid == 0) {                                         // pixels are dead: fetch the next band (of this or the next frame)
                 if (b + 1 < NB) issue_band(f, b + 1);
@@ -1100,7 +1152,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const
             }
             if (EDGE) {
                 const StripMap M2 = strip_map(warp, lane, ww, G.seg_rows_nms, by1, by0);
-                p2_nms(P, a_mag, S.cand, S.edge, S, M2, G.seg_rows_nms);
+                p2_nms(P, Dm, a_mag, S.cand, S.edge, S, M2, G.seg_rows_nms);
                 __syncthreads();
             }
         }
@@ -1108,7 +1160,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const
             const int sw = p3_hysteresis(S.cand, S.edge, h, ww, tid, nthr, [](int c) { return __syncthreads_or(c); });
             if (tid == 0 && p.stats) stat_add_one(S, 8, (unsigned long long)sw);
         }
-        p4_output(P, pa, 0u, p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr, tid, nthr);
+        p4_output(P, Dm, pa, 0u, p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr, tid, nthr);
         if (p.stats) count_planes<NR, EDGE>(p, S, S.cand, S.edge, S.mask, G.plane_bytes, plane_words, tid, nthr);
         __syncthreads();
     }
@@ -1134,7 +1186,18 @@ enum { SW_COMPUTE_THREADS = 320, SW_THREADS = 384, SW_MAXREG = 80 };      // reg
 
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int NR, int F0, int F1>
+// H, W > 0: the frame size is a compile-time constant (the host launches such a variant only for exactly that size, with the geometry
+// sw_static_geometry_ok() accepts); H = W = 0: any size that fits.
+template <int H, int W>
+__host__ __device__ constexpr int sw_seg_rows() { return (H + 4 * ((SW_COMPUTE_THREADS / 32) / (W / 32)) - 1) / (4 * ((SW_COMPUTE_THREADS / 32) / (W / 32))); }
+template <int H, int W>
+inline bool sw_static_geometry_ok(const FastGeom& g, int h, int w)
+{
+    return h == H && w == W && g.nsg == W / 32 && g.front_warps == SW_COMPUTE_THREADS / 32 && g.seg_rows_front == sw_seg_rows<H, W>() && g.mag_stride == W + 4 &&
+           g.plane_bytes == ((((H + 2) * (W / 32) * 4) + 15) & ~15) && g.tail_bytes == g.plane_bytes && g.n_bands == 1;
+}
+
+template <int NR, int F0, int F1, int H = 0, int W = 0>
 __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ FastParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -1144,36 +1207,40 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
     asm volatile("" : "+r"(sb));
     const SmemMap S = smem_map(sb, G);
     unsigned long long* s_red = reinterpret_cast<unsigned long long*>(smem + G.off_red);
-    const int h = p.h, w = p.w, ww = G.nsg;
+    constexpr bool STATIC = H > 0 && W > 0;
+    const Dims Dm = make_dims<H, W>(P);
+    const int h = Dm.h, w = Dm.w, ww = STATIC ? W / 32 : G.nsg;
+    const int seg_rows = STATIC ? sw_seg_rows<(STATIC ? H : 32), (STATIC ? W : 32)>() : G.seg_rows_front;
+    const int tail_bytes = STATIC ? Dm.plane_bytes : G.tail_bytes;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t frame_bytes = (uint32_t)h * w * 3;
     const int plane_words = h * ww;
     const int NC = SW_COMPUTE_THREADS;
     const int nfr = (int)blockIdx.x < p.n ? (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const uint32_t mask_set_bytes = (uint32_t)(NR * G.plane_bytes);
-    const uint32_t main_bytes = frame_bytes - (uint32_t)G.tail_bytes;
+    const uint32_t mask_set_bytes = (uint32_t)(NR * Dm.plane_bytes);
+    const uint32_t main_bytes = frame_bytes - (uint32_t)tail_bytes;
     const uint32_t bar_main = S.bar, bar_tail = S.bar + 8;
 
     init_tables<NR, F0, F1>(p, S, tid, nthr);
     stats_zero(S, tid);
-    zero_mag_borders(S.mag[0], h, w, G.mag_stride, tid, nthr);
+    zero_mag_borders(S.mag[0], h, w, Dm.mag_stride, tid, nthr);
     zero_plane_pads(S, plane_words, ww, tid, nthr);
     if (tid == 0) { mbar_init(bar_main, 1); mbar_init(bar_tail, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
 
     if (tid < NC) {
         // ------------------------------------------------ compute warps -----------------------------------------------
-        const StripMap M = strip_map(warp, lane, ww, G.seg_rows_front, h);
+        const StripMap M = strip_map(warp, lane, ww, seg_rows, h);
         const bool use_lut = p.dynamic || !p.lut_identity;
         // first strip-walk trip (a multiple of 3) in which some segment loads a row of the tail piece
-        const int nsegs = 4 * (G.front_warps / ww);
+        const int nsegs = 4 * ((NC >> 5) / ww);
         const int tail_row = (int)(main_bytes / (uint32_t)(w * 3));
-        int tail_k = tail_row - (nsegs - 1) * G.seg_rows_front + 1;
+        int tail_k = tail_row - (nsegs - 1) * seg_rows + 1;
         tail_k = tail_k < 0 ? 0 : (tail_k / 3) * 3;
         if (tid == 0 && nfr > 0) {
             const uint8_t* src = p.in + (size_t)blockIdx.x * frame_bytes;
             issue_frame_piece(S.pix[0], src, 0, main_bytes, bar_main);
-            if (G.tail_bytes) issue_frame_piece(S.pix[0], src, main_bytes, frame_bytes, bar_tail);
+            if (tail_bytes) issue_frame_piece(S.pix[0], src, main_bytes, frame_bytes, bar_tail);
         }
         uint32_t phase = 0;
 #ifdef TRS_PHASE_TIMERS
@@ -1189,19 +1256,19 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             const uint32_t a_edge = (j & 1) ? S.edge2 : S.edge;
             TRS_TICK(tk0);
             mbar_wait(bar_main, phase);
-            if (G.tail_bytes && use_lut) mbar_wait(bar_tail, phase);     // the table pass touches every pixel
+            if (tail_bytes && use_lut) mbar_wait(bar_tail, phase);       // the table pass touches every pixel
             TRS_TICK(tk1);
             adjust_in_place(p, S.pix[0], S, s_red, tid, NC, lane, [NC] { bar_sync(1, NC); });
             TRS_TICK(tk2);
             if (j >= 2) bar_sync(3, SW_THREADS);                         // the store warps are done with frame j-2: this plane set is free
             TRS_TICK(tk3);
-            p1_strip_walk<NR, true, F0, F1>(P, S.pix[0], S.mag[0], a_mask, S, M, G.seg_rows_front, (G.tail_bytes && !use_lut) ? bar_tail : 0u, phase, tail_k);
+            p1_strip_walk<NR, true, F0, F1>(P, Dm, S.pix[0], S.mag[0], a_mask, S, M, seg_rows, (tail_bytes && !use_lut) ? bar_tail : 0u, phase, tail_k);
             phase ^= 1u;
             bar_sync(1, NC);
             TRS_TICK(tk4);
             if (tid == 0 && j + 1 < nfr)                                 // pixels are dead: prefetch the next frame (all but its tail)
                 issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, 0, main_bytes, bar_main);
-            p2_nms(P, S.mag[0], S.cand, a_edge, S, M, G.seg_rows_front);
+            p2_nms(P, Dm, S.mag[0], S.cand, a_edge, S, M, seg_rows);
             bar_sync(1, NC);
             TRS_TICK(tk5);
             // hysteresis, first level only: every warp relaxes its own band, no CTA-wide round trip; the store warps finish the job
@@ -1225,7 +1292,7 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
         for (int j = 0; j < nfr; ++j) {
             const size_t f = blockIdx.x + (size_t)j * gridDim.x;
             uint32_t pa[3];
-            plane_sources(p, (j & 1) ? S.edge2 : S.edge, S.mask + (j & 1) * mask_set_bytes, G.plane_bytes, pa);
+            plane_sources(p, (j & 1) ? S.edge2 : S.edge, S.mask + (j & 1) * mask_set_bytes, Dm.plane_bytes, pa);
             bar_sync(2, SW_THREADS);
             {
                 // growth across the compute warps' bands: rounds over the whole plane until nothing changes (usually one checking pass)
@@ -1237,13 +1304,13 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
                     sw = p3_hysteresis(S.cand, a_edge, h, ww, tid - NC, NS, [NS](int c) { return bar_or(4, NS, c); });
                 if (p.stats) {                                           // (the candidate plane is counted before the tail copy lands on it)
                     if (tid == NC) stat_add_one(S, 8, (unsigned long long)sw + 1);
-                    count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, G.plane_bytes, plane_words, tid - NC, NS);
+                    count_planes<NR, true>(p, S, S.cand, a_edge, a_mask, Dm.plane_bytes, plane_words, tid - NC, NS);
                     bar_sync(4, NS);
                 }
-                if (tid == NC && G.tail_bytes && j + 1 < nfr)            // the candidate plane is dead: fetch the tail it was sitting in
+                if (tid == NC && tail_bytes && j + 1 < nfr)              // the candidate plane is dead: fetch the tail it was sitting in
                     issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, main_bytes, frame_bytes, bar_tail);
             }
-            p4_output(P, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid - NC,
+            p4_output(P, Dm, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid - NC,
                       SW_THREADS - NC);
             if (j + 2 < nfr) bar_arrive(3, SW_THREADS);
         }

@@ -62,8 +62,17 @@ enum { HOST_STREAMS = 3 };
 
 }  // namespace
 
+// Test-only switches (tests/test_gpu_parity.py forces every kernel variant through the same goldens): read from the environment ONCE,
+// when the context is created, so no call on the N = 1 latency path pays a getenv.
+struct TrsSwitches {
+    bool force_generic = false, no_banded = false, no_store_warp = false, resize_scalar = false, resize_gather = false;
+    int locate = 0;                    // 0 = by batch size, 1 = warp per car, 2 = thread per car
+    size_t host_chunk_bytes = (size_t)48 << 20;      // ~48 MB of frames per chunk of the host pipeline (the link saturates from ~16 MB up)
+};
+
 struct trs_ctx {
     int device = 0;
+    TrsSwitches sw;
     int sm_count = 0;
     int smem_optin = 0;
     int cc_major = 0, cc_minor = 0;
@@ -83,6 +92,7 @@ struct trs_ctx {
     float* st_f32[HOST_STREAMS] = {nullptr, nullptr, nullptr};
     size_t st_in_cap = 0, st_u8_cap = 0, st_f32_cap = 0;
     unsigned long long* stats_dev = nullptr;
+    cudaEvent_t host_entry = nullptr;  // orders the internal streams after the caller's stream at entry of the *_host calls
     // tub ingestion staging (grown on demand)
     uint8_t* jpg_blob = nullptr;   size_t jpg_blob_cap = 0;
     uint8_t* jpg_planes = nullptr; size_t jpg_planes_cap = 0;
@@ -211,6 +221,14 @@ template <int NR, bool EDGE, int F0, int F1>
 int launch_fast_tf(const trs::FastParams& fp, int grid, cudaStream_t st)
 {
     if (EDGE && fp.use_store_warp) {
+        // the reference's camera size with its default colour ranges (core/config.py:8-9,23) gets the variant with compile-time dimensions
+        if (NR == 2 && F0 >= 0 && trs::sw_static_geometry_ok<120, 160>(fp.g, fp.k.h, fp.k.w)) {
+            auto kern = trs::k_preprocess_sw<NR, F0, F1, (NR == 2 && F0 >= 0 ? 120 : 0), (NR == 2 && F0 >= 0 ? 160 : 0)>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sw 120x160)");
+            kern<<<grid, trs::SW_THREADS, fp.g.total, st>>>(fp);
+            return 0;
+        }
         cudaError_t e = cudaFuncSetAttribute(trs::k_preprocess_sw<NR, F0, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fp.g.total);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sw)");
         trs::k_preprocess_sw<NR, F0, F1><<<grid, trs::SW_THREADS, fp.g.total, st>>>(fp);
@@ -235,14 +253,16 @@ enum { DEFAULT_F0 = 8 | 16, DEFAULT_F1 = 1 | 2 | 4 | 16 };
 template <int NR, bool EDGE>
 int launch_fast_t(const trs::FastParams& fp, int grid, cudaStream_t st)
 {
-    if (NR == 2 && fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1)
+    // (the baked variant turns the hue bounds of range 1 into per-delta numerator thresholds, which needs an upper bound below the
+    // wrapped hues: preproc_fast.cuh HueThresholds)
+    if (NR == 2 && fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1 && fp.k.ranges[1].hi[0] <= 149)
         return launch_fast_tf<NR, EDGE, (NR == 2 ? (int)DEFAULT_F0 : -1), (NR == 2 ? (int)DEFAULT_F1 : -1)>(fp, grid, st);
     return launch_fast_tf<NR, EDGE, -1, -1>(fp, grid, st);
 }
 
 int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w, cudaStream_t st)
 {
-    if (getenv("TRS_FORCE_GENERIC")) return 0;
+    if (ctx->sw.force_generic) return 0;
     if (!k.word_io || (w % 32) != 0 || (((size_t)h * w * 3) % 16) != 0) return 0;
     if (!k.edge_enabled && k.n_ranges == 0) return 0;
     const int nsg = w / 32;
@@ -259,7 +279,7 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
         trs::FastGeom g = trs::fast_geometry(h, w, k.n_ranges, 0, nsg * quads, nsg * quads);
         if (g.threads > trs::FAST_MAX_THREADS) return 0;
         if (g.total > budget2) {
-            if (k.need_pixels || k.dynamic || !k.lut_identity || getenv("TRS_NO_BANDED")) return 0;
+            if (k.need_pixels || k.dynamic || !k.lut_identity || ctx->sw.no_banded) return 0;
             bool found = false;
             for (int nb = 2; nb <= h / 4 && !found; ++nb) {
                 const int bh = (h + nb - 1) / nb;
@@ -292,7 +312,7 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     // store-warp variant (k_preprocess_sw): edge filter on, every output channel a bit plane, ten compute warps, and the
     // double-buffered mask planes still fit two CTAs per SM
     fp.use_store_warp = 0;
-    if (fp.g.n_bands == 1 && k.edge_enabled && !k.need_pixels && fp.g.threads == trs::SW_COMPUTE_THREADS && !getenv("TRS_NO_STORE_WARP")) {
+    if (fp.g.n_bands == 1 && k.edge_enabled && !k.need_pixels && fp.g.threads == trs::SW_COMPUTE_THREADS && !ctx->sw.no_store_warp) {
         const trs::FastGeom g2 = trs::fast_geometry(h, w, k.n_ranges, 0, fp.g.front_warps, fp.g.back_warps, 2);
         const int budget2 = (ctx->smem_optin + 1024) / 2 - 1024;
         if (g2.total <= budget2) {
@@ -357,12 +377,24 @@ int launch_preprocess(trs_ctx* ctx, const uint8_t* in, int n, int h, int w, uint
     return 0;
 }
 
-int bind(trs_ctx* ctx)
+// staging buffers of the host pipeline grow on demand; the capacity is only recorded once all buffers of a kind exist, so a failed
+// allocation can never leave a stale capacity next to a null pointer
+template <class T>
+int grow_staging(T* (&bufs)[HOST_STREAMS], size_t& cap, size_t bytes)
 {
-    if (!ctx) return fail(TRS_E_ARG, "null context");
-    CU(cudaSetDevice(ctx->device));
+    if (cap >= bytes) return 0;
+    cap = 0;
+    for (int i = 0; i < HOST_STREAMS; ++i) { cudaFree(bufs[i]); bufs[i] = nullptr; }
+    for (int i = 0; i < HOST_STREAMS; ++i) CU(cudaMalloc(&bufs[i], bytes));
+    cap = bytes;
     return 0;
 }
+
+// first statement of every entry point that touches the device
+#define TRS_ENTER(ctx)                                                           \
+    if (!(ctx)) return fail(TRS_E_ARG, "null context");                          \
+    TrsDeviceGuard trs_guard_((ctx)->device);                                    \
+    if (trs_guard_.err != cudaSuccess) return cuda_fail(trs_guard_.err, "cudaSetDevice")
 
 }  // namespace
 
@@ -385,13 +417,20 @@ int trs_ctx_create(int device, trs_ctx** out)
     if (device < 0 || device >= count) return fail(TRS_E_ARG, "device %d of %d", device, count);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail(TRS_E_NODEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+    if (prop.major != 10) return fail(TRS_E_NODEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
     trs_ctx* c = new (std::nothrow) trs_ctx();
     if (!c) return fail(TRS_E_ARG, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     c->cc_major = prop.major; c->cc_minor = prop.minor;
+    c->sw.force_generic = getenv("TRS_FORCE_GENERIC") != nullptr;
+    c->sw.no_banded = getenv("TRS_NO_BANDED") != nullptr;
+    c->sw.no_store_warp = getenv("TRS_NO_STORE_WARP") != nullptr;
+    c->sw.resize_scalar = getenv("TRS_RESIZE_SCALAR") != nullptr;
+    c->sw.resize_gather = getenv("TRS_RESIZE_GATHER") != nullptr;
+    if (const char* e = getenv("TRS_LOCATE")) c->sw.locate = e[0] == 'w' ? 1 : 2;
+    if (const char* e = getenv("TRS_HOST_CHUNK_MB")) { const int mb = atoi(e); if (mb > 0) c->sw.host_chunk_bytes = (size_t)mb << 20; }
     trs_preproc_params d;
     default_params(&d);
     derive_params(c, &d);
@@ -402,11 +441,12 @@ int trs_ctx_create(int device, trs_ctx** out)
 int trs_ctx_destroy(trs_ctx* ctx)
 {
     if (!ctx) return 0;
-    cudaSetDevice(ctx->device);
+    TrsDeviceGuard guard(ctx->device);
     for (int i = 0; i < HOST_STREAMS; ++i) {
         if (ctx->hs[i]) cudaStreamDestroy(ctx->hs[i]);
         cudaFree(ctx->st_in[i]); cudaFree(ctx->st_u8[i]); cudaFree(ctx->st_f32[i]);
     }
+    if (ctx->host_entry) cudaEventDestroy(ctx->host_entry);
     cudaFree(ctx->wp_dev);
     cudaFree(ctx->stats_dev);
     cudaFree(ctx->jpg_blob); cudaFree(ctx->jpg_planes); cudaFree(ctx->jpg_meta);
@@ -434,8 +474,7 @@ int trs_set_preproc_params(trs_ctx* ctx, const trs_preproc_params* p)
 int trs_preprocess(trs_ctx* ctx, const uint8_t* in_dev, int n, int h, int w, uint8_t* out_u8_dev, float* out_f32_dev,
                    unsigned long long* stats_dev, void* stream)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
+    TRS_ENTER(ctx);
     if (n < 0 || h < 0 || w < 0) return fail(TRS_E_ARG, "negative size n=%d h=%d w=%d", n, h, w);
     if (n == 0 || h == 0 || w == 0) return 0;
     if (!in_dev) return fail(TRS_E_ARG, "null input");
@@ -445,8 +484,7 @@ int trs_preprocess(trs_ctx* ctx, const uint8_t* in_dev, int n, int h, int w, uin
 
 int trs_debug_canny_stages(trs_ctx* ctx, const uint8_t* in_dev, int h, int w, uint16_t* mag_dev, uint8_t* map_dev, void* stream)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
+    TRS_ENTER(ctx);
     if (!in_dev || h <= 0 || w <= 0) return fail(TRS_E_ARG, "bad argument");
     return launch_preprocess(ctx, in_dev, 1, h, w, nullptr, nullptr, nullptr, mag_dev, map_dev, true, (cudaStream_t)stream);
 }
@@ -454,8 +492,7 @@ int trs_debug_canny_stages(trs_ctx* ctx, const uint8_t* in_dev, int h, int w, ui
 int trs_normalise(trs_ctx* ctx, const uint8_t* in_dev, int n, int h_in, int w_in, int roi_y0, int roi_y1, int roi_x0, int roi_x1,
                   int h_out, int w_out, float* out_f32_dev, uint8_t* out_u8_dev, void* stream)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
+    TRS_ENTER(ctx);
     if (n < 0 || h_in < 0 || w_in < 0 || h_out < 0 || w_out < 0) return fail(TRS_E_ARG, "negative size");
     if (roi_y0 < 0 || roi_x0 < 0 || roi_y1 > h_in || roi_x1 > w_in || roi_y1 < roi_y0 || roi_x1 < roi_x0)
         return fail(TRS_E_ARG, "window rows [%d,%d) cols [%d,%d) outside a %dx%d frame", roi_y0, roi_y1, roi_x0, roi_x1, h_in, w_in);
@@ -484,7 +521,7 @@ int trs_normalise(trs_ctx* ctx, const uint8_t* in_dev, int n, int h_in, int w_in
     }
     trs::ResizeParams p{in_dev, out_f32_dev, out_u8_dev, n, h_in, w_in, roi_y0, roi_x0, roi_y1 - roi_y0, roi_x1 - roi_x0, h_out, w_out};
     if ((w_out * 3) % 4 == 0 && w_out + h_out <= trs::RESIZE_MAX_TAB && (!out_f32_dev || ((uintptr_t)out_f32_dev & 15) == 0) &&
-        (!out_u8_dev || ((uintptr_t)out_u8_dev & 3) == 0) && !getenv("TRS_RESIZE_SCALAR")) {
+        (!out_u8_dev || ((uintptr_t)out_u8_dev & 3) == 0) && !ctx->sw.resize_scalar) {
         const size_t rows = (size_t)n * h_out;
         const size_t cap = (size_t)ctx->sm_count * 16;
         // source rows staged in shared memory when they are 16-byte aligned (camera.py:36: 320x240 -> 160x120 is)
@@ -492,7 +529,7 @@ int trs_normalise(trs_ctx* ctx, const uint8_t* in_dev, int n, int h_in, int w_in
         const int span = (col_hi < w_in * 3 ? col_hi : w_in * 3) - col_lo;
         const size_t tab = ((sizeof(int) * 4 * (size_t)((w_out * 3) >> 2) + sizeof(int) * (size_t)h_out + 15) & ~(size_t)15);
         if ((w_in * 3) % 16 == 0 && ((uintptr_t)in_dev & 15) == 0 && span % 16 == 0 && tab + trs::RESIZE_DEPTH * (size_t)span <= 48 * 1024 &&
-            !getenv("TRS_RESIZE_GATHER")) {
+            !ctx->sw.resize_gather) {
             trs::k_crop_resize_rows<<<(int)(rows < cap ? rows : cap), trs::RESIZE_THREADS, tab + trs::RESIZE_DEPTH * (size_t)span, st>>>(p, col_lo, span);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             CU(cudaGetLastError());
@@ -514,8 +551,7 @@ int trs_normalise(trs_ctx* ctx, const uint8_t* in_dev, int n, int h_in, int w_in
 
 int trs_set_track(trs_ctx* ctx, const double* wp_xyz_host, int n_wp, double min_map, double max_map)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
+    TRS_ENTER(ctx);
     if (!wp_xyz_host || n_wp <= 0) return fail(TRS_E_ARG, "empty centre line");
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaFree(ctx->wp_dev);
@@ -530,15 +566,13 @@ int trs_set_track(trs_ctx* ctx, const double* wp_xyz_host, int n_wp, double min_
 
 int trs_locate(trs_ctx* ctx, const double* xyz_dev, int n, int32_t* idx_dev, double* segment_dev, void* stream)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
+    TRS_ENTER(ctx);
     if (!ctx->wp_dev) return fail(TRS_E_STATE, "trs_locate before trs_set_track");
     if (n < 0) return fail(TRS_E_ARG, "negative n");
     if (n == 0) return 0;
     if (!xyz_dev || (!idx_dev && !segment_dev)) return fail(TRS_E_ARG, "null pointer");
     // small batches: a warp per car with a shuffle reduction (a thread per car would not fill the GPU); TRS_LOCATE=warp|thread forces one
-    const char* force = getenv("TRS_LOCATE");
-    const bool warp_per_car = force ? force[0] == 'w' : n < ctx->sm_count * 256;      // measured crossover ~50 k cars (15 us vs 55 us below it)
+    const bool warp_per_car = ctx->sw.locate ? ctx->sw.locate == 1 : n < ctx->sm_count * 256;      // measured crossover ~50 k cars (15 us vs 55 us below it)
     if (warp_per_car) {
         const int warps_per_block = trs::LOCW_THREADS / 32;
         int grid = (n + warps_per_block - 1) / warps_per_block;
@@ -558,18 +592,51 @@ int trs_locate(trs_ctx* ctx, const double* xyz_dev, int n, int32_t* idx_dev, dou
     return 0;
 }
 
+int trs_probe_fp64(trs_ctx* ctx, double* dfma_tflops, double* dadd_tinst_per_s)
+{
+    TRS_ENTER(ctx);
+    const int grid = ctx->sm_count * 8, iters = 4096;
+    double* buf = nullptr;
+    CU(cudaMalloc(&buf, sizeof(double) * (size_t)grid * trs::PROBE64_THREADS));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double rate[2] = {0, 0};
+    cudaError_t err = cudaSuccess;
+    for (int which = 0; which < 2 && err == cudaSuccess; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {                      // rep 0 warms up
+            cudaEventRecord(e0, 0);
+            if (which == 0) trs::k_probe_fp64<true><<<grid, trs::PROBE64_THREADS>>>(buf, iters, 0.999999, 1e-9);
+            else trs::k_probe_fp64<false><<<grid, trs::PROBE64_THREADS>>>(buf, iters, 0.0, 1e-9);
+            cudaEventRecord(e1, 0);
+            err = cudaEventSynchronize(e1);
+            if (err != cudaSuccess) break;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep && ms < best) best = ms;
+        }
+        g_launches.fetch_add(4, std::memory_order_relaxed);
+        rate[which] = (double)grid * trs::PROBE64_THREADS * trs::PROBE64_ILP * (double)iters / ((double)best * 1e-3);      // lane-instructions per second
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (err != cudaSuccess) return cuda_fail(err, "fp64 probe");
+    if (dfma_tflops) *dfma_tflops = 2.0 * rate[0] / 1e12;
+    if (dadd_tinst_per_s) *dadd_tinst_per_s = rate[1] / 1e12;
+    return 0;
+}
+
 int trs_speed_control(trs_ctx* ctx, const double* cur_spd_dev, const float* model_spd_dev, const float* model_steer_dev, int n,
                       const trs_spd_params* p, double* steering_dev, double* throttle_dev, double* breaking_dev,
                       float* spd_feature_dev, void* stream)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
+    TRS_ENTER(ctx);
     if (n < 0 || !p) return fail(TRS_E_ARG, "bad argument");
     if (n == 0) return 0;
     if (!cur_spd_dev || !model_spd_dev || !model_steer_dev || !steering_dev || !throttle_dev || !breaking_dev)
         return fail(TRS_E_ARG, "null pointer");
     trs::SpdKParams k{p->threshold, p->reverse_multiplier, p->break_multiplier, p->smooth_threshold, p->use_break ? 1 : 0,
-                      p->smooth_steering ? 1 : 0};
+                      p->smooth_steering ? 1 : 0, p->numpy_legacy_promotion ? 1 : 0};
     int grid = (n + 255) / 256;
     const int cap = ctx->sm_count * 8;
     if (grid > cap) grid = cap;
@@ -583,8 +650,7 @@ int trs_speed_control(trs_ctx* ctx, const double* cur_spd_dev, const float* mode
 int trs_control_mux(trs_ctx* ctx, const int32_t* mode_dev, const double* usr_dev, const double* ai_dev, const double* speed_dev, int n,
                     const trs_ctl_params* p, double now_s, int32_t* last_mode_dev, double* launch_times_dev, double* out_dev, void* stream)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
+    TRS_ENTER(ctx);
     if (n < 0 || !p) return fail(TRS_E_ARG, "bad argument");
     if (n == 0) return 0;
     if (!mode_dev || !usr_dev || !ai_dev || !last_mode_dev || !launch_times_dev || !out_dev) return fail(TRS_E_ARG, "null pointer");
@@ -604,8 +670,7 @@ int trs_control_mux(trs_ctx* ctx, const int32_t* mode_dev, const double* usr_dev
 
 int trs_pwm_map(trs_ctx* ctx, const double* val_dev, int n, double min_map, double mid_map, double max_map, double* out_dev, void* stream)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
+    TRS_ENTER(ctx);
     if (n < 0) return fail(TRS_E_ARG, "negative n");
     if (n == 0) return 0;
     if (!val_dev || !out_dev) return fail(TRS_E_ARG, "null pointer");
@@ -621,8 +686,7 @@ int trs_pwm_map(trs_ctx* ctx, const double* val_dev, int n, double min_map, doub
 int trs_jpeg_decode_host(trs_ctx* ctx, const uint8_t* blob_host, const unsigned long long* offsets_host, int n, int h, int w,
                          uint8_t* out_u8_dev, void* stream)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
+    TRS_ENTER(ctx);
     if (n < 0 || h <= 0 || w <= 0) return fail(TRS_E_ARG, "bad size n=%d h=%d w=%d", n, h, w);
     if (n == 0) return 0;
     if (!blob_host || !offsets_host || !out_u8_dev) return fail(TRS_E_ARG, "null pointer");
@@ -836,10 +900,9 @@ int trs_host_free(void* p)
 }
 
 int trs_preprocess_host(trs_ctx* ctx, const uint8_t* in_host, int n, int h, int w, uint8_t* out_u8_host, float* out_f32_host,
-                        float* keep_f32_dev, unsigned long long* stats_host)
+                        float* keep_f32_dev, unsigned long long* stats_host, void* stream)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
+    TRS_ENTER(ctx);
     if (n < 0 || h < 0 || w < 0) return fail(TRS_E_ARG, "negative size");
     if (stats_host) memset(stats_host, 0, sizeof(unsigned long long) * TRS_STAT_COUNT);
     if (n == 0 || h == 0 || w == 0) return 0;
@@ -847,47 +910,56 @@ int trs_preprocess_host(trs_ctx* ctx, const uint8_t* in_host, int n, int h, int 
     if (!out_u8_host && !out_f32_host && !keep_f32_dev && !stats_host) return fail(TRS_E_ARG, "no output requested");
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t fb = (size_t)h * w * 3;
-    size_t chunk_bytes = (size_t)48 << 20;                     // ~48 MB of frames per chunk (the link saturates from ~16 MB up)
-    if (const char* e = getenv("TRS_HOST_CHUNK_MB")) { const int mb = atoi(e); if (mb > 0) chunk_bytes = (size_t)mb << 20; }
-    size_t chunk = chunk_bytes / fb;
+    size_t chunk = ctx->sw.host_chunk_bytes / fb;
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)n) chunk = n;
     chunk = (chunk + 3) & ~(size_t)3;                          // keeps every chunk base 16-byte aligned when fb % 4 == 0
     for (int i = 0; i < HOST_STREAMS; ++i)
         if (!ctx->hs[i]) CU(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
+    if (!ctx->host_entry) CU(cudaEventCreateWithFlags(&ctx->host_entry, cudaEventDisableTiming));
     const bool need_f32 = out_f32_host != nullptr;
-    if (ctx->st_in_cap < chunk * fb) {
-        for (int i = 0; i < HOST_STREAMS; ++i) { cudaFree(ctx->st_in[i]); ctx->st_in[i] = nullptr; CU(cudaMalloc(&ctx->st_in[i], chunk * fb)); }
-        ctx->st_in_cap = chunk * fb;
-    }
-    if (out_u8_host && ctx->st_u8_cap < chunk * fb) {
-        for (int i = 0; i < HOST_STREAMS; ++i) { cudaFree(ctx->st_u8[i]); ctx->st_u8[i] = nullptr; CU(cudaMalloc(&ctx->st_u8[i], chunk * fb)); }
-        ctx->st_u8_cap = chunk * fb;
-    }
-    if (need_f32 && !keep_f32_dev && ctx->st_f32_cap < chunk * fb * 4) {
-        for (int i = 0; i < HOST_STREAMS; ++i) { cudaFree(ctx->st_f32[i]); ctx->st_f32[i] = nullptr; CU(cudaMalloc(&ctx->st_f32[i], chunk * fb * 4)); }
-        ctx->st_f32_cap = chunk * fb * 4;
-    }
+    // staging buffers grow on demand; a capacity is only recorded once all three buffers of its kind exist
+    int rc = grow_staging(ctx->st_in, ctx->st_in_cap, chunk * fb);
+    if (!rc && out_u8_host) rc = grow_staging(ctx->st_u8, ctx->st_u8_cap, chunk * fb);
+    if (!rc && need_f32 && !keep_f32_dev) rc = grow_staging(ctx->st_f32, ctx->st_f32_cap, chunk * fb * 4);
+    if (rc) return rc;
+    // the internal streams start after everything the caller has queued on ITS stream (a consumer of keep_f32_dev from the previous
+    // step, the producer of a device-resident stats buffer, ...)
+    CU(cudaEventRecord(ctx->host_entry, (cudaStream_t)stream));
+    for (int i = 0; i < HOST_STREAMS; ++i) CU(cudaStreamWaitEvent(ctx->hs[i], ctx->host_entry, 0));
+    // from here on copies into the caller's host buffers may be in flight: every exit drains the internal streams first
+    auto drain = [&](int code) {
+        for (int i = 0; i < HOST_STREAMS; ++i) cudaStreamSynchronize(ctx->hs[i]);
+        return code;
+    };
+#define CUD(call)                                                       \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return drain(cuda_fail(_e, #call));      \
+    } while (0)
     if (stats_host) {
-        if (!ctx->stats_dev) CU(cudaMalloc(&ctx->stats_dev, sizeof(unsigned long long) * TRS_STAT_COUNT));
-        CU(cudaMemsetAsync(ctx->stats_dev, 0, sizeof(unsigned long long) * TRS_STAT_COUNT, ctx->hs[0]));
-        CU(cudaStreamSynchronize(ctx->hs[0]));
+        if (!ctx->stats_dev) CUD(cudaMalloc(&ctx->stats_dev, sizeof(unsigned long long) * TRS_STAT_COUNT));
+        CUD(cudaMemsetAsync(ctx->stats_dev, 0, sizeof(unsigned long long) * TRS_STAT_COUNT, ctx->hs[0]));
+        CUD(cudaStreamSynchronize(ctx->hs[0]));
     }
     int ci = 0;
     for (size_t f0 = 0; f0 < (size_t)n; f0 += chunk, ++ci) {
         const int s = ci % HOST_STREAMS;
         const size_t cn = (size_t)n - f0 < chunk ? (size_t)n - f0 : chunk;
         cudaStream_t st = ctx->hs[s];
-        CU(cudaMemcpyAsync(ctx->st_in[s], in_host + f0 * fb, cn * fb, cudaMemcpyHostToDevice, st));
+        CUD(cudaMemcpyAsync(ctx->st_in[s], in_host + f0 * fb, cn * fb, cudaMemcpyHostToDevice, st));
         uint8_t* du8 = out_u8_host ? ctx->st_u8[s] : nullptr;
         float* df32 = keep_f32_dev ? keep_f32_dev + f0 * fb : (need_f32 ? ctx->st_f32[s] : nullptr);
         rc = launch_preprocess(ctx, ctx->st_in[s], (int)cn, h, w, du8, df32, stats_host ? ctx->stats_dev : nullptr, nullptr, nullptr, false, st);
-        if (rc) return rc;
-        if (out_u8_host) CU(cudaMemcpyAsync(out_u8_host + f0 * fb, du8, cn * fb, cudaMemcpyDeviceToHost, st));
-        if (need_f32) CU(cudaMemcpyAsync(out_f32_host + f0 * fb, df32, cn * fb * 4, cudaMemcpyDeviceToHost, st));
+        if (rc) return drain(rc);
+        if (out_u8_host) CUD(cudaMemcpyAsync(out_u8_host + f0 * fb, du8, cn * fb, cudaMemcpyDeviceToHost, st));
+        if (need_f32) CUD(cudaMemcpyAsync(out_f32_host + f0 * fb, df32, cn * fb * 4, cudaMemcpyDeviceToHost, st));
     }
-    for (int i = 0; i < HOST_STREAMS; ++i) CU(cudaStreamSynchronize(ctx->hs[i]));
+    cudaError_t first = cudaSuccess;
+    for (int i = 0; i < HOST_STREAMS; ++i) { const cudaError_t e = cudaStreamSynchronize(ctx->hs[i]); if (first == cudaSuccess) first = e; }
+    if (first != cudaSuccess) return cuda_fail(first, "cudaStreamSynchronize(host pipeline)");
     if (stats_host) CU(cudaMemcpy(stats_host, ctx->stats_dev, sizeof(unsigned long long) * TRS_STAT_COUNT, cudaMemcpyDeviceToHost));
+#undef CUD
     return 0;
 }
 

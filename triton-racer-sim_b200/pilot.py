@@ -108,15 +108,22 @@ class PilotNet:
             self._create(want)
 
     def forward_device(self, frames: torch.Tensor, spd_feature: torch.Tensor = None, loc_feature: torch.Tensor = None, out=None):
-        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and tuple(frames.shape[1:]) == (self.h, self.w, 3), \
-            f"frames must be (N,{self.h},{self.w},3) uint8 on the GPU"
+        if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.device.index == self.device and frames.dtype == torch.uint8
+                and frames.dim() == 4 and tuple(frames.shape[1:]) == (self.h, self.w, 3)):
+            raise ValueError(f"frames must be (N,{self.h},{self.w},3) uint8 on cuda:{self.device}")
         frames = frames.contiguous()
         n = frames.shape[0]
+        if out is not None and not (out.is_cuda and out.device.index == self.device and out.dtype == torch.float32
+                                    and tuple(out.shape) == (n, 2) and out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous ({n}, 2) float32 tensor on cuda:{self.device}")
         self.reserve(n)
         if out is None:
             out = torch.empty((n, 2), dtype=torch.float32, device=frames.device)
         f32 = lambda t: None if t is None else t.to(device=frames.device, dtype=torch.float32).contiguous()
         spd_feature, loc_feature = f32(spd_feature), f32(loc_feature)
+        for t, name in ((spd_feature, "speed feature"), (loc_feature, "loc/segment feature")):
+            if t is not None and t.numel() != n:
+                raise ValueError(f"{name} must have {n} elements, got {t.numel()}")
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         stream = C.c_void_p(torch.cuda.current_stream(frames.device).cuda_stream)
         nat.check(self.ctx.lib.trs_pilot_forward(self.handle, ptr(frames), n, ptr(spd_feature), ptr(loc_feature), ptr(out), stream),
@@ -180,9 +187,13 @@ class KerasPilot(Component):
 
     def pilot_device(self, frames: torch.Tensor, speed: torch.Tensor = None, segment: torch.Tensor = None):
         """Batched body of KerasPilot.step (keras_pilot.py:48-117): three float64 tensors (N,)."""
+        if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.device.index == self.device):
+            raise ValueError(f"frames must live on cuda:{self.device}")
         n = frames.shape[0]
         dev = frames.device
         mt = self.model_type
+        if mt != ModelType.CNN_2D and (speed is None or speed.numel() != n):
+            raise ValueError(f"gym/speed must hold {n} values for this model type")
         lib, ctx = self.model.ctx.lib, self.model.ctx.handle
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         spd_feat = None
