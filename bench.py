@@ -8,7 +8,13 @@ A "step" is one pass of the fused observation chain (brightness/contrast -> HSV 
 merge -> /255 float tensor) over one batch of synthetic 120x160 frames, sharded by env index with no data-path
 collective.  Default workload = BASELINE.json's north-star configuration: 65,536 frames per GPU, u8 in, u8
 `cam/processed_img` + f32 normalised tensor out (345,600 algorithmic bytes per frame).
-Rank 0 prints ONE JSON line.
+Rank 0 prints ONE JSON line.  Besides the headline keys it carries, measured by every rank on its own shard (max over ranks):
+  stats_on                         the headline step with the per-step counters and their all-reduce inside the timed region
+  e2e (+ pcie_probe, tub_mode)     host buffers through the Component API; the copy-only ceiling of the box at this rank count
+  blocks.full_house_mask_240x320   BASELINE.json configs[2] at 65,536 frames per GPU
+  blocks.full_chain_240x320        the full chain (u8 + f32 out) at 240x320, 65,536 frames per GPU
+  blocks.full_pipeline_1M          configs[4]: 1,048,576 frames + car states per step over the N ranks (strong scaling)
+  other_workloads                  the remaining configurations, rank 0 only
 """
 from __future__ import annotations
 
@@ -27,7 +33,7 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # name: (h, w, frames per GPU, want_u8, want_f32, algorithmic bytes per frame)
     "full_chain_120x160": (120, 160, 65536, True, True, 57600 + 57600 + 230400),
-    "full_house_mask_240x320": (240, 320, 16384, True, False, 230400 + 230400),
+    "full_house_mask_240x320": (240, 320, 65536, True, False, 230400 + 230400),
     # BASELINE.json configs[4]: 1M frames + 1M car states per step over 8 GPUs = 131,072 of each per GPU; a step also runs the
     # nearest-waypoint lookup, the speed controller and the control multiplexer for the shard's cars (three more launches)
     "full_pipeline_1M_over_8": (120, 160, 131072, True, True, 57600 + 57600 + 230400),
@@ -35,8 +41,8 @@ WORKLOADS = {
 METRIC = "preprocessed frames/sec (120x160), full observation chain"
 METRICS = {"full_chain_120x160": METRIC, "full_house_mask_240x320": "preprocessed frames/sec (240x320), full-house colour + edge mask",
            "full_pipeline_1M_over_8": "preprocessed frames/sec (120x160), full observation pipeline incl. per-car lookup and control"}
-KERNELS = {"full_chain_120x160": "trs::k_preprocess_sw<2,24,23>", "full_house_mask_240x320": "trs::k_preprocess_banded<2,true,24,23>",
-           "full_pipeline_1M_over_8": "trs::k_preprocess_sw<2,24,23>"}
+KERNELS = {"full_chain_120x160": "trs::k_preprocess_sw<2,24,23,120,160>", "full_house_mask_240x320": "trs::k_preprocess_banded<2,true,24,23>",
+           "full_pipeline_1M_over_8": "trs::k_preprocess_sw<2,24,23,120,160>"}
 NOTES = {
     "full_chain_120x160": "bound by the ALU pipe / issue slots and phase barriers, not by HBM: ten compute warps per CTA run strip walk, NMS and "
                           "hysteresis while two store warps stream the previous frame out (the SM -> L2 write port tops out at 29 B/clk); "
@@ -48,6 +54,14 @@ NOTES = {
 
 
 _REAL_STDOUT = None
+
+
+def load_track(name: str):
+    """One of the reference's two recorded centre lines (car_templates/track_data/*.json: 'generated_track' 1,185 points,
+    'mountain_track' 2,664 points), as committed with the golden vectors (tests/golden/tracks.npz, key wp/<name>)."""
+    import numpy as np
+    with np.load(os.path.join(ROOT, "tests", "golden", "tracks.npz")) as z:
+        return np.ascontiguousarray(z[f"wp/{name}"], np.float64)
 
 
 def emit(line: dict):
@@ -199,9 +213,12 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
     import numpy as np
 
     from triton_racer_sim_b200 import FrameNormalise, ImgPreprocessing, LocationTracker, SpeedControl, synth
+    from triton_racer_sim_b200 import _native as nat2
     from triton_racer_sim_b200.config import full_house_config
     peak, _ = read_peaks()
     out = {}
+    sampler = ClockSampler(local)                  # one clock record over all of these short runs
+    sampler.start()
 
     def timed(fn, reps=5, warm=3):
         for _ in range(warm):
@@ -241,30 +258,41 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
     t = timed(lambda: cam.normalise_device(src240), reps=10)
     out["resize2x_normalise_4096"] = {"frames_per_s": 4096 / t, "GBps_algorithmic": 4096 * 288000 / t / 1e9}
     cam.onShutdown()
-    # configs[2]: full-house colour + edge mask at 240x320 (u8 -> u8): 460,800 algorithmic bytes per frame; banded kernel
-    fh = ImgPreprocessing(full_house_config(), device=local)
-    o240 = torch.empty_like(src240)
-    t = timed(lambda: fh.process_device(src240, out_u8=o240, want_f32=False), reps=3, warm=1)
-    out["full_house_mask_240x320"] = {"frames_per_s": 4096 / t, "GBps": 4096 * 460800 / t / 1e9, "hbm_frac": 4096 * 460800 / t / 1e9 / peak,
-                                       "note": "banded kernel (k_preprocess_banded): 6 B per pixel, instruction bound"}
-    fh.onShutdown()
-    del src240, o240, pool240
-    # configs[3]: nearest waypoint + speed control for 1M car states (FP64-ALU bound, 76 B of HBM traffic per state)
-    wp = synth.synthetic_track(1185)
-    xyz, cur, ms, st = synth.car_states(wp, 1 << 20, seed=4)
-    trk = LocationTracker(wp, device=local)
-    spd = SpeedControl(dict(spd_ctl_break=True), device=local)
-    d_xyz, d_cur = torch.from_numpy(xyz).to(dev), torch.from_numpy(cur).to(dev)
-    d_ms, d_st = torch.from_numpy(ms).to(dev), torch.from_numpy(st).to(dev)
-
-    def cars_step():
-        trk.locate_device(d_xyz)
-        spd.control_device(d_cur, d_st, d_ms)
-    t = timed(cars_step, reps=10)
+    del src240, pool240
+    # configs[3]: nearest waypoint + speed control for 1M car states on BOTH shipped centre lines (FP64-ALU bound, 76 B of HBM traffic per
+    # state): 9 algorithmic flops per (state, waypoint) = 3 subtractions, 3 absolute values, 2 additions, 1 comparison, of which the fp64
+    # pipe issues 6 instructions (|x| is an operand modifier)
     n = 1 << 20
-    out["waypoint_speed_1M_states"] = {"states_per_s": n / t, "waypoints": 1185, "fp64_gflops": n * 1185 * 9 / t / 1e9,
-                                        "hbm_GBps": n * 76 / t / 1e9, "note": "fp64 L1 argmin over the centre line, not HBM bound"}
-    trk.onShutdown()
+    try:
+        dfma_tflops, dadd_tinst = nat2.probe_fp64(local)
+    except Exception:
+        dfma_tflops, dadd_tinst = None, None
+    spd = SpeedControl(dict(spd_ctl_break=True), device=local)
+    out["waypoint_speed_1M_states"] = {}
+    for tname in ("generated_track", "mountain_track"):
+        wp = load_track(tname)
+        xyz, cur, ms, st = synth.car_states(wp, n, seed=4)
+        trk = LocationTracker(wp, device=local)
+        d_xyz, d_cur = torch.from_numpy(xyz).to(dev), torch.from_numpy(cur).to(dev)
+        d_ms, d_st = torch.from_numpy(ms).to(dev), torch.from_numpy(st).to(dev)
+
+        def cars_step():
+            trk.locate_device(d_xyz)
+            spd.control_device(d_cur, d_st, d_ms)
+        t = timed(cars_step, reps=10)
+        t_loc = timed(lambda: trk.locate_device(d_xyz), reps=10)
+        nw = wp.shape[0]
+        ent = {"states_per_s": n / t, "waypoints": int(nw), "ms": t * 1e3, "locate_only_ms": t_loc * 1e3, "hbm_GBps": n * 76 / t / 1e9,
+               "hbm_frac": n * 76 / t / 1e9 / peak}
+        if dfma_tflops:
+            ach = n * nw * 9 / t_loc / 1e12
+            ent["roofline"] = {"bound": "fp64", "achieved": ach, "peak": dfma_tflops, "unit": "TFLOP/s", "frac": ach / dfma_tflops,
+                               "fp64_pipe_frac": n * nw * 6 / t_loc / 1e12 / dadd_tinst, "peak_source": "trs_probe_fp64 on this GPU: dense DFMA chains "
+                               f"(2 flops per instruction); DADD rate {dadd_tinst:.2f} T lane-instr/s", "kernel": "trs::k_locate",
+                               "note": "achieved = 9 algorithmic flops per (state, waypoint) / locate time; fp64_pipe_frac = the 6 fp64-pipe instructions "
+                                       "per (state, waypoint) against the measured DADD issue rate (an add counts one flop, an FMA two)"}
+        out["waypoint_speed_1M_states"][tname] = ent
+        trk.onShutdown()
     spd.onShutdown()
     if cpu_legs:                      # the reference's pure-Python loop + math.atan laws on the host cores (bounded sample)
         try:
@@ -274,9 +302,9 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
                                                     "cpu_sample": f"{res['units']} states ({1500} per worker process), LocationTracker loop + pilot tail"})
         except Exception as e:
             out["waypoint_speed_1M_states"]["cpu_skipped"] = repr(e)
+    d_cur = torch.from_numpy(cur).to(dev)
     # the step after the speed controller: drive-mode select + launch locks + driver assistance, 1M cars
     from triton_racer_sim_b200 import ControlMultiplexer
-    from triton_racer_sim_b200 import _native as nat2
     mux = ControlMultiplexer(dict(ai_launch_boost_throttle_enabled=True, ai_launch_lock_steering_enabled=True), device=local)
     rng = np.random.default_rng(6)
     d_mode = torch.from_numpy(rng.integers(0, 3, n).astype(np.int32)).to(dev)
@@ -393,6 +421,7 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
         ctx.close()
     except Exception as e:                                               # Pillow missing on the box: report, do not fail the bench
         out["tub_jpeg_ingest_32768x120x160"] = {"skipped": repr(e)}
+    out["clocks"] = sampler.stop()
     return out
 
 
@@ -427,6 +456,101 @@ def run_reference(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# helpers shared by the timed blocks
+# ---------------------------------------------------------------------------------------------------------------------------
+class Rig:
+    """What every timed block needs: the rank layout, the device, barriers and max-over-ranks timing."""
+
+    def __init__(self, torch, dist, sharding, rank, world, local, dev):
+        self.torch, self.dist, self.sharding = torch, dist, sharding
+        self.rank, self.world, self.local, self.dev = rank, world, local, dev
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, step, steps, warmup, clocks=True):
+        """W warm-up steps, then K steps between CUDA events on the launching stream, barrier + synchronize on both sides, max over
+        ranks.  Returns (ms per step, clock record of rank 0 or None)."""
+        torch = self.torch
+        for _ in range(max(3, warmup)):
+            step()
+        self.barrier()
+        sampler = ClockSampler(self.local) if (clocks and self.rank == 0) else None
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        self.barrier()
+        ms = self.sharding.max_over_ranks(ev0.elapsed_time(ev1), device=self.dev) / steps
+        return ms, (sampler.stop() if sampler else None)
+
+
+def roofline_block(bytes_per_frame, frames_per_gpu, ms, kernel, note, traffic=None, traffic_source=None):
+    peak, peak_src = read_peaks()
+    achieved = bytes_per_frame * frames_per_gpu / (ms * 1e-3) / 1e9                   # per-GPU GB/s of algorithmic traffic
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+         "peak_source": peak_src, "bytes_per_frame": bytes_per_frame, "kernel": kernel, "note": note}
+    if traffic_source:
+        r["traffic_source"] = traffic_source
+    return r
+
+
+def read_traffic(workload, frames):
+    """DRAM bytes per launch of the dominant kernel from a committed `ncu --set full` capture (profiles/r02_traffic.json): used only when
+    the capture was taken at this run's frame count, otherwise scaled per frame and labelled."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            tj = json.load(f)
+        ent = tj.get(workload)
+        if not ent:
+            return None, None
+        per = ent["dram_bytes_per_frame"]
+        src = f"ncu --set full capture at {ent['frames']} frames/launch ({ent['file']}): dram__bytes_read.sum + dram__bytes_write.sum"
+        if ent["frames"] != frames:
+            src += f", scaled per frame to this run's {frames}"
+        return per * frames, src
+    except Exception:
+        return None, None
+
+
+def pcie_probe(rig, host_in, host_out, chunk_frames, reps=3):
+    """Copy-only twin of the host pipeline: the same pinned buffers, the same chunking over three streams (one H2D + one D2H per chunk),
+    no kernel.  Every rank runs it at the same time, so contention for the host's memory and PCIe root complexes is in the number."""
+    torch = rig.torch
+    n = host_in.shape[0]
+    streams = [torch.cuda.Stream(device=rig.dev) for _ in range(3)]
+    st_in = [torch.empty((chunk_frames,) + tuple(host_in.shape[1:]), dtype=torch.uint8, device=rig.dev) for _ in range(3)]
+    st_out = [torch.empty_like(b) for b in st_in]
+
+    def once():
+        for ci, f0 in enumerate(range(0, n, chunk_frames)):
+            s = ci % 3
+            cn = min(chunk_frames, n - f0)
+            with torch.cuda.stream(streams[s]):
+                st_in[s][:cn].copy_(host_in[f0:f0 + cn], non_blocking=True)
+                host_out[f0:f0 + cn].copy_(st_out[s][:cn], non_blocking=True)
+        for s in streams:
+            s.synchronize()
+    once()
+    rig.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    rig.barrier()
+    dt = rig.sharding.max_over_ranks(time.perf_counter() - t0, device=rig.dev) / reps
+    nbytes = n * host_in[0].numel()
+    return {"frames_per_s_per_rank": n / dt, "GBps_each_way_per_rank": nbytes / dt / 1e9,
+            "GBps_aggregate_both_ways": 2 * nbytes * rig.world / dt / 1e9,
+            "note": "copy-only: same pinned buffers and 48 MB chunks on three streams as trs_preprocess_host, no kernel, all ranks at once"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -438,7 +562,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true")
+    ap.add_argument("--no-blocks", action="store_true", help="skip the 240x320 / 1M-frame pipeline / statistics blocks")
+    ap.add_argument("--quick", action="store_true", help="the headline step only (kernel iteration, ncu)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = args.no_e2e = args.no_others = args.no_blocks = True
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # stdout carries exactly ONE line, the JSON: everything any library prints meanwhile (NCCL's version banner, torchrun warnings)
     # is sent to stderr at the file-descriptor level; the descriptor is restored for the final print
@@ -450,10 +578,11 @@ def main():
         return run_reference(args)
 
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # NCCL's version / debug lines must not share stdout with the JSON line
+    import numpy as np
     import torch
     import torch.distributed as dist
 
-    from triton_racer_sim_b200 import ImgPreprocessing, sharding, synth
+    from triton_racer_sim_b200 import ControlMultiplexer, ImgPreprocessing, LocationTracker, SpeedControl, sharding, synth
     from triton_racer_sim_b200 import _native as nat
     from triton_racer_sim_b200.config import full_house_config
 
@@ -462,6 +591,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    rig = Rig(torch, dist, sharding, rank, world, local, dev)
     h, w, frames, want_u8, want_f32, bytes_per_frame = WORKLOADS[args.workload]
     if args.frames:
         frames = args.frames
@@ -481,52 +611,52 @@ def main():
     out_u8 = torch.empty_like(batch) if want_u8 else None
     out_f32 = torch.empty(batch.shape, dtype=torch.float32, device=dev) if want_f32 else None
 
-    cars = None
-    if args.workload == "full_pipeline_1M_over_8":
-        import numpy as np
+    def make_cars(ncar, seed):
+        """The per-car stages of BASELINE.json configs[4]: nearest waypoint on the shipped centre line (tests/golden/tracks.npz holds both
+        recorded tracks), speed control, control multiplexer: three more launches per step."""
+        wp = load_track("generated_track")
+        xyz, cur, ms_, st_ = synth.car_states(wp, ncar, seed=seed)
+        rng = np.random.default_rng(40 + seed)
+        c = {"trk": LocationTracker(wp, device=local), "spd": SpeedControl(dict(spd_ctl_break=True), device=local),
+             "mux": ControlMultiplexer(dict(ai_launch_boost_throttle_enabled=True, ai_launch_lock_steering_enabled=True), device=local),
+             "xyz": torch.from_numpy(xyz).to(dev), "cur": torch.from_numpy(cur).to(dev), "ms": torch.from_numpy(ms_).to(dev),
+             "st": torch.from_numpy(st_).to(dev), "mode": torch.from_numpy(rng.integers(0, 3, ncar).astype(np.int32)).to(dev),
+             "usr": torch.from_numpy(rng.uniform(-1, 1, (3, ncar))).to(dev), "clock": 0.0}
+        c["prm"] = nat.ctl_params_from_cfg(c["mux"].cfg, locks=True, assist=True)
+        return c
 
-        from triton_racer_sim_b200 import ControlMultiplexer, LocationTracker, SpeedControl
-        from triton_racer_sim_b200 import _native as nat3
-        ncar = end - start
-        wp = synth.synthetic_track(1185)
-        xyz, cur, ms, st = synth.car_states(wp, ncar, seed=4 + rank)
-        rng = np.random.default_rng(40 + rank)
-        cars = {
-            "trk": LocationTracker(wp, device=local), "spd": SpeedControl(dict(spd_ctl_break=True), device=local),
-            "mux": ControlMultiplexer(dict(ai_launch_boost_throttle_enabled=True, ai_launch_lock_steering_enabled=True), device=local),
-            "xyz": torch.from_numpy(xyz).to(dev), "cur": torch.from_numpy(cur).to(dev), "ms": torch.from_numpy(ms).to(dev),
-            "st": torch.from_numpy(st).to(dev), "mode": torch.from_numpy(rng.integers(0, 3, ncar).astype(np.int32)).to(dev),
-            "usr": torch.from_numpy(rng.uniform(-1, 1, (3, ncar))).to(dev), "clock": 0.0,
-        }
-        cars["prm"] = nat3.ctl_params_from_cfg(cars["mux"].cfg, locks=True, assist=True)
+    def cars_step(c):
+        c["trk"].locate_device(c["xyz"])
+        s_, t_, b_, _ = c["spd"].control_device(c["cur"], c["st"], c["ms"])
+        c["clock"] += 0.05
+        c["mux"].mux_device(c["mode"], c["usr"], torch.stack([s_, t_, b_]), c["clock"], speed=c["cur"], params=c["prm"])
+
+    def close_cars(c):
+        for k in ("trk", "spd", "mux"):
+            c[k].onShutdown()
+
+    cars = make_cars(end - start, 4 + rank) if args.workload == "full_pipeline_1M_over_8" else None
 
     def step():
         comp.process_device(batch, out_u8=out_u8, out_f32=out_f32, want_u8=want_u8, want_f32=want_f32)
         if cars is not None:
-            cars["trk"].locate_device(cars["xyz"])
-            s_, t_, b_, _ = cars["spd"].control_device(cars["cur"], cars["st"], cars["ms"])
-            cars["clock"] += 0.05
-            cars["mux"].mux_device(cars["mode"], cars["usr"], torch.stack([s_, t_, b_]), cars["clock"], speed=cars["cur"], params=cars["prm"])
+            cars_step(cars)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    # ---- headline: K steps of the workload ------------------------------------------------------------------------------------
     for _ in range(args.warmup):
         step()
-    barrier()
+    rig.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = nat.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    rig.barrier()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
-    barrier()
+    rig.barrier()
     elapsed_ms = sharding.max_over_ranks(ev0.elapsed_time(ev1), device=dev)
     launches = nat.kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -534,11 +664,27 @@ def main():
     total_frames = frames * world
     value = total_frames / (ms_per_step * 1e-3)
 
-    # per-step statistics: the system's only collective (128 B all-reduce), outside the timed region
+    # ---- the same step with the per-step statistics ON: counters in the kernel + the system's only collective (a 192-byte all-reduce over
+    # NCCL) every step, inside the timed region (north_star: "NCCL used only to gather per-step statistics") ------------------------------
+    stats_on = None
     comp_stats = ImgPreprocessing(cfg, device=local, collect_stats=True)
-    comp_stats.process_device(batch[: min(1024, batch.shape[0])], want_f32=False)
-    st = torch.tensor([comp_stats.stats().get(k, 0) for k in nat.STAT_NAMES], dtype=torch.int64, device=dev)
-    st = sharding.reduce_stats(st)
+    last_stats = [None]
+
+    def step_stats():
+        comp_stats.process_device(batch, out_u8=out_u8, out_f32=out_f32, want_u8=want_u8, want_f32=want_f32)
+        last_stats[0] = sharding.reduce_stats(comp_stats._stats_dev)
+    if not args.no_blocks:
+        ms_s, clk_s = rig.timed(step_stats, max(10, args.steps // 2), args.warmup)
+        stats_on = {"ms_per_step": ms_s, "delta_ms_vs_stats_off": ms_s - ms_per_step, "value": total_frames / (ms_s * 1e-3), "unit": "frames/s",
+                    "steps": max(10, args.steps // 2), "collective": f"all_reduce(SUM) of {nat.STAT_COUNT} x int64 per step over {world} rank(s)"
+                    + (" (NCCL)" if world > 1 else " (single rank: no collective issued)"), "clocks": clk_s,
+                    "note": "counters (frames, mask / edge / strong / candidate pixels, hysteresis rounds) accumulated by the store warps, "
+                            "zeroed and all-reduced every step inside the timed region"}
+    else:
+        comp_stats.process_device(batch[: min(1024, batch.shape[0])], want_f32=False)
+        last_stats[0] = sharding.reduce_stats(comp_stats._stats_dev)
+    st = last_stats[0].cpu()
+    comp_stats.onShutdown()
 
     # ---- end to end through the Component API with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
@@ -552,15 +698,135 @@ def main():
         e2e_steps = max(3, args.steps // 4)
         for _ in range(2):
             comp.process_host(in_np, out_u8=out_np, keep_f32_dev=keep_f32)
-        barrier()
+        rig.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             comp.process_host(in_np, out_u8=out_np, keep_f32_dev=keep_f32)     # synchronises before returning
-        barrier()
+        rig.barrier()
         e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev) / e2e_steps
-        e2e = {"value": n_e2e * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": n_e2e * h * w * 3,
-               "d2h_bytes_per_step": n_e2e * h * w * 3, "frames_per_step": n_e2e * world,
-               "note": "host u8 frames -> Component.step -> host u8 cam/processed_img; f32 tensor produced and left on the GPU"}
+        fb = h * w * 3
+        e2e = {"value": n_e2e * world / e2e_s, "unit": "frames/s", "frames_per_step": n_e2e * world,
+               "h2d_bytes_per_step": n_e2e * fb * world, "d2h_bytes_per_step": n_e2e * fb * world,
+               "frames_per_step_per_rank": n_e2e, "h2d_bytes_per_step_per_rank": n_e2e * fb, "d2h_bytes_per_step_per_rank": n_e2e * fb,
+               "value_per_rank": n_e2e / e2e_s,
+               "note": "host u8 frames -> Component.step -> host u8 cam/processed_img; f32 tensor produced and left on the GPU; "
+                       "frames / bytes per step are whole-job figures (all ranks), *_per_rank beside them"}
+        # the copy-only ceiling of this box at this rank count
+        chunk_frames = max(1, ((48 << 20) // fb + 3) & ~3)
+        probe = pcie_probe(rig, host_in, host_out, chunk_frames)
+        e2e["pcie_ceiling_per_rank"] = probe["frames_per_s_per_rank"]
+        e2e["pcie_probe"] = probe
+        e2e["frac_of_pcie_ceiling"] = e2e["value_per_rank"] / probe["frames_per_s_per_rank"]
+        # tub mode (keras_train.py:33-57 + manage.py:103-104: "N tub records"): the recorder's JPEG files on the host -> GPU decode -> chain ->
+        # host u8; 6-7 KB per frame go in instead of 57.6 KB
+        try:
+            import io
+
+            from PIL import Image
+
+            from triton_racer_sim_b200 import tub
+            files = []
+            for f in pool_np[:256]:
+                b = io.BytesIO()
+                Image.fromarray(f).save(b, format='JPEG')                    # datastorage.py:78
+                files.append(b.getvalue())
+            blob, offsets = tub.pack_files([files[(start + i) % 256] for i in range(n_e2e)])
+            pinned = torch.empty(len(blob), dtype=torch.uint8, pin_memory=True)
+            pinned.numpy()[:] = blob
+            dec = torch.empty((n_e2e, h, w, 3), dtype=torch.uint8, device=dev)
+            tub_u8 = torch.empty_like(dec)
+
+            def tub_step():
+                tub.decode_jpeg_batch((pinned.numpy(), offsets), hw=(h, w), ctx=comp.ctx, out=dec)       # H2D of the files + decode (synchronises)
+                comp.process_device(dec, out_u8=tub_u8, out_f32=keep_f32, want_f32=want_f32)
+                host_out.copy_(tub_u8, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            for _ in range(2):
+                tub_step()
+            rig.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                tub_step()
+            rig.barrier()
+            tub_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev) / e2e_steps
+            e2e["tub_mode"] = {"value": n_e2e * world / tub_s, "unit": "frames/s", "frames_per_step": n_e2e * world,
+                               "h2d_bytes_per_step": int(len(blob)) * world, "d2h_bytes_per_step": n_e2e * fb * world,
+                               "h2d_bytes_per_frame": len(blob) / n_e2e,
+                               "note": "host JPEG files (Pillow-encoded, as the recorder writes them) -> trs_jpeg_decode_host -> fused chain -> host u8 "
+                                       "cam/processed_img; not chunk-pipelined: decode, chain and the D2H copy run back to back"}
+            del dec, tub_u8, pinned
+        except Exception as e:                                               # Pillow missing on the box: report, do not fail the bench
+            e2e["tub_mode"] = {"skipped": repr(e)}
+        del host_in, host_out
+
+    # ---- more configurations of BASELINE.json, every rank on its own shard, each with its own roofline block and clock record -----------
+    blocks = None
+    if not args.no_blocks:
+        blocks = {}
+        reps = max(10, args.steps // 2)
+        comp.onShutdown()
+        del batch, out_u8, out_f32
+        torch.cuda.empty_cache()
+        # configs[2]: full-house colour + edge mask, 65,536 x 240x320 per GPU (u8 -> u8), then the full chain (u8 + f32) at the same size
+        h2, w2, n2 = 240, 320, 65536
+        pool240 = torch.from_numpy(synth.frame_pool(256, h2, w2)).to(dev)
+        s2, e2_ = sharding.shard_range(n2 * world, rank, world)
+        b240 = synth.expand_torch(pool240, e2_ - s2, start=s2)
+        o240 = torch.empty_like(b240)
+        fh = ImgPreprocessing(cfg, device=local)
+        ms2, clk2 = rig.timed(lambda: fh.process_device(b240, out_u8=o240, want_f32=False), reps, args.warmup)
+        tr, trs = read_traffic("full_house_mask_240x320", n2)
+        blocks["full_house_mask_240x320"] = {
+            "metric": METRICS["full_house_mask_240x320"], "value": n2 * world / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2, "steps": reps,
+            "frames_per_gpu": n2, "scaling": "weak", "config": f"{n2} frames/GPU/step of {h2}x{w2}x3 u8 -> u8 processed_img (15.1 GB in + 15.1 GB out per GPU)",
+            "roofline": roofline_block(230400 + 230400, n2, ms2, KERNELS["full_house_mask_240x320"], NOTES["full_house_mask_240x320"], tr, trs), "clocks": clk2}
+        f240 = torch.empty(b240.shape, dtype=torch.float32, device=dev)
+        ms3, clk3 = rig.timed(lambda: fh.process_device(b240, out_u8=o240, out_f32=f240, want_f32=True), reps, args.warmup)
+        tr, trs = read_traffic("full_chain_240x320", n2)
+        blocks["full_chain_240x320"] = {
+            "metric": "preprocessed frames/sec (240x320), full observation chain", "value": n2 * world / (ms3 * 1e-3), "unit": "frames/s", "ms_per_step": ms3,
+            "steps": reps, "frames_per_gpu": n2, "scaling": "weak",
+            "config": f"{n2} frames/GPU/step of {h2}x{w2}x3 u8 -> u8 processed_img + f32 /255 tensor (15.1 GB in, 15.1 + 60.4 GB out per GPU)",
+            "roofline": roofline_block(230400 * 6, n2, ms3, KERNELS["full_house_mask_240x320"],
+                                       "18 algorithmic bytes per pixel like the 120x160 headline; banded kernel (frames do not fit shared memory whole)", tr, trs),
+            "clocks": clk3}
+        fh.onShutdown()
+        del b240, o240, f240, pool240
+        torch.cuda.empty_cache()
+        # configs[4]: the full observation pipeline over 1,048,576 frames + 1,048,576 car states per step, sharded by env index over the ranks
+        # (strong scaling: the total is fixed, a rank owns 1M / N of each).  A rank walks its shard in chunks of <= 131,072 frames (the
+        # per-GPU load of the 8-GPU configuration) that reuse one set of output buffers: 60 GB of inputs stay resident at N = 1.
+        total, chunk = 1 << 20, 131072
+        s5, e5 = sharding.shard_range(total, rank, world)
+        n5 = e5 - s5
+        in5 = synth.expand_torch(pool, n5, start=s5)
+        cn = min(chunk, n5)
+        o5 = torch.empty((cn, h, w, 3), dtype=torch.uint8, device=dev)
+        f5 = torch.empty((cn, h, w, 3), dtype=torch.float32, device=dev)
+        comp5 = ImgPreprocessing(cfg, device=local)
+        cars5 = make_cars(n5, 4 + rank)
+
+        def step5():
+            for c0 in range(0, n5, chunk):
+                c1 = min(n5, c0 + chunk)
+                comp5.process_device(in5[c0:c1], out_u8=o5[: c1 - c0], out_f32=f5[: c1 - c0], want_f32=True)
+            cars_step(cars5)
+        l0 = nat.kernel_launches()
+        ms5, clk5 = rig.timed(step5, reps, args.warmup)
+        per_step_launches = (nat.kernel_launches() - l0) // (reps + max(3, args.warmup))
+        blocks["full_pipeline_1M"] = {
+            "metric": METRICS["full_pipeline_1M_over_8"], "value": total / (ms5 * 1e-3), "unit": "frames/s", "ms_per_step": ms5, "steps": reps,
+            "frames_per_step": total, "car_states_per_step": total, "frames_per_gpu": n5, "scaling": "strong",
+            "launches_per_step_per_rank": int(per_step_launches),
+            "config": f"1,048,576 frames of {h}x{w}x3 + 1,048,576 car states per step over {world} rank(s): {n5} of each per GPU, frames in chunks of "
+                      f"<= {chunk}; fused chain (u8 + f32 out), nearest waypoint on the shipped centre line (1,185 points), speed control, multiplexer",
+            "roofline": roofline_block(bytes_per_frame, n5, ms5, KERNELS["full_pipeline_1M_over_8"], NOTES["full_pipeline_1M_over_8"]), "clocks": clk5}
+        comp5.onShutdown()
+        close_cars(cars5)
+        del in5, o5, f5
+        torch.cuda.empty_cache()
+    elif cars is not None:
+        close_cars(cars)
 
     # ---- the other BASELINE.json configurations, short runs on rank 0's GPU (reported, not the headline) -----------
     others = None
@@ -568,16 +834,7 @@ def main():
         others = other_workloads(torch, dev, local, pool, h, w, cpu_legs=not args.no_cpu_baseline)
 
     if rank == 0:
-        peak, peak_src = read_peaks()
-        achieved = bytes_per_frame * frames / (ms_per_step * 1e-3) / 1e9            # per-GPU GB/s of algorithmic traffic
-        traffic = None
-        try:                                                                        # DRAM bytes per frame from the committed ncu capture
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fjs:
-                tj = json.load(fjs)
-            if tj.get("workload") == args.workload:
-                traffic = tj["dram_bytes_per_frame"] * frames
-        except Exception:
-            pass
+        traffic, traffic_src = read_traffic(args.workload, frames)
         line = {
             "metric": METRICS[args.workload], "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -587,9 +844,7 @@ def main():
                                    "colour filter (2 HSV ranges) + 3-channel Canny, reference defaults",
                        "frames_per_gpu": frames, "h": h, "w": w, "sharding": f"env index, contiguous, {world} rank(s), no data-path collective",
                        "l2": f"inputs {frames * h * w * 3 / 1e9:.2f} GB + outputs per step, far larger than the 126 MB L2 (no flush needed)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "bytes_per_frame": bytes_per_frame, "kernel": KERNELS[args.workload],
-                         "note": NOTES[args.workload]},
+            "roofline": roofline_block(bytes_per_frame, frames, ms_per_step, KERNELS[args.workload], NOTES[args.workload], traffic, traffic_src),
             "clocks": clocks, "gpu_launches": int(launches),
             "stats_sample": dict(zip(nat.STAT_NAMES[:10], st.tolist()[:10])),
         }
@@ -597,6 +852,10 @@ def main():
             line["cpu_baseline"] = cpu_base
         if e2e is not None:
             line["e2e"] = e2e
+        if stats_on is not None:
+            line["stats_on"] = stats_on
+        if blocks is not None:
+            line["blocks"] = blocks
         if others is not None:
             line["other_workloads"] = others
         emit(line)

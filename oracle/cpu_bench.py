@@ -65,7 +65,9 @@ def _work(args):
             cv2_chain.full_chain(imgs[i & 63].copy(), cfg)          # the reference copies the frame too (img_preprocessing.py:20,29)
         return time.perf_counter() - t0
     if kind == "cars":
-        wp = synth.synthetic_track(1185).tolist()
+        # the reference's recorded centre line (car_templates/track_data/generated_track.json, 1,185 points) as committed with the goldens
+        with np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "tracks.npz")) as z:
+            wp = z["wp/generated_track"].tolist()
         xyz, cur, ms, st = synth.car_states(np.asarray(wp), frames, seed=worker)
         t0 = time.perf_counter()
         for k in range(frames):

@@ -96,6 +96,23 @@ def test_fresh_frames_against_oracle(h, w, n):
         assert np.array_equal(f32, oracle.normalise(want))
 
 
+@pytest.mark.parametrize("h,w,n", [(240, 320, 16), (120, 160, 32), (480, 160, 4), (200, 96, 6)])
+def test_every_golden_configuration_on_fresh_frames(golden_images, h, w, n):
+    """All seven reference-generated configurations (colour only, edge only, no filter, dynamic brightness + contrast, three ranges with
+    repeated destination channels, ...) on fresh frames at the second resolution and at sizes that need row bands: the banded kernel applies
+    the brightness / contrast table per band (the dynamic one from rows 40..118 of the frame in global memory) and re-reads the frame for
+    channels that keep the adjusted pixel; the no-filter configurations take the streaming kernel."""
+    from tests.helpers import image_cases
+    q = max(1, n // 4)
+    frames = synth.expand_numpy(synth.frame_pool(q, h, w, seed=77 + h + w), n, start=13 * q)      # four brightness shifts of q frames each
+    for cname, over in image_cases(golden_images).items():
+        cfg = cfg_for(over)
+        want = oracle.process_batch(frames, cfg)
+        got, f32 = run_device(cfg, frames)
+        assert np.array_equal(got, want), f"{cname} {h}x{w}: {describe(got, want)}"
+        assert np.array_equal(f32, oracle.normalise(want)), f"{cname} {h}x{w} f32"
+
+
 def test_adversarial_hysteresis_chains():
     """Serpentine weak chains hanging off a single strong pixel: the worst case for iterative flood fill."""
     h, w = 120, 160
@@ -308,10 +325,43 @@ def test_full_size_properties():
     lo, hi = 5 * n // 8, 6 * n // 8
     part, _ = comp.process_device(frames[lo:hi], want_f32=False)
     assert torch.equal(part, u8[lo:hi])
-    # (4) a sample of frames against the CPU oracle
-    pick = np.random.default_rng(0).integers(0, n, size=48)
-    want = oracle.process_batch(frames[pick].cpu().numpy(), cfg)
-    assert np.array_equal(u8[pick].cpu().numpy(), want)
+    # (4) EVERY distinct frame against the CPU oracle: frame i = pool[i % 256] + offset((i // 256) % 32), so the first 8,192 frames are all the
+    # distinct ones and each later block of 8,192 must repeat them bit for bit (which covers all 65,536)
+    distinct = 256 * 32
+    want = oracle.process_batch(frames[:distinct].cpu().numpy(), cfg)
+    assert np.array_equal(u8[:distinct].cpu().numpy(), want)
+    for k in range(1, n // distinct):
+        assert torch.equal(u8[k * distinct:(k + 1) * distinct], u8[:distinct]), f"block {k} differs from block 0"
+        assert torch.equal(f32[k * distinct:(k + 1) * distinct], f32[:distinct])
+    comp.onShutdown()
+
+
+@pytest.mark.parametrize("want_f32", [False, True])
+def test_full_size_properties_240x320(want_f32):
+    """The second resolution (BASELINE.json configs[2]: full-house mask at 240x320; and the full chain with the f32 tensor) through the
+    same properties on 8,192 frames: outputs are masks, the float tensor is exactly u8 / 255, counters agree with the written planes, a
+    shard of the batch reproduces the whole, and every distinct frame (64 x 32 = 2,048) equals the oracle."""
+    cfg = full_house_config()
+    pool = torch.from_numpy(synth.frame_pool(64, 240, 320)).to(DEV)
+    n = 8192
+    frames = synth.expand_torch(pool, n)
+    comp = ImgPreprocessing(cfg, device=0, collect_stats=True)
+    u8, f32 = comp.process_device(frames, want_f32=want_f32)
+    st = comp.stats()
+    assert st["frames"] == n
+    assert bool(((u8 == 0) | (u8 == 255)).all())
+    if want_f32:
+        assert bool((f32 == u8.to(torch.float32) / 255).all())
+    assert st["mask0"] == int((u8[..., 0] == 255).sum()) and st["mask1"] == int((u8[..., 1] == 255).sum())
+    assert st["edge"] == int((u8[..., 2] == 255).sum()) and st["edge"] <= st["cand"] and st["strong"] <= st["edge"]
+    lo, hi = 3 * n // 8, 4 * n // 8
+    part, _ = comp.process_device(frames[lo:hi], want_f32=False)
+    assert torch.equal(part, u8[lo:hi])
+    distinct = 64 * 32
+    want = oracle.process_batch(frames[:distinct].cpu().numpy(), cfg)
+    assert np.array_equal(u8[:distinct].cpu().numpy(), want)
+    for k in range(1, n // distinct):
+        assert torch.equal(u8[k * distinct:(k + 1) * distinct], u8[:distinct]), f"block {k} differs from block 0"
     comp.onShutdown()
 
 

@@ -144,6 +144,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t a)
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+// four pixels' bytes through a 256-entry table in shared memory
+__device__ __forceinline__ uint32_t lut4s(uint32_t a_lut, uint32_t v)
+{
+    return lds8(a_lut + (v & 0xff)) | (lds8(a_lut + ((v >> 8) & 0xff)) << 8) | (lds8(a_lut + ((v >> 16) & 0xff)) << 16) | (lds8(a_lut + (v >> 24)) << 24);
+}
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -459,7 +464,10 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
 // (a multiple of 3, before any segment loads such a row)
 // BANDED: a_pix / a_mag are VIRTUAL bases (the address image row 0 / magnitude row -1 would have), the segment rows of M lie in the
 // band's magnitude rows, and colour-mask rows are stored only inside [mask_lo, mask_hi).
-template <int NR, bool EDGE, int F0, int F1, bool BANDED = false>
+// SEG > 0 (a multiple of 3): seg_rows is this compile-time constant AND the segments tile the frame exactly (every lane owns SEG rows,
+// r1 == r0 + SEG): the first and the last trip are peeled, so the steady-state row step carries no step-number tests, no row-range
+// predicates and a constant row advance (the two replicated-border cases fall on peeled steps).
+template <int NR, bool EDGE, int F0, int F1, bool BANDED = false, int SEG = 0>
 __device__ __forceinline__ void p1_strip_walk(const FastParams& P, const Dims& Dm, uint32_t a_pix, uint32_t a_mag, uint32_t a_mask, const SmemMap& S,
                                               const StripMap& M, int seg_rows, uint32_t tail_bar = 0, uint32_t tail_parity = 0, int tail_k = 0,
                                               int mask_lo = 0, int mask_hi = 1 << 30)
@@ -488,7 +496,12 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, const Dims& D
     uint32_t mp = mask_base + y_row * prb;                                // mask plane byte of row y_row
     uint32_t gp = mag_base + (r0 + 1) * MS2;                              // magnitude row of the next output row (row y lives at row index y + 1)
 
-    auto row_step = [&](int k, uint32_t (&Dn)[6], uint32_t (&Hn)[6], const uint32_t (&D0)[6], const uint32_t (&D1)[6], const uint32_t (&H0)[6]) {
+    // do_mask / do_sobel: std::integral_constant<int, 1> on, <0> off, <-1> decided from the step number k at run time;
+    // adv: bytes to the next pixel row (< 0: the run-time replicated-border rule)
+    auto row_step = [&](auto mask_tag, auto sobel_tag, int adv, int k, uint32_t (&Dn)[6], uint32_t (&Hn)[6], const uint32_t (&D0)[6],
+                        const uint32_t (&D1)[6], const uint32_t (&H0)[6]) {
+        constexpr int MK = decltype(mask_tag)::value, SB = decltype(sobel_tag)::value;
+        constexpr bool EXACT = SEG > 0;
         // load image row r0 - 1 + k into slot n; emit output row y = r0 + k - 2
         const uint32_t w0 = lds32(rp), w1 = lds32(rp + 4), w2 = lds32(rp + 8);
         uint32_t A[3], B[3];
@@ -510,8 +523,8 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, const Dims& D
             }
         }
         // ---- colour masks for the loaded row ---------------------------------------------------------
-        if (NR > 0 && k >= 1 && k <= seg_rows) {                 // warp-uniform: the halo rows above and below belong to other segments
-            const bool row_in = M.store_lane && y_row < r1 && (!BANDED || (y_row >= mask_lo && y_row < mask_hi));      // the loaded row belongs to this segment (and band)
+        if (NR > 0 && (MK < 0 ? (k >= 1 && k <= seg_rows) : MK == 1)) {      // warp-uniform: the halo rows above and below belong to other segments
+            const bool row_in = M.store_lane && (EXACT || y_row < r1) && (!BANDED || (y_row >= mask_lo && y_row < mask_hi));      // the loaded row belongs to this segment (and band)
             uint32_t okm[NR > 0 ? NR : 1][2];                    // per range: half masks for pixels (0,2) and (1,3)
             hsv_masks_of<NR, F0, F1>(P, A, B, S.sdiv, S.hue, okm);
             if (NR == 2) {
@@ -533,7 +546,7 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, const Dims& D
             }
         }
         // ---- Sobel combine for output row y = r0 + k - 2 ----------------------------------------------
-        if (EDGE && k >= 2) {
+        if (EDGE && (SB < 0 ? k >= 2 : SB == 1)) {
             const int y = r0 + k - 2;
             uint32_t mg[2], dxs[2], dys[2];
 #pragma unroll
@@ -575,21 +588,49 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, const Dims& D
             uint2 v;      // pixel order: (A.lo, B.lo) = pixels (0, 1), (A.hi, B.hi) = pixels (2, 3)
             v.x = prmt(mg[0], mg[1], 0x5410) | (prmt(code[0], code[1], 0x5410) << 11);
             v.y = prmt(mg[0], mg[1], 0x7632) | (prmt(code[0], code[1], 0x7632) << 11);
-            sts64_if(M.ok && y < r1, gp, v);
+            if (EXACT) sts64(gp, v); else sts64_if(M.ok && y < r1, gp, v);
             gp += MS2;
         }
         // advance to the next image row: the pixel address stays put while the row index is outside [1, h - 1] (replicated borders)
-        ++y_row;
-        if ((unsigned)(y_row - 1) < (unsigned)(h - 1)) rp += row_bytes;
+        if (adv >= 0) {
+            rp += adv;
+        } else {
+            ++y_row;
+            if ((unsigned)(y_row - 1) < (unsigned)(h - 1)) rp += row_bytes;
+        }
         mp += prb;
     };
+    using On = std::integral_constant<int, 1>;
+    using Off = std::integral_constant<int, 0>;
+    using Rt = std::integral_constant<int, -1>;
     // rolling window by register renaming: slots (k % 3)
+    if (SEG > 0) {
+        static_assert(SEG % 3 == 0, "the peeled walk keeps the slot rotation of whole trips");
+        // step k loads image row r0 - 1 + k (clamped) and, from k = 2 on, emits magnitude row r0 + k - 2; masks belong to steps 1 .. SEG.
+        // The row address stands still once at the top of the frame (after step 0 of the first segment) and once at the bottom
+        // (after step SEG of the last one).
+        if (tail_bar && tail_k < 3) mbar_wait(tail_bar, tail_parity);
+        row_step(Off{}, Off{}, r0 == 0 ? 0 : row_bytes, 0, D[0], Hs[0], D[1], D[2], Hs[1]);
+        row_step(On{}, Off{}, row_bytes, 1, D[1], Hs[1], D[2], D[0], Hs[2]);
+        row_step(On{}, On{}, row_bytes, 2, D[2], Hs[2], D[0], D[1], Hs[0]);
+#pragma unroll 1
+        for (int k = 3; k < SEG; k += 3) {
+            if (tail_bar && k == tail_k) mbar_wait(tail_bar, tail_parity);
+            row_step(On{}, On{}, row_bytes, k, D[0], Hs[0], D[1], D[2], Hs[1]);
+            row_step(On{}, On{}, row_bytes, k + 1, D[1], Hs[1], D[2], D[0], Hs[2]);
+            row_step(On{}, On{}, row_bytes, k + 2, D[2], Hs[2], D[0], D[1], Hs[0]);
+        }
+        if (tail_bar && tail_k >= SEG) mbar_wait(tail_bar, tail_parity);
+        row_step(On{}, On{}, r1 == h ? 0 : row_bytes, SEG, D[0], Hs[0], D[1], D[2], Hs[1]);
+        row_step(Off{}, On{}, 0, SEG + 1, D[1], Hs[1], D[2], D[0], Hs[2]);
+        return;
+    }
 #pragma unroll 1
     for (int k = 0; k < nsteps; k += 3) {
         if (tail_bar && k == tail_k) mbar_wait(tail_bar, tail_parity);
-        row_step(k, D[0], Hs[0], D[1], D[2], Hs[1]);                 // new = slot0, y-1 = slot1, y = slot2
-        if (k + 1 < nsteps) row_step(k + 1, D[1], Hs[1], D[2], D[0], Hs[2]);
-        if (k + 2 < nsteps) row_step(k + 2, D[2], Hs[2], D[0], D[1], Hs[0]);
+        row_step(Rt{}, Rt{}, -1, k, D[0], Hs[0], D[1], D[2], Hs[1]);                 // new = slot0, y-1 = slot1, y = slot2
+        if (k + 1 < nsteps) row_step(Rt{}, Rt{}, -1, k + 1, D[1], Hs[1], D[2], D[0], Hs[2]);
+        if (k + 2 < nsteps) row_step(Rt{}, Rt{}, -1, k + 2, D[2], Hs[2], D[0], D[1], Hs[0]);
     }
 }
 
@@ -627,9 +668,13 @@ __device__ __forceinline__ void stats_flush(const PreKParams& p, const SmemMap& 
 // =========================================================================================================
 // P2: non-maximum suppression, strip walk over the magnitude plane, two pixels per compare
 // =========================================================================================================
+// SEG > 0 (a multiple of 3): seg_rows is this constant and every lane owns exactly SEG rows (see p1_strip_walk): no row-range predicates,
+// no clamp on the row fetched ahead (the fetch past the last row lands in the planes behind the magnitude buffer and is never used).
+template <int SEG = 0>
 __device__ __forceinline__ void p2_nms(const FastParams& P, const Dims& Dm, uint32_t a_mag, uint32_t a_cand, uint32_t a_edge, const SmemMap& S,
                                        const StripMap& M, int seg_rows)
 {
+    constexpr bool EXACT = SEG > 0;
     uint32_t n_strong = 0;
     const int h = Dm.h, prb = Dm.w >> 3, MS2 = Dm.mag_stride * 2;
     const uint32_t mbase = a_mag + 2 * (4 + 4 * M.strip);
@@ -637,12 +682,12 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, const Dims& Dm, uint
     // one row as packed pairs of magnitudes: P01=(m0,m1) P23=(m2,m3) L01=(m-1,m0) M12=(m1,m2) R23=(m3,m4); raw keeps the codes
     struct Row { uint32_t p01, p23, l01, m12, r23, raw01, raw23; };
     struct Raw { uint2 c; uint32_t ml, mr; };                       // a row as loaded: the loads run one step ahead of their use
-    auto fetch_row = [&](int y) {
-        const uint32_t rp = mbase + (y + 1) * MS2;
+    auto fetch_at = [&](uint32_t rp) {
         Raw q;
         q.c = lds64(rp); q.ml = lds16(rp - 2); q.mr = lds16(rp + 8);
         return q;
     };
+    auto fetch_row = [&](int y) { return fetch_at(mbase + (y + 1) * MS2); };
     auto unpack_row = [&](const Raw& q) {
         Row r;
         r.raw01 = q.c.x; r.raw23 = q.c.y;
@@ -656,12 +701,13 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, const Dims& Dm, uint
     const int ya = M.r0;
     Raw ahead;
     uint32_t cp = cbase + ya * prb, ep = ebase + ya * prb;          // plane bytes of the row being decided
+    uint32_t ap = mbase + (ya + 3) * MS2;                           // EXACT: running address of the row fetched ahead (row ya + 2 + k at step k)
     // rolling three-row window by register renaming (three steps per trip): step k decides row ya + k from rows (up, ce) and loads dn
     auto nms_step = [&](int k, const Row& up, const Row& ce, Row& dn) {
         const int y = ya + k;
-        const bool row_in = y < M.r1;
+        const bool row_in = EXACT || y < M.r1;
         dn = unpack_row(ahead);
-        ahead = fetch_row(min(y + 2, h));
+        if (EXACT) { ahead = fetch_at(ap); ap += MS2; } else { ahead = fetch_row(min(y + 2, h)); }
         uint32_t cm[2], sm[2];
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
@@ -691,11 +737,21 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, const Dims& Dm, uint
     };
     Row ra = load_row(ya - 1), rb = load_row(ya), rc;
     ahead = fetch_row(min(ya + 1, h));
+    if (EXACT) {
+        static_assert(SEG % 3 == 0, "whole trips only");
 #pragma unroll 1
-    for (int k = 0; k < seg_rows; k += 3) {
-        nms_step(k, ra, rb, rc);
-        if (k + 1 < seg_rows) nms_step(k + 1, rb, rc, ra);
-        if (k + 2 < seg_rows) nms_step(k + 2, rc, ra, rb);
+        for (int k = 0; k < SEG; k += 3) {
+            nms_step(k, ra, rb, rc);
+            nms_step(k + 1, rb, rc, ra);
+            nms_step(k + 2, rc, ra, rb);
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < seg_rows; k += 3) {
+            nms_step(k, ra, rb, rc);
+            if (k + 1 < seg_rows) nms_step(k + 1, rb, rc, ra);
+            if (k + 2 < seg_rows) nms_step(k + 2, rc, ra, rb);
+        }
     }
     if (P.k.stats) stat_add(S, 6, n_strong);
 }
@@ -776,8 +832,11 @@ __device__ __forceinline__ int p3_hysteresis(uint32_t a_cand, uint32_t a_edge, i
 // P4: merge + normalise, written once.  pa[c] = shared address of the bit plane (row 0) feeding output channel c,
 // or 0 if that channel keeps the adjusted pixel.
 // =========================================================================================================
+// gpix != nullptr: the adjusted pixels are not resident any more (banded kernel): the frame is read again from global memory (an L2 hit: it was
+// streamed in a moment ago) and goes through the brightness / contrast table at a_lut if use_lut.
 __device__ __forceinline__ void p4_output(const FastParams& P, const Dims& Dm, const uint32_t (&pa)[3], uint32_t a_pix, uint8_t* __restrict__ gout,
-                                          float* __restrict__ gf32, int t0, int tstride)
+                                          float* __restrict__ gf32, int t0, int tstride, const uint8_t* __restrict__ gpix = nullptr, uint32_t a_lut = 0,
+                                          bool use_lut = false)
 {
     const int npb = Dm.h * (Dm.w >> 3);                // groups of 8 pixels = plane bytes
     if (!P.k.need_pixels) {
@@ -843,8 +902,15 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const Dims& Dm, c
         // some channel keeps the adjusted pixel: bytes from the resident frame, floats by correctly rounded x/255
         const float rcp = 1.0f / 255.0f;
         for (int g = t0; g < 2 * npb; g += tstride) {          // groups of 4 pixels
-            const uint32_t src = a_pix + 12 * g;
-            uint32_t wv[3] = {lds32(src), lds32(src + 4), lds32(src + 8)};
+            uint32_t wv[3];
+            if (gpix) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(gpix) + 3 * (size_t)g;
+                wv[0] = __ldg(src); wv[1] = __ldg(src + 1); wv[2] = __ldg(src + 2);
+                if (use_lut) { wv[0] = lut4s(a_lut, wv[0]); wv[1] = lut4s(a_lut, wv[1]); wv[2] = lut4s(a_lut, wv[2]); }
+            } else {
+                const uint32_t src = a_pix + 12 * g;
+                wv[0] = lds32(src); wv[1] = lds32(src + 4); wv[2] = lds32(src + 8);
+            }
             uint8_t b[12];
 #pragma unroll
             for (int k = 0; k < 12; ++k) b[k] = (uint8_t)(wv[k >> 2] >> ((k & 3) * 8));
@@ -945,11 +1011,6 @@ __device__ __forceinline__ void zero_plane_pads(const SmemMap& S, int plane_word
         sts32(S.edge - 4 * ww + 4 * i, 0); sts32(S.edge + 4 * (plane_words + i), 0);       // (the pads of the candidate plane are never read)
         sts32(S.edge2 - 4 * ww + 4 * i, 0); sts32(S.edge2 + 4 * (plane_words + i), 0);
     }
-}
-
-__device__ __forceinline__ uint32_t lut4s(uint32_t a_lut, uint32_t v)
-{
-    return lds8(a_lut + (v & 0xff)) | (lds8(a_lut + ((v >> 8) & 0xff)) << 8) | (lds8(a_lut + ((v >> 16) & 0xff)) << 16) | (lds8(a_lut + (v >> 24)) << 24);
 }
 
 // brightness / contrast on the resident frame (only when the table is not the identity); `sync` is the barrier of the
@@ -1089,13 +1150,45 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_fast(const _
     if (p.stats) stats_flush(p, S, tid);          // (the frame loop ends with a CTA-wide barrier)
 }
 
+// Dynamic brightness for a frame that is NOT resident in shared memory: exact channel sums over rows 40..118 (img_preprocessing.py:88) straight
+// from global memory (row bytes and frame bytes multiples of 4), then delta = (baseline - sum of channel means) / 3 as float32.  Every thread
+// of the CTA calls it; contains CTA-wide barriers; s_red = three u64 accumulators (+ the statistics slots behind them).
+__device__ __forceinline__ float dynamic_delta_global(const PreKParams& p, const uint8_t* __restrict__ gfr, unsigned long long* s_red, int tid, int nthr, int lane)
+{
+    const int h = p.h, w = p.w, row_words = (w * 3) >> 2;
+    const int y0 = min(40, h), y1 = min(119, h);
+    const uint32_t* roi = reinterpret_cast<const uint32_t*>(gfr + (size_t)y0 * w * 3);
+    const int nw = (y1 - y0) * row_words;
+    uint32_t c0 = 0, c1 = 0, c2 = 0;                             // word i of the region starts with channel i % 3 (4 i % 3 == i % 3)
+    for (int i = tid; i < nw; i += nthr) {
+        const uint32_t v = __ldg(roi + i);
+        const int ph = i % 3;
+        const uint32_t a = __dp4a(v, 0x01000001u, 0u), b = __dp4a(v, 0x00000100u, 0u), c = __dp4a(v, 0x00010000u, 0u);      // bytes (0, 3) | 1 | 2
+        if (ph == 0) { c0 += a; c1 += b; c2 += c; } else if (ph == 1) { c1 += a; c2 += b; c0 += c; } else { c2 += a; c0 += b; c1 += c; }
+    }
+    for (int o = 16; o; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    if (tid < 3) s_red[tid] = 0;
+    __syncthreads();
+    if (lane == 0) { atomicAdd(&s_red[0], (unsigned long long)c0); atomicAdd(&s_red[1], (unsigned long long)c1); atomicAdd(&s_red[2], (unsigned long long)c2); }
+    __syncthreads();
+    const float fdelta = (float)brightness_delta(s_red[0], s_red[1], s_red[2], (double)((y1 - y0) * w), p.baseline);
+    if (tid == 0 && p.stats) s_red[4 + 9] += s_red[0] + s_red[1] + s_red[2];
+    __syncthreads();                                             // (the accumulators are zeroed again by the next frame's call)
+    return fdelta;
+}
+
 // =========================================================================================================
 // Banded kernel: frames too large to be resident (240x320: 230 KB) go through the same phases band by band.  Per band of
 // band_h rows: one bulk copy of the band's pixel rows plus a two-row halo, the strip walk over the band's magnitude rows
 // (one extra row above and below, recomputed instead of kept), NMS for the band's rows into the FULL-FRAME candidate /
 // edge planes (colour masks likewise); the next band's copy is issued as soon as the strip walk is done.  After the last
-// band: hysteresis and output over the whole frame from the bit planes.  Every output channel must be a bit plane and the
-// brightness / contrast table the identity (the pixels are gone by the time the output is written).
+// band: hysteresis and output over the whole frame from the bit planes.  A brightness / contrast table is applied to each band's rows as
+// they land (the dynamic one is built first from the frame's rows 40..118 in global memory); an output channel that keeps the adjusted pixel
+// reads the frame again in the output phase (from L2: 296 frames in flight are 68 MB).
 // =========================================================================================================
 template <int NR, bool EDGE, int F0, int F1>
 __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const __grid_constant__ FastParams P)
@@ -1131,7 +1224,16 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const
     uint32_t phase = 0;
     uint32_t pa[3];
     plane_sources(p, S.edge, S.mask, G.plane_bytes, pa);
+    unsigned long long* s_red = reinterpret_cast<unsigned long long*>(smem + G.off_red);
+    const bool use_lut = p.dynamic || !p.lut_identity;
     for (int f = blockIdx.x; f < p.n; f += gridDim.x) {
+        if (p.dynamic) {
+            // the brightness statistic covers rows 40..118 (img_preprocessing.py:88), which no single band holds: exact channel sums from the
+            // frame in global memory while the first band's copy is in flight (the bands read those rows again, from L2), then this frame's table
+            const float fdelta = dynamic_delta_global(p, p.in + (size_t)f * frame_bytes, s_red, tid, nthr, lane);
+            for (int i = tid; i < 256; i += nthr) sts8(S.lut + i, adjust_entry(i, true, fdelta, p.foff, p.fratio));
+            __syncthreads();
+        }
         for (int b = 0; b < NB; ++b) {
             const int by0 = b * BH, by1 = min(by0 + BH, h);
             const int m0 = EDGE ? max(by0 - 1, 0) : by0, m1 = EDGE ? min(by1 + 1, h) : by1;      // magnitude rows of this band
@@ -1140,6 +1242,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const
             const uint32_t a_mag = S.mag[0] - (uint32_t)(m0 * MS * 2);                            // virtual address of magnitude row -1
             mbar_wait(S.bar, phase);
             phase ^= 1u;
+            if (use_lut) {                                          // brightness / contrast on the band's pixel rows as they land (halo rows twice)
+                const int nwords = (min(by1 + 2, h) - p0) * (int)(row_bytes >> 2);
+                for (int i = tid; i < nwords; i += nthr) sts32(S.pix[0] + 4 * i, lut4s(S.lut, lds32(S.pix[0] + 4 * i)));
+                __syncthreads();
+            }
             if (EDGE && m1 == h) {                                  // the zero row below the frame: earlier bands left data there
                 for (int i = tid; i < MS; i += nthr) sts16(a_mag + 2 * ((h + 1) * MS + i), 0);
             }
@@ -1160,7 +1267,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const
             const int sw = p3_hysteresis(S.cand, S.edge, h, ww, tid, nthr, [](int c) { return __syncthreads_or(c); });
             if (tid == 0 && p.stats) stat_add_one(S, 8, (unsigned long long)sw);
         }
-        p4_output(P, Dm, pa, 0u, p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr, tid, nthr);
+        p4_output(P, Dm, pa, 0u, p.out_u8 ? p.out_u8 + (size_t)f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + (size_t)f * frame_bytes : nullptr, tid, nthr,
+                  p.in + (size_t)f * frame_bytes, S.lut, use_lut);
         if (p.stats) count_planes<NR, EDGE>(p, S, S.cand, S.edge, S.mask, G.plane_bytes, plane_words, tid, nthr);
         __syncthreads();
     }
@@ -1194,7 +1302,8 @@ template <int H, int W>
 inline bool sw_static_geometry_ok(const FastGeom& g, int h, int w)
 {
     return h == H && w == W && g.nsg == W / 32 && g.front_warps == SW_COMPUTE_THREADS / 32 && g.seg_rows_front == sw_seg_rows<H, W>() && g.mag_stride == W + 4 &&
-           g.plane_bytes == ((((H + 2) * (W / 32) * 4) + 15) & ~15) && g.tail_bytes == g.plane_bytes && g.n_bands == 1;
+           g.plane_bytes == ((((H + 2) * (W / 32) * 4) + 15) & ~15) && g.tail_bytes == g.plane_bytes && g.n_bands == 1 &&
+           sw_seg_rows<H, W>() % 3 == 0 && 4 * ((SW_COMPUTE_THREADS / 32) / (W / 32)) * sw_seg_rows<H, W>() == H;      // the segments tile the rows exactly
 }
 
 template <int NR, int F0, int F1, int H = 0, int W = 0>
@@ -1262,13 +1371,14 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             TRS_TICK(tk2);
             if (j >= 2) bar_sync(3, SW_THREADS);                         // the store warps are done with frame j-2: this plane set is free
             TRS_TICK(tk3);
-            p1_strip_walk<NR, true, F0, F1>(P, Dm, S.pix[0], S.mag[0], a_mask, S, M, seg_rows, (tail_bytes && !use_lut) ? bar_tail : 0u, phase, tail_k);
+            p1_strip_walk<NR, true, F0, F1, false, (STATIC ? sw_seg_rows<(STATIC ? H : 32), (STATIC ? W : 32)>() : 0)>(
+                P, Dm, S.pix[0], S.mag[0], a_mask, S, M, seg_rows, (tail_bytes && !use_lut) ? bar_tail : 0u, phase, tail_k);
             phase ^= 1u;
             bar_sync(1, NC);
             TRS_TICK(tk4);
             if (tid == 0 && j + 1 < nfr)                                 // pixels are dead: prefetch the next frame (all but its tail)
                 issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, 0, main_bytes, bar_main);
-            p2_nms(P, Dm, S.mag[0], S.cand, a_edge, S, M, seg_rows);
+            p2_nms<(STATIC ? sw_seg_rows<(STATIC ? H : 32), (STATIC ? W : 32)>() : 0)>(P, Dm, S.mag[0], S.cand, a_edge, S, M, seg_rows);
             bar_sync(1, NC);
             TRS_TICK(tk5);
             // hysteresis, first level only: every warp relaxes its own band, no CTA-wide round trip; the store warps finish the job
@@ -1317,6 +1427,63 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
         if (p.stats) {                                                   // the store warps are the last to touch the counters
             bar_sync(4, SW_THREADS - NC);
             stats_flush(p, S, tid - NC);
+        }
+    }
+}
+
+// =========================================================================================================
+// No colour filter, no edge filter (the reference's default configuration, core/config.py:22,25): __process is the brightness /
+// contrast table alone (img_preprocessing.py:37-43), fused with the /255 tensor.  A pure stream: one CTA per frame at a time, the table
+// of the frame in shared memory (static, or dynamic from the frame's rows 40..118), one 32-bit word in, one word + one 128-bit store out.
+// Frame bytes and row bytes must be multiples of 4.
+// =========================================================================================================
+enum { ADJ_THREADS = 256 };
+__global__ void __launch_bounds__(ADJ_THREADS) k_adjust_stream(const __grid_constant__ PreKParams p)
+{
+    __shared__ __align__(16) uint8_t s_lut[256];
+    __shared__ unsigned long long s_red[4 + 16];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    const size_t frame_bytes = (size_t)p.h * p.w * 3;
+    const int nwords = (int)(frame_bytes >> 2);
+    const bool use_lut = p.dynamic || !p.lut_identity;
+    const uint32_t a_lut = smem_u32(s_lut);
+    const float rcp = 1.0f / 255.0f;
+    for (int i = tid; i < 256; i += nthr) s_lut[i] = p.lut[i];
+    for (int i = tid; i < 4 + 16; i += nthr) s_red[i] = 0;
+    __syncthreads();
+    for (int f = blockIdx.x; f < p.n; f += gridDim.x) {
+        const uint8_t* gfr = p.in + (size_t)f * frame_bytes;
+        if (p.dynamic) {
+            const float fdelta = dynamic_delta_global(p, gfr, s_red, tid, nthr, lane);
+            for (int i = tid; i < 256; i += nthr) s_lut[i] = adjust_entry(i, true, fdelta, p.foff, p.fratio);
+            __syncthreads();
+        }
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(gfr);
+        uint32_t* du8 = p.out_u8 ? reinterpret_cast<uint32_t*>(p.out_u8 + (size_t)f * frame_bytes) : nullptr;
+        float4* df32 = p.out_f32 ? reinterpret_cast<float4*>(p.out_f32 + (size_t)f * frame_bytes) : nullptr;
+        for (int i = tid; i < nwords; i += nthr) {
+            uint32_t v = __ldg(src + i);
+            if (use_lut) v = lut4s(a_lut, v);
+            if (du8) du8[i] = v;
+            if (df32) {
+                float q[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float x = (float)((v >> (8 * k)) & 0xffu);
+                    const float q0 = __fmul_rn(x, rcp);
+                    q[k] = __fmaf_rn(__fmaf_rn(-q0, 255.0f, x), rcp, q0);      // x / 255 correctly rounded (all 256 inputs checked)
+                }
+                df32[i] = make_float4(q[0], q[1], q[2], q[3]);
+            }
+        }
+        if (p.dynamic) __syncthreads();                           // the table is rewritten for the next frame
+    }
+    if (p.stats) {
+        __syncthreads();
+        if (tid == 0) {
+            const int mine = (int)blockIdx.x < p.n ? (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            if (mine) atomicAdd(&p.stats[0], (unsigned long long)mine);
+            if (s_red[4 + 9]) atomicAdd(&p.stats[9], s_red[4 + 9]);
         }
     }
 }

@@ -263,8 +263,18 @@ int launch_fast_t(const trs::FastParams& fp, int grid, cudaStream_t st)
 int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w, cudaStream_t st)
 {
     if (ctx->sw.force_generic) return 0;
+    if (!k.edge_enabled && k.n_ranges == 0) {
+        // no filter at all (the reference's defaults): the brightness / contrast table + /255 as a pure stream
+        if (!k.word_io || ctx->sw.no_banded) return 0;
+        int grid = ctx->sm_count * 8;
+        if (grid > n) grid = n;
+        trs::k_adjust_stream<<<grid, trs::ADJ_THREADS, 0, st>>>(k);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { cuda_fail(e, "k_adjust_stream launch"); return -100 - (int)e; }
+        return 1;
+    }
     if (!k.word_io || (w % 32) != 0 || (((size_t)h * w * 3) % 16) != 0) return 0;
-    if (!k.edge_enabled && k.n_ranges == 0) return 0;
     const int nsg = w / 32;
     trs::FastParams fp;
     memset(&fp, 0, sizeof fp);
@@ -279,7 +289,7 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
         trs::FastGeom g = trs::fast_geometry(h, w, k.n_ranges, 0, nsg * quads, nsg * quads);
         if (g.threads > trs::FAST_MAX_THREADS) return 0;
         if (g.total > budget2) {
-            if (k.need_pixels || k.dynamic || !k.lut_identity || ctx->sw.no_banded) return 0;
+            if (ctx->sw.no_banded) return 0;
             bool found = false;
             for (int nb = 2; nb <= h / 4 && !found; ++nb) {
                 const int bh = (h + nb - 1) / nb;
