@@ -34,20 +34,23 @@ WORKLOADS = {
     # name: (h, w, frames per GPU, want_u8, want_f32, algorithmic bytes per frame)
     "full_chain_120x160": (120, 160, 65536, True, True, 57600 + 57600 + 230400),
     "full_house_mask_240x320": (240, 320, 65536, True, False, 230400 + 230400),
+    "full_chain_240x320": (240, 320, 65536, True, True, 230400 * 6),
     # BASELINE.json configs[4]: 1M frames + 1M car states per step over 8 GPUs = 131,072 of each per GPU; a step also runs the
     # nearest-waypoint lookup, the speed controller and the control multiplexer for the shard's cars (three more launches)
     "full_pipeline_1M_over_8": (120, 160, 131072, True, True, 57600 + 57600 + 230400),
 }
 METRIC = "preprocessed frames/sec (120x160), full observation chain"
 METRICS = {"full_chain_120x160": METRIC, "full_house_mask_240x320": "preprocessed frames/sec (240x320), full-house colour + edge mask",
+           "full_chain_240x320": "preprocessed frames/sec (240x320), full observation chain",
            "full_pipeline_1M_over_8": "preprocessed frames/sec (120x160), full observation pipeline incl. per-car lookup and control"}
 KERNELS = {"full_chain_120x160": "trs::k_preprocess_sw<2,24,23,120,160>", "full_house_mask_240x320": "trs::k_preprocess_banded<2,true,24,23>",
-           "full_pipeline_1M_over_8": "trs::k_preprocess_sw<2,24,23,120,160>"}
+           "full_chain_240x320": "trs::k_preprocess_banded<2,true,24,23>", "full_pipeline_1M_over_8": "trs::k_preprocess_sw<2,24,23,120,160>"}
 NOTES = {
     "full_chain_120x160": "bound by the ALU pipe / issue slots and phase barriers, not by HBM: ten compute warps per CTA run strip walk, NMS and "
                           "hysteresis while two store warps stream the previous frame out (the SM -> L2 write port tops out at 29 B/clk); "
                           "see DESIGN.md 4.1 and profiles/",
     "full_house_mask_240x320": "6 algorithmic bytes per pixel: instruction bound by construction (SURVEY.md 8d); banded kernel, DESIGN.md 4.3",
+    "full_chain_240x320": "18 algorithmic bytes per pixel like the 120x160 headline; banded kernel (frames do not fit shared memory whole)",
     "full_pipeline_1M_over_8": "frames as full_chain_120x160; the per-car kernels (FP64 argmin over 1,185 waypoints, speed control, multiplexer) "
                                "add three launches per step and are counted in the step time but not in the algorithmic bytes",
 }
@@ -799,11 +802,10 @@ def main():
         ms3, clk3 = rig.timed(lambda: fh.process_device(b240, out_u8=o240, out_f32=f240, want_f32=True), reps, args.warmup)
         tr, trs = read_traffic("full_chain_240x320", n2)
         blocks["full_chain_240x320"] = {
-            "metric": "preprocessed frames/sec (240x320), full observation chain", "value": n2 * world / (ms3 * 1e-3), "unit": "frames/s", "ms_per_step": ms3,
+            "metric": METRICS["full_chain_240x320"], "value": n2 * world / (ms3 * 1e-3), "unit": "frames/s", "ms_per_step": ms3,
             "steps": reps, "frames_per_gpu": n2, "scaling": "weak",
             "config": f"{n2} frames/GPU/step of {h2}x{w2}x3 u8 -> u8 processed_img + f32 /255 tensor (15.1 GB in, 15.1 + 60.4 GB out per GPU)",
-            "roofline": roofline_block(230400 * 6, n2, ms3, KERNELS["full_house_mask_240x320"],
-                                       "18 algorithmic bytes per pixel like the 120x160 headline; banded kernel (frames do not fit shared memory whole)", tr, trs),
+            "roofline": roofline_block(230400 * 6, n2, ms3, KERNELS["full_chain_240x320"], NOTES["full_chain_240x320"], tr, trs),
             "clocks": clk3}
         fh.onShutdown()
         del b240, o240, f240, pool240
