@@ -285,15 +285,18 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
         t = timed(cars_step, reps=10)
         t_loc = timed(lambda: trk.locate_device(d_xyz), reps=10)
         nw = wp.shape[0]
-        ent = {"states_per_s": n / t, "waypoints": int(nw), "ms": t * 1e3, "locate_only_ms": t_loc * 1e3, "hbm_GBps": n * 76 / t / 1e9,
-               "hbm_frac": n * 76 / t / 1e9 / peak}
+        nd = int(np.unique(wp, axis=0).shape[0])          # the kernel evaluates each distinct point once (a repeat cannot win the strict `<`)
+        ent = {"states_per_s": n / t, "waypoints": int(nw), "distinct_waypoints": nd, "ms": t * 1e3, "locate_only_ms": t_loc * 1e3,
+               "hbm_GBps": n * 76 / t / 1e9, "hbm_frac": n * 76 / t / 1e9 / peak,
+               "reference_loop_equivalent_tflops": n * nw * 9 / t_loc / 1e12}
         if dfma_tflops:
-            ach = n * nw * 9 / t_loc / 1e12
+            ach = n * nd * 9 / t_loc / 1e12
             ent["roofline"] = {"bound": "fp64", "achieved": ach, "peak": dfma_tflops, "unit": "TFLOP/s", "frac": ach / dfma_tflops,
-                               "fp64_pipe_frac": n * nw * 6 / t_loc / 1e12 / dadd_tinst, "peak_source": "trs_probe_fp64 on this GPU: dense DFMA chains "
+                               "fp64_pipe_frac": n * nd * 6 / t_loc / 1e12 / dadd_tinst, "peak_source": "trs_probe_fp64 on this GPU: dense DFMA chains "
                                f"(2 flops per instruction); DADD rate {dadd_tinst:.2f} T lane-instr/s", "kernel": "trs::k_locate",
-                               "note": "achieved = 9 algorithmic flops per (state, waypoint) / locate time; fp64_pipe_frac = the 6 fp64-pipe instructions "
-                                       "per (state, waypoint) against the measured DADD issue rate (an add counts one flop, an FMA two)"}
+                               "note": "achieved = 9 flops per (state, DISTINCT waypoint) actually evaluated / locate time; fp64_pipe_frac = the 6 "
+                                       "fp64-pipe instructions per evaluation against the measured DADD issue rate (an add counts one flop, an FMA two); "
+                                       "reference_loop_equivalent_tflops counts the reference's loop over all recorded points"}
         out["waypoint_speed_1M_states"][tname] = ent
         trk.onShutdown()
     spd.onShutdown()
@@ -733,46 +736,49 @@ def main():
                 b = io.BytesIO()
                 Image.fromarray(f).save(b, format='JPEG')                    # datastorage.py:78
                 files.append(b.getvalue())
-            # four chunks: a chunk's D2H copy runs on a second stream under the next chunk's upload + decode + chain
-            nchunk = 4
-            bounds = [(c * n_e2e // nchunk, (c + 1) * n_e2e // nchunk) for c in range(nchunk)]
-            packs, total_blob = [], 0
-            for a, b_ in bounds:
-                blob, offsets = tub.pack_files([files[(start + i) % 256] for i in range(a, b_)])
-                pinned = torch.empty(len(blob), dtype=torch.uint8, pin_memory=True)
-                pinned.numpy()[:] = blob
-                packs.append((pinned, offsets))
-                total_blob += len(blob)
+            # a stream of batches (the trainer's generator walks the tub batch by batch, keras_train.py:33-57): batch k's D2H copy runs on a
+            # second stream under batch k + 1's upload + decode + chain (two sets of device / host buffers); every copy is inside the timed region
+            blob, offsets = tub.pack_files([files[(start + i) % 256] for i in range(n_e2e)])
+            pinned = torch.empty(len(blob), dtype=torch.uint8, pin_memory=True)
+            pinned.numpy()[:] = blob
+            total_blob = len(blob)
             dec = torch.empty((n_e2e, h, w, 3), dtype=torch.uint8, device=dev)
-            tub_u8 = torch.empty_like(dec)
+            tub_u8 = [torch.empty_like(dec) for _ in range(2)]
+            tub_host = [host_out, torch.empty((n_e2e, h, w, 3), dtype=torch.uint8, pin_memory=True)]
             copy_stream = torch.cuda.Stream(device=dev)
+            copied = [None, None]
 
-            def tub_step():
+            def tub_steps(k_steps):
                 main = torch.cuda.current_stream()
-                for (a, b_), (pinned, offsets) in zip(bounds, packs):
-                    tub.decode_jpeg_batch((pinned.numpy(), offsets), hw=(h, w), ctx=comp.ctx, out=dec[a:b_])   # H2D of the files + decode (synchronises)
-                    comp.process_device(dec[a:b_], out_u8=tub_u8[a:b_], out_f32=keep_f32[a:b_] if want_f32 else None, want_f32=want_f32)
+                for k in range(k_steps):
+                    s_ = k & 1
+                    if copied[s_] is not None:
+                        copied[s_].synchronize()                             # buffer set s_ is free again (its D2H copy of batch k - 2 is done)
+                    tub.decode_jpeg_batch((pinned.numpy(), offsets), hw=(h, w), ctx=comp.ctx, out=dec)       # H2D of the files + decode (synchronises)
+                    comp.process_device(dec, out_u8=tub_u8[s_], out_f32=keep_f32, want_f32=want_f32)
                     done = torch.cuda.Event()
                     done.record(main)
                     copy_stream.wait_event(done)
                     with torch.cuda.stream(copy_stream):
-                        host_out[a:b_].copy_(tub_u8[a:b_], non_blocking=True)
+                        tub_host[s_].copy_(tub_u8[s_], non_blocking=True)
+                        copied[s_] = torch.cuda.Event()
+                        copied[s_].record(copy_stream)
                 copy_stream.synchronize()
                 main.synchronize()
-            for _ in range(2):
-                tub_step()
+            tub_steps(2)
             rig.barrier()
+            tsteps = max(6, e2e_steps)
             t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                tub_step()
+            tub_steps(tsteps)
             rig.barrier()
-            tub_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev) / e2e_steps
-            e2e["tub_mode"] = {"value": n_e2e * world / tub_s, "unit": "frames/s", "frames_per_step": n_e2e * world,
+            tub_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev) / tsteps
+            e2e["tub_mode"] = {"value": n_e2e * world / tub_s, "unit": "frames/s", "frames_per_step": n_e2e * world, "steps": tsteps,
                                "h2d_bytes_per_step": int(total_blob) * world, "d2h_bytes_per_step": n_e2e * fb * world,
                                "h2d_bytes_per_frame": total_blob / n_e2e, "value_per_rank": n_e2e / tub_s,
                                "note": "host JPEG files (Pillow-encoded, as the recorder writes them) -> trs_jpeg_decode_host -> fused chain -> host u8 "
-                                       "cam/processed_img, in four chunks: a chunk's D2H copy overlaps the next chunk's upload, decode and chain"}
-            del dec, tub_u8, packs
+                                       "cam/processed_img for a stream of batches: batch k's D2H copy overlaps batch k + 1's upload, decode and chain "
+                                       "(pipeline fill and drain inside the timed region)"}
+            del dec, tub_u8, tub_host, pinned
         except Exception as e:                                               # Pillow missing on the box: report, do not fail the bench
             e2e["tub_mode"] = {"skipped": repr(e)}
         del host_in, host_out

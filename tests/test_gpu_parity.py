@@ -482,3 +482,97 @@ def test_driver_assistance_and_pwm_map():
         a, b, c = g[f"pwm/{name}/map"]
         assert np.array_equal(three_segment_map(torch.from_numpy(v.copy()).to(DEV), a, b, c).cpu().numpy(), g[f"pwm/{name}"]), name
     assert three_segment_map(-0.5, 430, 350, 300) == 350 + (350 - 430) * -0.5
+
+
+# ---- robustness of the boundary (round-1 advisor findings) ------------------------------------------------------------------------
+def test_device_methods_validate_their_tensors():
+    """A CPU tensor, a wrong dtype or a wrong shape must raise in Python: handed to the library they would become an illegal-address
+    fault that poisons the CUDA context."""
+    from triton_racer_sim_b200 import ControlMultiplexer
+    frames = torch.from_numpy(synth.frame_pool(2, 120, 160)).to(DEV)
+    comp = ImgPreprocessing(full_house_config(), device=0)
+    with pytest.raises(ValueError):
+        comp.process_device(frames.cpu())
+    with pytest.raises(ValueError):
+        comp.process_device(frames, out_u8=torch.empty(frames.shape, dtype=torch.uint8))                 # output on the CPU
+    with pytest.raises(ValueError):
+        comp.process_device(frames, out_f32=torch.empty((1, 120, 160, 3), dtype=torch.float32, device=DEV), want_f32=True)
+    with pytest.raises(ValueError):
+        comp.process_host(frames.cpu().numpy(), keep_f32_dev=torch.empty(frames.shape, dtype=torch.float32))
+    comp.onShutdown()
+    norm = FrameNormalise(device=0)
+    with pytest.raises(ValueError):
+        norm.normalise_device(frames.cpu())
+    norm.onShutdown()
+    trk = LocationTracker(synth.synthetic_track(50), device=0)
+    with pytest.raises(ValueError):
+        trk.locate_device(torch.zeros((4, 3), dtype=torch.float64))
+    with pytest.raises(ValueError):
+        trk.locate_device(torch.zeros((4, 3), dtype=torch.float32, device=DEV))
+    trk.onShutdown()
+    spd = SpeedControl({}, device=0)
+    with pytest.raises(ValueError):
+        spd.control_device(torch.zeros(4, dtype=torch.float64), torch.zeros(4), torch.zeros(4))
+    with pytest.raises(ValueError):
+        spd.control_device(torch.zeros(4, dtype=torch.float64, device=DEV), torch.zeros(3, device=DEV), torch.zeros(4, device=DEV))
+    spd.onShutdown()
+    mux = ControlMultiplexer({}, device=0)
+    with pytest.raises(ValueError):
+        mux.mux_device(torch.zeros(4, dtype=torch.int32, device=DEV), torch.zeros((3, 4), dtype=torch.float64), torch.zeros((3, 4), dtype=torch.float64, device=DEV), 0.0)
+    with pytest.raises(ValueError):
+        mux.mux_device(torch.zeros(4, dtype=torch.int32, device=DEV), torch.zeros((3, 5), dtype=torch.float64, device=DEV),
+                       torch.zeros((3, 4), dtype=torch.float64, device=DEV), 0.0)
+    mux.onShutdown()
+    # the context survived all of that
+    comp = ImgPreprocessing(full_house_config(), device=0)
+    u8, _ = comp.process_device(frames)
+    assert np.array_equal(u8.cpu().numpy(), oracle.process_batch(frames.cpu().numpy(), full_house_config()))
+    comp.onShutdown()
+
+
+def test_host_pipeline_waits_for_work_on_the_callers_stream():
+    """trs_preprocess_host writes keep_f32_dev from internal streams: a consumer of the previous step's tensor that is still queued on the
+    caller's stream (here: a long spin, then a clone) must see the OLD contents."""
+    cfg = full_house_config()
+    a = synth.frame_pool(64, 120, 160, seed=5)
+    b = synth.frame_pool(64, 120, 160, seed=6)
+    comp = ImgPreprocessing(cfg, device=0)
+    keep = torch.zeros((64, 120, 160, 3), dtype=torch.float32, device=DEV)
+    ua, _ = comp.process_host(a, keep_f32_dev=keep)
+    want_a = oracle.normalise(oracle.process_batch(a, cfg))
+    assert np.array_equal(keep.cpu().numpy(), want_a)
+    torch.cuda._sleep(400_000_000)                       # ~0.2 s of spinning on the current stream ...
+    snap = keep.clone()                                  # ... then the consumer of step A's tensor
+    ub, _ = comp.process_host(b, keep_f32_dev=keep)      # step B must not overwrite `keep` before the clone has run
+    torch.cuda.synchronize()
+    assert np.array_equal(snap.cpu().numpy(), want_a), "the host pipeline overwrote keep_f32_dev while the caller's stream was still reading it"
+    assert np.array_equal(keep.cpu().numpy(), oracle.normalise(oracle.process_batch(b, cfg)))
+    comp.onShutdown()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_calls_leave_the_callers_current_device_alone(golden_tracks):
+    """A component bound to cuda:1 while torch's current device is cuda:0: every entry point must run on its own device and put the
+    caller's device back (PyTorch derives its current device from cudaGetDevice)."""
+    cfg = full_house_config()
+    frames = synth.frame_pool(8, 120, 160, seed=3)
+    torch.cuda.set_device(0)
+    comp = ImgPreprocessing(cfg, device=1, normalised_key='cam/normalised_img')
+    assert torch.cuda.current_device() == 0
+    u8, f32 = comp.process_device(torch.from_numpy(frames).to("cuda:1"))
+    assert torch.cuda.current_device() == 0
+    probe = torch.empty(4, device="cuda")                # a device-less allocation after the call lands on the caller's device
+    assert probe.device.index == 0
+    torch.cuda.synchronize(1)
+    want = oracle.process_batch(frames, cfg)
+    assert np.array_equal(u8.cpu().numpy(), want) and np.array_equal(f32.cpu().numpy(), oracle.normalise(want))
+    h8, _ = comp.process_host(frames)
+    assert torch.cuda.current_device() == 0 and np.array_equal(h8, want)
+    comp.onShutdown()
+    wp, xyz = golden_tracks["wp/generated_track"], golden_tracks["xyz/generated_track"]
+    trk = LocationTracker(wp, 0, 10, device=1)
+    idx, _ = trk.locate_device(torch.from_numpy(xyz).to("cuda:1"))
+    assert torch.cuda.current_device() == 0
+    assert np.array_equal(idx.cpu().numpy(), golden_tracks["idx/generated_track"])
+    trk.onShutdown()
+    assert torch.cuda.current_device() == 0

@@ -215,28 +215,31 @@ __global__ void __launch_bounds__(RESIZE_THREADS) k_crop_resize_rows(const __gri
 // (track_data_process.py:89-107).  The centre line sits in shared memory as (x,y,z,pad) f64 quads; every lane
 // of a warp reads the same waypoint (broadcast), each thread carries CARS cars so one shared-memory read
 // feeds CARS distance evaluations.  Distances are summed left to right exactly as the reference does.
+// Recorded centre lines repeat points (generated_track: 917 distinct of 1,185; mountain_track: 1,260 of 2,664): a repeat can never win
+// the strict `<` against its first occurrence, so the host uploads only the first occurrences, in order, as (x, y, z, original index)
+// quads, and the kernels return the original index: fewer evaluations, the reference's argmin bit for bit.  n_wp = points the reference
+// loops over (the divisor of the segment map), n_u = distinct points evaluated here.
 // ------------------------------------------------------------------------------------------------------
 enum { LOC_THREADS = 256, LOC_CARS = 2, LOC_TILE = 1024 };
 
-__global__ void __launch_bounds__(LOC_THREADS) k_locate(const double* __restrict__ wp, int n_wp, double min_map, double max_map,
+__global__ void __launch_bounds__(LOC_THREADS) k_locate(const double4* __restrict__ wp, int n_u, int n_wp, double min_map, double max_map,
                                                        const double* __restrict__ xyz, int n, int32_t* __restrict__ idx_out,
                                                        double* __restrict__ seg_out)
 {
     __shared__ double4 s_wp[LOC_TILE];
     const int base = (blockIdx.x * LOC_THREADS + threadIdx.x) * LOC_CARS;
     double px[LOC_CARS], py[LOC_CARS], pz[LOC_CARS], best[LOC_CARS];
-    int sel[LOC_CARS];
+    double sel[LOC_CARS];                                        // original index of the best point so far, as carried in the quad
 #pragma unroll
     for (int c = 0; c < LOC_CARS; ++c) {
         const int k = min(base + c, n - 1);
         px[c] = xyz[3 * (size_t)k]; py[c] = xyz[3 * (size_t)k + 1]; pz[c] = xyz[3 * (size_t)k + 2];
-        best[c] = 100.0; sel[c] = 0;
+        best[c] = 100.0; sel[c] = 0.0;
     }
-    for (int t0 = 0; t0 < n_wp; t0 += LOC_TILE) {
-        const int tn = min(LOC_TILE, n_wp - t0);
+    for (int t0 = 0; t0 < n_u; t0 += LOC_TILE) {
+        const int tn = min(LOC_TILE, n_u - t0);
         __syncthreads();
-        for (int i = threadIdx.x; i < tn; i += LOC_THREADS)
-            s_wp[i] = make_double4(wp[3 * (size_t)(t0 + i)], wp[3 * (size_t)(t0 + i) + 1], wp[3 * (size_t)(t0 + i) + 2], 0.0);
+        for (int i = threadIdx.x; i < tn; i += LOC_THREADS) s_wp[i] = wp[t0 + i];
         __syncthreads();
 #pragma unroll 4
         for (int i = 0; i < tn; ++i) {
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(LOC_THREADS) k_locate(const double* __restrict
 #pragma unroll
             for (int c = 0; c < LOC_CARS; ++c) {
                 const double d = __dadd_rn(__dadd_rn(fabs(__dsub_rn(px[c], q.x)), fabs(__dsub_rn(py[c], q.y))), fabs(__dsub_rn(pz[c], q.z)));
-                if (d < best[c]) { best[c] = d; sel[c] = t0 + i; }
+                if (d < best[c]) { best[c] = d; sel[c] = q.w; }
             }
         }
     }
@@ -252,9 +255,9 @@ __global__ void __launch_bounds__(LOC_THREADS) k_locate(const double* __restrict
     for (int c = 0; c < LOC_CARS; ++c) {
         const int k = base + c;
         if (k < n) {
-            if (idx_out) idx_out[k] = sel[c];
+            if (idx_out) idx_out[k] = (int)sel[c];
             if (seg_out) {
-                const double q = __ddiv_rn((double)sel[c], (double)n_wp);
+                const double q = __ddiv_rn(sel[c], (double)n_wp);
                 seg_out[k] = __dadd_rn(__dmul_rn(q, __dsub_rn(max_map, min_map)), min_map);
             }
         }
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(PROBE64_THREADS) k_probe_fp64(double* __restri
 // A thread per car would leave the GPU empty at these sizes.
 enum { LOCW_THREADS = 256 };
 
-__global__ void __launch_bounds__(LOCW_THREADS) k_locate_warp(const double* __restrict__ wp, int n_wp, double min_map, double max_map,
+__global__ void __launch_bounds__(LOCW_THREADS) k_locate_warp(const double4* __restrict__ wp, int n_u, int n_wp, double min_map, double max_map,
                                                               const double* __restrict__ xyz, int n, int32_t* __restrict__ idx_out,
                                                               double* __restrict__ seg_out)
 {
@@ -297,10 +300,10 @@ __global__ void __launch_bounds__(LOCW_THREADS) k_locate_warp(const double* __re
         const double px = xyz[3 * (size_t)k], py = xyz[3 * (size_t)k + 1], pz = xyz[3 * (size_t)k + 2];
         double best = 100.0;                                     // track_data_process.py:93: the running minimum starts at 100
         int sel = 0x7fffffff;                                    // "nothing closer than 100 yet"
-        for (int i = lane; i < n_wp; i += 32) {
-            const double d = __dadd_rn(__dadd_rn(fabs(__dsub_rn(px, __ldg(wp + 3 * (size_t)i))), fabs(__dsub_rn(py, __ldg(wp + 3 * (size_t)i + 1)))),
-                                       fabs(__dsub_rn(pz, __ldg(wp + 3 * (size_t)i + 2))));
-            if (d < best) { best = d; sel = i; }
+        for (int i = lane; i < n_u; i += 32) {
+            const double2 qa = __ldg(reinterpret_cast<const double2*>(wp + i)), qb = __ldg(reinterpret_cast<const double2*>(wp + i) + 1);
+            const double d = __dadd_rn(__dadd_rn(fabs(__dsub_rn(px, qa.x)), fabs(__dsub_rn(py, qa.y))), fabs(__dsub_rn(pz, qb.x)));
+            if (d < best) { best = d; sel = (int)qb.y; }           // original indices ascend with i: a lane keeps the first index of its own minimum
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <new>
@@ -82,8 +83,8 @@ struct trs_ctx {
     trs_preproc_params user{};
     trs::PreKParams kp{};              // derived, geometry fields filled per call
     // track
-    double* wp_dev = nullptr;
-    int n_wp = 0;
+    double* wp_dev = nullptr;          // distinct waypoints in order of first occurrence: (x, y, z, original index) quads
+    int n_wp = 0, n_wp_distinct = 0;
     double min_map = 0, max_map = 10;
     // host pipeline
     cudaStream_t hs[HOST_STREAMS] = {nullptr, nullptr, nullptr};
@@ -564,11 +565,33 @@ int trs_set_track(trs_ctx* ctx, const double* wp_xyz_host, int n_wp, double min_
     TRS_ENTER(ctx);
     if (!wp_xyz_host || n_wp <= 0) return fail(TRS_E_ARG, "empty centre line");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    // A repeated point can never beat its first occurrence under the reference's strict `<` (track_data_process.py:95): only first
+    // occurrences are uploaded, each with its original index (compared by value, so -0.0 == 0.0 and a NaN is never a repeat)
+    std::vector<double> quads;
+    quads.reserve(4 * (size_t)n_wp);
+    {
+        struct Key { double x, y, z; };
+        auto norm = [](double v) { return v == 0.0 ? 0.0 : v; };
+        std::vector<std::pair<Key, int>> seen;                        // sorted by (x, y, z) among comparable values
+        seen.reserve((size_t)n_wp);
+        auto less = [](const Key& a, const Key& b) { return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z); };
+        for (int i = 0; i < n_wp; ++i) {
+            const Key k{norm(wp_xyz_host[3 * i]), norm(wp_xyz_host[3 * i + 1]), norm(wp_xyz_host[3 * i + 2])};
+            bool repeat = false;
+            if (k.x == k.x && k.y == k.y && k.z == k.z) {              // (points with a NaN are always kept)
+                auto it = std::lower_bound(seen.begin(), seen.end(), k, [&](const std::pair<Key, int>& a, const Key& b) { return less(a.first, b); });
+                repeat = it != seen.end() && it->first.x == k.x && it->first.y == k.y && it->first.z == k.z;
+                if (!repeat) seen.insert(it, std::make_pair(k, i));
+            }
+            if (!repeat) { quads.push_back(wp_xyz_host[3 * i]); quads.push_back(wp_xyz_host[3 * i + 1]); quads.push_back(wp_xyz_host[3 * i + 2]); quads.push_back((double)i); }
+        }
+    }
     cudaFree(ctx->wp_dev);
     ctx->wp_dev = nullptr;
-    CU(cudaMalloc(&ctx->wp_dev, sizeof(double) * 3 * (size_t)n_wp));
-    CU(cudaMemcpy(ctx->wp_dev, wp_xyz_host, sizeof(double) * 3 * (size_t)n_wp, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->wp_dev, sizeof(double) * quads.size()));
+    CU(cudaMemcpy(ctx->wp_dev, quads.data(), sizeof(double) * quads.size(), cudaMemcpyHostToDevice));
     ctx->n_wp = n_wp;
+    ctx->n_wp_distinct = (int)(quads.size() / 4);
     ctx->min_map = min_map;
     ctx->max_map = max_map;
     return 0;
@@ -588,15 +611,16 @@ int trs_locate(trs_ctx* ctx, const double* xyz_dev, int n, int32_t* idx_dev, dou
         int grid = (n + warps_per_block - 1) / warps_per_block;
         const int cap = ctx->sm_count * 8;
         if (grid > cap) grid = cap;
-        trs::k_locate_warp<<<grid, trs::LOCW_THREADS, 0, (cudaStream_t)stream>>>(ctx->wp_dev, ctx->n_wp, ctx->min_map, ctx->max_map, xyz_dev, n, idx_dev,
-                                                                                 segment_dev);
+        trs::k_locate_warp<<<grid, trs::LOCW_THREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double4*>(ctx->wp_dev), ctx->n_wp_distinct, ctx->n_wp,
+                                                                                 ctx->min_map, ctx->max_map, xyz_dev, n, idx_dev, segment_dev);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CU(cudaGetLastError());
         return 0;
     }
     const int per_block = trs::LOC_THREADS * trs::LOC_CARS;
     const int grid = (n + per_block - 1) / per_block;
-    trs::k_locate<<<grid, trs::LOC_THREADS, 0, (cudaStream_t)stream>>>(ctx->wp_dev, ctx->n_wp, ctx->min_map, ctx->max_map, xyz_dev, n, idx_dev, segment_dev);
+    trs::k_locate<<<grid, trs::LOC_THREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double4*>(ctx->wp_dev), ctx->n_wp_distinct, ctx->n_wp, ctx->min_map,
+                                                                       ctx->max_map, xyz_dev, n, idx_dev, segment_dev);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CU(cudaGetLastError());
     return 0;
