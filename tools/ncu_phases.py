@@ -6,8 +6,26 @@ import csv, re, subprocess, sys, os
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import ncu_lines
 
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'triton-racer-sim_b200', 'csrc')
+FILES = ('preproc_fast.cuh', 'preproc_bsw.cuh')
+
+
+def phase_tables():
+    return {f: phase_table(os.path.join(CSRC, f)) for f in FILES if os.path.exists(os.path.join(CSRC, f))}
+
+
+def phase_of(tables, src):
+    """src = (file, line) of a SASS instruction -> phase name or None"""
+    if not src or src[0] not in tables:
+        return None
+    cur = None
+    for ln, name in tables[src[0]]:
+        if src[1] >= ln: cur = name
+    return cur
+
+
 def phase_table(src_path):
-    names = {'hsv_masks_of': 'hsv', 'p1_strip_walk': 'p1', 'p1b_colour_masks': 'p1b', 'p2_nms': 'p2', 'p3_hysteresis': 'p3', 'p3_relax_band': 'p3', 'p4_output': 'p4',
+    names = {'p2_nms_lagged': 'p2', 'k_preprocess_bsw': 'main', 'wait_progress': 'sync', 'hsv_masks_of': 'hsv', 'p1_strip_walk': 'p1', 'p1b_colour_masks': 'p1b', 'p2_nms': 'p2', 'p3_hysteresis': 'p3', 'p3_relax_band': 'p3', 'p4_output': 'p4',
              'init_tables': 'prolog', 'k_preprocess_fast': 'main', 'k_preprocess_sw': 'main', 'k_preprocess_banded': 'main'}
     marks = []
     for i, ln in enumerate(open(src_path), 1):
@@ -18,12 +36,7 @@ def phase_table(src_path):
 
 def main():
     rep, lib, ksub, frames = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4])
-    marks = phase_table(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'triton-racer-sim_b200', 'csrc', 'preproc_fast.cuh'))
-    def phase_of(line):
-        cur = None
-        for ln, name in marks:
-            if line >= ln: cur = name
-        return cur
+    tables = phase_tables()
     sl = ncu_lines.sass_lines(lib, ksub)
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines())); hdr = rows[1]; body = rows[2:]
@@ -32,9 +45,8 @@ def main():
     cur = '?'; agg = {}; ti = ts = 0
     for (addr, text, src), r in zip(sl, body):
         inst = int(r[ci['Instructions Executed']] or 0); smp = int(r[ci['# Samples']] or 0)
-        if src and src[0] == 'preproc_fast.cuh':
-            ph = phase_of(src[1])
-            if ph: cur = ph
+        ph = phase_of(tables, src)
+        if ph: cur = ph
         a = agg.setdefault(cur, [0, 0]); a[0] += inst; a[1] += smp; ti += inst; ts += smp
     print(f'total warp-instr per frame {ti / frames:.0f}')
     for k, (i, s) in sorted(agg.items(), key=lambda kv: -kv[1][0]):

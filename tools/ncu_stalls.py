@@ -6,12 +6,7 @@ import ncu_lines, ncu_phases
 
 def main():
     rep, lib, ksub = sys.argv[1:4]
-    marks = ncu_phases.phase_table(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'triton-racer-sim_b200', 'csrc', 'preproc_fast.cuh'))
-    def phase_of(line):
-        cur = None
-        for ln, name in marks:
-            if line >= ln: cur = name
-        return cur
+    tables = ncu_phases.phase_tables()
     sl = ncu_lines.sass_lines(lib, ksub)
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines())); hdr = rows[1]; body = rows[2:]
@@ -20,9 +15,8 @@ def main():
     assert len(sl) == len(body)
     cur = '?'; agg = {}; tot = 0
     for (addr, text, src), r in zip(sl, body):
-        if src and src[0] == 'preproc_fast.cuh':
-            ph = phase_of(src[1])
-            if ph: cur = ph
+        ph = ncu_phases.phase_of(tables, src)
+        if ph: cur = ph
         a = agg.setdefault(cur, {})
         for c in stall_cols:
             v = int(r[ci[c]] or 0)

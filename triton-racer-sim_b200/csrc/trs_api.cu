@@ -24,6 +24,7 @@
 #include "misc_kernels.cuh"
 #include "preproc_kernel.cuh"
 #include "preproc_fast.cuh"
+#include "preproc_bsw.cuh"
 #include "trs_internal.h"
 
 namespace {
@@ -336,6 +337,21 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     int grid = ctx->sm_count * 2;
     if (grid > n) grid = n;
     int rc;
+    // 240x320 (BASELINE.json configs[2]) with the reference's default ranges: banded store-warp kernel with compile-time geometry
+    if (h == 240 && w == 320 && k.n_ranges == 2 && k.edge_enabled && !k.need_pixels && !k.dynamic && k.lut_identity && !ctx->sw.no_store_warp &&
+        fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1 && k.ranges[1].hi[0] <= 149) {
+        using L = trs::BswLayout<240, 320, 24, 2>;
+        auto kern = trs::k_preprocess_bsw<2, (int)DEFAULT_F0, (int)DEFAULT_F1, 240, 320, 24>;
+        if (L::TOTAL <= (ctx->smem_optin + 1024) / 2 - 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+            if (e != cudaSuccess) { cuda_fail(e, "cudaFuncSetAttribute(bsw 240x320)"); return -100 - (int)e; }
+            kern<<<grid, L::THREADS, L::TOTAL, st>>>(fp);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) { cuda_fail(e, "k_preprocess_bsw launch"); return -100 - (int)e; }
+            return 1;
+        }
+    }
     switch (k.n_ranges * 2 + (k.edge_enabled ? 1 : 0)) {
     case 1: rc = launch_fast_t<0, true>(fp, grid, st); break;
     case 2: rc = launch_fast_t<1, false>(fp, grid, st); break;
