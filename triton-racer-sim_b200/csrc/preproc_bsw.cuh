@@ -159,7 +159,8 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_bsw(const __grid_constant__ 
     asm volatile("" : "+r"(sb));
     constexpr int NCW = L::NCW, NC = 32 * NCW, NS = 64, NT = NC + NS, NB = L::NB, SEG = L::SEG, ww = W / 32, NSLOT = L::NSLOT;
     constexpr uint32_t frame_bytes = (uint32_t)H * W * 3;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // (tells the compiler the role branch below is warp-uniform)
     SmemMap S;
     S.pix[0] = S.pix[1] = sb + L::OFF_PIX + 16;
     S.mag[0] = S.mag[1] = sb + L::OFF_MAG;
@@ -196,7 +197,7 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_bsw(const __grid_constant__ 
         issue_frame_load(S.pix[0], p.in + f * frame_bytes + (size_t)p0 * L::ROWB, (uint32_t)(p1 - p0) * L::ROWB, bar_pix);
     };
 
-    if (tid < NC) {
+    if (warp < NCW) {
         // ------------------------------------------------ compute warps -----------------------------------------------
         const int seg = lane >> 3;
         StripMap M;

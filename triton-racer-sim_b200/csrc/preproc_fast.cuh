@@ -163,6 +163,17 @@ __device__ __forceinline__ void sts64_if(bool on, uint32_t a, uint2 v)
     asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\n@p st.shared.v2.u32 [%0], {%1,%2};\n}\n" ::"r"(a), "r"(v.x), "r"(v.y), "r"((uint32_t)on) : "memory");
 }
 
+// predicated global stores (the output loops keep every lane in the loop and switch the stores of the idle lanes off)
+__device__ __forceinline__ void stg128_if(bool on, void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %5, 0;\n@p st.global.v4.u32 [%0], {%1,%2,%3,%4};\n}\n" ::"l"(__cvta_generic_to_global(p)), "r"(a), "r"(b),
+                 "r"(c), "r"(d), "r"((uint32_t)on) : "memory");
+}
+__device__ __forceinline__ void stg32_if(bool on, void* p, uint32_t a)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.global.u32 [%0], %1;\n}\n" ::"l"(__cvta_generic_to_global(p)), "r"(a), "r"((uint32_t)on) : "memory");
+}
+
 // Frame dimensions as the phase functions see them.  The store-warp kernel is also instantiated with the reference's camera size
 // (120 x 160, core/config.py:8-9) as compile-time constants: every row stride, plane pitch and loop bound of the walks becomes an
 // immediate instead of a constant-bank load plus address arithmetic per row step.
@@ -859,7 +870,10 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const Dims& Dm, c
         const uint32_t mX0 = 1u << shX, mX1 = 2u << shX, mY = 1u << shY, mZ = 1u << shZ;
         const uint32_t fX0 = one >> shX, fX1 = one >> (shX + 1), fY = one >> shY, fZ = one >> shZ;
         const uint32_t qX0 = 128u >> shX, qY = (128u >> shY) << 8, qZ = (128u >> shZ) << 16, qX1 = (128u >> (shX + 1)) << 24;
-        if (lane < 30) {
+        // lanes 30 and 31 run the same instructions with their stores predicated off: the loop stays warp-uniform (inside a divergent
+        // region the compiler re-derives the global-memory descriptor of every store: two R2UR per STG)
+        const bool act = lane < 30;
+        {
             const int nfull = npb / 5;                       // warp-iterations whose five groups all exist
             const int nwi = (npb + 4) / 5;
             const int per = (nwi + nw - 1) / nw;
@@ -868,29 +882,29 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const Dims& Dm, c
                 uint32_t ax = paX + 5 * w0 + gl, ay = paY + 5 * w0 + gl, az = paZ + 5 * w0 + gl;
                 uint4* fp = reinterpret_cast<uint4*>(gf32) + 30 * w0 + lane;
                 uint32_t* up = reinterpret_cast<uint32_t*>(gout) + 30 * w0 + lane;
-                auto one_iter = [&](int k) {
+                auto one_iter = [&](int k, bool on) {
                     const uint32_t xs = lds8(ax + 5 * k), ys = lds8(ay + 5 * k), zs = lds8(az + 5 * k);
                     const uint32_t b0 = xs & mX0, b1 = ys & mY, b2 = zs & mZ, b3 = xs & mX1;
                     if (decltype(has_f32)::value) {
                         const uint32_t f0 = b0 * fX0, f1 = b1 * fY, f2 = b2 * fZ, f3 = b3 * fX1;
-                        fp[30 * k] = make_uint4(f0, f1, f2, f3);
+                        stg128_if(on, fp + 30 * k, f0, f1, f2, f3);
                         // byte 2 of 1.0f is 0x80: its sign bit replicated over a byte is the u8 value
                         // (three ALU-pipe permutes measured 1.3 % faster end to end than four FMA-pipe multiplies + one permute)
-                        if (decltype(has_u8)::value) up[30 * k] = prmt(prmt_sx(f0, f1, 0x00ea), prmt_sx(f2, f3, 0x00ea), 0x5410);
+                        if (decltype(has_u8)::value) stg32_if(on, up + 30 * k, prmt(prmt_sx(f0, f1, 0x00ea), prmt_sx(f2, f3, 0x00ea), 0x5410));
                     } else if (decltype(has_u8)::value) {
-                        up[30 * k] = prmt_sx(b0 * qX0 + b1 * qY + b2 * qZ + b3 * qX1, 0, 0xba98);
+                        stg32_if(on, up + 30 * k, prmt_sx(b0 * qX0 + b1 * qY + b2 * qZ + b3 * qX1, 0, 0xba98));
                     }
                 };
                 int wi = w0;
 #pragma unroll 1
                 for (; wi + 4 <= wf; wi += 4) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) one_iter(k);
+                    for (int k = 0; k < 4; ++k) one_iter(k, act);
                     ax += 20; ay += 20; az += 20; fp += 120; up += 120;
                 }
 #pragma unroll 1
                 for (; wi < w1; ++wi) {
-                    if (5 * wi + gl < npb) one_iter(0);
+                    one_iter(0, act && 5 * wi + gl < npb);
                     ax += 5; ay += 5; az += 5; fp += 30; up += 30;
                 }
             };
@@ -1321,7 +1335,8 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
     const int h = Dm.h, w = Dm.w, ww = STATIC ? W / 32 : G.nsg;
     const int seg_rows = STATIC ? sw_seg_rows<(STATIC ? H : 32), (STATIC ? W : 32)>() : G.seg_rows_front;
     const int tail_bytes = STATIC ? Dm.plane_bytes : G.tail_bytes;
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // (tells the compiler that the role branch below is warp-uniform)
     const uint32_t frame_bytes = (uint32_t)h * w * 3;
     const int plane_words = h * ww;
     const int NC = SW_COMPUTE_THREADS;
@@ -1337,7 +1352,7 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
     if (tid == 0) { mbar_init(bar_main, 1); mbar_init(bar_tail, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
 
-    if (tid < NC) {
+    if (warp < (NC >> 5)) {
         // ------------------------------------------------ compute warps -----------------------------------------------
         const StripMap M = strip_map(warp, lane, ww, seg_rows, h);
         const bool use_lut = p.dynamic || !p.lut_identity;
