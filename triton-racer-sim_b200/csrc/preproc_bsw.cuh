@@ -21,13 +21,14 @@
 //    slab by the store warps): the store warps arrive on a slot's barrier when its slab is written and a strip walk waits for the slot it
 //    is about to reuse, so the first bands of a frame never wait for the store warps to get going.  The edge plane is double-buffered
 //    by frame parity, the candidate plane is handed back by a "hysteresis finished" barrier.
+//  * NSW store warps per CTA: two at 240x320 (two CTAs per SM), one at 120x160 (five compute warps, four CTAs per SM).
 //  * One named barrier per frame among the compute warps (before the hysteresis, whose row bands cut across the column blocks).
 #pragma once
 #include "preproc_fast.cuh"
 
 namespace trs {
 
-template <int H, int W, int R, int NR>
+template <int H, int W, int R, int NR, int NSW = 2>
 struct BswLayout {
     static_assert(W % 32 == 0 && H % R == 0 && R % 12 == 0, "column blocks of 32 pixels, whole bands, four segments of a multiple of 3 rows");
     static constexpr int NCW = W / 32;                                 // compute warps = column blocks
@@ -57,7 +58,7 @@ struct BswLayout {
     static constexpr int OFF_SYNC = OFF_BAR + 8 * NBAR;                // strip-walk counter
     static constexpr int OFF_RED = (OFF_SYNC + 16 + 15) & ~15;
     static constexpr int TOTAL = OFF_RED + 32 + 128;
-    static constexpr int THREADS = 32 * (NCW + 2);
+    static constexpr int THREADS = 32 * (NCW + NSW);
 };
 
 __device__ __forceinline__ uint32_t atom_inc_acq_rel(uint32_t a)
@@ -78,7 +79,6 @@ __device__ __forceinline__ void p2_nms_lagged(const FastParams& P, const Dims& D
                                               bool store_lane, int r0, uint32_t a_up, uint32_t a_ce, uint32_t slot, bool tail, bool tail_lane)
 {
     static_assert(SEG % 3 == 0, "whole trips only");
-    uint32_t n_strong = 0;
     const int prb = Dm.w >> 3, MS2 = Dm.mag_stride * 2;
     const uint32_t mbase = a_mag + 2 * (4 + 4 * strip);
     struct Row { uint32_t p01, p23, l01, m12, r23, raw01, raw23; };
@@ -124,7 +124,6 @@ __device__ __forceinline__ void p2_nms_lagged(const FastParams& P, const Dims& D
         merge_nibble_pairs(top, other, bc, bs);
         sts8_if(store, cp, bc);
         sts8_if(store, ep, bs);
-        if (P.k.stats && store) n_strong += __popc(bs & 0xffu);
         cp += prb; ep += prb;
     };
     Row ra = unpack_row(fetch_at(a_up)), rb = unpack_row(fetch_at(a_ce)), rc;
@@ -143,21 +142,20 @@ __device__ __forceinline__ void p2_nms_lagged(const FastParams& P, const Dims& D
         ahead.c = make_uint2(0u, 0u); ahead.ml = 0; ahead.mr = 0;
         nms_step(store_lane && tail_lane, ra, rb, rc);
     }
-    if (P.k.stats) stat_add(S, 6, n_strong);
 }
 
 // =========================================================================================================
 // the kernel: NCW compute warps + 2 store warps, two CTAs per SM
 // =========================================================================================================
-template <int NR, int F0, int F1, int H, int W, int R>
+template <int NR, int F0, int F1, int H, int W, int R, int NSW = 2>
 __global__ void __maxnreg__(SW_MAXREG) k_preprocess_bsw(const __grid_constant__ FastParams P)
 {
-    using L = BswLayout<H, W, R, NR>;
+    using L = BswLayout<H, W, R, NR, NSW>;
     extern __shared__ __align__(16) uint8_t smem[];
     const PreKParams& p = P.k;
     uint32_t sb = smem_u32(smem);
     asm volatile("" : "+r"(sb));
-    constexpr int NCW = L::NCW, NC = 32 * NCW, NS = 64, NT = NC + NS, NB = L::NB, SEG = L::SEG, ww = W / 32, NSLOT = L::NSLOT;
+    constexpr int NCW = L::NCW, NC = 32 * NCW, NS = 32 * NSW, NT = NC + NS, NB = L::NB, SEG = L::SEG, ww = W / 32, NSLOT = L::NSLOT;
     constexpr uint32_t frame_bytes = (uint32_t)H * W * 3;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // (tells the compiler the role branch below is warp-uniform)
@@ -187,7 +185,7 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_bsw(const __grid_constant__ 
     zero_plane_pads(S, H * ww, ww, tid, NT);
     if (tid == 0) sts32(a_cnt, 0);
     for (int i = tid; i < L::STASH_ROW / 4; i += NT) sts32(a_zero + 4 * i, 0);
-    if (tid < L::NBAR) mbar_init(S.bar + 8 * tid, tid >= 2 + 2 * NCW ? 2u : 1u);      // a slot's barrier takes both store warps
+    if (tid < L::NBAR) mbar_init(S.bar + 8 * tid, tid >= 2 + 2 * NCW ? (uint32_t)NSW : 1u);      // a slot's barrier takes every store warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -246,6 +244,7 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_bsw(const __grid_constant__ 
                 if (++slot == NSLOT) { slot = 0; ++round; }
             }
             bar_sync(1, NC);                                      // the hysteresis bands cut across the column blocks
+            if (p.stats) count_strong_band(S, a_edge, H, ww, lane, warp, NCW);
             p3_relax_band(S.cand, a_edge, H, ww, lane, warp, NCW);
             bar_arrive(2, NT);                                    // planes of frame j are final: the store warps take them from here
         }
@@ -262,7 +261,7 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_bsw(const __grid_constant__ 
             bar_sync(2, NT);
             int sw = 0;                                           // growth across the compute warps' row bands (usually one checking pass)
             if (bar_or(4, NS, p3_check_band_boundaries(S.cand, a_edge, H, ww, (H + NCW - 1) / NCW, st, NS)))
-                sw = p3_hysteresis(S.cand, a_edge, H, ww, st, NS, [](int c) { return bar_or(4, 64, c); });
+                sw = p3_hysteresis(S.cand, a_edge, H, ww, st, NS, [](int c) { return bar_or(4, 32 * NSW, c); });
             if (p.stats) {
                 if (st == 0) stat_add_one(S, 8, (unsigned long long)sw + 1);
                 count_planes<0, true>(p, S, S.cand, a_edge, 0u, 0, H * ww, st, NS);

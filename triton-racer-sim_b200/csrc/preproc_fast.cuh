@@ -169,6 +169,10 @@ __device__ __forceinline__ void stg128_if(bool on, void* p, uint32_t a, uint32_t
     asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %5, 0;\n@p st.global.v4.u32 [%0], {%1,%2,%3,%4};\n}\n" ::"l"(__cvta_generic_to_global(p)), "r"(a), "r"(b),
                  "r"(c), "r"(d), "r"((uint32_t)on) : "memory");
 }
+__device__ __forceinline__ void stg64_if(bool on, void* p, uint32_t a, uint32_t b)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\n@p st.global.v2.u32 [%0], {%1,%2};\n}\n" ::"l"(__cvta_generic_to_global(p)), "r"(a), "r"(b), "r"((uint32_t)on) : "memory");
+}
 __device__ __forceinline__ void stg32_if(bool on, void* p, uint32_t a)
 {
     asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.global.u32 [%0], %1;\n}\n" ::"l"(__cvta_generic_to_global(p)), "r"(a), "r"((uint32_t)on) : "memory");
@@ -374,7 +378,7 @@ struct SatThresholds {
 // Hue bounds without computing the hue: h = (h0 * hdiv[d] + 2048) >> 12 is monotone in the numerator h0, and the wrapped values (h0 < 0:
 // h + 180 >= 150) can never pass an upper bound <= 149, so "lo <= h <= hi" is "A_lo[d] <= h0 <= A_hi[d]".  Used when the live-bound words
 // are compile-time constants, exactly one of two ranges bounds the hue on both sides and the other does not look at it (the reference's
-// defaults, core/config.py:23); the host only picks such a variant when that upper bound is <= 149.  The table (in the place of hdiv) holds
+// defaults, core/config.py:23); the host only picks such a variant when that upper bound is <= 59 (see hsv_masks_of).  The table (in the place of hdiv) holds
 // the two thresholds of a delta d, biased by 2048 like the packed numerators, as 16-bit halves.
 template <int NR, int F0, int F1>
 struct HueThresholds {
@@ -435,15 +439,20 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
             // hue numerator + 2048 (always positive): g-b | b-r+2d | r-g+4d, chosen by v==r, then v==g
             const uint32_t gb = X[1] + 0x08000800u - X[2];
             const uint32_t br = X[2] + 0x08000800u - X[0] + d2[half] + d2[half];
-            const uint32_t rg = X[0] + 0x08000800u - X[1] + (d2[half] << 2);
-            const uint32_t eqr = heq_mask(v2[half], X[0]), eqg = heq_mask(v2[half], X[1]);
-            const uint32_t h02 = bsel(eqr, gb, bsel(eqg, br, rg));
+            const uint32_t eqr = heq_mask(v2[half], X[0]);
             if (HueThresholds<NR, F0, F1>::use) {
+                // (the host picks this variant only for an upper hue bound below 60: a pixel whose strongest channel is blue alone has a hue of
+                // 120 .. 179; pushed through the green formula its numerator lies in [2d, 3d], a hue of 60 .. 90, which fails the bound just
+                // the same, so the third numerator and the second equality test are never needed)
+                const uint32_t h02 = bsel(eqr, gb, br);
                 constexpr int HR = HueThresholds<NR, F0, F1>::range;
                 const uint32_t tl = lds32(mad_u32(d2[half] & 0xffffu, 4u, a_hue)), th = lds32(mad_u32(d2[half] >> 16, 4u, a_hue));
                 okm[HR][half] &= hge_mask(h02, prmt(tl, th, 0x5410)) & hle_mask(h02, prmt(tl, th, 0x7632));
                 continue;
             }
+            const uint32_t rg = X[0] + 0x08000800u - X[1] + (d2[half] << 2);
+            const uint32_t eqg = heq_mask(v2[half], X[1]);
+            const uint32_t h02 = bsel(eqr, gb, bsel(eqg, br, rg));
             // ((h0 + 2048) hd + (2048 - 2048 hd)) >> 12 == (h0 hd + 2048) >> 12
             const int tl = (int)lds32(a_hue + 4 * (d2[half] & 0xffffu)), th = (int)lds32(a_hue + 4 * (d2[half] >> 16));
             int hlo = ((int)(h02 & 0xffffu) * tl + (2048 - 2048 * tl)) >> 12;
@@ -681,7 +690,9 @@ __device__ __forceinline__ void stats_flush(const PreKParams& p, const SmemMap& 
 // =========================================================================================================
 // SEG > 0 (a multiple of 3): seg_rows is this constant and every lane owns exactly SEG rows (see p1_strip_walk): no row-range predicates,
 // no clamp on the row fetched ahead (the fetch past the last row lands in the planes behind the magnitude buffer and is never used).
-template <int SEG = 0>
+// COUNT = false: the caller counts the strong pixels itself (count_strong_band before the hysteresis touches the plane), which keeps the
+// population count out of every row step.
+template <int SEG = 0, bool COUNT = true>
 __device__ __forceinline__ void p2_nms(const FastParams& P, const Dims& Dm, uint32_t a_mag, uint32_t a_cand, uint32_t a_edge, const SmemMap& S,
                                        const StripMap& M, int seg_rows)
 {
@@ -743,7 +754,7 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, const Dims& Dm, uint
         merge_nibble_pairs(top, other, bc, bs);
         sts8_if(M.store_lane && row_in, cp, bc);
         sts8_if(M.store_lane && row_in, ep, bs);
-        if (P.k.stats && M.store_lane && row_in) n_strong += __popc(bs & 0xffu);
+        if (COUNT && P.k.stats && M.store_lane && row_in) n_strong += __popc(bs & 0xffu);
         cp += prb; ep += prb;
     };
     Row ra = load_row(ya - 1), rb = load_row(ya), rc;
@@ -764,7 +775,7 @@ __device__ __forceinline__ void p2_nms(const FastParams& P, const Dims& Dm, uint
             if (k + 2 < seg_rows) nms_step(k + 2, rc, ra, rb);
         }
     }
-    if (P.k.stats) stat_add(S, 6, n_strong);
+    if (COUNT && P.k.stats) stat_add(S, 6, n_strong);
 }
 
 // =========================================================================================================
@@ -791,6 +802,17 @@ __device__ __forceinline__ int p3_update_word(uint32_t a_cand, uint32_t a_edge, 
     if (ne == e) return 0;
     sts32(ea, ne);
     return 1;
+}
+
+// statistics: the strong pixels of a warp's band of rows, counted from the edge plane BEFORE anything is grown into it (a warp's relaxation
+// writes its own rows only, so the count taken right before it is exact)
+__device__ __forceinline__ void count_strong_band(const SmemMap& S, uint32_t a_edge, int h, int ww, int lane, int gw, int nw)
+{
+    const int rows_per = (h + nw - 1) / nw;
+    const int y0 = min(h, gw * rows_per), y1 = min(h, y0 + rows_per);
+    uint32_t n = 0;
+    for (int i = y0 * ww + lane; i < y1 * ww; i += 32) n += __popc(lds32(a_edge + 4 * i));
+    stat_add(S, 6, n);
 }
 
 // one warp relaxes its band of rows to a local fixed point; returns whether anything changed
@@ -861,6 +883,38 @@ __device__ __forceinline__ void p4_output(const FastParams& P, const Dims& Dm, c
         // bit -> value expansion is one AND (ALU pipe) and multiplies by lane constants (FMA pipe): (x & 1<<sh) * (K >> sh);
         // the u8 word is assembled as 0x80-per-byte and widened to 0xff by one sign-replicating byte permute.
         const int lane = t0 & 31, gw = t0 >> 5, nw = tstride >> 5;
+        if (!gf32) {
+            // u8 image only (BASELINE.json configs[2], the mask workload): a lane expands one group of 8 pixels = one byte of each plane
+            // into its 24 output bytes.  A nibble times 0x10204080 puts pixel q's bit on the sign bit of byte q (no two partial products
+            // meet inside a nibble), one sign-replicating permute widens the four sign bits to 0xff / 0x00 bytes, and two permutes per
+            // output word interleave the three channels: 39 instructions per 24 bytes instead of 10 per 4.
+            if (!gout) return;
+            const int per = (npb + nw - 1) / nw;
+            const int g0 = min(npb, gw * per), g1 = min(npb, g0 + per);
+            auto spread = [](uint32_t b, uint32_t& lo, uint32_t& hi) {
+                lo = prmt_sx((b & 0x0fu) * 0x10204080u, 0, 0xba98);
+                hi = prmt_sx((b & 0xf0u) * 0x01020408u, 0, 0xba98);
+            };
+            uint32_t ax = pa[0] + g0 + lane, ay = pa[1] + g0 + lane, az = pa[2] + g0 + lane;
+            uint2* dst = reinterpret_cast<uint2*>(gout + (size_t)(g0 + lane) * 24);
+#pragma unroll 1
+            for (int g = g0; g < g1; g += 32) {
+                const bool on = g + lane < g1;
+                uint32_t X[2], Y[2], Z[2];
+                spread(lds8(ax), X[0], X[1]);
+                spread(lds8(ay), Y[0], Y[1]);
+                spread(lds8(az), Z[0], Z[1]);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {               // pixels 4q .. 4q + 3: (x0 y0 z0 x1) (y1 z1 x2 y2) (z2 x3 y3 z3)
+                    const uint32_t w0 = prmt(prmt(X[q], Y[q], 0x1040), Z[q], 0x3410);
+                    const uint32_t w1 = prmt(prmt(X[q], Y[q], 0x6205), Z[q], 0x3250);
+                    const uint32_t w2 = prmt(prmt(X[q], Y[q], 0x0730), Z[q], 0x7216);
+                    if (q == 0) { stg64_if(on, dst, w0, w1); X[0] = w2; } else { stg64_if(on, dst + 1, X[0], w0); stg64_if(on, dst + 2, w1, w2); }
+                }
+                ax += 32; ay += 32; az += 32; dst += 96;
+            }
+            return;
+        }
         const int gl = lane / 6, sc = lane - 6 * gl, r = sc % 3, hi4 = 4 * (sc / 3);
         const uint32_t paX = r == 0 ? pa[0] : (r == 1 ? pa[1] : pa[2]);
         const uint32_t paY = r == 0 ? pa[1] : (r == 1 ? pa[2] : pa[0]);
@@ -1393,9 +1447,10 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             TRS_TICK(tk4);
             if (tid == 0 && j + 1 < nfr)                                 // pixels are dead: prefetch the next frame (all but its tail)
                 issue_frame_piece(S.pix[0], p.in + (f + gridDim.x) * frame_bytes, 0, main_bytes, bar_main);
-            p2_nms<(STATIC ? sw_seg_rows<(STATIC ? H : 32), (STATIC ? W : 32)>() : 0)>(P, Dm, S.mag[0], S.cand, a_edge, S, M, seg_rows);
+            p2_nms<(STATIC ? sw_seg_rows<(STATIC ? H : 32), (STATIC ? W : 32)>() : 0), false>(P, Dm, S.mag[0], S.cand, a_edge, S, M, seg_rows);
             bar_sync(1, NC);
             TRS_TICK(tk5);
+            if (p.stats) count_strong_band(S, a_edge, h, ww, lane, warp, NC >> 5);
             // hysteresis, first level only: every warp relaxes its own band, no CTA-wide round trip; the store warps finish the job
             p3_relax_band(S.cand, a_edge, h, ww, lane, warp, NC >> 5);
 #ifdef TRS_PHASE_TIMERS

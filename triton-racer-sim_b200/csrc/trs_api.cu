@@ -255,9 +255,9 @@ enum { DEFAULT_F0 = 8 | 16, DEFAULT_F1 = 1 | 2 | 4 | 16 };
 template <int NR, bool EDGE>
 int launch_fast_t(const trs::FastParams& fp, int grid, cudaStream_t st)
 {
-    // (the baked variant turns the hue bounds of range 1 into per-delta numerator thresholds, which needs an upper bound below the
-    // wrapped hues: preproc_fast.cuh HueThresholds)
-    if (NR == 2 && fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1 && fp.k.ranges[1].hi[0] <= 149)
+    // (the baked variant turns the hue bounds of range 1 into per-delta numerator thresholds and skips the blue-max hue formula, which
+    // needs an upper bound below 60: preproc_fast.cuh HueThresholds / hsv_masks_of)
+    if (NR == 2 && fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1 && fp.k.ranges[1].hi[0] <= 59)
         return launch_fast_tf<NR, EDGE, (NR == 2 ? (int)DEFAULT_F0 : -1), (NR == 2 ? (int)DEFAULT_F1 : -1)>(fp, grid, st);
     return launch_fast_tf<NR, EDGE, -1, -1>(fp, grid, st);
 }
@@ -339,7 +339,7 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     int rc;
     // 240x320 (BASELINE.json configs[2]) with the reference's default ranges: banded store-warp kernel with compile-time geometry
     if (h == 240 && w == 320 && k.n_ranges == 2 && k.edge_enabled && !k.need_pixels && !k.dynamic && k.lut_identity && !ctx->sw.no_store_warp &&
-        fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1 && k.ranges[1].hi[0] <= 149) {
+        fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1 && k.ranges[1].hi[0] <= 59) {
         using L = trs::BswLayout<240, 320, 24, 2>;
         auto kern = trs::k_preprocess_bsw<2, (int)DEFAULT_F0, (int)DEFAULT_F1, 240, 320, 24>;
         if (L::TOTAL <= (ctx->smem_optin + 1024) / 2 - 1024) {
