@@ -43,14 +43,14 @@ METRIC = "preprocessed frames/sec (120x160), full observation chain"
 METRICS = {"full_chain_120x160": METRIC, "full_house_mask_240x320": "preprocessed frames/sec (240x320), full-house colour + edge mask",
            "full_chain_240x320": "preprocessed frames/sec (240x320), full observation chain",
            "full_pipeline_1M_over_8": "preprocessed frames/sec (120x160), full observation pipeline incl. per-car lookup and control"}
-KERNELS = {"full_chain_120x160": "trs::k_preprocess_sw<2,24,23,120,160>", "full_house_mask_240x320": "trs::k_preprocess_banded<2,true,24,23>",
-           "full_chain_240x320": "trs::k_preprocess_banded<2,true,24,23>", "full_pipeline_1M_over_8": "trs::k_preprocess_sw<2,24,23,120,160>"}
+KERNELS = {"full_chain_120x160": "trs::k_preprocess_sw<2,24,23,120,160>", "full_house_mask_240x320": "trs::k_preprocess_bsw<2,24,23,240,320,24,2>",
+           "full_chain_240x320": "trs::k_preprocess_bsw<2,24,23,240,320,24,2>", "full_pipeline_1M_over_8": "trs::k_preprocess_sw<2,24,23,120,160>"}
 NOTES = {
     "full_chain_120x160": "bound by the ALU pipe / issue slots and phase barriers, not by HBM: ten compute warps per CTA run strip walk, NMS and "
                           "hysteresis while two store warps stream the previous frame out (the SM -> L2 write port tops out at 29 B/clk); "
                           "see DESIGN.md 4.1 and profiles/",
-    "full_house_mask_240x320": "6 algorithmic bytes per pixel: instruction bound by construction (SURVEY.md 8d); banded kernel, DESIGN.md 4.3",
-    "full_chain_240x320": "18 algorithmic bytes per pixel like the 120x160 headline; banded kernel (frames do not fit shared memory whole)",
+    "full_house_mask_240x320": "6 algorithmic bytes per pixel: instruction bound by construction (SURVEY.md 8d); banded store-warp kernel, DESIGN.md 4.3",
+    "full_chain_240x320": "18 algorithmic bytes per pixel like the 120x160 headline; banded store-warp kernel (frames do not fit shared memory whole), DESIGN.md 4.3",
     "full_pipeline_1M_over_8": "frames as full_chain_120x160; the per-car kernels (FP64 argmin over 1,185 waypoints, speed control, multiplexer) "
                                "add three launches per step and are counted in the step time but not in the algorithmic bytes",
 }
@@ -132,6 +132,8 @@ class ClockSampler:
             idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].strip().isdigit() else self.gpu
             handle = nv.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            for _ in range(3):                     # the first queries of a process take tens of milliseconds: pay for them before the timed region
+                nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
             self.nv = nv
             self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
             self.thread.start()

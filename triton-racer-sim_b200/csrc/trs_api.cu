@@ -67,7 +67,7 @@ enum { HOST_STREAMS = 3 };
 // Test-only switches (tests/test_gpu_parity.py forces every kernel variant through the same goldens): read from the environment ONCE,
 // when the context is created, so no call on the N = 1 latency path pays a getenv.
 struct TrsSwitches {
-    bool force_generic = false, no_banded = false, no_store_warp = false, resize_scalar = false, resize_gather = false;
+    bool force_generic = false, no_banded = false, no_store_warp = false, resize_scalar = false, resize_gather = false, bsw120 = false;
     int locate = 0;                    // 0 = by batch size, 1 = warp per car, 2 = thread per car
     size_t host_chunk_bytes = (size_t)48 << 20;      // ~48 MB of frames per chunk of the host pipeline (the link saturates from ~16 MB up)
 };
@@ -262,6 +262,28 @@ int launch_fast_t(const trs::FastParams& fp, int grid, cudaStream_t st)
     return launch_fast_tf<NR, EDGE, -1, -1>(fp, grid, st);
 }
 
+// Banded store-warp kernel (preproc_bsw.cuh) for one compile-time geometry.  Returns 1 if launched, 0 if it does not fit, < 0 on error.
+template <int H, int W, int R, int NSW>
+int launch_bsw(trs_ctx* ctx, const trs::FastParams& fp, int n, cudaStream_t st)
+{
+    using L = trs::BswLayout<H, W, R, 2, NSW>;
+    auto kern = trs::k_preprocess_bsw<2, (int)DEFAULT_F0, (int)DEFAULT_F1, H, W, R, NSW>;
+    if (L::TOTAL > (ctx->smem_optin + 1024) / 2 - 1024) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaFuncSetAttribute(bsw)"); return -100 - (int)e; }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, L::THREADS, L::TOTAL);
+    if (e != cudaSuccess) { cuda_fail(e, "occupancy(bsw)"); return -100 - (int)e; }
+    if (per_sm < 1) return 0;
+    int grid = ctx->sm_count * per_sm;
+    if (grid > n) grid = n;
+    kern<<<grid, L::THREADS, L::TOTAL, st>>>(fp);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { cuda_fail(e, "k_preprocess_bsw launch"); return -100 - (int)e; }
+    return 1;
+}
+
 int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w, cudaStream_t st)
 {
     if (ctx->sw.force_generic) return 0;
@@ -338,19 +360,15 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     if (grid > n) grid = n;
     int rc;
     // 240x320 (BASELINE.json configs[2]) with the reference's default ranges: banded store-warp kernel with compile-time geometry
-    if (h == 240 && w == 320 && k.n_ranges == 2 && k.edge_enabled && !k.need_pixels && !k.dynamic && k.lut_identity && !ctx->sw.no_store_warp &&
-        fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1 && k.ranges[1].hi[0] <= 59) {
-        using L = trs::BswLayout<240, 320, 24, 2>;
-        auto kern = trs::k_preprocess_bsw<2, (int)DEFAULT_F0, (int)DEFAULT_F1, 240, 320, 24>;
-        if (L::TOTAL <= (ctx->smem_optin + 1024) / 2 - 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-            if (e != cudaSuccess) { cuda_fail(e, "cudaFuncSetAttribute(bsw 240x320)"); return -100 - (int)e; }
-            kern<<<grid, L::THREADS, L::TOTAL, st>>>(fp);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            e = cudaGetLastError();
-            if (e != cudaSuccess) { cuda_fail(e, "k_preprocess_bsw launch"); return -100 - (int)e; }
-            return 1;
-        }
+    const bool bsw_ok = k.n_ranges == 2 && k.edge_enabled && !k.need_pixels && !k.dynamic && k.lut_identity && !ctx->sw.no_store_warp &&
+                        fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1 && k.ranges[1].hi[0] <= 59;
+    if (bsw_ok && h == 240 && w == 320) {
+        rc = launch_bsw<240, 320, 24, 2>(ctx, fp, n, st);
+        if (rc) return rc;
+    }
+    if (bsw_ok && h == 120 && w == 160 && ctx->sw.bsw120) {      // experiment: the same kernel on the resident size
+        rc = launch_bsw<120, 160, 24, 1>(ctx, fp, n, st);
+        if (rc) return rc;
     }
     switch (k.n_ranges * 2 + (k.edge_enabled ? 1 : 0)) {
     case 1: rc = launch_fast_t<0, true>(fp, grid, st); break;
@@ -454,6 +472,7 @@ int trs_ctx_create(int device, trs_ctx** out)
     c->sw.force_generic = getenv("TRS_FORCE_GENERIC") != nullptr;
     c->sw.no_banded = getenv("TRS_NO_BANDED") != nullptr;
     c->sw.no_store_warp = getenv("TRS_NO_STORE_WARP") != nullptr;
+    c->sw.bsw120 = getenv("TRS_BSW120") != nullptr;
     c->sw.resize_scalar = getenv("TRS_RESIZE_SCALAR") != nullptr;
     c->sw.resize_gather = getenv("TRS_RESIZE_GATHER") != nullptr;
     if (const char* e = getenv("TRS_LOCATE")) c->sw.locate = e[0] == 'w' ? 1 : 2;
