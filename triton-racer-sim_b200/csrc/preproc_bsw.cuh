@@ -147,8 +147,8 @@ __device__ __forceinline__ void p2_nms_lagged(const FastParams& P, const Dims& D
 // =========================================================================================================
 // the kernel: NCW compute warps + 2 store warps, two CTAs per SM
 // =========================================================================================================
-template <int NR, int F0, int F1, int H, int W, int R, int NSW = 2>
-__global__ void __maxnreg__(SW_MAXREG) k_preprocess_bsw(const __grid_constant__ FastParams P)
+template <int NR, int F0, int F1, int H, int W, int R, int NSW = 2, int MAXREG = SW_MAXREG>
+__global__ void __maxnreg__(MAXREG) k_preprocess_bsw(const __grid_constant__ FastParams P)
 {
     using L = BswLayout<H, W, R, NR, NSW>;
     extern __shared__ __align__(16) uint8_t smem[];

@@ -67,7 +67,7 @@ enum { HOST_STREAMS = 3 };
 // Test-only switches (tests/test_gpu_parity.py forces every kernel variant through the same goldens): read from the environment ONCE,
 // when the context is created, so no call on the N = 1 latency path pays a getenv.
 struct TrsSwitches {
-    bool force_generic = false, no_banded = false, no_store_warp = false, resize_scalar = false, resize_gather = false, bsw120 = false;
+    bool force_generic = false, no_banded = false, no_store_warp = false, resize_scalar = false, resize_gather = false;
     int locate = 0;                    // 0 = by batch size, 1 = warp per car, 2 = thread per car
     size_t host_chunk_bytes = (size_t)48 << 20;      // ~48 MB of frames per chunk of the host pipeline (the link saturates from ~16 MB up)
 };
@@ -263,11 +263,11 @@ int launch_fast_t(const trs::FastParams& fp, int grid, cudaStream_t st)
 }
 
 // Banded store-warp kernel (preproc_bsw.cuh) for one compile-time geometry.  Returns 1 if launched, 0 if it does not fit, < 0 on error.
-template <int H, int W, int R, int NSW>
+template <int H, int W, int R, int NSW, int MAXREG = trs::SW_MAXREG>
 int launch_bsw(trs_ctx* ctx, const trs::FastParams& fp, int n, cudaStream_t st)
 {
     using L = trs::BswLayout<H, W, R, 2, NSW>;
-    auto kern = trs::k_preprocess_bsw<2, (int)DEFAULT_F0, (int)DEFAULT_F1, H, W, R, NSW>;
+    auto kern = trs::k_preprocess_bsw<2, (int)DEFAULT_F0, (int)DEFAULT_F1, H, W, R, NSW, MAXREG>;
     if (L::TOTAL > (ctx->smem_optin + 1024) / 2 - 1024) return 0;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) { cuda_fail(e, "cudaFuncSetAttribute(bsw)"); return -100 - (int)e; }
@@ -364,10 +364,6 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
                         fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1 && k.ranges[1].hi[0] <= 59;
     if (bsw_ok && h == 240 && w == 320) {
         rc = launch_bsw<240, 320, 24, 2>(ctx, fp, n, st);
-        if (rc) return rc;
-    }
-    if (bsw_ok && h == 120 && w == 160 && ctx->sw.bsw120) {      // experiment: the same kernel on the resident size
-        rc = launch_bsw<120, 160, 24, 1>(ctx, fp, n, st);
         if (rc) return rc;
     }
     switch (k.n_ranges * 2 + (k.edge_enabled ? 1 : 0)) {
@@ -472,7 +468,6 @@ int trs_ctx_create(int device, trs_ctx** out)
     c->sw.force_generic = getenv("TRS_FORCE_GENERIC") != nullptr;
     c->sw.no_banded = getenv("TRS_NO_BANDED") != nullptr;
     c->sw.no_store_warp = getenv("TRS_NO_STORE_WARP") != nullptr;
-    c->sw.bsw120 = getenv("TRS_BSW120") != nullptr;
     c->sw.resize_scalar = getenv("TRS_RESIZE_SCALAR") != nullptr;
     c->sw.resize_gather = getenv("TRS_RESIZE_GATHER") != nullptr;
     if (const char* e = getenv("TRS_LOCATE")) c->sw.locate = e[0] == 'w' ? 1 : 2;
