@@ -28,13 +28,19 @@ def features(n, seed):
     return (rng.uniform(0, 1, n).astype(np.float32), rng.uniform(0, 10, n).astype(np.float32))
 
 
-def test_layer_by_layer():
-    n, h, w = 9, 120, 160
+@pytest.mark.parametrize("rowconv", ["1", "0"])
+@pytest.mark.parametrize("n,h,w,cap", [(9, 120, 160, 16), (7, 240, 320, 4), (5, 96, 94, 8)])
+def test_layer_by_layer(monkeypatch, rowconv, n, h, w, cap):
+    """rowconv: conv2 / conv3 as GEMMs per input row (k_pilot_rowconv, the default) or per (output row, kernel row) (k_pilot_gemm)."""
+    monkeypatch.setenv("TRS_PILOT_ROWCONV", rowconv)
     frames = synth.frame_pool(n, h, w, seed=11)
     wts = ref.random_weights(ref.CNN_2D_FULL_HOUSE, h, w, seed=3)
     spd, loc = features(n, 1)
-    net = PilotNet(ModelType.CNN_2D_FULL_HOUSE, wts, h, w, device=0, max_batch=16)
+    net = PilotNet(ModelType.CNN_2D_FULL_HOUSE, wts, h, w, device=0, max_batch=cap)
     out = net.forward_device(torch.from_numpy(frames).cuda(), torch.from_numpy(spd).cuda(), torch.from_numpy(loc).cuda()).cpu().numpy()
+    if n > cap:                                               # the activations of the last chunk are what the workspace holds
+        frames, spd, loc, out = frames[-(n % cap or cap):], spd[-(n % cap or cap):], loc[-(n % cap or cap):], out[-(n % cap or cap):]
+        n = frames.shape[0]
     prev = frames.astype(np.float32) / np.float32(255)       # conv1 reads the u8 frame itself (1 / 255 folded into its weights)
     report = []
     for layer in range(1, 8):

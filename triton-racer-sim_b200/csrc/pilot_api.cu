@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -36,6 +37,9 @@ struct Layer {
     int kh = 0, kw = 0, stride = 1, cin = 0, cin_mem = 0, cout = 0, npad = 0, stages = 0;
     int hi = 0, wi = 0, ho = 0, wo = 0;
     GemmGeom g{};
+    bool row = false;             // stride-2, five-row layer run by k_pilot_rowconv (GEMMs per input row)
+    GemmGeom gr{};                // its tiling: lanes = bx output columns x bn frames, by = output rows per tile
+    alignas(64) CUtensorMap map_a_row;
     alignas(64) CUtensorMap map_a;
     alignas(64) CUtensorMap map_b;
     __half* w_dev = nullptr;      // [npad][nkb * 64]
@@ -83,6 +87,20 @@ void choose_box(int wo, int ho, int* bx, int* by, int* bn, bool conv1 = false)
         }
 }
 
+// k_pilot_rowconv: accumulator rows = bx output columns x bn frames (<= 128): the split of the output width that fills the most rows
+void choose_row_box(int wo, int* bx, int* bn)
+{
+    double best = -1;
+    *bx = 1; *bn = 1;
+    for (int x = 1; x <= std::min(wo, BLOCK_M); ++x) {
+        const int xt = (wo + x - 1) / x, n = BLOCK_M / x;
+        const double eff = (double)wo * n / ((double)xt * BLOCK_M);
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && x > *bx)) { best = eff; *bx = x; *bn = n; }
+    }
+}
+
+constexpr int ROW_STAGES = 6;
+
 const trs_tensor* find(const trs_tensor* w, int n, const std::string& name)
 {
     for (int i = 0; i < n; ++i)
@@ -124,6 +142,22 @@ int launch_gemm(const Layer& L, int nf, int sm_count, cudaStream_t st)
     return 0;
 }
 
+template <int F, int KCH, int LAST>
+int launch_rowconv(const Layer& L, int nf, int sm_count, cudaStream_t st)
+{
+    GemmGeom g = L.gr;
+    g.nf = nf;
+    const long long tiles = (long long)g.x_tiles * g.y_tiles * ((nf + g.bn - 1) / g.bn);
+    if (tiles > 0x7fffffffLL) return trs_i_fail(TRS_E_RANGE, "too many tiles in one launch: lower max_batch");
+    g.tiles = (int)tiles;
+    const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)sm_count);      // 512 TMEM columns: one CTA per SM
+    k_pilot_rowconv<F, KCH, LAST, ROW_STAGES><<<grid, GEMM_THREADS, rowconv_smem_bytes<F>(KCH, ROW_STAGES), st>>>(
+        L.map_a_row, L.map_b, g, L.b_dev, static_cast<__half*>(L.out));
+    CU(cudaGetLastError());
+    trs_i_count_launches(1);
+    return 0;
+}
+
 template <int NPAD, int STAGES, bool F32>
 cudaError_t allow_smem()
 {
@@ -136,6 +170,7 @@ struct trs_pilot {
     trs_ctx* ctx = nullptr;
     int device = 0, sm_count = 0;
     int kind = 0, h = 0, w = 0, cap = 0;
+    bool no_rowconv = false;          // TRS_PILOT_ROWCONV=0 (tests run both formulations of conv2 / conv3)
     Layer L[N_CONV + 1];              // seven convolutions + the first Dense layers of the heads as one GEMM
     Conv1Geom c1{};
     float* partial = nullptr;         // (cap, ldp) fp32
@@ -164,6 +199,13 @@ int encode_maps(trs_pilot* p, Layer& L, bool weights_only = false)
         CUresult r = enc(&L.map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, L.in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return trs_i_fail(TRS_E_STATE, "cuTensorMapEncodeTiled (activations %dx%dx%d) failed: CUresult %d", L.hi, L.wi, L.cin_mem, (int)r);
+        if (L.row) {
+            // the same view, one input row of bx output columns x bn frames per box
+            const cuuint32_t rbox[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)L.gr.bx, 1u, 1u, (cuuint32_t)L.gr.bn};
+            r = enc(&L.map_a_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, L.in, dims, strides, rbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return trs_i_fail(TRS_E_STATE, "cuTensorMapEncodeTiled (input rows %dx%dx%d) failed: CUresult %d", L.hi, L.wi, L.cin_mem, (int)r);
+        }
     }
     {
         const cuuint64_t dims[2] = {(cuuint64_t)L.g.nkb * BLOCK_K, (cuuint64_t)L.npad};
@@ -264,6 +306,18 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
         g.ldc = L.cout;
         g.last_steps = ((L.kw * L.cin_mem - (g.kchunks - 1) * BLOCK_K) + UMMA_K - 1) / UMMA_K;
         L.out_bytes_per_frame = (size_t)L.ho * L.wo * L.cout * sizeof(__half);
+        // the two stride-2 layers behind conv1 (24 -> 32 and 32 -> 64 channels: kernel-row runs of 120 and 160 values) have row-GEMM instantiations
+        const bool row2 = L.npad == 32 && g.kchunks == 2 && g.last_steps == 4, row3 = L.npad == 64 && g.kchunks == 3 && g.last_steps == 2;
+        if (i > 0 && L.kh == 5 && L.stride == 2 && L.cout == L.npad && (row2 || row3) && !p->no_rowconv) {
+            const int oyt = 256 / L.npad;
+            GemmGeom& r = L.gr;
+            r = g;
+            choose_row_box(L.wo, &r.bx, &r.bn);
+            r.by = oyt;
+            r.x_tiles = (L.wo + r.bx - 1) / r.bx;
+            r.y_tiles = (L.ho + oyt - 1) / oyt;
+            L.row = true;
+        }
         hi = L.ho; wi = L.wo; cin = cin_mem = L.cout;
     }
     const int flat = hi * wi * cin;                       // Flatten of the NHWC tensor (keras_train.py:153)
@@ -376,11 +430,18 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
     CU((allow_smem<128, 3, false>()));
     CU((allow_smem<128, 3, true>()));
     CU((allow_smem<256, 4, true>()));
+    for (int i = 1; i < N_CONV; ++i) {
+        const Layer& L = p->L[i];
+        if (!L.row) continue;
+        if (L.npad == 32) CU(cudaFuncSetAttribute(k_pilot_rowconv<32, 2, 4, ROW_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_smem_bytes<32>(2, ROW_STAGES)));
+        else CU(cudaFuncSetAttribute(k_pilot_rowconv<64, 3, 2, ROW_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_smem_bytes<64>(3, ROW_STAGES)));
+    }
     return 0;
 }
 
 int run_layer(const Layer& L, int nf, bool f32, int sms, cudaStream_t st)
 {
+    if (L.row) return L.npad == 32 ? launch_rowconv<32, 2, 4>(L, nf, sms, st) : launch_rowconv<64, 3, 2>(L, nf, sms, st);
     if (f32) return L.npad == 256 ? launch_gemm<256, 4, true>(L, nf, sms, st) : launch_gemm<128, 3, true>(L, nf, sms, st);
     switch (L.npad) {
         case 32: return launch_gemm<32, 5, false>(L, nf, sms, st);
@@ -408,6 +469,7 @@ int trs_pilot_create(trs_ctx* ctx, int model_type, int h, int w, const trs_tenso
     p->device = trs_i_ctx_device(ctx);
     p->sm_count = trs_i_ctx_sm_count(ctx);
     p->kind = model_type; p->h = h; p->w = w; p->cap = max_batch;
+    if (const char* e = getenv("TRS_PILOT_ROWCONV")) p->no_rowconv = e[0] == '0';
     TrsDeviceGuard guard(p->device);
     if (guard.err != cudaSuccess) { delete p; return trs_i_cuda_fail(guard.err, "cudaSetDevice"); }
     const int rc = build(p, weights, n_weights);

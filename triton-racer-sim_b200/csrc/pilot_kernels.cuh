@@ -88,6 +88,23 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// keep a loop-invariant value in a register: without this the compiler rematerialises shared-window addresses (S2UR SR_CgaCtaId + ULEA,
+// ~30 cycles of latency each) and kernel parameters (LDC) inside the single-thread issue loops, whose cost is pure dependent latency
+__device__ __forceinline__ uint32_t keep(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ int keep(int x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)      // non-blocking probe
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 // A wait that cannot hang the GPU: a barrier that has not flipped after 2^22 polls (each poll already blocks for the hardware's
 // try_wait time limit) is a protocol bug -> trap instead of spinning forever.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
@@ -106,6 +123,17 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         __nanosleep(40);
         if (++spins == (1u << 22)) __trap();
     }
+}
+
+// One lane of a converged warp.  Code under `if (elect_one())` is known to the compiler to run in a single lane, so the uniform-datapath
+// instructions in it (UTCHMMA, UTMALDG, UTCBAR) are emitted once; under `if (lane == 0)` each of them is wrapped in an
+// ELECT / PLOP3 / BRA.U.ANY loop over the "active lanes", which made the MMA-issuing thread the bottleneck of every layer
+// (profiles/r02_pilot.md: 134 instructions per four MMAs).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4)
@@ -240,50 +268,57 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
+        if (elect_one()) {
+            const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+            uint32_t s = 0, ph = 0;                                  // ring position; ph = parity of the stage's NEXT completion
             TileWalk tw;
             for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g)) {
                 const int x0 = tw.xt * g.bx, y0 = tw.yt * g.by, n0 = tw.nt * g.bn;
                 int kr = 0, ch = 0;
-                for (int kb = 0; kb < g.nkb; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, round = it / STAGES;
-                    if (round > 0) mbar_wait(smem_u32(&bar_empty[s]), (round - 1) & 1u);
-                    const uint32_t full = smem_u32(&bar_full[s]);
+                for (int kb = 0; kb < g.nkb; ++kb) {
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);              // (a fresh barrier passes a wait on parity 1)
+                    const uint32_t full = full0 + 8 * s;
                     mbar_expect_tx(full, rows_box * (BLOCK_K * 2) + B_STAGE_BYTES);
                     const uint32_t a_dst = tiles + s * STAGE_BYTES;
                     tma_load_5d(a_dst, &map_a, full, ch * BLOCK_K, x0, kr, y0, n0);
                     tma_load_2d(a_dst + A_STAGE_BYTES, &map_b, full, kb * BLOCK_K, 0);
                     if (++ch == g.kchunks) { ch = 0; ++kr; }
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_f16(NPAD);
-            uint32_t it = 0, ti = 0;
+            const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+            const uint32_t accf0 = smem_u32(&bar_acc_full[0]), acce0 = smem_u32(&bar_acc_empty[0]);
+            const uint64_t da0 = umma_desc_sw128(tiles), db0 = umma_desc_sw128(tiles + A_STAGE_BYTES);
+            uint32_t s = 0, ph = 0, ti = 0;
             for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++ti) {
                 const uint32_t acc = ti & 1u, use = ti >> 1;
-                if (use > 0) mbar_wait(smem_u32(&bar_acc_empty[acc]), (use - 1) & 1u);     // epilogue has drained this accumulator
+                mbar_wait(acce0 + 8 * acc, (use & 1u) ^ 1u);         // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + acc * NPAD;
                 int ch = 0;
-                for (int kb = 0; kb < g.nkb; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, round = it / STAGES;
-                    mbar_wait(smem_u32(&bar_full[s]), round & 1u);
+                for (int kb = 0; kb < g.nkb; ++kb) {
+                    mbar_wait(full0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_src = tiles + s * STAGE_BYTES;
-                    const uint64_t da = umma_desc_sw128(a_src), db = umma_desc_sw128(a_src + A_STAGE_BYTES);
+                    const uint64_t da = da0 + (uint64_t)(s * (STAGE_BYTES >> 4)), db = db0 + (uint64_t)(s * (STAGE_BYTES >> 4));
                     const bool last = ++ch == g.kchunks;            // the last chunk of a kernel row may be mostly padding
                     if (last) ch = 0;
-                    const int steps = last ? g.last_steps : BLOCK_K / UMMA_K;
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)      // +32 bytes inside the swizzle atom per K step
-                        if (k < steps) umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
-                    umma_commit(smem_u32(&bar_empty[s]));           // stage free once these MMAs have read it
+                    umma_f16(d_tmem, da, db, idesc, (uint32_t)(kb != 0));
+                    if (!last || g.last_steps == BLOCK_K / UMMA_K) {   // +32 bytes inside the swizzle atom per K step
+                        umma_f16(d_tmem, da + 2u, db + 2u, idesc, 1u);
+                        umma_f16(d_tmem, da + 4u, db + 4u, idesc, 1u);
+                        umma_f16(d_tmem, da + 6u, db + 6u, idesc, 1u);
+                    } else {
+                        for (int k = 1; k < g.last_steps; ++k) umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+                    }
+                    umma_commit(empty0 + 8 * s);                    // stage free once these MMAs have read it
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(smem_u32(&bar_acc_full[acc]));          // accumulator complete
+                umma_commit(accf0 + 8 * acc);                       // accumulator complete
             }
         }
         __syncwarp();
@@ -328,6 +363,210 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
                             const int col = c + 8 * j + 2 * e;
                             const float a = fmaxf(__uint_as_float(v[8 * j + 2 * e]) + bias_s[col], 0.0f);
                             const float b = fmaxf(__uint_as_float(v[8 * j + 2 * e + 1]) + bias_s[col + 1], 0.0f);
+                            const __half2 h = __floats2half2_rn(a, b);
+                            p[e] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        dst[j] = make_uint4(p[0], p[1], p[2], p[3]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// Stride-2 convolutions with five kernel rows (conv2, conv3: keras_train.py:137-139 | 199-201) as GEMMs per INPUT row.
+//
+// In k_pilot_gemm a kernel-row run of the input (kw * C contiguous values of input row iy) is the A operand of an N = filters MMA once
+// per (output row, kernel row) it belongs to: 2.5 times on average at stride 2, and with N = 32 / 64 those MMAs are bound by their
+// operand fetch from shared memory, not by arithmetic.  Here the accumulator rows are (frame, output column) and the
+// accumulator COLUMNS are (output row of the tile, filter): input row iy = 2 oy + kr contributes through kernel rows of its own parity
+// only, so ONE MMA with N = 3 F (even rows: kernel rows 4, 2, 0) or 2 F (odd rows: 3, 1) multiplies the run with the weights of all those
+// kernel rows at once and adds into the column blocks of the output rows oy = (iy - kr) / 2, which are adjacent.  The weights sit in shared
+// memory for the CTA's lifetime as [W4 | W2 | W0] and [W3 | W1] (per 64-wide K chunk); at the top and bottom of a tile a sub-range of those
+// blocks is addressed through the descriptor's start address.  Every A run is fetched once per tile (2 OYT + 3 input rows for OYT output rows).
+// The first contribution to an output row (kernel row 0) must overwrite: that K step is issued as two MMAs (accumulating blocks, fresh block).
+// Warp roles and barriers as in k_pilot_gemm; one CTA per SM (two accumulators of 256 TMEM columns: OYT = 256 / F output rows each).
+template <int F>
+constexpr int rowconv_smem_bytes(int kchunks, int stages) { return 1024 + kchunks * 5 * F * BLOCK_K * 2 + stages * A_STAGE_BYTES; }
+
+template <int F, int KCH, int LAST_STEPS, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS) k_pilot_rowconv(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_b, const GemmGeom g,
+                                                                const float* __restrict__ bias, __half* __restrict__ out)
+{
+    constexpr int OYT = 256 / F;                          // output rows per tile
+    constexpr int BLK = F * BLOCK_K * 2;                  // bytes of one kernel row's filters, one K chunk (a multiple of 1024)
+    constexpr int TMEM_COLS = 512;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[STAGES];
+    __shared__ __align__(8) uint64_t bar_empty[STAGES];
+    __shared__ __align__(8) uint64_t bar_acc_full[2];
+    __shared__ __align__(8) uint64_t bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_w;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float bias_s[F];
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_even = base, b_odd = b_even + (uint32_t)(KCH * 3 * BLK), a_stages = b_odd + (uint32_t)(KCH * 2 * BLK);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rows_box = (uint32_t)(g.bx * g.bn);
+
+    for (int i = threadIdx.x; i < F; i += GEMM_THREADS) bias_s[i] = __ldg(bias + i);
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(smem_u32(&bar_full[s]), 1);
+                mbar_init(smem_u32(&bar_empty[s]), 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(smem_u32(&bar_acc_full[a]), 1);
+                mbar_init(smem_u32(&bar_acc_empty[a]), 4);
+            }
+            mbar_init(smem_u32(&bar_w), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // the weights, once: kernel row kr goes to block j of its parity's operand ([4 | 2 | 0] or [3 | 1])
+            const uint32_t wbar = smem_u32(&bar_w);
+            mbar_expect_tx(wbar, (uint32_t)(KCH * 5 * BLK));
+            for (int kr = 0; kr < 5; ++kr) {
+                const int odd = kr & 1, j = odd ? (3 - kr) / 2 : (4 - kr) / 2;
+                for (int c = 0; c < KCH; ++c)
+                    tma_load_2d((odd ? b_odd + (uint32_t)(c * 2 * BLK) : b_even + (uint32_t)(c * 3 * BLK)) + (uint32_t)(j * BLK), &map_b, wbar,
+                                (kr * KCH + c) * BLOCK_K, 0);
+            }
+            const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+            uint32_t s = 0, ph = 0;
+            TileWalk tw;
+            for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g)) {
+                const int x0 = tw.xt * g.bx, oy0 = tw.yt * OYT, n0 = tw.nt * g.bn;
+                const int nrows = 2 * min(OYT, g.ho - oy0) + 3;
+                for (int r = 0; r < nrows; ++r) {
+                    const int iy = 2 * oy0 + r;
+                    const int oyc = min(iy >> 1, g.ho - 1), krc = iy - 2 * oyc;      // the map addresses input rows as 2 oy + kr
+                    for (int ch = 0; ch < KCH; ++ch) {
+                        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                        const uint32_t full = full0 + 8 * s;
+                        mbar_expect_tx(full, rows_box * (BLOCK_K * 2));
+                        tma_load_5d(a_stages + s * A_STAGE_BYTES, &map_a, full, ch * BLOCK_K, x0, krc, oyc, n0);
+                        if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t full0 = keep(smem_u32(&bar_full[0])), empty0 = keep(smem_u32(&bar_empty[0]));
+            const uint32_t accf0 = keep(smem_u32(&bar_acc_full[0])), acce0 = keep(smem_u32(&bar_acc_empty[0]));
+            const uint64_t da0 = umma_desc_sw128(a_stages);
+            const int ho = keep(g.ho);
+            const uint32_t idesc1 = keep(umma_idesc_f16(F));
+            mbar_wait(smem_u32(&bar_w), 0);
+            uint32_t s = 0, ph = 0, ti = 0;
+            bool ready = false;                                                        // the next stage's barrier was seen complete already
+            TileWalk tw;
+            for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g), ++ti) {
+                const int oyn = min(OYT, ho - tw.yt * OYT), nrows = 2 * oyn + 3;
+                const uint32_t acc = ti & 1u, use = ti >> 1;
+                mbar_wait(acce0 + 8 * acc, (use & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + acc * 256u;
+                for (int r = 0; r < nrows; ++r) {
+                    const int odd = r & 1, hh = r >> 1;
+                    // blocks j_lo .. j_hi of this parity's operand are live; block j adds into output row oyl0 + (j - j_lo) of the tile
+                    const int j_lo = odd ? max(0, 1 - hh) : max(0, 2 - hh);
+                    const int j_hi = odd ? min(1, oyn - hh) : min(2, oyn + 1 - hh);
+                    const int oyl0 = (odd ? hh - 1 : hh - 2) + j_lo;
+                    const bool fresh = !odd && j_hi == 2;                              // kernel row 0: first contribution to output row hh
+                    const uint32_t b_par = odd ? b_odd : b_even, b_chunk = (uint32_t)((odd ? 2 : 3) * BLK);
+                    const uint32_t idesc_all = umma_idesc_f16((j_hi - j_lo + 1) * F), idesc_acc = umma_idesc_f16((j_hi - j_lo) * F);
+                    const uint32_t d_row = d_tmem + (uint32_t)(oyl0 * F);
+                    uint64_t db = umma_desc_sw128(b_par + (uint32_t)(j_lo * BLK));
+#pragma unroll
+                    for (int ch = 0; ch < KCH; ++ch, db += (uint64_t)(b_chunk >> 4)) {
+                        if (!ready) mbar_wait(full0 + 8 * s, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t da = da0 + (uint64_t)(s * (A_STAGE_BYTES >> 4));
+                        const uint32_t s_now = s;
+                        if (++s == STAGES) { s = 0; ph ^= 1u; }
+                        ready = mbar_test(full0 + 8 * s, ph);                         // probe the next stage while this one's MMAs are issued
+                        if (ch == 0 && fresh) {
+                            if (j_lo < 2) umma_f16(d_row, da, db, idesc_acc, 1u);
+                            umma_f16(d_tmem + (uint32_t)(hh * F), da, db + (uint64_t)(((2 - j_lo) * BLK) >> 4), idesc1, 0u);
+                        } else {
+                            umma_f16(d_row, da, db, idesc_all, 1u);
+                        }
+#pragma unroll
+                        for (int k = 1; k < (ch == KCH - 1 ? LAST_STEPS : BLOCK_K / UMMA_K); ++k)      // +32 bytes inside the swizzle atom per K step
+                            umma_f16(d_row, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_all, 1u);
+                        umma_commit(empty0 + 8 * s_now);
+                    }
+                }
+                umma_commit(accf0 + 8 * acc);
+            }
+        }
+        __syncwarp();
+    } else {
+        // epilogue: thread = accumulator row = (frame, output column); its OYT x F columns are OYT pixels of F channels
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int rx = r % g.bx, rn = r / g.bx;
+        uint32_t ti = 0;
+        TileWalk tw;
+        for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g), ++ti) {
+            const int x = tw.xt * g.bx + rx, oy0 = tw.yt * OYT, n = tw.nt * g.bn + rn;
+            const int oyn = min(OYT, g.ho - oy0);
+            const bool live = (uint32_t)r < rows_box && x < g.wo && n < g.nf;
+            const uint32_t acc = ti & 1u, use = ti >> 1;
+            mbar_wait_relaxed(smem_u32(&bar_acc_full[acc]), use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int oyl = 0; oyl < oyn; ++oyl) {
+                const size_t row = ((size_t)n * g.ho + oy0 + oyl) * g.wo + x;
+#pragma unroll
+                for (int c = 0; c < F; c += 32) {
+                    uint32_t v[16], u[16];
+                    tmem_ld16(taddr + (uint32_t)(oyl * F + c), v);
+                    tmem_ld16(taddr + (uint32_t)(oyl * F + c + 16), u);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (!live) continue;
+                    uint4* dst = reinterpret_cast<uint4*>(out + row * g.ldc + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (c + 8 * j >= g.n_valid) break;
+                        uint32_t p[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = 8 * j + 2 * e;
+                            const uint32_t xa = col < 16 ? v[col & 15] : u[col & 15], xb = col < 16 ? v[(col + 1) & 15] : u[(col + 1) & 15];
+                            const float a = fmaxf(__uint_as_float(xa) + bias_s[c + col], 0.0f);
+                            const float b = fmaxf(__uint_as_float(xb) + bias_s[c + col + 1], 0.0f);
                             const __half2 h = __floats2half2_rn(a, b);
                             p[e] = *reinterpret_cast<const uint32_t*>(&h);
                         }
@@ -515,7 +754,7 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
             // named barrier after finishing the reads of the previous tile, so no second barrier is needed.
         }
     } else if (warp == 4) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_f16(C1_NPAD);
             mbar_wait(smem_u32(&bar_w), 0);
             const uint64_t db0 = umma_desc_sw128(b_smem), db1 = umma_desc_sw128(b_smem + C1_NPAD * BLOCK_K * 2);
