@@ -170,7 +170,11 @@ struct trs_pilot {
     trs_ctx* ctx = nullptr;
     int device = 0, sm_count = 0;
     int kind = 0, h = 0, w = 0, cap = 0;
-    bool no_rowconv = false;          // TRS_PILOT_ROWCONV=0 (tests run both formulations of conv2 / conv3)
+    bool no_rowconv = false;          // TRS_PILOT_ROWCONV=0 (tests run both formulations of conv1 / conv2 / conv3)
+    bool c1_rows = false;             // conv1 per input row (k_pilot_conv1r): frame rows are a multiple of 16 bytes
+    GemmGeom c1r{};
+    __half* w1r_dev = nullptr;        // [W4 | W2 | W0 | W3 | W1] x 32 filters x 64 K slots
+    alignas(64) CUtensorMap map_w1r;
     Layer L[N_CONV + 1];              // seven convolutions + the first Dense layers of the heads as one GEMM
     Conv1Geom c1{};
     float* partial = nullptr;         // (cap, ldp) fp32
@@ -276,6 +280,7 @@ void destroy(trs_pilot* p)
     }
     cudaFree(p->partial);
     cudaFree(p->blob_dev);
+    cudaFree(p->w1r_dev);
     delete p;
 }
 
@@ -345,6 +350,42 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
         for (int j = 0; j < L.cout; ++j) filt[j] = {k->data, j, L.cout};
         if ((rc = upload_weights(L, filt, std::vector<float>(b->data, b->data + L.cout), i == 0))) return rc;
         if ((rc = encode_maps(p, L, i == 0))) return rc;
+    }
+
+    // conv1 per input row: geometry, weights regrouped by kernel-row parity, their tensor map
+    if (!p->no_rowconv && p->w % 16 == 0) {
+        Layer& L = p->L[0];
+        GemmGeom& r = p->c1r;
+        r = L.g;
+        double best = -1;
+        for (int x = 1; x <= std::min(L.wo, 40); ++x) {                 // (2 x + 3) pixels x 3 bytes (+ misalignment) inside a 256-byte patch row
+            const int xt = (L.wo + x - 1) / x, n = std::min(BLOCK_M / x, 4);
+            const double eff = (double)L.wo * n / ((double)xt * BLOCK_M);
+            if (eff > best + 1e-9 || (eff > best - 1e-9 && x > r.bx)) { best = eff; r.bx = x; r.bn = n; }
+        }
+        r.by = C1R_OYT;
+        r.x_tiles = (L.wo + r.bx - 1) / r.bx;
+        r.y_tiles = (L.ho + C1R_OYT - 1) / C1R_OYT;
+        const trs_tensor* k = find(w, nw, "conv1/kernel");
+        std::vector<__half> hb((size_t)5 * C1_NPAD * BLOCK_K, __float2half(0.0f));
+        const int order[5] = {4, 2, 0, 3, 1};
+        for (int b = 0; b < 5; ++b)
+            for (int f = 0; f < L.cout; ++f)
+                for (int e = 0; e < 15; ++e)
+                    hb[((size_t)b * C1_NPAD + f) * BLOCK_K + e] = __float2half_rn(k->data[((size_t)order[b] * 15 + e) * L.cout + f] / 255.0f);
+        CU(cudaMalloc(&p->w1r_dev, hb.size() * sizeof(__half)));
+        CU(cudaMemcpy(p->w1r_dev, hb.data(), hb.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        EncodeTiledFn enc = encode_fn();
+        if (!enc) return trs_i_fail(TRS_E_STATE, "cuTensorMapEncodeTiled is not available from this driver");
+        const cuuint64_t dims[2] = {(cuuint64_t)BLOCK_K, (cuuint64_t)5 * C1_NPAD};
+        const cuuint64_t strides[1] = {(cuuint64_t)BLOCK_K * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)C1_NPAD};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult cr = enc(&p->map_w1r, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->w1r_dev, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return trs_i_fail(TRS_E_STATE, "cuTensorMapEncodeTiled (conv1 row weights) failed: CUresult %d", (int)cr);
+        CU(cudaFuncSetAttribute(k_pilot_conv1r, cudaFuncAttributeMaxDynamicSharedMemorySize, c1r_smem_bytes(r.bn)));
+        p->c1_rows = true;
     }
 
     // heads (keras_train.py:155-166 | 213-241)
@@ -502,7 +543,29 @@ int trs_pilot_forward(trs_pilot* p, const uint8_t* frames_dev, int n, const floa
     const float* feat1 = spd_feature_dev;
     for (int done = 0; done < n; done += p->cap) {
         const int m = std::min(p->cap, n - done);
-        {
+        const uint8_t* chunk = frames_dev + (size_t)done * frame_bytes;
+        if (p->c1_rows && ((uintptr_t)chunk & 15) == 0) {
+            // conv1 per input row: the patch of a tile is one 3-D TMA box over this chunk's frames (bytes of a row, rows, frames)
+            const Layer& L = p->L[0];
+            GemmGeom g = p->c1r;
+            g.nf = m;
+            const long long tiles = (long long)g.x_tiles * g.y_tiles * ((m + g.bn - 1) / g.bn);
+            if (tiles > 0x7fffffffLL) return trs_i_fail(TRS_E_RANGE, "too many tiles in one launch: lower max_batch");
+            g.tiles = (int)tiles;
+            EncodeTiledFn enc = encode_fn();
+            alignas(64) CUtensorMap map_in;
+            const cuuint64_t dims[3] = {(cuuint64_t)p->w * 3, (cuuint64_t)p->h, (cuuint64_t)m};
+            const cuuint64_t strides[2] = {(cuuint64_t)p->w * 3, (cuuint64_t)frame_bytes};
+            const cuuint32_t box[3] = {(cuuint32_t)C1R_ROWB, (cuuint32_t)C1R_ROWS, (cuuint32_t)g.bn};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult cr = enc(&map_in, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(chunk), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) return trs_i_fail(TRS_E_STATE, "cuTensorMapEncodeTiled (frames %dx%d) failed: CUresult %d", p->h, p->w, (int)cr);
+            const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)p->sm_count);
+            k_pilot_conv1r<<<grid, C1R_THREADS, c1r_smem_bytes(g.bn), st>>>(map_in, p->map_w1r, g, L.b_dev, static_cast<__half*>(L.out));
+            CU(cudaGetLastError());
+            trs_i_count_launches(1);
+        } else {
             const Layer& L = p->L[0];
             GemmGeom g = L.g;
             g.nf = m;
@@ -512,8 +575,7 @@ int trs_pilot_forward(trs_pilot* p, const uint8_t* frames_dev, int n, const floa
             Conv1Geom c = p->c1;
             c.total_bytes = (unsigned long long)m * frame_bytes;
             const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)p->sm_count * 2);
-            k_pilot_conv1<<<grid, C1_THREADS, c1_smem_bytes(), st>>>(L.map_b, g, c, frames_dev + (size_t)done * frame_bytes, L.b_dev,
-                                                                     static_cast<__half*>(L.out));
+            k_pilot_conv1<<<grid, C1_THREADS, c1_smem_bytes(), st>>>(L.map_b, g, c, chunk, L.b_dev, static_cast<__half*>(L.out));
             CU(cudaGetLastError());
             trs_i_count_launches(1);
         }

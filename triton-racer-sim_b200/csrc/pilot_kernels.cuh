@@ -143,6 +143,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1)
 {
     asm volatile(
@@ -821,6 +828,242 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
     if (warp == 4) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C1_TMEM_COLS) : "memory");
+    }
+}
+
+// First convolution per INPUT row (the formulation of k_pilot_rowconv with the builders of k_pilot_conv1).
+//
+// k_pilot_conv1 builds five im2col rows (one per kernel row) for every output pixel; here a builder thread turns the 15 bytes of ONE
+// kernel-row run of an input row into 16 fp16 values once, and one MMA with N = 3 x 32 (even input rows: kernel rows 4, 2, 0) or
+// 2 x 32 (odd rows: 3, 1) adds it into the accumulator columns of the output rows it belongs to: 17 row builds per 7 output rows
+// instead of 35.  Accumulator rows = (frame, output column), columns = (output row of the tile, filter); A goes through tensor memory
+// (tcgen05.st, TS-form MMA: K = 16 is one step).  The tile's input patch (<= 17 rows x 256 bytes x bn frames of u8) arrives by ONE 3-D TMA
+// box per tile through a three-deep ring instead of per-thread global loads.  Needs rows of a multiple of 16 bytes (width % 16 == 0).
+// Warps: 0-3 and 4-7 two builder sets (even / odd A stages), 8-11 epilogue, 12 TMA producer, 13 TMEM + MMA issue.  One CTA per SM.
+constexpr int C1R_THREADS = 448;
+constexpr int C1R_OYT = 7;                                // output rows per tile: 7 x 32 accumulator columns, twice
+constexpr int C1R_ROWS = 2 * C1R_OYT + 3;                 // input rows of a tile
+constexpr int C1R_ROWB = 256;                             // patch row pitch: (2 bx + 3) pixels x 3 bytes <= 256
+constexpr int C1R_ASTAGES = 4;                            // A stages of 16 TMEM columns: the runs of input rows 2t and 2t + 1
+constexpr int C1R_PSTAGES = 3;
+constexpr int C1R_ACC_COLS = C1R_OYT * C1_NPAD;           // 224
+constexpr int C1R_TMEM_A0 = 2 * C1R_ACC_COLS;             // 448: four A stages of 16 columns behind the accumulators
+constexpr int C1R_W_BYTES = 5 * C1_NPAD * BLOCK_K * 2;    // [W4 | W2 | W0 | W3 | W1], 32 filters x 64 K slots (16 used) each
+constexpr int c1r_smem_bytes(int bn) { return 1024 + C1R_W_BYTES + C1R_PSTAGES * C1R_ROWS * C1R_ROWB * bn; }
+
+__global__ void __launch_bounds__(C1R_THREADS) k_pilot_conv1r(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b,
+                                                              const GemmGeom g, const float* __restrict__ bias, __half* __restrict__ out)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_pfull[C1R_PSTAGES];
+    __shared__ __align__(8) uint64_t bar_pempty[C1R_PSTAGES];
+    __shared__ __align__(8) uint64_t bar_afull[C1R_ASTAGES];
+    __shared__ __align__(8) uint64_t bar_aempty[C1R_ASTAGES];
+    __shared__ __align__(8) uint64_t bar_acc_full[2];
+    __shared__ __align__(8) uint64_t bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_w;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float bias_s[C1_NPAD];
+
+    constexpr int BLK = C1_NPAD * BLOCK_K * 2;            // 4096: one kernel row's filters
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_even = base, b_odd = base + 3 * BLK, patch0 = base + C1R_W_BYTES;
+    const uint32_t pstage_bytes = (uint32_t)(C1R_ROWS * C1R_ROWB * g.bn);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rows_box = (uint32_t)(g.bx * g.bn);
+
+    for (int i = threadIdx.x; i < C1_NPAD; i += C1R_THREADS) bias_s[i] = __ldg(bias + i);
+    if (warp == 13) {
+        if (lane == 0) {
+            for (int s = 0; s < C1R_PSTAGES; ++s) { mbar_init(smem_u32(&bar_pfull[s]), 1); mbar_init(smem_u32(&bar_pempty[s]), 8); }
+            for (int s = 0; s < C1R_ASTAGES; ++s) { mbar_init(smem_u32(&bar_afull[s]), 4); mbar_init(smem_u32(&bar_aempty[s]), 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bar_acc_full[a]), 1); mbar_init(smem_u32(&bar_acc_empty[a]), 4); }
+            mbar_init(smem_u32(&bar_w), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp < 8) {
+        // ---- builders: thread r of a set owns accumulator row r = (frame rn, output column rx) of the tile ----
+        const int set = warp >> 2;
+        const int r = threadIdx.x & 127;
+        const bool live = (uint32_t)r < rows_box;
+        const int rx = live ? r % g.bx : 0, rn = live ? r / g.bx : 0;
+        const uint32_t lane_off = (uint32_t)(rn * C1R_ROWS * C1R_ROWB + 6 * rx);       // this row's first byte in patch row 0 of its frame
+        const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C1R_TMEM_A0;
+        const uint32_t pfull0 = keep(smem_u32(&bar_pfull[0])), pempty0 = keep(smem_u32(&bar_pempty[0]));
+        const uint32_t afull0 = keep(smem_u32(&bar_afull[0])), aempty0 = keep(smem_u32(&bar_aempty[0]));
+        const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
+        const uint32_t sel = 0x3210u + 0x1111u * (lane_off & 3u);                     // 6 rx is even: misalignment 0 or 2
+        // one kernel-row run (15 bytes from `wsrc` on, word-aligned below it) -> 16 fp16 values -> 8 TMEM columns of this thread's lane
+        auto build_run = [&](uint32_t wsrc, uint32_t tcol) {
+            uint32_t w0, w1, w2, w3, w4;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wsrc));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(wsrc));
+            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(wsrc));
+            asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(w3) : "r"(wsrc));
+            asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(w4) : "r"(wsrc));
+            const uint32_t bw[4] = {__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel), __byte_perm(w3, w4, sel)};
+            uint32_t hv[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                // bytes (x0 x1 x2 x3) -> halves 1024 + x (0x64xx), minus 1024 -> the integers 0..255, exact in fp16
+                const uint32_t lo = __byte_perm(bw[q], 0x64646464u, 0x4140), hi = __byte_perm(bw[q], 0x64646464u, 0x4342);
+                const __half2 hl = __hsub2(*reinterpret_cast<const __half2*>(&lo), k1024);
+                const __half2 hh = __hsub2(*reinterpret_cast<const __half2*>(&hi), k1024);
+                hv[2 * q] = *reinterpret_cast<const uint32_t*>(&hl);
+                hv[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            tmem_st8(tcol, hv);
+        };
+        uint32_t it = 0, ps = 0, pph = 0;                                             // it: row pairs since the kernel started
+        TileWalk tw;
+        for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g)) {
+            const int oyn = min(C1R_OYT, g.ho - tw.yt * C1R_OYT), npairs = oyn + 2;   // rows 2t, 2t + 1; the last pair has no odd row
+            mbar_wait(pfull0 + 8 * ps, pph);
+            const uint32_t src0 = patch0 + ps * pstage_bytes + (lane_off & ~3u);
+            for (int t = 0; t < npairs; ++t, ++it) {
+                if ((int)(it & 1u) != set) continue;
+                const uint32_t s = it % C1R_ASTAGES, round = it / C1R_ASTAGES;
+                mbar_wait(aempty0 + 8 * s, (round & 1u) ^ 1u);                       // the MMAs that read this A stage last have completed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                build_run(src0 + (uint32_t)(2 * t * C1R_ROWB), a_lane + 16u * s);
+                if (t + 1 < npairs) build_run(src0 + (uint32_t)((2 * t + 1) * C1R_ROWB), a_lane + 16u * s + 8u);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(afull0 + 8 * s);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pempty0 + 8 * ps);                             // this warp has read the last byte of the patch
+            if (++ps == C1R_PSTAGES) { ps = 0; pph ^= 1u; }
+        }
+    } else if (warp == 12) {
+        if (elect_one()) {
+            const uint32_t wbar = smem_u32(&bar_w);
+            mbar_expect_tx(wbar, (uint32_t)C1R_W_BYTES);
+            for (int j = 0; j < 5; ++j) tma_load_2d(base + (uint32_t)(j * BLK), &map_b, wbar, 0, j * C1_NPAD);
+            const uint32_t pfull0 = keep(smem_u32(&bar_pfull[0])), pempty0 = keep(smem_u32(&bar_pempty[0]));
+            uint32_t ps = 0, pph = 0;
+            TileWalk tw;
+            for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g)) {
+                mbar_wait(pempty0 + 8 * ps, pph ^ 1u);
+                mbar_expect_tx(pfull0 + 8 * ps, pstage_bytes);
+                tma_load_3d(patch0 + ps * pstage_bytes, &map_in, pfull0 + 8 * ps, 6 * tw.xt * g.bx, 2 * tw.yt * C1R_OYT, tw.nt * g.bn);
+                if (++ps == C1R_PSTAGES) { ps = 0; pph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 13) {
+        if (elect_one()) {
+            const uint32_t afull0 = keep(smem_u32(&bar_afull[0])), aempty0 = keep(smem_u32(&bar_aempty[0]));
+            const uint32_t accf0 = keep(smem_u32(&bar_acc_full[0])), acce0 = keep(smem_u32(&bar_acc_empty[0]));
+            const int ho = keep(g.ho);
+            const uint32_t idesc1 = keep(umma_idesc_f16(C1_NPAD));
+            mbar_wait(smem_u32(&bar_w), 0);
+            const uint64_t db_e = umma_desc_sw128(b_even), db_o = umma_desc_sw128(b_odd);      // [W4 | W2 | W0], [W3 | W1]
+            const uint32_t idesc2 = keep(umma_idesc_f16(2 * C1_NPAD)), idesc3 = keep(umma_idesc_f16(3 * C1_NPAD));
+            const uint32_t a_tmem0 = tmem_base + C1R_TMEM_A0;
+            uint32_t it = 0, ti = 0;
+            TileWalk tw;
+            for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g), ++ti) {
+                const int oyn = min(C1R_OYT, ho - tw.yt * C1R_OYT), npairs = oyn + 2;
+                const uint32_t acc = ti & 1u, use = ti >> 1;
+                mbar_wait(acce0 + 8 * acc, (use & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)C1R_ACC_COLS;
+                for (int t = 0; t < npairs; ++t, ++it) {
+                    const uint32_t s = it % C1R_ASTAGES, round = it / C1R_ASTAGES;
+                    const uint32_t a_e = a_tmem0 + 16u * s, a_o = a_e + 8u;
+                    mbar_wait(afull0 + 8 * s, round & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (t >= 2 && t < oyn) {
+                        // steady state: even row 2t adds kernel rows 4, 2 into output rows t - 2, t - 1 and starts output row t with kernel
+                        // row 0; odd row 2t + 1 adds kernel rows 3, 1 into output rows t - 1, t
+                        const uint32_t d = d_tmem + (uint32_t)((t - 2) * C1_NPAD);
+                        umma_f16_ts(d, a_e, db_e, idesc2, 1u);
+                        umma_f16_ts(d + 2u * C1_NPAD, a_e, db_e + (uint64_t)((2 * BLK) >> 4), idesc1, 0u);
+                        umma_f16_ts(d + (uint32_t)C1_NPAD, a_o, db_o, idesc2, 1u);
+                    } else {
+                        // the top and bottom of the tile: only the kernel rows whose output row lies inside it
+                        const int je_lo = max(0, 2 - t), je_hi = min(2, oyn + 1 - t);
+                        const uint32_t d_e = d_tmem + (uint32_t)((t - 2 + je_lo) * C1_NPAD);
+                        const uint64_t db = db_e + (uint64_t)((je_lo * BLK) >> 4);
+                        if (je_hi == 2) {                                            // kernel row 0 starts output row t
+                            if (je_lo < 2) umma_f16_ts(d_e, a_e, db, umma_idesc_f16((2 - je_lo) * C1_NPAD), 1u);
+                            umma_f16_ts(d_tmem + (uint32_t)(t * C1_NPAD), a_e, db_e + (uint64_t)((2 * BLK) >> 4), idesc1, 0u);
+                        } else {
+                            umma_f16_ts(d_e, a_e, db, umma_idesc_f16((je_hi - je_lo + 1) * C1_NPAD), 1u);
+                        }
+                        if (t <= oyn) {                                              // odd row 2t + 1 exists
+                            const int jo_lo = max(0, 1 - t), jo_hi = min(1, oyn - t);
+                            umma_f16_ts(d_tmem + (uint32_t)((t - 1 + jo_lo) * C1_NPAD), a_o, db_o + (uint64_t)((jo_lo * BLK) >> 4),
+                                        umma_idesc_f16((jo_hi - jo_lo + 1) * C1_NPAD), 1u);
+                        }
+                    }
+                    umma_commit(aempty0 + 8 * s);
+                }
+                umma_commit(accf0 + 8 * acc);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue (warps 8..11): thread = accumulator row = (frame, output column); OYT x 32 columns = OYT pixels ----
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int rx = r % g.bx, rn = r / g.bx;
+        uint32_t ti = 0;
+        TileWalk tw;
+        for (tw.init(g, blockIdx.x, gridDim.x); tw.tile < g.tiles; tw.next(g), ++ti) {
+            const int x = tw.xt * g.bx + rx, oy0 = tw.yt * C1R_OYT, n = tw.nt * g.bn + rn;
+            const int oyn = min(C1R_OYT, g.ho - oy0);
+            const bool live = (uint32_t)r < rows_box && x < g.wo && n < g.nf;
+            const uint32_t acc = ti & 1u, use = ti >> 1;
+            mbar_wait_relaxed(smem_u32(&bar_acc_full[acc]), use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + acc * (uint32_t)C1R_ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int oyl = 0; oyl < oyn; ++oyl) {
+                const size_t row = ((size_t)n * g.ho + oy0 + oyl) * g.wo + x;
+                uint32_t v[16], u[16];
+                tmem_ld16(taddr + (uint32_t)(oyl * C1_NPAD), v);
+                tmem_ld16(taddr + (uint32_t)(oyl * C1_NPAD + 16), u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (!live) continue;
+                uint4* dst = reinterpret_cast<uint4*>(out + row * g.ldc);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (8 * j >= g.n_valid) break;
+                    uint32_t p[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = 8 * j + 2 * e;
+                        const uint32_t xa = col < 16 ? v[col & 15] : u[col & 15], xb = col < 16 ? v[(col + 1) & 15] : u[(col + 1) & 15];
+                        const float a = fmaxf(__uint_as_float(xa) + bias_s[col], 0.0f);
+                        const float b = fmaxf(__uint_as_float(xb) + bias_s[col + 1], 0.0f);
+                        const __half2 h = __floats2half2_rn(a, b);
+                        p[e] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    dst[j] = make_uint4(p[0], p[1], p[2], p[3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 13) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
