@@ -100,6 +100,9 @@ void choose_row_box(int wo, int* bx, int* bn)
 }
 
 constexpr int ROW_STAGES = 6;
+// conv2 (32 filters): one CTA per SM with 2 x 256 accumulator columns (eight output rows per tile).  Two CTAs per SM with 2 x 128 columns
+// each (four-row tiles, 16 % more input rows) measured the same.
+constexpr int ROW2_ACC = 256, ROW2_STAGES = 6;
 
 const trs_tensor* find(const trs_tensor* w, int n, const std::string& name)
 {
@@ -142,7 +145,7 @@ int launch_gemm(const Layer& L, int nf, int sm_count, cudaStream_t st)
     return 0;
 }
 
-template <int F, int KCH, int LAST>
+template <int F, int KCH, int LAST, int STAGES, int ACC_COLS>
 int launch_rowconv(const Layer& L, int nf, int sm_count, cudaStream_t st)
 {
     GemmGeom g = L.gr;
@@ -150,8 +153,8 @@ int launch_rowconv(const Layer& L, int nf, int sm_count, cudaStream_t st)
     const long long tiles = (long long)g.x_tiles * g.y_tiles * ((nf + g.bn - 1) / g.bn);
     if (tiles > 0x7fffffffLL) return trs_i_fail(TRS_E_RANGE, "too many tiles in one launch: lower max_batch");
     g.tiles = (int)tiles;
-    const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)sm_count);      // 512 TMEM columns: one CTA per SM
-    k_pilot_rowconv<F, KCH, LAST, ROW_STAGES><<<grid, GEMM_THREADS, rowconv_smem_bytes<F>(KCH, ROW_STAGES), st>>>(
+    const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)sm_count * (512 / (2 * ACC_COLS)));      // TMEM columns per CTA: 2 x ACC_COLS
+    k_pilot_rowconv<F, KCH, LAST, STAGES, ACC_COLS><<<grid, GEMM_THREADS, rowconv_smem_bytes<F>(KCH, STAGES), st>>>(
         L.map_a_row, L.map_b, g, L.b_dev, static_cast<__half*>(L.out));
     CU(cudaGetLastError());
     trs_i_count_launches(1);
@@ -314,7 +317,7 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
         // the two stride-2 layers behind conv1 (24 -> 32 and 32 -> 64 channels: kernel-row runs of 120 and 160 values) have row-GEMM instantiations
         const bool row2 = L.npad == 32 && g.kchunks == 2 && g.last_steps == 4, row3 = L.npad == 64 && g.kchunks == 3 && g.last_steps == 2;
         if (i > 0 && L.kh == 5 && L.stride == 2 && L.cout == L.npad && (row2 || row3) && !p->no_rowconv) {
-            const int oyt = 256 / L.npad;
+            const int oyt = (row2 ? ROW2_ACC : 256) / L.npad;
             GemmGeom& r = L.gr;
             r = g;
             choose_row_box(L.wo, &r.bx, &r.bn);
@@ -474,15 +477,15 @@ int build(trs_pilot* p, const trs_tensor* w, int nw)
     for (int i = 1; i < N_CONV; ++i) {
         const Layer& L = p->L[i];
         if (!L.row) continue;
-        if (L.npad == 32) CU(cudaFuncSetAttribute(k_pilot_rowconv<32, 2, 4, ROW_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_smem_bytes<32>(2, ROW_STAGES)));
-        else CU(cudaFuncSetAttribute(k_pilot_rowconv<64, 3, 2, ROW_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_smem_bytes<64>(3, ROW_STAGES)));
+        if (L.npad == 32) CU(cudaFuncSetAttribute(k_pilot_rowconv<32, 2, 4, ROW2_STAGES, ROW2_ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_smem_bytes<32>(2, ROW2_STAGES)));
+        else CU(cudaFuncSetAttribute(k_pilot_rowconv<64, 3, 2, ROW_STAGES, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_smem_bytes<64>(3, ROW_STAGES)));
     }
     return 0;
 }
 
 int run_layer(const Layer& L, int nf, bool f32, int sms, cudaStream_t st)
 {
-    if (L.row) return L.npad == 32 ? launch_rowconv<32, 2, 4>(L, nf, sms, st) : launch_rowconv<64, 3, 2>(L, nf, sms, st);
+    if (L.row) return L.npad == 32 ? launch_rowconv<32, 2, 4, ROW2_STAGES, ROW2_ACC>(L, nf, sms, st) : launch_rowconv<64, 3, 2, ROW_STAGES, 256>(L, nf, sms, st);
     if (f32) return L.npad == 256 ? launch_gemm<256, 4, true>(L, nf, sms, st) : launch_gemm<128, 3, true>(L, nf, sms, st);
     switch (L.npad) {
         case 32: return launch_gemm<32, 5, false>(L, nf, sms, st);

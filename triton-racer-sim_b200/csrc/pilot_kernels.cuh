@@ -405,14 +405,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_gemm(const __grid_consta
 template <int F>
 constexpr int rowconv_smem_bytes(int kchunks, int stages) { return 1024 + kchunks * 5 * F * BLOCK_K * 2 + stages * A_STAGE_BYTES; }
 
-template <int F, int KCH, int LAST_STEPS, int STAGES>
+template <int F, int KCH, int LAST_STEPS, int STAGES, int ACC_COLS = 256>
 __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_rowconv(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b, const GemmGeom g,
                                                                 const float* __restrict__ bias, __half* __restrict__ out)
 {
-    constexpr int OYT = 256 / F;                          // output rows per tile
+    constexpr int OYT = ACC_COLS / F;                     // output rows per tile (ACC_COLS = 128: two CTAs per SM, two independent MMA chains)
     constexpr int BLK = F * BLOCK_K * 2;                  // bytes of one kernel row's filters, one K chunk (a multiple of 1024)
-    constexpr int TMEM_COLS = 512;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[STAGES];
     __shared__ __align__(8) uint64_t bar_empty[STAGES];
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_rowconv(const __grid_con
                 const uint32_t acc = ti & 1u, use = ti >> 1;
                 mbar_wait(acce0 + 8 * acc, (use & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem_base + acc * 256u;
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)ACC_COLS;
                 for (int r = 0; r < nrows; ++r) {
                     const int odd = r & 1, hh = r >> 1;
                     // blocks j_lo .. j_hi of this parity's operand are live; block j adds into output row oyl0 + (j - j_lo) of the tile
@@ -529,8 +529,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_rowconv(const __grid_con
                             umma_f16(d_row, da, db, idesc_all, 1u);
                         }
 #pragma unroll
-                        for (int k = 1; k < (ch == KCH - 1 ? LAST_STEPS : BLOCK_K / UMMA_K); ++k)      // +32 bytes inside the swizzle atom per K step
+                        for (int k = 1; k < (ch == KCH - 1 ? LAST_STEPS : BLOCK_K / UMMA_K); ++k) {    // +32 bytes inside the swizzle atom per K step
                             umma_f16(d_row, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_all, 1u);
+                        }
                         umma_commit(empty0 + 8 * s_now);
                     }
                 }
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_pilot_rowconv(const __grid_con
             const uint32_t acc = ti & 1u, use = ti >> 1;
             mbar_wait_relaxed(smem_u32(&bar_acc_full[acc]), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * (uint32_t)ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int oyl = 0; oyl < oyn; ++oyl) {
                 const size_t row = ((size_t)n * g.ho + oy0 + oyl) * g.wo + x;
@@ -839,12 +840,14 @@ __global__ void __launch_bounds__(C1_THREADS) k_pilot_conv1(const __grid_constan
 // instead of 35.  Accumulator rows = (frame, output column), columns = (output row of the tile, filter); A goes through tensor memory
 // (tcgen05.st, TS-form MMA: K = 16 is one step).  The tile's input patch (<= 17 rows x 256 bytes x bn frames of u8) arrives by ONE 3-D TMA
 // box per tile through a three-deep ring instead of per-thread global loads.  Needs rows of a multiple of 16 bytes (width % 16 == 0).
-// Warps: 0-3 and 4-7 two builder sets (even / odd A stages), 8-11 epilogue, 12 TMA producer, 13 TMEM + MMA issue.  One CTA per SM.
-constexpr int C1R_THREADS = 448;
-constexpr int C1R_OYT = 7;                                // output rows per tile: 7 x 32 accumulator columns, twice
+// Warps: C1R_SETS builder sets of four (row pairs round-robin), then four epilogue warps, the TMA producer, TMEM + MMA issue.  One CTA per SM.
+constexpr int C1R_SETS = 2;                               // builder sets of four warps (a set covers the 128 TMEM lanes)
+constexpr int C1R_THREADS = 128 * C1R_SETS + 192;         // + four epilogue warps, the TMA producer, the MMA issuer
+constexpr int C1R_OYT = 7;                                // output rows per tile: 7 x 32 accumulator columns, twice (the rest of TMEM holds A stages)
 constexpr int C1R_ROWS = 2 * C1R_OYT + 3;                 // input rows of a tile
 constexpr int C1R_ROWB = 256;                             // patch row pitch: (2 bx + 3) pixels x 3 bytes <= 256
-constexpr int C1R_ASTAGES = 4;                            // A stages of 16 TMEM columns: the runs of input rows 2t and 2t + 1
+constexpr int C1R_ASTAGES = 4;                            // A stages of 16 TMEM columns (the runs of input rows 2t and 2t + 1); eight stages with
+                                                          // six-row tiles, or a third builder set, measured no faster: the MMA chain paces the kernel
 constexpr int C1R_PSTAGES = 3;
 constexpr int C1R_ACC_COLS = C1R_OYT * C1_NPAD;           // 224
 constexpr int C1R_TMEM_A0 = 2 * C1R_ACC_COLS;             // 448: four A stages of 16 columns behind the accumulators
@@ -873,9 +876,10 @@ __global__ void __launch_bounds__(C1R_THREADS) k_pilot_conv1r(const __grid_const
     const uint32_t rows_box = (uint32_t)(g.bx * g.bn);
 
     for (int i = threadIdx.x; i < C1_NPAD; i += C1R_THREADS) bias_s[i] = __ldg(bias + i);
-    if (warp == 13) {
+    constexpr int W_EPI = 4 * C1R_SETS, W_TMA = W_EPI + 4, W_MMA = W_EPI + 5;
+    if (warp == W_MMA) {
         if (lane == 0) {
-            for (int s = 0; s < C1R_PSTAGES; ++s) { mbar_init(smem_u32(&bar_pfull[s]), 1); mbar_init(smem_u32(&bar_pempty[s]), 8); }
+            for (int s = 0; s < C1R_PSTAGES; ++s) { mbar_init(smem_u32(&bar_pfull[s]), 1); mbar_init(smem_u32(&bar_pempty[s]), 4 * C1R_SETS); }
             for (int s = 0; s < C1R_ASTAGES; ++s) { mbar_init(smem_u32(&bar_afull[s]), 4); mbar_init(smem_u32(&bar_aempty[s]), 1); }
             for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bar_acc_full[a]), 1); mbar_init(smem_u32(&bar_acc_empty[a]), 4); }
             mbar_init(smem_u32(&bar_w), 1);
@@ -890,7 +894,7 @@ __global__ void __launch_bounds__(C1R_THREADS) k_pilot_conv1r(const __grid_const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp < 8) {
+    if (warp < W_EPI) {
         // ---- builders: thread r of a set owns accumulator row r = (frame rn, output column rx) of the tile ----
         const int set = warp >> 2;
         const int r = threadIdx.x & 127;
@@ -902,8 +906,8 @@ __global__ void __launch_bounds__(C1R_THREADS) k_pilot_conv1r(const __grid_const
         const uint32_t afull0 = keep(smem_u32(&bar_afull[0])), aempty0 = keep(smem_u32(&bar_aempty[0]));
         const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
         const uint32_t sel = 0x3210u + 0x1111u * (lane_off & 3u);                     // 6 rx is even: misalignment 0 or 2
-        // one kernel-row run (15 bytes from `wsrc` on, word-aligned below it) -> 16 fp16 values -> 8 TMEM columns of this thread's lane
-        auto build_run = [&](uint32_t wsrc, uint32_t tcol) {
+        // one kernel-row run (15 bytes from `wsrc` on, word-aligned below it) -> 16 fp16 values (8 registers)
+        auto build_run = [&](uint32_t wsrc, uint32_t (&hv)[8]) {
             uint32_t w0, w1, w2, w3, w4;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wsrc));
             asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(wsrc));
@@ -911,7 +915,6 @@ __global__ void __launch_bounds__(C1R_THREADS) k_pilot_conv1r(const __grid_const
             asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(w3) : "r"(wsrc));
             asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(w4) : "r"(wsrc));
             const uint32_t bw[4] = {__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel), __byte_perm(w3, w4, sel)};
-            uint32_t hv[8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 // bytes (x0 x1 x2 x3) -> halves 1024 + x (0x64xx), minus 1024 -> the integers 0..255, exact in fp16
@@ -921,7 +924,18 @@ __global__ void __launch_bounds__(C1R_THREADS) k_pilot_conv1r(const __grid_const
                 hv[2 * q] = *reinterpret_cast<const uint32_t*>(&hl);
                 hv[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&hh);
             }
-            tmem_st8(tcol, hv);
+        };
+        // The stores of a pair are left in flight while the next pair is converted: their completion (tcgen05.wait::st) and the arrival
+        // on the stage's barrier come right before the next pair's stores.
+        uint32_t pending = 0;                                                         // barrier of the pair whose stores are in flight
+        auto flush = [&]() {
+            if (pending) {
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pending);
+                pending = 0;
+            }
         };
         uint32_t it = 0, ps = 0, pph = 0;                                             // it: row pairs since the kernel started
         TileWalk tw;
@@ -930,22 +944,24 @@ __global__ void __launch_bounds__(C1R_THREADS) k_pilot_conv1r(const __grid_const
             mbar_wait(pfull0 + 8 * ps, pph);
             const uint32_t src0 = patch0 + ps * pstage_bytes + (lane_off & ~3u);
             for (int t = 0; t < npairs; ++t, ++it) {
-                if ((int)(it & 1u) != set) continue;
+                if ((int)(it % C1R_SETS) != set) continue;
                 const uint32_t s = it % C1R_ASTAGES, round = it / C1R_ASTAGES;
+                uint32_t he[8], ho_[8];
+                build_run(src0 + (uint32_t)(2 * t * C1R_ROWB), he);
+                build_run(src0 + (uint32_t)(min(2 * t + 1, C1R_ROWS - 1) * C1R_ROWB), ho_);   // (the last pair's odd row is never multiplied)
+                flush();
                 mbar_wait(aempty0 + 8 * s, (round & 1u) ^ 1u);                       // the MMAs that read this A stage last have completed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                build_run(src0 + (uint32_t)(2 * t * C1R_ROWB), a_lane + 16u * s);
-                if (t + 1 < npairs) build_run(src0 + (uint32_t)((2 * t + 1) * C1R_ROWB), a_lane + 16u * s + 8u);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(afull0 + 8 * s);
+                tmem_st8(a_lane + 16u * s, he);
+                tmem_st8(a_lane + 16u * s + 8u, ho_);
+                pending = afull0 + 8 * s;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(pempty0 + 8 * ps);                             // this warp has read the last byte of the patch
             if (++ps == C1R_PSTAGES) { ps = 0; pph ^= 1u; }
         }
-    } else if (warp == 12) {
+        flush();
+    } else if (warp == W_TMA) {
         if (elect_one()) {
             const uint32_t wbar = smem_u32(&bar_w);
             mbar_expect_tx(wbar, (uint32_t)C1R_W_BYTES);
@@ -961,7 +977,7 @@ __global__ void __launch_bounds__(C1R_THREADS) k_pilot_conv1r(const __grid_const
             }
         }
         __syncwarp();
-    } else if (warp == 13) {
+    } else if (warp == W_MMA) {
         if (elect_one()) {
             const uint32_t afull0 = keep(smem_u32(&bar_afull[0])), aempty0 = keep(smem_u32(&bar_aempty[0]));
             const uint32_t accf0 = keep(smem_u32(&bar_acc_full[0])), acce0 = keep(smem_u32(&bar_acc_empty[0]));
@@ -1015,7 +1031,7 @@ __global__ void __launch_bounds__(C1R_THREADS) k_pilot_conv1r(const __grid_const
         }
         __syncwarp();
     } else {
-        // ---- epilogue (warps 8..11): thread = accumulator row = (frame, output column); OYT x 32 columns = OYT pixels ----
+        // ---- epilogue warps: thread = accumulator row = (frame, output column); OYT x 32 columns = OYT pixels ----
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int rx = r % g.bx, rn = r / g.bx;
@@ -1061,7 +1077,7 @@ __global__ void __launch_bounds__(C1R_THREADS) k_pilot_conv1r(const __grid_const
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 13) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
