@@ -350,7 +350,7 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
                  "roofline": {"bound": "tensor", "achieved": 2 * macs * npil / t / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                               "frac": 2 * macs * npil / t / 1e12 / tpeak, "peak_source": tsrc,
                               "note": "algorithmic flops of the reference's layers (no padding counted); fp16 operands, fp32 accumulate; "
-                                      "bound by the operand fetch of small-N MMAs (N = 24..128 filters: ~64 B/clk shared memory -> tensor core), see DESIGN.md 4.8"},
+                                      "stride-2 layers as GEMMs per input row (N = 3F / 2F), single-lane roles through elect.sync; paced by MMA completion on small-N tiles, not by the tensor pipe: DESIGN.md 4.8, profiles/r02_pilot.md"},
                  "launches_per_16384_frames": 10,
                  "note": "u8 frames + gym/speed + loc/segment -> model -> speed control (ai/steering, ai/throttle, ai/breaking)"}
         fh1 = ImgPreprocessing(full_house_config(), device=local)
