@@ -365,6 +365,33 @@ def test_full_size_properties_240x320(want_f32):
     comp.onShutdown()
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("h,w,n", [(240, 320, 1536), (120, 160, 3072)])
+@pytest.mark.parametrize("cname", ["dyn_contrast", "exotic", "static_contrast", "edge_only", "colour_only"])
+def test_non_default_configurations_many_frames_per_cta(golden_images, cname, h, w, n):
+    """Every kernel keeps a CTA busy with frame after frame, and the hand-over between its warps (plane sets by frame parity, the tail copy,
+    the per-frame brightness table, the alternating ROI accumulators) only shows with several frames per CTA: five to eleven frames per CTA
+    here, at both resolutions, for the configurations with a brightness / contrast table (static, or rebuilt per frame from rows 40..118),
+    run-time colour ranges, and channels that keep the adjusted pixel.  Every frame against the oracle, the ROI statistic against a direct
+    sum.  (A store-warp kernel that deadlocked with a table and more than two frames per CTA went unnoticed by the small-batch tests.)"""
+    from tests.helpers import image_cases
+    over = image_cases(golden_images).get(cname) or dict(preprocessing_color_filter_enabled=True, preprocessing_edge_detection_enabled=True,
+                                                           preprocessing_contrast_enhancement_ratio=1.6, preprocessing_contrast_enhancement_offset=90)
+    cfg = cfg_for(over)
+    frames = synth.expand_numpy(synth.frame_pool(96, h, w, seed=411), n, start=7)      # brightness shifts of 96 frames
+    want = oracle.process_batch(frames, cfg)
+    comp = ImgPreprocessing(cfg, device=0, normalised_key='cam/normalised_img', collect_stats=True)
+    u8, f32 = comp.process_device(torch.from_numpy(frames).to(DEV))
+    st = comp.stats()
+    got = u8.cpu().numpy()
+    assert np.array_equal(got, want), f"{cname}: {describe(got, want)}"
+    assert np.array_equal(f32.cpu().numpy(), oracle.normalise(want))
+    assert st["frames"] == n
+    if cfg["preprocessing_dynamic_brightness_enabled"]:
+        assert st["roi_sum"] == int(frames[:, 40:119].astype(np.uint64).sum())
+    comp.onShutdown()
+
+
 @pytest.mark.parametrize("hsvs", [
     None,                                                                     # the reference's defaults (core/config.py:23)
     [[[0, 0, 130], [180, 70, 255]], [[25, 100.5, 155], [43, 255, 255]]],       # same live bounds, other saturation thresholds

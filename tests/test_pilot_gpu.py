@@ -74,6 +74,26 @@ def test_models_end_to_end(mt, n, cap):
     net.close()
 
 
+def test_frames_that_are_not_16_byte_aligned_take_the_per_thread_loads():
+    """k_pilot_conv1r reads its patches through a TMA tensor map (16-byte aligned base); a view that starts 4 bytes into an allocation
+    must fall back to k_pilot_conv1 and give the same outputs."""
+    n, h, w = 6, 120, 160
+    frames = synth.frame_pool(n, h, w, seed=21)
+    wts = ref.random_weights(ref.CNN_2D, h, w, seed=4)
+    net = PilotNet(ModelType.CNN_2D, wts, h, w, device=0, max_batch=8)
+    aligned = torch.from_numpy(frames).cuda()
+    raw = torch.empty(frames.size + 64, dtype=torch.uint8, device='cuda')
+    shifted = raw[4:4 + frames.size].view(n, h, w, 3)
+    shifted.copy_(aligned)
+    assert shifted.data_ptr() % 16 == 4
+    a = net.forward_device(aligned).cpu().numpy()
+    b = net.forward_device(shifted).cpu().numpy()
+    want = ref.forward(wts, ref.CNN_2D, frames)
+    assert np.abs(a - want).max() <= E2E_TOL and np.abs(b - want).max() <= E2E_TOL
+    assert np.abs(a - b).max() <= 2e-3, np.abs(a - b).max()
+    net.close()
+
+
 @pytest.mark.parametrize("h,w", [(240, 320), (122, 166), (96, 94)])
 def test_other_frame_sizes(h, w):
     n = 5

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Frames/s of every reference-generated configuration (tests/golden/images.npz cases_json) at one frame size, device-resident inputs.
-usage: tools/bench_configs.py [h w n]   (default 240 320 8192) -> one JSON object on stdout"""
+usage: tools/bench_configs.py [h w n [config,config,...]]   (default 240 320 8192, every configuration) -> one JSON object on stdout"""
 import json
 import os
 import sys
@@ -19,7 +19,11 @@ pool = torch.from_numpy(synth.frame_pool(128, h, w)).cuda()
 frames = synth.expand_torch(pool, n)
 u8, f32 = torch.empty_like(frames), torch.empty(frames.shape, dtype=torch.float32, device="cuda")
 out = {"h": h, "w": w, "frames": n, "configs": {}}
+only = sys.argv[4].split(",") if len(sys.argv) >= 5 else None
 for name, over in cases.items():
+    if only and name not in only:
+        continue
+    print("config", name, file=sys.stderr, flush=True)
     comp = ImgPreprocessing(cfg_for(over), device=0)
     for want_f32 in (False, True):
         fn = lambda: comp.process_device(frames, out_u8=u8, out_f32=f32 if want_f32 else None, want_f32=want_f32)
@@ -34,7 +38,8 @@ for name, over in cases.items():
         torch.cuda.synchronize()
         out["configs"].setdefault(name, {})["u8+f32" if want_f32 else "u8"] = n / (e0.elapsed_time(e1) / 10 * 1e-3)
     comp.onShutdown()
-base = out["configs"]["full_house"]
+base = out["configs"].get("full_house")
 for name, v in out["configs"].items():
-    v["vs_full_house"] = {k: v[k] / base[k] for k in ("u8", "u8+f32")}
+    if base:
+        v["vs_full_house"] = {k: v[k] / base[k] for k in ("u8", "u8+f32")}
 print(json.dumps(out))

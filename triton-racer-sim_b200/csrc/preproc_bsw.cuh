@@ -52,12 +52,12 @@ struct BswLayout {
     static constexpr int OFF_STASH = OFF_EDGE + 2 * PLANE;             // NCW x 8 lanes x 2 rows, then one zero row
     static constexpr int OFF_SDIV = (OFF_STASH + NCW * 8 * STASH_LANE + STASH_ROW + 15) & ~15;
     static constexpr int OFF_HUE = OFF_SDIV + 1024;
-    static constexpr int OFF_LUT = OFF_PIX + 16;                       // (the static table is never used here: init_tables parks it in the pixel buffer)
     static constexpr int OFF_BAR = OFF_HUE + 1024;                     // mbarriers: pixels, hysteresis finished, 2 per compute warp, 1 per mask slot
     static constexpr int NBAR = 2 + 2 * NCW + NSLOT;
     static constexpr int OFF_SYNC = OFF_BAR + 8 * NBAR;                // strip-walk counter
     static constexpr int OFF_RED = (OFF_SYNC + 16 + 15) & ~15;
-    static constexpr int TOTAL = OFF_RED + 32 + 128;
+    static constexpr int OFF_LUT = OFF_RED + 32 + 128;                 // brightness / contrast table (static, or rebuilt per frame)
+    static constexpr int TOTAL = OFF_LUT + 256;
     static constexpr int THREADS = 32 * (NCW + NSW);
 };
 
@@ -147,7 +147,12 @@ __device__ __forceinline__ void p2_nms_lagged(const FastParams& P, const Dims& D
 // =========================================================================================================
 // the kernel: NCW compute warps + 2 store warps, two CTAs per SM
 // =========================================================================================================
-template <int NR, int F0, int F1, int H, int W, int R, int NSW = 2, int MAXREG = SW_MAXREG>
+// LUT: a brightness / contrast table that is not the identity.  The strip walk applies it to the pixel words as it loads them (the column-block
+// warps have no common moment at which the band's rows could be rewritten in place).  The dynamic table of a frame is built at the top of the
+// frame from exact channel sums over rows 40..118 (img_preprocessing.py:88), read from global memory by the compute warps (the bands read those
+// rows again, from L2); the sums of two consecutive frames alternate between two sets of accumulators, so two barriers among the compute
+// warps per frame are enough.
+template <int NR, int F0, int F1, int H, int W, int R, int NSW = 2, int MAXREG = SW_MAXREG, bool LUT = false>
 __global__ void __maxnreg__(MAXREG) k_preprocess_bsw(const __grid_constant__ FastParams P)
 {
     using L = BswLayout<H, W, R, NR, NSW>;
@@ -184,6 +189,7 @@ __global__ void __maxnreg__(MAXREG) k_preprocess_bsw(const __grid_constant__ Fas
     }
     zero_plane_pads(S, H * ww, ww, tid, NT);
     if (tid == 0) sts32(a_cnt, 0);
+    if (tid < 6) sts32(S.red + 4 * tid, 0);                        // ROI sums: three u32 per frame parity
     for (int i = tid; i < L::STASH_ROW / 4; i += NT) sts32(a_zero + 4 * i, 0);
     if (tid < L::NBAR) mbar_init(S.bar + 8 * tid, tid >= 2 + 2 * NCW ? (uint32_t)NSW : 1u);      // a slot's barrier takes every store warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -212,6 +218,39 @@ __global__ void __maxnreg__(MAXREG) k_preprocess_bsw(const __grid_constant__ Fas
         for (int j = 0; j < nfr; ++j) {
             const size_t f = blockIdx.x + (size_t)j * gridDim.x;
             const uint32_t a_edge = (j & 1) ? S.edge2 : S.edge;
+            if (LUT && p.dynamic) {
+                constexpr int Y0 = H < 40 ? H : 40, Y1 = H < 119 ? H : 119, NTRI = (Y1 - Y0) * L::ROWB / 12;      // groups of four pixels = three words
+                const uint32_t* roi = reinterpret_cast<const uint32_t*>(p.in + f * frame_bytes + (size_t)Y0 * L::ROWB);
+                uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll 4
+                for (int i = tid; i < NTRI; i += NC) {
+                    const uint32_t w0 = __ldg(roi + 3 * i), w1 = __ldg(roi + 3 * i + 1), w2 = __ldg(roi + 3 * i + 2);      // R G B R | G B R G | B R G B
+                    c0 = __dp4a(w2, 0x00000100u, __dp4a(w1, 0x00010000u, __dp4a(w0, 0x01000001u, c0)));
+                    c1 = __dp4a(w2, 0x00010000u, __dp4a(w1, 0x01000001u, __dp4a(w0, 0x00000100u, c1)));
+                    c2 = __dp4a(w2, 0x01000001u, __dp4a(w1, 0x00000100u, __dp4a(w0, 0x00010000u, c2)));
+                }
+                for (int o = 16; o; o >>= 1) {
+                    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+                    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+                    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+                }
+                const uint32_t a_sum = S.red + 12 * (uint32_t)(j & 1);
+                if (lane == 0) {
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_sum), "r"(c0) : "memory");
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_sum + 4), "r"(c1) : "memory");
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_sum + 8), "r"(c2) : "memory");
+                }
+                bar_sync(3, NC);
+                const uint32_t s0 = lds32(a_sum), s1 = lds32(a_sum + 4), s2 = lds32(a_sum + 8);
+                const float fdelta = (float)brightness_delta(s0, s1, s2, (double)((Y1 - Y0) * W), p.baseline);
+                for (int i = tid; i < 256; i += NC) sts8(S.lut + i, adjust_entry(i, true, fdelta, p.foff, p.fratio));
+                if (tid == 0) {
+                    const uint32_t a_next = S.red + 12 * (uint32_t)((j + 1) & 1);      // (last touched a frame ago, before that frame's hysteresis barrier)
+                    sts32(a_next, 0); sts32(a_next + 4, 0); sts32(a_next + 8, 0);
+                    if (p.stats) stat_add_one(S, 9, (unsigned long long)s0 + s1 + s2);
+                }
+                bar_sync(3, NC);
+            }
 #pragma unroll 1
             for (int b = 0; b < NB; ++b, ++gb) {
                 if (round) mbar_wait(bar_slot + 8 * slot, (round - 1) & 1u);      // the store warps have written the slab that sat in this slot
@@ -221,7 +260,7 @@ __global__ void __maxnreg__(MAXREG) k_preprocess_bsw(const __grid_constant__ Fas
                 const uint32_t a_pix = S.pix[0] - (uint32_t)(max(R * b - 1, 0) * L::ROWB);               // virtual address of image row 0
                 const uint32_t a_mag = S.mag[0] + (uint32_t)((b & 1) * R * L::MS2) - (uint32_t)((R * b + 1) * L::MS2);      // ... of magnitude row -1
                 const uint32_t a_mask = S.mask + (uint32_t)(slot * L::SLOTB) - (uint32_t)(R * b * L::PRB);           // ... of mask row 0
-                p1_strip_walk<NR, true, F0, F1, false, SEG>(P, Dm, a_pix, a_mag, a_mask, S, M, SEG);
+                p1_strip_walk<NR, true, F0, F1, false, SEG, LUT>(P, Dm, a_pix, a_mag, a_mask, S, M, SEG);
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(my_bar + 8 * (gb & 1u));

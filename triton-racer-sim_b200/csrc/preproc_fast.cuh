@@ -149,6 +149,15 @@ __device__ __forceinline__ uint32_t lut4s(uint32_t a_lut, uint32_t v)
 {
     return lds8(a_lut + (v & 0xff)) | (lds8(a_lut + ((v >> 8) & 0xff)) << 8) | (lds8(a_lut + ((v >> 16) & 0xff)) << 16) | (lds8(a_lut + (v >> 24)) << 24);
 }
+// ... of bytes 1..3 / bytes 0..2 only (the neighbour pixel of a strip); the fourth byte comes back as zero
+__device__ __forceinline__ uint32_t lut3s_hi(uint32_t a_lut, uint32_t v)
+{
+    return (lds8(a_lut + ((v >> 8) & 0xff)) << 8) | (lds8(a_lut + ((v >> 16) & 0xff)) << 16) | (lds8(a_lut + (v >> 24)) << 24);
+}
+__device__ __forceinline__ uint32_t lut3s_lo(uint32_t a_lut, uint32_t v)
+{
+    return lds8(a_lut + (v & 0xff)) | (lds8(a_lut + ((v >> 8) & 0xff)) << 8) | (lds8(a_lut + ((v >> 16) & 0xff)) << 16);
+}
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -205,6 +214,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// (the probe carries a suspend-time hint, which the compiler turns into a NANOSLEEP.SYNCS on the retry path; a hand-written probe + branch loop
+// and explicit nanosleep back-offs of 32 / 128 ns all measured the same frames/s at both resolutions: the retries fill idle issue slots)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done;
@@ -212,7 +223,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"      // %3: suspend-time hint, the warp sleeps instead of spinning
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     } while (!done);
@@ -390,12 +401,26 @@ template <int NR, int F0, int F1>
 __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t (&A)[3], const uint32_t (&B)[3], uint32_t a_sdiv, uint32_t a_hue,
                                              uint32_t (&okm)[NR > 0 ? NR : 1][2])
 {
-    uint32_t fl[NR > 0 ? NR : 1];
+    // fl[r]: which compares are emitted for range r.  A range whose live-bound word is only known at run time gets ALL of them, unconditionally:
+    // a bound that cannot fail was stored by the host as a pattern that never fails (a lower bound <= 0 compares as 0 or -1, an upper bound
+    // >= 255 as itself, capped at 2047), and six packed compares in a row cost less than six predicated ones.  Whether the saturation and the
+    // hue are computed at all stays a run-time decision (hl[r] / P.need_sat: a range without such a bound passes on a saturation or hue of 0).
+    constexpr bool RT0 = F0 < 0, RT1 = F1 < 0;
+    uint32_t fl[NR > 0 ? NR : 1], hl[NR > 0 ? NR : 1];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) fl[r] = r == 0 ? live_flags<F0>(P.fr[0]) : (r == 1 ? live_flags<F1>(P.fr[1]) : P.fr[r].flags);
+    for (int r = 0; r < NR; ++r) {
+        const bool rt = r == 0 ? RT0 : (r == 1 ? RT1 : true);
+        const uint32_t live = r == 0 ? live_flags<F0>(P.fr[0]) : (r == 1 ? live_flags<F1>(P.fr[1]) : P.fr[r].flags);
+        fl[r] = rt ? 63u : live;
+        hl[r] = live & 3u;
+    }
     uint32_t any_s = 0, any_h = 0;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) { any_s |= fl[r] & 12u; any_h |= fl[r] & 3u; }
+    for (int r = 0; r < NR; ++r) {
+        const bool rt = r == 0 ? RT0 : (r == 1 ? RT1 : true);
+        any_s |= rt ? (P.fr[r].flags & 12u) : (fl[r] & 12u);
+        any_h |= hl[r];
+    }
     uint32_t v2[2], d2[2];
     uint32_t alive = 0;
 #pragma unroll
@@ -429,7 +454,7 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
             if (fl[r] & 16u) ok &= hge_mask(v2[half], R.lo[2]);
             if (fl[r] & 32u) ok &= hle_mask(v2[half], R.hi[2]);
             okm[r][half] = ok;
-            if (fl[r] & 3u) alive |= ok;
+            if (hl[r]) alive |= ok;
         }
     }
     if (any_h && __any_sync(0xffffffffu, alive != 0u)) {
@@ -473,7 +498,7 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
         // no pixel of the warp can pass a range with a live hue bound: those ranges are all-zero here
 #pragma unroll
         for (int r = 0; r < NR; ++r)
-            if (fl[r] & 3u) { okm[r][0] = 0; okm[r][1] = 0; }
+            if (hl[r]) { okm[r][0] = 0; okm[r][1] = 0; }
     }
 }
 
@@ -487,7 +512,9 @@ __device__ __forceinline__ void hsv_masks_of(const FastParams& P, const uint32_t
 // SEG > 0 (a multiple of 3): seg_rows is this compile-time constant AND the segments tile the frame exactly (every lane owns SEG rows,
 // r1 == r0 + SEG): the first and the last trip are peeled, so the steady-state row step carries no step-number tests, no row-range
 // predicates and a constant row advance (the two replicated-border cases fall on peeled steps).
-template <int NR, bool EDGE, int F0, int F1, bool BANDED = false, int SEG = 0>
+// LUT: the brightness / contrast table at S.lut is applied to every pixel word as it is loaded (the pixel rows stay raw: kernels whose warps
+// cannot agree on a moment to rewrite the rows in place).
+template <int NR, bool EDGE, int F0, int F1, bool BANDED = false, int SEG = 0, bool LUT = false>
 __device__ __forceinline__ void p1_strip_walk(const FastParams& P, const Dims& Dm, uint32_t a_pix, uint32_t a_mag, uint32_t a_mask, const SmemMap& S,
                                               const StripMap& M, int seg_rows, uint32_t tail_bar = 0, uint32_t tail_parity = 0, int tail_k = 0,
                                               int mask_lo = 0, int mask_hi = 1 << 30)
@@ -523,11 +550,13 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, const Dims& D
         constexpr int MK = decltype(mask_tag)::value, SB = decltype(sobel_tag)::value;
         constexpr bool EXACT = SEG > 0;
         // load image row r0 - 1 + k into slot n; emit output row y = r0 + k - 2
-        const uint32_t w0 = lds32(rp), w1 = lds32(rp + 4), w2 = lds32(rp + 8);
+        uint32_t w0 = lds32(rp), w1 = lds32(rp + 4), w2 = lds32(rp + 8);
+        if (LUT) { w0 = lut4s(S.lut, w0); w1 = lut4s(S.lut, w1); w2 = lut4s(S.lut, w2); }
         uint32_t A[3], B[3];
         unpack_planar(w0, w1, w2, A, B);
         if (EDGE) {
             uint32_t wl = lds32(rp - 4), wr = lds32(rp + 12);       // bytes 1..3 of wl = pixel -1, bytes 0..2 of wr = pixel 4
+            if (LUT) { wl = lut3s_hi(S.lut, wl); wr = lut3s_lo(S.lut, wr); }
             if (left_edge) wl = w0 << 8;                            // (the 16 spare bytes in front of the frame keep rp - 4 inside the window)
             if (right_edge) wr = w2 >> 8;
             // neighbours: Lh = pixels (-1,1), Rh = pixels (2,4)
@@ -1354,8 +1383,12 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const
 //     hysteresis, P3) are double-buffered by frame parity, so the store warps have a whole frame time;
 //   * the shared memory for the second edge plane comes from the candidate plane, which only lives from P2 to P3 and sits
 //     on the last 2.4 KB of the frame buffer: those bytes of the next frame arrive by a second, later bulk copy.
-// Hand-over: named barrier 2 = "planes of frame j are final" (compute warps arrive, store warps sync),
-//            named barrier 3 = "done with frame j's planes" (store warps arrive, compute warps sync before P1 of frame j + 2).
+// Hand-over: named barrier 2 = "planes of frame j are final" (compute warps arrive, store warps sync);
+//            "done with frame j's planes" is one mbarrier per plane set (frame parity): the store warps arrive after the output of frame j,
+//            the compute warps wait for that phase before P1 of frame j + 2.  (A named barrier cannot carry this direction: the store warps
+//            may finish frame j + 1 before the compute warps have asked about frame j - with a brightness / contrast table the compute warps
+//            first wait for the tail copy the store warps issue and then rewrite the frame - and a second round of arrivals on a named
+//            barrier whose first round is still open completes it early and strands the late compute warps.)
 // Compute-only phases use named barrier 1.
 // =========================================================================================================
 enum { SW_COMPUTE_THREADS = 320, SW_THREADS = 384, SW_MAXREG = 80 };      // register allocation rounds a CTA up to a multiple of 4 warps
@@ -1397,13 +1430,17 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
     const int nfr = (int)blockIdx.x < p.n ? (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t mask_set_bytes = (uint32_t)(NR * Dm.plane_bytes);
     const uint32_t main_bytes = frame_bytes - (uint32_t)tail_bytes;
-    const uint32_t bar_main = S.bar, bar_tail = S.bar + 8;
+    const uint32_t bar_main = S.bar, bar_tail = S.bar + 8, bar_free = S.bar + 16;      // bar_free + 8 q: plane set q has been written out
 
     init_tables<NR, F0, F1>(p, S, tid, nthr);
     stats_zero(S, tid);
     zero_mag_borders(S.mag[0], h, w, Dm.mag_stride, tid, nthr);
     zero_plane_pads(S, plane_words, ww, tid, nthr);
-    if (tid == 0) { mbar_init(bar_main, 1); mbar_init(bar_tail, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) {
+        mbar_init(bar_main, 1); mbar_init(bar_tail, 1);
+        mbar_init(bar_free, (SW_THREADS - SW_COMPUTE_THREADS) / 32); mbar_init(bar_free + 8, (SW_THREADS - SW_COMPUTE_THREADS) / 32);      // one arrival per store warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     if (warp < (NC >> 5)) {
@@ -1438,7 +1475,7 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             TRS_TICK(tk1);
             adjust_in_place(p, S.pix[0], S, s_red, tid, NC, lane, [NC] { bar_sync(1, NC); });
             TRS_TICK(tk2);
-            if (j >= 2) bar_sync(3, SW_THREADS);                         // the store warps are done with frame j-2: this plane set is free
+            if (j >= 2) mbar_wait(bar_free + 8 * (j & 1), (uint32_t)((j >> 1) - 1) & 1u);      // the store warps are done with frame j-2: this plane set is free
             TRS_TICK(tk3);
             p1_strip_walk<NR, true, F0, F1, false, (STATIC ? sw_seg_rows<(STATIC ? H : 32), (STATIC ? W : 32)>() : 0)>(
                 P, Dm, S.pix[0], S.mag[0], a_mask, S, M, seg_rows, (tail_bytes && !use_lut) ? bar_tail : 0u, phase, tail_k);
@@ -1492,7 +1529,8 @@ __global__ void __maxnreg__(SW_MAXREG) k_preprocess_sw(const __grid_constant__ F
             }
             p4_output(P, Dm, pa, S.pix[0], p.out_u8 ? p.out_u8 + f * frame_bytes : nullptr, p.out_f32 ? p.out_f32 + f * frame_bytes : nullptr, tid - NC,
                       SW_THREADS - NC);
-            if (j + 2 < nfr) bar_arrive(3, SW_THREADS);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free + 8 * (j & 1));          // (use k of a plane set's barrier is its phase k: frame j + 2 waits for phase j >> 1)
         }
         if (p.stats) {                                                   // the store warps are the last to touch the counters
             bar_sync(4, SW_THREADS - NC);

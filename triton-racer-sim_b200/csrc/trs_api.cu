@@ -263,11 +263,12 @@ int launch_fast_t(const trs::FastParams& fp, int grid, cudaStream_t st)
 }
 
 // Banded store-warp kernel (preproc_bsw.cuh) for one compile-time geometry.  Returns 1 if launched, 0 if it does not fit, < 0 on error.
-template <int H, int W, int R, int NSW, int MAXREG = trs::SW_MAXREG>
+// LUT: a brightness / contrast table that is not the identity.
+template <int H, int W, int R, int NSW, int MAXREG = trs::SW_MAXREG, bool LUT = false>
 int launch_bsw(trs_ctx* ctx, const trs::FastParams& fp, int n, cudaStream_t st)
 {
     using L = trs::BswLayout<H, W, R, 2, NSW>;
-    auto kern = trs::k_preprocess_bsw<2, (int)DEFAULT_F0, (int)DEFAULT_F1, H, W, R, NSW, MAXREG>;
+    auto kern = trs::k_preprocess_bsw<2, (int)DEFAULT_F0, (int)DEFAULT_F1, H, W, R, NSW, MAXREG, LUT>;
     if (L::TOTAL > (ctx->smem_optin + 1024) / 2 - 1024) return 0;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) { cuda_fail(e, "cudaFuncSetAttribute(bsw)"); return -100 - (int)e; }
@@ -360,10 +361,14 @@ int try_launch_fast(trs_ctx* ctx, const trs::PreKParams& k, int n, int h, int w,
     if (grid > n) grid = n;
     int rc;
     // 240x320 (BASELINE.json configs[2]) with the reference's default ranges: banded store-warp kernel with compile-time geometry
-    const bool bsw_ok = k.n_ranges == 2 && k.edge_enabled && !k.need_pixels && !k.dynamic && k.lut_identity && !ctx->sw.no_store_warp &&
+    // (any brightness / contrast setting: the table is applied as the strip walk loads its words.  Ranges whose live bounds are only known at
+    // run time stay on k_preprocess_banded: measured at 240x320 with the reference-generated "exotic" configuration, 1.50 M frames/s there
+    // against 1.36 M here - the run-time colour tests take twice the instructions and the table on top of them costs more per loaded word than
+    // the banded kernel's in-place pass)
+    const bool bsw_ok = k.n_ranges == 2 && k.edge_enabled && !k.need_pixels && !ctx->sw.no_store_warp &&
                         fp.fr[0].flags == DEFAULT_F0 && fp.fr[1].flags == DEFAULT_F1 && k.ranges[1].hi[0] <= 59;
     if (bsw_ok && h == 240 && w == 320) {
-        rc = launch_bsw<240, 320, 24, 2>(ctx, fp, n, st);
+        rc = (k.dynamic || !k.lut_identity) ? launch_bsw<240, 320, 24, 2, trs::SW_MAXREG, true>(ctx, fp, n, st) : launch_bsw<240, 320, 24, 2>(ctx, fp, n, st);
         if (rc) return rc;
     }
     switch (k.n_ranges * 2 + (k.edge_enabled ? 1 : 0)) {
