@@ -434,6 +434,30 @@ def test_other_kernels_still_match(golden_images, monkeypatch, env):
         assert np.array_equal(f32, oracle.normalise(expected))
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("env,h,w,n", [
+    (None, 96, 128, 2400),                      # store-warp kernel, run-time geometry (not the 120x160 instantiation)
+    (None, 64, 96, 2400),                       # three strip groups per row
+    ("TRS_NO_STORE_WARP", 120, 160, 2400),      # resident kernel without store warps
+    ("TRS_NO_STORE_WARP", 240, 320, 1200),      # banded kernel (every configuration; the default one normally takes the banded store-warp kernel)
+    ("TRS_FORCE_GENERIC", 122, 166, 1500),      # generic kernel (width not a multiple of 32)
+    ("TRS_FORCE_GENERIC", 120, 160, 1500),
+])
+def test_every_kernel_variant_with_many_frames_per_cta(golden_images, monkeypatch, env, h, w, n):
+    """The hand-over protocols between the warps of a CTA (and the prefetch of the next frame) are only exercised when a CTA runs several
+    frames back to back: four to eight frames per CTA through every kernel variant, four configurations each, every frame against the oracle."""
+    from tests.helpers import image_cases
+    if env:
+        monkeypatch.setenv(env, "1")
+    frames = synth.expand_numpy(synth.frame_pool(64, h, w, seed=97 + h), n, start=5)
+    cases = image_cases(golden_images)
+    for cname in ("full_house", "dyn_contrast", "exotic", "edge_only"):
+        cfg = cfg_for(cases[cname])
+        want = oracle.process_batch(frames, cfg)
+        got, _ = run_device(cfg, frames, want_f32=False)
+        assert np.array_equal(got, want), f"{env} {h}x{w} {cname}: {describe(got, want)}"
+
+
 # ---- per-car control post-processing (SURVEY.md 8(f) rank 3): bit-exact f64 selects / divisions -----------------------------------
 def _control_golden():
     import os
