@@ -1119,18 +1119,25 @@ __device__ __forceinline__ void adjust_in_place(const PreKParams& p, uint32_t a_
     const int h = p.h, w = p.w, row_bytes = w * 3;
     if (p.dynamic) {
         const int y0 = min(40, h), y1 = min(119, h);
-        unsigned long long s0 = 0, s1 = 0, s2 = 0;
+        // four pixels = three words (R G B R | G B R G | B R G B) per trip, byte sums by dot products with 0/1 selectors; a thread's share stays
+        // far below 2^32 (every caller has a width that is a multiple of 4, so the region is whole groups)
+        uint32_t c0 = 0, c1 = 0, c2 = 0;
         const int npix = (y1 - y0) * w;
         const uint32_t roi = a_pix + y0 * row_bytes;
-        for (int i = t0; i < npix; i += tstride) { s0 += lds8(roi + 3 * i); s1 += lds8(roi + 3 * i + 1); s2 += lds8(roi + 3 * i + 2); }
+        for (int i = t0; i < (npix >> 2); i += tstride) {
+            const uint32_t w0 = lds32(roi + 12 * i), w1 = lds32(roi + 12 * i + 4), w2 = lds32(roi + 12 * i + 8);
+            c0 = __dp4a(w2, 0x00000100u, __dp4a(w1, 0x00010000u, __dp4a(w0, 0x01000001u, c0)));
+            c1 = __dp4a(w2, 0x00010000u, __dp4a(w1, 0x01000001u, __dp4a(w0, 0x00000100u, c1)));
+            c2 = __dp4a(w2, 0x01000001u, __dp4a(w1, 0x00000100u, __dp4a(w0, 0x00010000u, c2)));
+        }
         for (int o = 16; o; o >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, o);
         }
         if (t0 < 3) s_red[t0] = 0;
         sync();
-        if (lane == 0) { atomicAdd(&s_red[0], s0); atomicAdd(&s_red[1], s1); atomicAdd(&s_red[2], s2); }
+        if (lane == 0) { atomicAdd(&s_red[0], (unsigned long long)c0); atomicAdd(&s_red[1], (unsigned long long)c1); atomicAdd(&s_red[2], (unsigned long long)c2); }
         sync();
         const float fdelta = (float)brightness_delta(s_red[0], s_red[1], s_red[2], (double)npix, p.baseline);
         if (t0 == 0 && p.stats) s_red[4 + 9] += s_red[0] + s_red[1] + s_red[2];
@@ -1138,8 +1145,12 @@ __device__ __forceinline__ void adjust_in_place(const PreKParams& p, uint32_t a_
         sync();
     }
     if (p.dynamic || !p.lut_identity) {
-        const int nwords = (h * row_bytes) >> 2;
-        for (int i = t0; i < nwords; i += tstride) sts32(a_pix + 4 * i, lut4s(S.lut, lds32(a_pix + 4 * i)));
+        const int nquads = (h * row_bytes) >> 4;                  // (the frame is a whole number of 16-byte pieces and starts on one)
+        for (int i = t0; i < nquads; i += tstride) {
+            uint4 v = lds128(a_pix + 16 * i);
+            v.x = lut4s(S.lut, v.x); v.y = lut4s(S.lut, v.y); v.z = lut4s(S.lut, v.z); v.w = lut4s(S.lut, v.w);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_pix + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
         sync();
     }
 }
