@@ -286,19 +286,33 @@ def other_workloads(torch, dev, local, pool120, h, w, cpu_legs=True):
             spd.control_device(d_cur, d_st, d_ms)
         t = timed(cars_step, reps=10)
         t_loc = timed(lambda: trk.locate_device(d_xyz), reps=10)
+        # the scanning kernel (every distinct point for every state: what small tables and non-finite centre lines still get) beside it
+        os.environ["TRS_LOCATE"] = "thread"
+        try:
+            trk_scan = LocationTracker(wp, device=local)
+        finally:
+            del os.environ["TRS_LOCATE"]
+        t_scan = timed(lambda: trk_scan.locate_device(d_xyz), reps=10)
+        trk_scan.onShutdown()
         nw = wp.shape[0]
-        nd = int(np.unique(wp, axis=0).shape[0])          # the kernel evaluates each distinct point once (a repeat cannot win the strict `<`)
+        nd = int(np.unique(wp, axis=0).shape[0])          # the kernels evaluate each distinct point at most once (a repeat cannot win the strict `<`)
         ent = {"states_per_s": n / t, "waypoints": int(nw), "distinct_waypoints": nd, "ms": t * 1e3, "locate_only_ms": t_loc * 1e3,
+               "locate_only_states_per_s": n / t_loc, "locate_kernels": "trs::k_locate_grid (+ trs::k_locate_warp for the cars it puts off)",
                "hbm_GBps": n * 76 / t / 1e9, "hbm_frac": n * 76 / t / 1e9 / peak,
-               "reference_loop_equivalent_tflops": n * nw * 9 / t_loc / 1e12}
+               "reference_loop_equivalent_tflops": n * nw * 9 / t_loc / 1e12,
+               "note": "the grid walk evaluates the reference's distance only for the points in the cells around a car (about 20-30 of them) and "
+                       "proves every other point farther away: the reference's argmin, bit for bit, so flops per state are no longer a measure of "
+                       "the work; 76 B of HBM traffic per state (locate + speed control) is the remaining roofline, and the step is far from it "
+                       "(divergent per-car walks through a shared-memory table)",
+               "scan": {"locate_only_ms": t_scan * 1e3, "states_per_s": n / t_scan, "speedup_of_the_grid_walk": t_scan / t_loc}}
         if dfma_tflops:
-            ach = n * nd * 9 / t_loc / 1e12
-            ent["roofline"] = {"bound": "fp64", "achieved": ach, "peak": dfma_tflops, "unit": "TFLOP/s", "frac": ach / dfma_tflops,
-                               "fp64_pipe_frac": n * nd * 6 / t_loc / 1e12 / dadd_tinst, "peak_source": "trs_probe_fp64 on this GPU: dense DFMA chains "
+            ach = n * nd * 9 / t_scan / 1e12
+            ent["scan"]["roofline"] = {"bound": "fp64", "achieved": ach, "peak": dfma_tflops, "unit": "TFLOP/s", "frac": ach / dfma_tflops,
+                               "fp64_pipe_frac": n * nd * 6 / t_scan / 1e12 / dadd_tinst, "peak_source": "trs_probe_fp64 on this GPU: dense DFMA chains "
                                f"(2 flops per instruction); DADD rate {dadd_tinst:.2f} T lane-instr/s", "kernel": "trs::k_locate",
-                               "note": "achieved = 9 flops per (state, DISTINCT waypoint) actually evaluated / locate time; fp64_pipe_frac = the 6 "
+                               "note": "achieved = 9 flops per (state, DISTINCT waypoint) evaluated / scan time; fp64_pipe_frac = the 6 "
                                        "fp64-pipe instructions per evaluation against the measured DADD issue rate (an add counts one flop, an FMA two); "
-                                       "reference_loop_equivalent_tflops counts the reference's loop over all recorded points"}
+                                       "reference_loop_equivalent_tflops counts the reference's loop over all recorded points against the default path's time"}
         out["waypoint_speed_1M_states"][tname] = ent
         trk.onShutdown()
     spd.onShutdown()

@@ -134,6 +134,8 @@ int trs_set_track(trs_ctx* ctx, const double* wp_xyz_host, int n_wp, double min_
 /*
  * Replaces LocationTracker.step/localize/__find_closest/__map (track_data_process.py:77-107) for N cars.
  *   xyz_dev (N,3) f64; idx_dev (N) i32 — nullable; segment_dev (N) f64 — nullable.
+ *   Large batches keep a per-context scratch list (cars finished by a second kernel in the same stream): issue the
+ *   calls of one context on one stream at a time, or use a context per stream.
  */
 int trs_locate(trs_ctx* ctx, const double* xyz_dev, int n, int32_t* idx_dev, double* segment_dev,
                void* stream);
@@ -277,7 +279,7 @@ int trs_preprocess_host(trs_ctx* ctx, const uint8_t* in_host, int n, int h, int 
 
 /*
  * Measurement aid (bench.py): the FP64 pipe rate of the context's GPU, the denominator of the nearest-waypoint kernel's roofline
- * (trs_locate is FP64-ALU bound).  dfma_tflops: dense DFMA chains, 2 flops per lane-instruction; dadd_tinst_per_s:
+ * (the scanning kernels behind trs_locate are FP64-ALU bound).  dfma_tflops: dense DFMA chains, 2 flops per lane-instruction; dadd_tinst_per_s:
  * 10^12 DADD lane-instructions per second.  Synchronises.
  */
 int trs_probe_fp64(trs_ctx* ctx, double* dfma_tflops, double* dadd_tinst_per_s);

@@ -238,10 +238,10 @@ def test_locate_golden_tracks(golden_tracks):
         trk2.onShutdown()
 
 
-@pytest.mark.parametrize("which", ["warp", "thread"])
+@pytest.mark.parametrize("which", ["warp", "thread", "grid"])
 def test_locate_both_kernels_on_the_golden_states(golden_tracks, monkeypatch, which):
-    """The warp-per-car kernel (shuffle reduction on (distance, index); default for small batches) and the thread-per-car kernel on the
-    reference's own outputs, ties and > 100 sentinel cases included."""
+    """The warp-per-car kernel (shuffle reduction on (distance, index); default for small batches), the thread-per-car scan and the grid walk
+    (default for large batches) on the reference's own outputs, ties and > 100 sentinel cases included."""
     monkeypatch.setenv("TRS_LOCATE", which)
     for name in ("generated_track", "mountain_track"):
         wp, xyz = golden_tracks[f"wp/{name}"], golden_tracks[f"xyz/{name}"]
@@ -273,6 +273,48 @@ def test_locate_large_batch_against_oracle(golden_tracks):
     trk = LocationTracker(wp, device=0)
     idx, _ = trk.locate_device(torch.from_numpy(xyz).to(DEV))
     assert np.array_equal(idx.cpu().numpy(), oracle.locate(wp, xyz)[0])
+    trk.onShutdown()
+
+
+@pytest.mark.timeout(300)
+def test_locate_grid_walk_on_adversarial_cars(golden_tracks, monkeypatch):
+    """The grid walk must return the reference's first-index argmin for every car, not only for cars near the centre line: cars exactly on cell
+    corners and edges (cell sides are powers of two), on the points themselves and on repeated points, in the middle of the loop (many rings:
+    put off to the warp-per-car kernel), outside the bounding box just inside and just outside the 100 limit, with NaN / infinite coordinates;
+    a centre line far from the origin, one scaled to millimetres and one to kilometres (other cell sizes), and one too small for a grid."""
+    monkeypatch.setenv("TRS_LOCATE", "grid")
+    rng = np.random.default_rng(99)
+    for name in ("generated_track", "mountain_track"):
+        base = golden_tracks[f"wp/{name}"]
+        for scale, shift in ((1.0, 0.0), (1.0, 1.0e6), (1e-3, 0.0), (1e3, -5.0e4)):
+            wp = base * scale + shift
+            lo, hi = wp.min(0), wp.max(0)
+            ext = max(hi[0] - lo[0], hi[2] - lo[2])
+            c = 2.0 ** np.ceil(np.log2(ext / 32.0))                  # the library's cell side
+            n = 6000
+            cars = [wp[rng.integers(0, len(wp), n)] + rng.standard_normal((n, 3)) * np.array([1.5, 0.05, 1.5]) * scale,           # near the line
+                    wp[rng.integers(0, len(wp), 500)],                                                                           # on points
+                    np.stack([rng.uniform(lo[0] - 20 * scale, hi[0] + 20 * scale, n), rng.uniform(lo[1], hi[1], n),
+                              rng.uniform(lo[2] - 20 * scale, hi[2] + 20 * scale, n)], 1),                                       # anywhere around
+                    np.stack([c * rng.integers(np.floor(lo[0] / c) - 2, np.floor(hi[0] / c) + 3, 2000), rng.uniform(lo[1], hi[1], 2000),
+                              c * rng.integers(np.floor(lo[2] / c) - 2, np.floor(hi[2] / c) + 3, 2000)], 1),                     # cell corners
+                    np.stack([c * rng.integers(np.floor(lo[0] / c), np.floor(hi[0] / c) + 1, 2000), rng.uniform(lo[1], hi[1], 2000),
+                              rng.uniform(lo[2], hi[2], 2000)], 1),                                                               # cell edges
+                    np.stack([lo[0] - rng.uniform(95, 105, 1000), rng.uniform(lo[1], hi[1], 1000), rng.uniform(lo[2], hi[2], 1000)], 1),   # around the limit
+                    np.array([[np.nan, 1, 1], [1, np.nan, 1], [1, 1, np.nan], [np.inf, 0, 0], [0, 0, -np.inf], [1e300, 1e300, 1e300]])]
+            xyz = np.ascontiguousarray(np.concatenate(cars))
+            with np.errstate(invalid="ignore"):
+                iw, sw_ = oracle.locate(wp, xyz)
+            trk = LocationTracker(wp, device=0)
+            idx, seg = trk.locate_device(torch.from_numpy(xyz).to(DEV))
+            got = idx.cpu().numpy()
+            assert np.array_equal(got, iw), f"{name} x{scale} +{shift}: {int((got != iw).sum())} of {len(iw)} differ, first {np.nonzero(got != iw)[0][:5]}"
+            assert np.array_equal(seg.cpu().numpy(), sw_)
+            trk.onShutdown()
+    wp = synth.synthetic_track(40)                               # fewer than 64 points: no grid, the scanning kernel answers
+    xyz, _, _, _ = synth.car_states(wp, 3000, seed=8)
+    trk = LocationTracker(wp, device=0)
+    assert np.array_equal(trk.locate_device(torch.from_numpy(xyz).to(DEV))[0].cpu().numpy(), oracle.locate(wp, xyz)[0])
     trk.onShutdown()
 
 

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <mutex>
 #include <new>
@@ -68,7 +69,7 @@ enum { HOST_STREAMS = 3 };
 // when the context is created, so no call on the N = 1 latency path pays a getenv.
 struct TrsSwitches {
     bool force_generic = false, no_banded = false, no_store_warp = false, resize_scalar = false, resize_gather = false;
-    int locate = 0;                    // 0 = by batch size, 1 = warp per car, 2 = thread per car
+    int locate = 0;                    // 0 = by batch size, 1 = warp per car, 2 = thread per car, 3 = grid
     size_t host_chunk_bytes = (size_t)48 << 20;      // ~48 MB of frames per chunk of the host pipeline (the link saturates from ~16 MB up)
 };
 
@@ -86,6 +87,11 @@ struct trs_ctx {
     // track
     double* wp_dev = nullptr;          // distinct waypoints in order of first occurrence: (x, y, z, original index) quads
     int n_wp = 0, n_wp_distinct = 0;
+    double* wp_grid_dev = nullptr;     // the same quads sorted by grid cell (k_locate_grid), nullptr: no grid for this centre line
+    int* wp_cells_dev = nullptr;       // start of every cell in wp_grid_dev, ncell + 1 entries
+    trs::LocGrid grid{};
+    int* defer_dev = nullptr;          // [0] = count, [1 ..] = cars k_locate_grid left to the warp-per-car kernel
+    size_t defer_cap = 0;              // cars the list can hold
     double min_map = 0, max_map = 10;
     // host pipeline
     cudaStream_t hs[HOST_STREAMS] = {nullptr, nullptr, nullptr};
@@ -475,7 +481,7 @@ int trs_ctx_create(int device, trs_ctx** out)
     c->sw.no_store_warp = getenv("TRS_NO_STORE_WARP") != nullptr;
     c->sw.resize_scalar = getenv("TRS_RESIZE_SCALAR") != nullptr;
     c->sw.resize_gather = getenv("TRS_RESIZE_GATHER") != nullptr;
-    if (const char* e = getenv("TRS_LOCATE")) c->sw.locate = e[0] == 'w' ? 1 : 2;
+    if (const char* e = getenv("TRS_LOCATE")) c->sw.locate = e[0] == 'w' ? 1 : (e[0] == 'g' ? 3 : 2);
     if (const char* e = getenv("TRS_HOST_CHUNK_MB")) { const int mb = atoi(e); if (mb > 0) c->sw.host_chunk_bytes = (size_t)mb << 20; }
     trs_preproc_params d;
     default_params(&d);
@@ -493,7 +499,7 @@ int trs_ctx_destroy(trs_ctx* ctx)
         cudaFree(ctx->st_in[i]); cudaFree(ctx->st_u8[i]); cudaFree(ctx->st_f32[i]);
     }
     if (ctx->host_entry) cudaEventDestroy(ctx->host_entry);
-    cudaFree(ctx->wp_dev);
+    cudaFree(ctx->wp_dev); cudaFree(ctx->wp_grid_dev); cudaFree(ctx->wp_cells_dev); cudaFree(ctx->defer_dev);
     cudaFree(ctx->stats_dev);
     cudaFree(ctx->jpg_blob); cudaFree(ctx->jpg_planes); cudaFree(ctx->jpg_meta);
     delete ctx;
@@ -629,6 +635,54 @@ int trs_set_track(trs_ctx* ctx, const double* wp_xyz_host, int n_wp, double min_
     ctx->n_wp_distinct = (int)(quads.size() / 4);
     ctx->min_map = min_map;
     ctx->max_map = max_map;
+    // uniform grid over (x, z) for k_locate_grid: cells of side 2^k, at most 34 along either axis (side 4 for the shipped centre lines: the 3 x 3 cells
+    // around a car on the line then prove its nearest point), points sorted by cell.  No grid
+    // (the scanning kernels serve every batch) for non-finite coordinates, for a table that does not fit shared memory, or for a handful of points.
+    cudaFree(ctx->wp_grid_dev); ctx->wp_grid_dev = nullptr;
+    cudaFree(ctx->wp_cells_dev); ctx->wp_cells_dev = nullptr;
+    const int nu = ctx->n_wp_distinct;
+    bool finite = true;
+    for (double v : quads) finite = finite && std::isfinite(v);
+    if (finite && nu >= 64) {
+        trs::LocGrid g{};
+        g.x0 = g.x1 = quads[0]; g.y0 = g.y1 = quads[1]; g.z0 = g.z1 = quads[2];
+        for (int i = 0; i < nu; ++i) {
+            g.x0 = std::min(g.x0, quads[4 * i]); g.x1 = std::max(g.x1, quads[4 * i]);
+            g.y0 = std::min(g.y0, quads[4 * i + 1]); g.y1 = std::max(g.y1, quads[4 * i + 1]);
+            g.z0 = std::min(g.z0, quads[4 * i + 2]); g.z1 = std::max(g.z1, quads[4 * i + 2]);
+        }
+        const double ext = std::max(g.x1 - g.x0, g.z1 - g.z0);
+        int k = ext > 0 ? (int)std::ceil(std::log2(ext / 32.0)) : 0;
+        k = std::max(-60, std::min(60, k));
+        g.c = std::ldexp(1.0, k); g.inv_c = std::ldexp(1.0, -k);
+        g.ox = std::floor(g.x0 * g.inv_c); g.oz = std::floor(g.z0 * g.inv_c);
+        const double dnx = std::floor(g.x1 * g.inv_c) - g.ox + 1, dnz = std::floor(g.z1 * g.inv_c) - g.oz + 1;
+        const size_t smem = sizeof(double) * 4 * (size_t)nu + sizeof(int) * ((size_t)(dnx * dnz) + 1);
+        if (dnx >= 1 && dnz >= 1 && dnx <= 80 && dnz <= 80 && std::fabs(g.ox) < 1e9 && std::fabs(g.oz) < 1e9 && smem <= (size_t)ctx->smem_optin - 1024) {
+            g.nx = (int)dnx; g.nz = (int)dnz; g.n_u = nu;
+            const int ncell = g.nx * g.nz;
+            std::vector<int> cell((size_t)nu), order((size_t)nu), start((size_t)ncell + 1, 0);
+            for (int i = 0; i < nu; ++i) {
+                const int ci = (int)(std::floor(quads[4 * i] * g.inv_c) - g.ox), cj = (int)(std::floor(quads[4 * i + 2] * g.inv_c) - g.oz);
+                cell[i] = cj * g.nx + ci;
+                ++start[(size_t)cell[i] + 1];
+            }
+            for (int c = 0; c < ncell; ++c) start[(size_t)c + 1] += start[c];
+            std::vector<int> fill(start.begin(), start.end() - 1);
+            for (int i = 0; i < nu; ++i) order[(size_t)fill[cell[i]]++] = i;
+            std::vector<double> sorted(4 * (size_t)nu);
+            for (int t = 0; t < nu; ++t) {                       // (x, z, y, original index): see locg_eval
+                const double* q = &quads[4 * (size_t)order[t]];
+                sorted[4 * (size_t)t] = q[0]; sorted[4 * (size_t)t + 1] = q[2]; sorted[4 * (size_t)t + 2] = q[1]; sorted[4 * (size_t)t + 3] = q[3];
+            }
+            CU(cudaMalloc(&ctx->wp_grid_dev, sizeof(double) * sorted.size()));
+            CU(cudaMemcpy(ctx->wp_grid_dev, sorted.data(), sizeof(double) * sorted.size(), cudaMemcpyHostToDevice));
+            CU(cudaMalloc(&ctx->wp_cells_dev, sizeof(int) * start.size()));
+            CU(cudaMemcpy(ctx->wp_cells_dev, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
+            CU(cudaFuncSetAttribute(trs::k_locate_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->grid = g;
+        }
+    }
     return 0;
 }
 
@@ -639,8 +693,34 @@ int trs_locate(trs_ctx* ctx, const double* xyz_dev, int n, int32_t* idx_dev, dou
     if (n < 0) return fail(TRS_E_ARG, "negative n");
     if (n == 0) return 0;
     if (!xyz_dev || (!idx_dev && !segment_dev)) return fail(TRS_E_ARG, "null pointer");
-    // small batches: a warp per car with a shuffle reduction (a thread per car would not fill the GPU); TRS_LOCATE=warp|thread forces one
+    // small batches: a warp per car with a shuffle reduction (a thread per car would not fill the GPU); large ones: the grid walk, with the
+    // cars it puts off finished by the warp-per-car kernel; TRS_LOCATE=warp|thread|grid forces one
     const bool warp_per_car = ctx->sw.locate ? ctx->sw.locate == 1 : n < ctx->sm_count * 256;      // measured crossover ~50 k cars (15 us vs 55 us below it)
+    if (!warp_per_car && ctx->sw.locate != 2 && ctx->wp_grid_dev) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->defer_cap < (size_t)n) {
+            cudaFree(ctx->defer_dev); ctx->defer_dev = nullptr; ctx->defer_cap = 0;
+            CU(cudaMalloc(&ctx->defer_dev, sizeof(int) * ((size_t)n + 1)));
+            ctx->defer_cap = (size_t)n;
+        }
+        cudaStream_t st = (cudaStream_t)stream;
+        CU(cudaMemsetAsync(ctx->defer_dev, 0, sizeof(int), st));
+        const trs::LocGrid& g = ctx->grid;
+        const size_t smem = sizeof(double) * 4 * (size_t)g.n_u + sizeof(int) * ((size_t)g.nx * g.nz + 1);
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trs::k_locate_grid, trs::LOCG_THREADS, smem));
+        per_sm = std::max(1, per_sm);
+        int grid = (n + trs::LOCG_THREADS - 1) / trs::LOCG_THREADS;
+        grid = std::min(grid, ctx->sm_count * per_sm);
+        trs::k_locate_grid<<<grid, trs::LOCG_THREADS, smem, st>>>(reinterpret_cast<const double4*>(ctx->wp_grid_dev), ctx->wp_cells_dev, g, ctx->n_wp, ctx->min_map,
+                                                                  ctx->max_map, xyz_dev, n, idx_dev, segment_dev, ctx->defer_dev + 1, ctx->defer_dev);
+        CU(cudaGetLastError());
+        trs::k_locate_warp<<<ctx->sm_count * 2, trs::LOCW_THREADS, 0, st>>>(reinterpret_cast<const double4*>(ctx->wp_dev), ctx->n_wp_distinct, ctx->n_wp, ctx->min_map,
+                                                                            ctx->max_map, xyz_dev, n, idx_dev, segment_dev, ctx->defer_dev + 1, ctx->defer_dev);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (warp_per_car) {
         const int warps_per_block = trs::LOCW_THREADS / 32;
         int grid = (n + warps_per_block - 1) / warps_per_block;
