@@ -1351,8 +1351,12 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2) k_preprocess_banded(const
             mbar_wait(S.bar, phase);
             phase ^= 1u;
             if (use_lut) {                                          // brightness / contrast on the band's pixel rows as they land (halo rows twice)
-                const int nwords = (min(by1 + 2, h) - p0) * (int)(row_bytes >> 2);
-                for (int i = tid; i < nwords; i += nthr) sts32(S.pix[0] + 4 * i, lut4s(S.lut, lds32(S.pix[0] + 4 * i)));
+                const int nquads = (min(by1 + 2, h) - p0) * (int)(row_bytes >> 4);      // (a row is a whole number of 16-byte pieces: w % 32 == 0)
+                for (int i = tid; i < nquads; i += nthr) {
+                    uint4 v = lds128(S.pix[0] + 16 * i);
+                    v.x = lut4s(S.lut, v.x); v.y = lut4s(S.lut, v.y); v.z = lut4s(S.lut, v.z); v.w = lut4s(S.lut, v.w);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(S.pix[0] + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                }
                 __syncthreads();
             }
             if (EDGE && m1 == h) {                                  // the zero row below the frame: earlier bands left data there
