@@ -4,10 +4,12 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from tests.conftest import ROOT
 from triton_racer_sim_b200 import Component, default_config, sharding, synth
 
 
@@ -126,3 +128,76 @@ def test_tub_labels_and_features_follow_the_reference_loaders():
     for r in recs:
         assert np.array_equal(tub.labels_and_features([r], "FullHouseDataLoader")[1][0],
                               np.asarray(np.asarray((r['gym/speed'] / 20, r['loc/segment'])), dtype=np.float32))
+
+
+# ---- nearest waypoint through the grid (csrc/loc_grid.h compiled for the host) ------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def locate_host(tmp_path_factory):
+    import ctypes as C
+    import subprocess
+    out = tmp_path_factory.mktemp("loc") / "liblocchk.so"
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", str(out), os.path.join(ROOT, "tests", "host_locate_check.cpp")])
+    lib = C.CDLL(str(out))
+    lib.locate_grid_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+
+    def run(wp, xyz):
+        wp, xyz = np.ascontiguousarray(wp, np.float64), np.ascontiguousarray(xyz, np.float64)
+        idx = np.zeros(len(xyz), np.int32)
+        stats = np.zeros(6, np.int64)
+        assert lib.locate_grid_host(wp.ctypes.data, len(wp), xyz.ctypes.data, len(xyz), idx.ctypes.data, stats.ctypes.data) == 0
+        return idx, stats
+    return run
+
+
+def _adversarial_cars(wp, rng, scale, n=4000):
+    lo, hi = wp.min(0), wp.max(0)
+    ext = max(hi[0] - lo[0], hi[2] - lo[2])
+    c = 2.0 ** np.ceil(np.log2(ext / 32.0))                     # the library's cell side
+    return np.ascontiguousarray(np.concatenate([
+        wp[rng.integers(0, len(wp), n)] + rng.standard_normal((n, 3)) * np.array([1.5, 0.05, 1.5]) * scale,                       # near the line
+        wp[rng.integers(0, len(wp), 300)],                                                                                       # on points (repeats included)
+        np.stack([rng.uniform(lo[0] - 20 * scale, hi[0] + 20 * scale, n), rng.uniform(lo[1], hi[1], n),
+                  rng.uniform(lo[2] - 20 * scale, hi[2] + 20 * scale, n)], 1),                                                   # anywhere around (many rings)
+        np.stack([c * rng.integers(np.floor(lo[0] / c) - 2, np.floor(hi[0] / c) + 3, 1500), rng.uniform(lo[1], hi[1], 1500),
+                  c * rng.integers(np.floor(lo[2] / c) - 2, np.floor(hi[2] / c) + 3, 1500)], 1),                                 # cell corners
+        np.stack([c * rng.integers(np.floor(lo[0] / c), np.floor(hi[0] / c) + 1, 1500), rng.uniform(lo[1], hi[1], 1500),
+                  rng.uniform(lo[2], hi[2], 1500)], 1),                                                                           # cell edges
+        np.stack([lo[0] - rng.uniform(95, 105, 500), rng.uniform(lo[1], hi[1], 500), rng.uniform(lo[2], hi[2], 500)], 1),        # around the 100 limit
+        np.array([[np.nan, 1, 1], [1, np.nan, 1], [1, 1, np.nan], [np.inf, 0, 0], [0, 0, -np.inf], [1e300, 1e300, 1e300], [-1e300, 0, 1e300]])]))
+
+
+def test_grid_walk_returns_the_reference_index(locate_host):
+    """The product's grid walk (the source the kernel compiles, built for the host) against the oracle's scan, which follows
+    track_data_process.py:89-107: both shipped centre lines, shifted far from the origin and scaled to other cell sizes; cars near the line, on
+    points, on cell corners and edges, anywhere around the bounding box (put off to the scan after six rings), at the 100 limit, NaN / infinite."""
+    import oracle
+    tracks = np.load(os.path.join(ROOT, "tests", "golden", "tracks.npz"))
+    rng = np.random.default_rng(2024)
+    for name in ("generated_track", "mountain_track"):
+        base = tracks[f"wp/{name}"]
+        # the reference's own outputs first
+        idx, stats = locate_host(base, tracks[f"xyz/{name}"])
+        assert np.array_equal(idx, tracks[f"idx/{name}"])
+        assert stats[0] == 1 and stats[5] == 2 and stats[1] <= 34 and stats[2] <= 34          # cells of side 4
+        put_off = 0
+        for scale, shift in ((1.0, 0.0), (1.0, 1.0e6), (1e-3, 0.0), (1e3, -5.0e4), (1.0, -3.0)):
+            wp = base * scale + shift
+            xyz = _adversarial_cars(wp, rng, scale)
+            with np.errstate(invalid="ignore", over="ignore"):
+                want, _ = oracle.locate(wp, xyz)
+            got, stats = locate_host(wp, xyz)
+            bad = np.nonzero(got != want)[0]
+            assert len(bad) == 0, f"{name} x{scale} +{shift}: {len(bad)} of {len(want)} differ, first {bad[:5]}: {xyz[bad[:5]]}"
+            put_off += int(stats[3])
+        assert put_off > 0                                       # the deferred path is exercised
+    # no grid: a handful of points, a non-finite point
+    wp = synth.synthetic_track(40)
+    xyz, _, _, _ = synth.car_states(wp, 2000, seed=8)
+    got, stats = locate_host(wp, xyz)
+    assert stats[0] == 0 and np.array_equal(got, oracle.locate(wp, xyz)[0])
+    wp = tracks["wp/generated_track"].copy()
+    wp[17, 1] = np.inf
+    xyz, _, _, _ = synth.car_states(tracks["wp/generated_track"], 2000, seed=9)
+    got, stats = locate_host(wp, xyz)
+    with np.errstate(invalid="ignore"):
+        assert stats[0] == 0 and np.array_equal(got, oracle.locate(wp, xyz)[0])

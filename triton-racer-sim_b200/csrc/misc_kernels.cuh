@@ -1,5 +1,6 @@
 // misc_kernels.cuh — normalise/crop/resize, waypoint lookup, speed control (sm_100a).
 #pragma once
+#include "loc_grid.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -326,111 +327,32 @@ __global__ void __launch_bounds__(LOCW_THREADS) k_locate_warp(const double4* __r
     }
 }
 
-// K6c: the same argmin through a uniform grid over (x, z): LARGE batches.  The distinct points are bucketed into square cells of side c (a power of two, so
-// floor(x / c) is exact and a point's and a car's cell are decided by the same exact rule), sorted by cell (row-major, rows along z) with the prefix
-// array of cell starts.  A car visits the cells around its own in rings of growing Chebyshev radius; every point in a ring beyond r is at least
-// r c + m away in L1 (m = the car's distance to the nearest edge of its own cell), and so is its COMPUTED distance: the bound is representable or
-// shrunk below the exact value, rounding is monotone, and the three terms are summed in the reference's order.  So the walk stops as soon as the
-// best distance so far is strictly below that bound (a tie could still hide a smaller index at equality) or the bound reaches the reference's
-// starting minimum of 100.  Inside the visited set the argmin is taken on the pair (distance, original index), which is the reference's
-// first-index rule.  Every evaluated distance is the same three subtractions and two additions as in k_locate, so the result is the reference's
-// bit for bit, with ~20-30 evaluations per car instead of ~1,000 (cars within a few units of the centre line).
-// A car that has not settled after LOCG_MAX_RINGS rings (far from the line but inside its bounding box) is appended to a list for the
-// warp-per-car kernel, so one such car never holds its warp for a scan of the whole grid.
-// Table in shared memory: quads in cell order + cell starts; persistent CTAs, cars by grid stride.
+// K6c: the same argmin through a uniform grid over (x, z): LARGE batches.  The algorithm and why it returns the reference's index bit for bit are in
+// loc_grid.h (host / device functions, also compiled by the CPU-side test): ~40 distance evaluations per car instead of ~1,000.  A car that has not
+// settled after the 3 x 3 block and LOCG_MAX_RINGS rings (far from the line but inside its bounding box) is appended to a list for the warp-per-car
+// kernel, so one such car never holds its warp for a scan of the whole grid.  Table in shared memory: quads in cell order + cell starts;
+// persistent CTAs, cars by grid stride.
 // ------------------------------------------------------------------------------------------------------
-enum { LOCG_THREADS = 256, LOCG_MAX_RINGS = 6 };
+enum { LOCG_THREADS = 256 };
 
-struct LocGrid {
-    double c, inv_c;                   // cell side (2^k) and its reciprocal
-    double ox, oz;                     // floor(min x / c), floor(min z / c) as doubles (exact integers)
-    double x0, x1, y0, y1, z0, z1;     // bounding box of the points
-    int nx, nz;                        // cells along x and z
-    int n_u;                           // points
-};
-
-// Quads of the grid table are (x, z, y, original index): the first 16 bytes give |dx| + |dz|, which can only be smaller than the distance
-// (rounding is monotone and |dy| >= 0), so a point that already loses on it is dropped before its second half is read — the walk is bound by
-// shared-memory wavefronts (every lane reads its own point), not by arithmetic.
-__device__ __forceinline__ void locg_eval(const double4* s_q, int a, int b, double x, double y, double z, double& best, int& sel)
-{
-    for (int k = a; k < b; ++k) {
-        const double2 xz = reinterpret_cast<const double2*>(s_q + k)[0];
-        const double ax = fabs(__dsub_rn(x, xz.x)), az = fabs(__dsub_rn(z, xz.y));
-        if (__dadd_rn(ax, az) > best) continue;
-        const double2 yi = reinterpret_cast<const double2*>(s_q + k)[1];
-        const double d = __dadd_rn(__dadd_rn(ax, fabs(__dsub_rn(y, yi.x))), az);
-        const int qi = (int)yi.y;
-        if (d < best || (d == best && qi < sel)) { best = d; sel = qi; }
-    }
-}
-
-__global__ void __launch_bounds__(LOCG_THREADS) k_locate_grid(const double4* __restrict__ quads, const int* __restrict__ cell_start, const LocGrid G, int n_wp,
+__global__ void __launch_bounds__(LOCG_THREADS) k_locate_grid(const double* __restrict__ quads, const int* __restrict__ cell_start, const LocGrid G, int n_wp,
                                                               double min_map, double max_map, const double* __restrict__ xyz, int n,
                                                               int32_t* __restrict__ idx_out, double* __restrict__ seg_out, int* __restrict__ defer_list,
                                                               int* __restrict__ defer_count)
 {
     extern __shared__ __align__(16) uint8_t locg_smem[];
-    double4* s_q = reinterpret_cast<double4*>(locg_smem);
-    int* s_cs = reinterpret_cast<int*>(locg_smem + sizeof(double4) * (size_t)G.n_u);
+    double* s_q = reinterpret_cast<double*>(locg_smem);
+    int* s_cs = reinterpret_cast<int*>(locg_smem + sizeof(double) * 4 * (size_t)G.n_u);
     const int ncell = G.nx * G.nz;
-    for (int i = threadIdx.x; i < G.n_u; i += LOCG_THREADS) s_q[i] = quads[i];
+    for (int i = threadIdx.x; i < G.n_u; i += LOCG_THREADS) reinterpret_cast<double4*>(s_q)[i] = reinterpret_cast<const double4*>(quads)[i];
     for (int i = threadIdx.x; i <= ncell; i += LOCG_THREADS) s_cs[i] = cell_start[i];
     __syncthreads();
-    const int nx = G.nx, nz = G.nz;
     for (int k = blockIdx.x * LOCG_THREADS + threadIdx.x; k < n; k += gridDim.x * LOCG_THREADS) {
-        const double x = xyz[3 * (size_t)k], y = xyz[3 * (size_t)k + 1], z = xyz[3 * (size_t)k + 2];
-        double best = 100.0;                                     // track_data_process.py:93
-        int sel = 0x7fffffff;
-        bool defer = false;
-        // L1 distance to the points' bounding box, summed like a distance: nothing can be closer than that
-        const double bx = fmax(fmax(__dsub_rn(G.x0, x), __dsub_rn(x, G.x1)), 0.0), by = fmax(fmax(__dsub_rn(G.y0, y), __dsub_rn(y, G.y1)), 0.0),
-                     bz = fmax(fmax(__dsub_rn(G.z0, z), __dsub_rn(z, G.z1)), 0.0);
-        if (__dadd_rn(__dadd_rn(bx, by), bz) < 100.0) {          // (false for a NaN coordinate too: the reference's `<` never fires then, index 0)
-            const double fx = floor(__dmul_rn(x, G.inv_c)), fz = floor(__dmul_rn(z, G.inv_c));
-            const double lim = 1073741824.0;
-            const int cx = (int)fmin(fmax(__dsub_rn(fx, G.ox), -lim), lim), cz = (int)fmin(fmax(__dsub_rn(fz, G.oz), -lim), lim);
-            // distance to the nearest edge of the car's own cell, shrunk so that rounding can only make the bound smaller
-            const double ex = __dmul_rn(fx, G.c), ez = __dmul_rn(fz, G.c);
-            double m = fmin(fmin(__dsub_rn(x, ex), __dsub_rn(__dadd_rn(ex, G.c), x)), fmin(__dsub_rn(z, ez), __dsub_rn(__dadd_rn(ez, G.c), z)));
-            m = fmax(__dmul_rn(m, 0.999), 0.0);
-            const int r_out = max(max(max(-cx, cx - (nx - 1)), max(-cz, cz - (nz - 1))), 0);      // rings nearer than this lie outside the grid
-            const int r_end = max(max(cx, nx - 1 - cx), max(cz, nz - 1 - cz));                    // the last ring that touches the grid
-            // rings 0 and 1 together, row by row (three contiguous point ranges): with cells this size that settles nearly every car on the line,
-            // and a warp runs three long loops instead of five short ones
-            bool settled = false;
-            if (r_out <= 1) {
-                const int i0 = max(cx - 1, 0), i1 = min(cx + 1, nx - 1);
-                if (i0 <= i1)
-                    for (int j = max(cz - 1, 0); j <= min(cz + 1, nz - 1); ++j) locg_eval(s_q, s_cs[j * nx + i0], s_cs[j * nx + i1 + 1], x, y, z, best, sel);
-                const double bound = __dadd_rn(G.c, m);          // every point in a ring beyond 1 is at least this far
-                settled = best < bound || bound >= 100.0;
-            }
-            int r = max(r_out, 2), rings = 0;
-            while (!settled && r <= r_end) {
-                const int i0 = max(cx - r, 0), i1 = min(cx + r, nx - 1);
-                if (i0 <= i1) {                                  // the ring's two full rows of cells: contiguous point ranges
-                    const int jt = cz - r, jb = cz + r;
-                    if (jt >= 0 && jt < nz) locg_eval(s_q, s_cs[jt * nx + i0], s_cs[jt * nx + i1 + 1], x, y, z, best, sel);
-                    if (jb >= 0 && jb < nz) locg_eval(s_q, s_cs[jb * nx + i0], s_cs[jb * nx + i1 + 1], x, y, z, best, sel);
-                }
-                const int j0 = max(cz - r + 1, 0), j1 = min(cz + r - 1, nz - 1);
-                for (int j = j0; j <= j1; ++j) {                 // ... and the two cells at its sides in every row between
-                    const int il = cx - r, ir = cx + r;
-                    if (il >= 0 && il < nx) locg_eval(s_q, s_cs[j * nx + il], s_cs[j * nx + il + 1], x, y, z, best, sel);
-                    if (ir >= 0 && ir < nx) locg_eval(s_q, s_cs[j * nx + ir], s_cs[j * nx + ir + 1], x, y, z, best, sel);
-                }
-                const double bound = __dadd_rn(__dmul_rn((double)r, G.c), m);      // every point in a ring beyond r is at least this far
-                ++r;
-                if (best < bound || bound >= 100.0) break;
-                if (++rings >= LOCG_MAX_RINGS && r <= r_end) { defer = true; break; }
-            }
-        }
-        if (defer) {
+        const int idx = locg_walk(G, s_q, s_cs, xyz[3 * (size_t)k], xyz[3 * (size_t)k + 1], xyz[3 * (size_t)k + 2]);
+        if (idx == LOCG_DEFERRED) {
             defer_list[atomicAdd(defer_count, 1)] = k;
             continue;
         }
-        const int idx = sel == 0x7fffffff ? 0 : sel;
         if (idx_out) idx_out[k] = idx;
         if (seg_out) {
             const double q = __ddiv_rn((double)idx, (double)n_wp);

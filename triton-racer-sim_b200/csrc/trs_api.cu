@@ -606,27 +606,8 @@ int trs_set_track(trs_ctx* ctx, const double* wp_xyz_host, int n_wp, double min_
     TRS_ENTER(ctx);
     if (!wp_xyz_host || n_wp <= 0) return fail(TRS_E_ARG, "empty centre line");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    // A repeated point can never beat its first occurrence under the reference's strict `<` (track_data_process.py:95): only first
-    // occurrences are uploaded, each with its original index (compared by value, so -0.0 == 0.0 and a NaN is never a repeat)
-    std::vector<double> quads;
-    quads.reserve(4 * (size_t)n_wp);
-    {
-        struct Key { double x, y, z; };
-        auto norm = [](double v) { return v == 0.0 ? 0.0 : v; };
-        std::vector<std::pair<Key, int>> seen;                        // sorted by (x, y, z) among comparable values
-        seen.reserve((size_t)n_wp);
-        auto less = [](const Key& a, const Key& b) { return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z); };
-        for (int i = 0; i < n_wp; ++i) {
-            const Key k{norm(wp_xyz_host[3 * i]), norm(wp_xyz_host[3 * i + 1]), norm(wp_xyz_host[3 * i + 2])};
-            bool repeat = false;
-            if (k.x == k.x && k.y == k.y && k.z == k.z) {              // (points with a NaN are always kept)
-                auto it = std::lower_bound(seen.begin(), seen.end(), k, [&](const std::pair<Key, int>& a, const Key& b) { return less(a.first, b); });
-                repeat = it != seen.end() && it->first.x == k.x && it->first.y == k.y && it->first.z == k.z;
-                if (!repeat) seen.insert(it, std::make_pair(k, i));
-            }
-            if (!repeat) { quads.push_back(wp_xyz_host[3 * i]); quads.push_back(wp_xyz_host[3 * i + 1]); quads.push_back(wp_xyz_host[3 * i + 2]); quads.push_back((double)i); }
-        }
-    }
+    // only first occurrences are uploaded, each with its original index (loc_grid.h)
+    const std::vector<double> quads = trs::locg_distinct_quads(wp_xyz_host, n_wp);
     cudaFree(ctx->wp_dev);
     ctx->wp_dev = nullptr;
     CU(cudaMalloc(&ctx->wp_dev, sizeof(double) * quads.size()));
@@ -635,53 +616,20 @@ int trs_set_track(trs_ctx* ctx, const double* wp_xyz_host, int n_wp, double min_
     ctx->n_wp_distinct = (int)(quads.size() / 4);
     ctx->min_map = min_map;
     ctx->max_map = max_map;
-    // uniform grid over (x, z) for k_locate_grid: cells of side 2^k, at most 34 along either axis (side 4 for the shipped centre lines: the 3 x 3 cells
-    // around a car on the line then prove its nearest point), points sorted by cell.  No grid
-    // (the scanning kernels serve every batch) for non-finite coordinates, for a table that does not fit shared memory, or for a handful of points.
+    // uniform grid over (x, z) for k_locate_grid (loc_grid.h); none for non-finite coordinates, a handful of points or a table beyond shared memory:
+    // the scanning kernels serve every batch then
     cudaFree(ctx->wp_grid_dev); ctx->wp_grid_dev = nullptr;
     cudaFree(ctx->wp_cells_dev); ctx->wp_cells_dev = nullptr;
-    const int nu = ctx->n_wp_distinct;
-    bool finite = true;
-    for (double v : quads) finite = finite && std::isfinite(v);
-    if (finite && nu >= 64) {
-        trs::LocGrid g{};
-        g.x0 = g.x1 = quads[0]; g.y0 = g.y1 = quads[1]; g.z0 = g.z1 = quads[2];
-        for (int i = 0; i < nu; ++i) {
-            g.x0 = std::min(g.x0, quads[4 * i]); g.x1 = std::max(g.x1, quads[4 * i]);
-            g.y0 = std::min(g.y0, quads[4 * i + 1]); g.y1 = std::max(g.y1, quads[4 * i + 1]);
-            g.z0 = std::min(g.z0, quads[4 * i + 2]); g.z1 = std::max(g.z1, quads[4 * i + 2]);
-        }
-        const double ext = std::max(g.x1 - g.x0, g.z1 - g.z0);
-        int k = ext > 0 ? (int)std::ceil(std::log2(ext / 32.0)) : 0;
-        k = std::max(-60, std::min(60, k));
-        g.c = std::ldexp(1.0, k); g.inv_c = std::ldexp(1.0, -k);
-        g.ox = std::floor(g.x0 * g.inv_c); g.oz = std::floor(g.z0 * g.inv_c);
-        const double dnx = std::floor(g.x1 * g.inv_c) - g.ox + 1, dnz = std::floor(g.z1 * g.inv_c) - g.oz + 1;
-        const size_t smem = sizeof(double) * 4 * (size_t)nu + sizeof(int) * ((size_t)(dnx * dnz) + 1);
-        if (dnx >= 1 && dnz >= 1 && dnx <= 80 && dnz <= 80 && std::fabs(g.ox) < 1e9 && std::fabs(g.oz) < 1e9 && smem <= (size_t)ctx->smem_optin - 1024) {
-            g.nx = (int)dnx; g.nz = (int)dnz; g.n_u = nu;
-            const int ncell = g.nx * g.nz;
-            std::vector<int> cell((size_t)nu), order((size_t)nu), start((size_t)ncell + 1, 0);
-            for (int i = 0; i < nu; ++i) {
-                const int ci = (int)(std::floor(quads[4 * i] * g.inv_c) - g.ox), cj = (int)(std::floor(quads[4 * i + 2] * g.inv_c) - g.oz);
-                cell[i] = cj * g.nx + ci;
-                ++start[(size_t)cell[i] + 1];
-            }
-            for (int c = 0; c < ncell; ++c) start[(size_t)c + 1] += start[c];
-            std::vector<int> fill(start.begin(), start.end() - 1);
-            for (int i = 0; i < nu; ++i) order[(size_t)fill[cell[i]]++] = i;
-            std::vector<double> sorted(4 * (size_t)nu);
-            for (int t = 0; t < nu; ++t) {                       // (x, z, y, original index): see locg_eval
-                const double* q = &quads[4 * (size_t)order[t]];
-                sorted[4 * (size_t)t] = q[0]; sorted[4 * (size_t)t + 1] = q[2]; sorted[4 * (size_t)t + 2] = q[1]; sorted[4 * (size_t)t + 3] = q[3];
-            }
-            CU(cudaMalloc(&ctx->wp_grid_dev, sizeof(double) * sorted.size()));
-            CU(cudaMemcpy(ctx->wp_grid_dev, sorted.data(), sizeof(double) * sorted.size(), cudaMemcpyHostToDevice));
-            CU(cudaMalloc(&ctx->wp_cells_dev, sizeof(int) * start.size()));
-            CU(cudaMemcpy(ctx->wp_cells_dev, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
-            CU(cudaFuncSetAttribute(trs::k_locate_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ctx->grid = g;
-        }
+    trs::LocGrid g{};
+    std::vector<double> sorted;
+    std::vector<int> start;
+    if (trs::locg_build(quads, (size_t)ctx->smem_optin - 1024, g, sorted, start)) {
+        CU(cudaMalloc(&ctx->wp_grid_dev, sizeof(double) * sorted.size()));
+        CU(cudaMemcpy(ctx->wp_grid_dev, sorted.data(), sizeof(double) * sorted.size(), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&ctx->wp_cells_dev, sizeof(int) * start.size()));
+        CU(cudaMemcpy(ctx->wp_cells_dev, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
+        CU(cudaFuncSetAttribute(trs::k_locate_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trs::locg_table_bytes(g)));
+        ctx->grid = g;
     }
     return 0;
 }
@@ -706,13 +654,13 @@ int trs_locate(trs_ctx* ctx, const double* xyz_dev, int n, int32_t* idx_dev, dou
         cudaStream_t st = (cudaStream_t)stream;
         CU(cudaMemsetAsync(ctx->defer_dev, 0, sizeof(int), st));
         const trs::LocGrid& g = ctx->grid;
-        const size_t smem = sizeof(double) * 4 * (size_t)g.n_u + sizeof(int) * ((size_t)g.nx * g.nz + 1);
+        const size_t smem = trs::locg_table_bytes(g);
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trs::k_locate_grid, trs::LOCG_THREADS, smem));
         per_sm = std::max(1, per_sm);
         int grid = (n + trs::LOCG_THREADS - 1) / trs::LOCG_THREADS;
         grid = std::min(grid, ctx->sm_count * per_sm);
-        trs::k_locate_grid<<<grid, trs::LOCG_THREADS, smem, st>>>(reinterpret_cast<const double4*>(ctx->wp_grid_dev), ctx->wp_cells_dev, g, ctx->n_wp, ctx->min_map,
+        trs::k_locate_grid<<<grid, trs::LOCG_THREADS, smem, st>>>(ctx->wp_grid_dev, ctx->wp_cells_dev, g, ctx->n_wp, ctx->min_map,
                                                                   ctx->max_map, xyz_dev, n, idx_dev, segment_dev, ctx->defer_dev + 1, ctx->defer_dev);
         CU(cudaGetLastError());
         trs::k_locate_warp<<<ctx->sm_count * 2, trs::LOCW_THREADS, 0, st>>>(reinterpret_cast<const double4*>(ctx->wp_dev), ctx->n_wp_distinct, ctx->n_wp, ctx->min_map,
