@@ -653,7 +653,7 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, const Dims& D
     using Off = std::integral_constant<int, 0>;
     using Rt = std::integral_constant<int, -1>;
     // rolling window by register renaming: slots (k % 3)
-    if (SEG > 0) {
+    if constexpr (SEG > 0) {
         static_assert(SEG % 3 == 0, "the peeled walk keeps the slot rotation of whole trips");
         // step k loads image row r0 - 1 + k (clamped) and, from k = 2 on, emits magnitude row r0 + k - 2; masks belong to steps 1 .. SEG.
         // The row address stands still once at the top of the frame (after step 0 of the first segment) and once at the bottom
@@ -672,14 +672,14 @@ __device__ __forceinline__ void p1_strip_walk(const FastParams& P, const Dims& D
         if (tail_bar && tail_k >= SEG) mbar_wait(tail_bar, tail_parity);
         row_step(On{}, On{}, r1 == h ? 0 : row_bytes, SEG, D[0], Hs[0], D[1], D[2], Hs[1]);
         row_step(Off{}, On{}, 0, SEG + 1, D[1], Hs[1], D[2], D[0], Hs[2]);
-        return;
-    }
+    } else {
 #pragma unroll 1
-    for (int k = 0; k < nsteps; k += 3) {
-        if (tail_bar && k == tail_k) mbar_wait(tail_bar, tail_parity);
-        row_step(Rt{}, Rt{}, -1, k, D[0], Hs[0], D[1], D[2], Hs[1]);                 // new = slot0, y-1 = slot1, y = slot2
-        if (k + 1 < nsteps) row_step(Rt{}, Rt{}, -1, k + 1, D[1], Hs[1], D[2], D[0], Hs[2]);
-        if (k + 2 < nsteps) row_step(Rt{}, Rt{}, -1, k + 2, D[2], Hs[2], D[0], D[1], Hs[0]);
+        for (int k = 0; k < nsteps; k += 3) {
+            if (tail_bar && k == tail_k) mbar_wait(tail_bar, tail_parity);
+            row_step(Rt{}, Rt{}, -1, k, D[0], Hs[0], D[1], D[2], Hs[1]);             // new = slot0, y-1 = slot1, y = slot2
+            if (k + 1 < nsteps) row_step(Rt{}, Rt{}, -1, k + 1, D[1], Hs[1], D[2], D[0], Hs[2]);
+            if (k + 2 < nsteps) row_step(Rt{}, Rt{}, -1, k + 2, D[2], Hs[2], D[0], D[1], Hs[0]);
+        }
     }
 }
 
