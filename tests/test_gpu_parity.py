@@ -409,7 +409,7 @@ def test_full_size_properties_240x320(want_f32):
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize("h,w,n", [(240, 320, 1536), (120, 160, 3072)])
-@pytest.mark.parametrize("cname", ["dyn_contrast", "exotic", "static_contrast", "edge_only", "colour_only"])
+@pytest.mark.parametrize("cname", ["dyn_contrast", "exotic", "static_contrast", "edge_only", "colour_only", "adjust_only", "adjust_dynamic"])
 def test_non_default_configurations_many_frames_per_cta(golden_images, cname, h, w, n):
     """Every kernel keeps a CTA busy with frame after frame, and the hand-over between its warps (plane sets by frame parity, the tail copy,
     the per-frame brightness table, the alternating ROI accumulators) only shows with several frames per CTA: five to eleven frames per CTA
@@ -417,8 +417,12 @@ def test_non_default_configurations_many_frames_per_cta(golden_images, cname, h,
     run-time colour ranges, and channels that keep the adjusted pixel.  Every frame against the oracle, the ROI statistic against a direct
     sum.  (A store-warp kernel that deadlocked with a table and more than two frames per CTA went unnoticed by the small-batch tests.)"""
     from tests.helpers import image_cases
-    over = image_cases(golden_images).get(cname) or dict(preprocessing_color_filter_enabled=True, preprocessing_edge_detection_enabled=True,
-                                                           preprocessing_contrast_enhancement_ratio=1.6, preprocessing_contrast_enhancement_offset=90)
+    extra = {"static_contrast": dict(preprocessing_color_filter_enabled=True, preprocessing_edge_detection_enabled=True,
+                                     preprocessing_contrast_enhancement_ratio=1.6, preprocessing_contrast_enhancement_offset=90),
+             "adjust_dynamic": dict(preprocessing_dynamic_brightness_enabled=True, preprocessing_contrast_enhancement_ratio=1.25,
+                                    preprocessing_brightness_baseline=380)}      # no filter: the streaming kernel with a table per frame
+    cases = image_cases(golden_images)
+    over = cases[cname] if cname in cases else extra[cname]
     cfg = cfg_for(over)
     frames = synth.expand_numpy(synth.frame_pool(96, h, w, seed=411), n, start=7)      # brightness shifts of 96 frames
     want = oracle.process_batch(frames, cfg)
