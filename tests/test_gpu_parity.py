@@ -311,6 +311,17 @@ def test_locate_grid_walk_on_adversarial_cars(golden_tracks, monkeypatch):
             assert np.array_equal(got, iw), f"{name} x{scale} +{shift}: {int((got != iw).sum())} of {len(iw)} differ, first {np.nonzero(got != iw)[0][:5]}"
             assert np.array_equal(seg.cpu().numpy(), sw_)
             trk.onShutdown()
+    # a nearest point at a distance of exactly 100 inside the bounding box: the reference's strict `<` against its starting minimum keeps index 0
+    wp = np.array([[i, 0, 0] for i in range(40)] + [[1000 + i, 0, 1000] for i in range(40)], np.float64)
+    xyz = np.array([[89, 0, 50], [89, 0, 49.999], [89, 0, 50.001], [88, 1, 50], [1000, -50, 950], [1039, 0, 1100]], np.float64)
+    want = oracle.locate(wp, xyz)[0]
+    assert list(want) == [0, 39, 0, 0, 0, 0]
+    for which in ("grid", "warp", "thread"):
+        monkeypatch.setenv("TRS_LOCATE", which)
+        trk = LocationTracker(wp, device=0)
+        assert np.array_equal(trk.locate_device(torch.from_numpy(xyz).to(DEV))[0].cpu().numpy(), want), which
+        trk.onShutdown()
+    monkeypatch.setenv("TRS_LOCATE", "grid")
     wp = synth.synthetic_track(40)                               # fewer than 64 points: no grid, the scanning kernel answers
     xyz, _, _, _ = synth.car_states(wp, 3000, seed=8)
     trk = LocationTracker(wp, device=0)

@@ -190,6 +190,13 @@ def test_grid_walk_returns_the_reference_index(locate_host):
             assert len(bad) == 0, f"{name} x{scale} +{shift}: {len(bad)} of {len(want)} differ, first {bad[:5]}: {xyz[bad[:5]]}"
             put_off += int(stats[3])
         assert put_off > 0                                       # the deferred path is exercised
+    # a nearest point at a distance of exactly 100 inside the bounding box: the reference's strict `<` against its starting minimum keeps index 0
+    wp = np.array([[i, 0, 0] for i in range(40)] + [[1000 + i, 0, 1000] for i in range(40)], np.float64)
+    xyz = np.array([[89, 0, 50], [89, 0, 49.999], [89, 0, 50.001], [88, 1, 50], [1000, -50, 950], [1039, 0, 1100]], np.float64)
+    want = oracle.locate(wp, xyz)[0]
+    assert list(want) == [0, 39, 0, 0, 0, 0]
+    got, stats = locate_host(wp, xyz)
+    assert stats[0] == 1 and stats[5] == 6 and np.array_equal(got, want)
     # no grid: a handful of points, a non-finite point
     wp = synth.synthetic_track(40)
     xyz, _, _, _ = synth.car_states(wp, 2000, seed=8)

@@ -75,7 +75,8 @@ LOCG_HD void locg_eval(const double* q, int a, int b, double x, double y, double
 #endif
         const double d = locg_add(locg_add(ax, fabs(locg_sub(y, qy))), az);      // (|dx| + |dy|) + |dz|, as the reference sums it
         const int qi = (int)qw;
-        if (d < best || (d == best && qi < sel)) { best = d; sel = qi; }
+        // (a distance of exactly 100 never wins: the reference's minimum starts there and its test is strict)
+        if (d < best || (d == best && qi < sel && best < 100.0)) { best = d; sel = qi; }
     }
 }
 
