@@ -208,3 +208,27 @@ def test_grid_walk_returns_the_reference_index(locate_host):
     got, stats = locate_host(wp, xyz)
     with np.errstate(invalid="ignore"):
         assert stats[0] == 0 and np.array_equal(got, oracle.locate(wp, xyz)[0])
+
+
+# ---- bench.py contract pieces that run without a GPU ----------------------------------------------------------------------------------------------
+def test_reference_arm_prints_a_contract_line():
+    """`bench.py --impl reference` times the reference's call sequence (the port under oracle/) on the host cores and prints ONE JSON line with
+    the contract's keys; without a GPU the product arm refuses to run instead of falling back."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["metric"].startswith("preprocessed frames/sec (120x160)") and d["config"]["workload"] == "full_chain_120x160"
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if not torch.cuda.is_available():
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                             timeout=600, cwd=ROOT)
+        assert not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]          # no number without the GPU
+        assert "no CPU path" in (out.stdout + out.stderr)
