@@ -12,7 +12,9 @@ KERNELS = [("k_preprocess_swILi2ELi24ELi23ELi120ELi160", "k_preprocess_sw<2,24,2
            ("k_preprocess_bandedILi2ELb1ELi24ELi23", "k_preprocess_banded<2,true,24,23> (240x320)", ["UBLKCP", "SYNCS", "HFMA2", "IDP.4A"]),
            ("k_pilot_gemmILi128ELi3ELb0", "k_pilot_gemm<128,3,false> (pilot convolutions, implicit GEMM)", ["UTMALDG", "UTCHMMA", "LDTM", "SYNCS", "UTCBAR"]),
            ("k_pilot_conv1", "k_pilot_conv1 (first convolution from u8 frames, A operand through tensor memory)", ["UTCHMMA", "STTM", "LDTM", "UTMALDG", "SYNCS"]),
-           ("k_locateEPKd", "k_locate (nearest waypoint, fp64)", ["DADD", "DSETP", "LDS"]),
+           ("k_locate_grid", "k_locate_grid (nearest waypoint through the grid, fp64)", ["DADD", "DSETP", "LDS.128", "ATOMS", "ATOMG", "RED"]),
+           ("k_locateEPKd", "k_locate (nearest waypoint, scanning kernel, fp64)", ["DADD", "DSETP", "LDS"]),
+           ("k_preprocess_bswILi2ELi24ELi23ELi240ELi320ELi24ELi2ELi80ELb0", "k_preprocess_bsw<2,24,23,240,320,24,2,80,false> (240x320, default configuration)", ["UBLKCP", "SYNCS", "HFMA2", "HSET2", "VIMNMX3", "ATOMS"]),
            ("k_jpeg_entropy", "k_jpeg_entropy (tub ingestion)", ["SHF", "LDG", "IMAD"])]
 arch = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True)
 arch = ", ".join(l.split(":", 1)[1].strip() for l in (arch.stdout + arch.stderr).splitlines() if ":" in l)
