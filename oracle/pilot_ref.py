@@ -5,10 +5,11 @@ Restates Keras_2D_CNN.get_model (TritonRacerSim/components/keras_train.py:127-17
 (components/keras_pilot.py:49-50,59,68-71,81,98-104).  Weights are a dict of numpy arrays in Keras layout under the reference's layer
 names ("conv1/kernel" (kh,kw,in,out), "dense1/kernel" (in,out), "…/bias").
 
-PARITY UNPINNED: TensorFlow is not installed in this image, so this restatement cannot be checked against the reference's own
-model objects; it follows the layer list line by line (VALID padding, ReLU, NHWC Flatten order, Concatenate order) and is itself
-checked against an independent explicit-loop numpy restatement of the same layer list (tests/test_pilot_host.py).  A floating-point
-kernel is compared with it within a stated tolerance (tests/test_pilot_gpu.py), not bit for bit.
+PARITY: TensorFlow is not installed in this image, so Keras' own float32 kernels are unpinned.  The GRAPH is pinned: tests/golden/pilot.npz holds
+the outputs of the reference's own get_model / KerasPilot.step code, imported unmodified and run over a float64 numpy stand-in for the Keras
+primitives (tests/golden/make_golden_pilot.py), and tests/test_pilot_host.py holds this restatement to them within 2e-5; its Conv2D / Dense
+conventions are also checked against an explicit-loop numpy restatement.  A floating-point kernel is compared with it within a stated tolerance
+(tests/test_pilot_gpu.py), not bit for bit.
 """
 import numpy as np
 import torch

@@ -119,3 +119,55 @@ def test_pilot_without_a_gpu_fails_loudly():
     from triton_racer_sim_b200.pilot import ModelType, PilotNet
     with pytest.raises((nat.NativeError, RuntimeError)):
         PilotNet(ModelType.CNN_2D, ref.random_weights(ref.CNN_2D), device=0)
+
+
+# ---- the reference's own model-building and step code, executed over a numpy stand-in for the Keras primitives (tests/golden/pilot.npz) ----------
+def _pilot_golden():
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pilot.npz"))
+    return g, json.loads(bytes(g["meta_json"]).decode())
+
+
+def test_checker_matches_the_graph_the_reference_code_builds():
+    """tests/golden/make_golden_pilot.py imports keras_train.py / keras_pilot.py unmodified, lets the reference's `get_model` build its graphs and
+    its `KerasPilot.step` feed them (the `/255`, the reshapes, the input tuple (img, spd, features), keras_pilot.py:49-104), with only Conv2D / Dense /
+    Flatten / Concatenate supplied by a float64 numpy stand-in.  The fp32 checker the CUDA kernels are compared with (oracle/pilot_ref.py) must give
+    those outputs: same layers, names, shapes, concatenation and input order, for all four model types at two frame sizes."""
+    from triton_racer_sim_b200 import synth
+    g, meta = _pilot_golden()
+    assert len(meta["cases"]) == 8
+    for case in meta["cases"]:
+        mt, h, w, n = case["model_type"], case["h"], case["w"], case["n"]
+        wts = ref.random_weights(mt, h, w, seed=case["weight_seed"])
+        assert sorted({k.split("/")[0] for k in wts}) == case["layers"]                       # the reference's layer names, every trainable one
+        frames = synth.frame_pool(n, h, w, seed=case["frame_seed"])
+        speed, segment = g[f"speed/{mt}/{h}x{w}"], g[f"segment/{mt}/{h}x{w}"]
+        spd_feature = (speed / 20).astype(np.float32)                                          # keras_pilot.py:68, :100
+        got = ref.forward(wts, mt, frames, spd_feature=spd_feature, loc_feature=segment.astype(np.float32))
+        for cname in meta["cfgs"]:
+            want = g[f"model_out/{mt}/{h}x{w}/{cname}"]
+            assert want.shape == (n, 2) and np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (mt, h, w, np.abs(got - want).max())
+    assert [c["inputs"] for c in meta["cases"] if c["model_type"] == ref.CNN_2D_FULL_HOUSE][0] == ["img_input", "current_spd_input", "feature_vec_input"]
+    # the reference's cnn_2d / cnn_2d_speed_as_feature pilots raise on every frame: `__cap` gets the whole (steering, throttle) row
+    assert sorted(meta["reference_raises"]) == [str(ref.CNN_2D), str(ref.CNN_2D_SPD_FTR)]
+
+
+def test_speed_control_tail_matches_the_reference_step():
+    """(steering, throttle, breaking) as the reference's KerasPilot.step returned them for the speed-control model types (keras_pilot.py:78-118:
+    cap, x 20, calcThrottle / calcBreak, smoothing), against the oracle's speed controller fed the same model outputs."""
+    import oracle
+    from tests.helpers import cfg_for
+    g, meta = _pilot_golden()
+    checked = 0
+    for case in meta["cases"]:
+        mt, h, w = case["model_type"], case["h"], case["w"]
+        if mt not in (ref.CNN_2D_SPD_CTL, ref.CNN_2D_FULL_HOUSE):
+            continue
+        for cname, over in meta["cfgs"].items():
+            out, want = g[f"model_out/{mt}/{h}x{w}/{cname}"], g[f"ctl/{mt}/{h}x{w}/{cname}"]
+            s, t, b, _ = oracle.speed_control(g[f"speed/{mt}/{h}x{w}"], out[:, 1], out[:, 0], cfg_for(over))
+            assert np.array_equal(s, want[:, 0]), (mt, cname)
+            assert np.allclose(t, want[:, 1], rtol=1e-5, atol=0) and np.allclose(b, want[:, 2], rtol=1e-5, atol=0), (mt, cname)
+            checked += len(want)
+    assert checked >= 40
