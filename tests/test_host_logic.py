@@ -130,6 +130,42 @@ def test_tub_labels_and_features_follow_the_reference_loaders():
                               np.asarray(np.asarray((r['gym/speed'] / 20, r['loc/segment'])), dtype=np.float32))
 
 
+def test_tub_loaders_against_the_reference_run(tmp_path):
+    """tests/golden/tub.npz: `loader.dataset` of the reference's four loader classes, run unmodified over a recorder-style tub
+    (tests/golden/make_golden_tub.py).  Labels and feature vectors must be the reference's float32 values bit for bit, the record count must stop
+    at the first missing file, and the JPEG files must decode (Pillow here; the CUDA decoder is held to Pillow in test_jpeg_gpu.py) to the frames
+    the reference divided by 255."""
+    import io
+    import json
+
+    from PIL import Image
+
+    from triton_racer_sim_b200 import tub
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tub.npz"))
+    records = json.loads(bytes(g["records_json"]).decode())
+    ends = np.cumsum(g["jpeg_sizes"])
+    files = [bytes(g["jpeg_blob"][e - s:e]) for s, e in zip(g["jpeg_sizes"], ends)]
+    for i, (f, r) in enumerate(zip(files, records), start=1):
+        (tmp_path / f"img_{i}.jpg").write_bytes(f)
+        (tmp_path / f"record_{i}.json").write_text(json.dumps(r))
+    assert tub.count_records(str(tmp_path)) == len(records) == 7
+    for i, f in enumerate(files):
+        assert np.array_equal(np.asarray(Image.open(io.BytesIO(f))), g["frames_u8"][i]) and tub.jpeg_size(f) == g["frames_u8"].shape[1:3]
+    for cname in ("DataLoader", "SpeedFeatureDataLoader", "SpeedCtlDataLoader", "FullHouseDataLoader"):
+        lab, ft = tub.labels_and_features(records, cname)
+        want_l, want_f = g[f"labels/{cname}"], g[f"features/{cname}"]
+        assert lab.dtype == np.float32 and np.array_equal(lab, want_l), cname
+        if ft is None:
+            # the reference's np.asarray(None, dtype=float32) for loaders without features: a NaN scalar per record
+            assert want_f.shape == (7,) and np.isnan(want_f).all(), cname
+        else:
+            assert ft.dtype == np.float32 and np.array_equal(ft, want_f), cname
+    for model, cname in tub.LOADER_OF_MODEL.items():                                          # keras_train.py:384-398
+        assert np.array_equal(tub.labels_and_features(records, model)[0], g[f"labels/{cname}"])
+    (tmp_path / "record_4.json").unlink()
+    assert tub.count_records(str(tmp_path)) == int(g["count_with_record_4_missing"]) == 3
+
+
 # ---- nearest waypoint through the grid (csrc/loc_grid.h compiled for the host) ------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def locate_host(tmp_path_factory):

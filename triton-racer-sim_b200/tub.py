@@ -96,6 +96,15 @@ def labels_and_features(records, loader="DataLoader"):
     return labels, feats
 
 
+def count_records(tub_path: str) -> int:
+    """Number of complete records, counted as the reference does: consecutive indices from 1, the first missing file ends the folder
+    (keras_train.py:36-39, 54-56)."""
+    i = 1
+    while os.path.exists(os.path.join(tub_path, f"record_{i}.json")) and os.path.exists(os.path.join(tub_path, f"img_{i}.jpg")):
+        i += 1
+    return i - 1
+
+
 class TubReader:
     """A tub folder as the reference's loaders see it: records 1..N, ``img_{i}.jpg`` + ``record_{i}.json`` (keras_train.py:36-46)."""
 
@@ -106,10 +115,7 @@ class TubReader:
 
     def count(self) -> int:
         """Number of complete records, counted as the reference does: consecutive indices from 1 (keras_train.py:36-39)."""
-        i = 1
-        while os.path.exists(os.path.join(self.path, f"record_{i}.json")) and os.path.exists(os.path.join(self.path, f"img_{i}.jpg")):
-            i += 1
-        return i - 1
+        return count_records(self.path)
 
     def load(self, indices):
         """-> (frames (N,H,W,3) uint8 CUDA tensor, list of record dicts) for the given record indices."""
