@@ -137,3 +137,16 @@ def test_telemetry_packets_like_the_gym_interface():
     packets[3]["image"] = packets[3]["image"][:50] + "!" + packets[3]["image"][51:]
     with pytest.raises(ValueError):
         tub.decode_telemetry_batch(packets, hw=(120, 160), device=0)
+
+
+def test_telemetry_fixture_from_the_reference_run():
+    """tests/golden/telemetry.npz: what the reference's own GymInterface.on_msg_recv / step publish for six simulator packets
+    (tests/golden/make_golden_telemetry.py runs that code unmodified with a socket-less SDClient): image and the five floats, bit for bit."""
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "telemetry.npz"))
+    packets = json.loads(bytes(g["packets_json"]).decode())
+    got = tub.decode_telemetry_batch(packets, device=0)
+    assert np.array_equal(got["cam/img"].cpu().numpy(), g["images"])
+    for j, key in enumerate(("gym/x", "gym/y", "gym/z", "gym/speed", "gym/cte")):
+        assert np.array_equal(got[key].cpu().numpy(), g["floats"][:, j]), key
