@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generate tests/golden/tub.npz by running the reference's own tub loaders (TritonRacerSim/components/keras_train.py:22-119, 264-325:
 DataLoader, SpeedFeatureDataLoader, SpeedCtlDataLoader, FullHouseDataLoader, imported UNMODIFIED from /root/reference) over a small tub
-written the way the recorder writes it (components/datastorage.py:67-79: `Image.fromarray(img).save('img_i.jpg')` + `record_i.json`).
+written by the reference's own recorder (components/datastorage.py, DataStorage.step + its file thread, also imported unmodified).
 
 TensorFlow is not installed in this image; the loaders only touch it after the per-record loop (`tf.data.Dataset.from_tensors(...)`), so the
 stand-in of make_golden_pilot.py plus a do-nothing `tf.data.Dataset` is enough to run `load()`; what is stored is `loader.dataset`, the list
@@ -13,7 +13,9 @@ import io
 import json
 import os
 import sys
+import shutil
 import tempfile
+import time
 
 import numpy as np
 from PIL import Image
@@ -50,36 +52,56 @@ from triton_racer_sim_b200 import synth  # noqa: E402
 LOADER_CLASSES = ["DataLoader", "SpeedFeatureDataLoader", "SpeedCtlDataLoader", "FullHouseDataLoader"]
 
 
-def write_tub(folder, frames, records, skip=()):
-    for i, (f, r) in enumerate(zip(frames, records), start=1):
-        if i in skip:
-            continue
-        Image.fromarray(f).save(os.path.join(folder, f"img_{i}.jpg"))              # datastorage.py:78
-        with open(os.path.join(folder, f"record_{i}.json"), "w") as fh:           # datastorage.py:72-75
-            json.dump(r, fh)
+def write_tub(folder, frames, values):
+    """The tub as the reference's recorder writes it: DataStorage.step once per frame with recording on (datastorage.py:25-34), its file thread
+    stores `img_k.jpg` + `record_k.json` (:67-79, :98-112).  The thread numbers the records from 0 while the loaders read from 1
+    (keras_train.py:36): the first recorded frame is never loaded."""
+    from TritonRacerSim.components.datastorage import DataStorage
+    ds = DataStorage(storage_path=folder)
+    keys = ds.step_inputs[:-2]
+    for f, v in zip(frames, values):
+        row = dict(v)
+        row['cam/img'] = f
+        ds.step(*[row[k] for k in keys], False, True)                            # usr/del_record, usr/toggle_record
+    last = os.path.join(folder, f"record_{len(frames) - 1}.json")
+    for _ in range(2000):
+        if os.path.exists(last) and os.path.getsize(last) > 0:
+            break
+        time.sleep(0.005)
+    time.sleep(0.05)
+    ds.on = False
+    return keys
 
 
 def main():
-    n, h, w = 7, 24, 32
+    n, h, w = 8, 24, 32
     frames = synth.frame_pool(n, h, w, seed=61)
     rng = np.random.default_rng(61)
-    records = [{"mux/steering": float(rng.uniform(-1, 1)), "mux/throttle": float(rng.uniform(-1, 1)), "mux/breaking": 0.0,
-                "gym/speed": float(rng.uniform(0, 25)), "gym/cte": float(rng.normal()), "loc/segment": float(rng.uniform(0, 10)),
-                "usr/mode": "human"} for _ in range(n)]
-    arrays = {"records_json": np.frombuffer(json.dumps(records).encode(), np.uint8)}
-    with tempfile.TemporaryDirectory() as full, tempfile.TemporaryDirectory() as gap:
-        write_tub(full, frames, records)
-        write_tub(gap, frames, records, skip=(4,))
-        files = []
-        for i in range(1, n + 1):
+    values = [{"mux/steering": float(rng.uniform(-1, 1)), "mux/throttle": float(rng.uniform(-1, 1)), "mux/break": 0.0,
+               "gym/speed": float(rng.uniform(0, 25)), "gym/cte": float(rng.normal()), "loc/segment": float(rng.uniform(0, 10)),
+               "gym/x": float(rng.normal(50, 20)), "gym/y": 0.56, "gym/z": float(rng.normal(30, 20))} for _ in range(n)]
+    arrays = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        full, gap = os.path.join(tmp, "records_1"), os.path.join(tmp, "records_2")
+        write_tub(full, frames, values)
+        shutil.copytree(full, gap)
+        os.remove(os.path.join(gap, "record_4.json"))
+        names = sorted(os.listdir(full))
+        assert names == sorted([f"img_{i}.jpg" for i in range(n)] + [f"record_{i}.json" for i in range(n)]), names
+        files, records = [], []
+        for i in range(n):                                                        # every file the recorder wrote, index 0 included
             with open(os.path.join(full, f"img_{i}.jpg"), "rb") as fh:
                 files.append(fh.read())
+            with open(os.path.join(full, f"record_{i}.json")) as fh:
+                records.append(json.load(fh))
+        arrays["records_json"] = np.frombuffer(json.dumps(records).encode(), np.uint8)
         arrays["jpeg_blob"] = np.frombuffer(b"".join(files), np.uint8)
         arrays["jpeg_sizes"] = np.asarray([len(f) for f in files], np.int64)
+        arrays["recorded_frames_u8"] = frames
         for cname in LOADER_CLASSES:
             loader = getattr(ref_train, cname)(full)
             loader.load(train_val_split=0.8, batch_size=2)
-            assert len(loader.dataset) == n
+            assert len(loader.dataset) == n - 1                                   # records 1 .. n-1
             imgs = np.stack([d[0] for d in loader.dataset])
             assert imgs.dtype == np.float32
             u8 = np.rint(imgs * 255).astype(np.uint8)
@@ -88,7 +110,7 @@ def main():
             assert np.array_equal(arrays["frames_u8"], u8)
             arrays[f"labels/{cname}"] = np.stack([d[2] for d in loader.dataset])
             feats = [d[1] for d in loader.dataset]
-            arrays[f"features/{cname}"] = np.stack(feats) if feats[0].size else np.zeros((n, 0), np.float32)
+            arrays[f"features/{cname}"] = np.stack(feats)
             assert arrays[f"labels/{cname}"].dtype == np.float32
             short = getattr(ref_train, cname)(gap)
             short.load(train_val_split=0.8, batch_size=1)

@@ -131,10 +131,11 @@ def test_tub_labels_and_features_follow_the_reference_loaders():
 
 
 def test_tub_loaders_against_the_reference_run(tmp_path):
-    """tests/golden/tub.npz: `loader.dataset` of the reference's four loader classes, run unmodified over a recorder-style tub
-    (tests/golden/make_golden_tub.py).  Labels and feature vectors must be the reference's float32 values bit for bit, the record count must stop
-    at the first missing file, and the JPEG files must decode (Pillow here; the CUDA decoder is held to Pillow in test_jpeg_gpu.py) to the frames
-    the reference divided by 255."""
+    """tests/golden/tub.npz: a tub written by the reference's own recorder (DataStorage.step + its file thread) and `loader.dataset` of the
+    reference's four loader classes over it, all run unmodified (tests/golden/make_golden_tub.py).  Labels and feature vectors must be the
+    reference's float32 values bit for bit; the record count must start at 1 (the recorder numbers from 0, so its first frame is never loaded)
+    and stop at the first missing file; the JPEG files must decode (Pillow here; the CUDA decoder is held to Pillow in test_jpeg_gpu.py) to the
+    frames the reference divided by 255."""
     import io
     import json
 
@@ -142,14 +143,16 @@ def test_tub_loaders_against_the_reference_run(tmp_path):
 
     from triton_racer_sim_b200 import tub
     g = np.load(os.path.join(ROOT, "tests", "golden", "tub.npz"))
-    records = json.loads(bytes(g["records_json"]).decode())
+    recorded = json.loads(bytes(g["records_json"]).decode())                    # record_0 .. record_7 as the recorder wrote them
     ends = np.cumsum(g["jpeg_sizes"])
     files = [bytes(g["jpeg_blob"][e - s:e]) for s, e in zip(g["jpeg_sizes"], ends)]
-    for i, (f, r) in enumerate(zip(files, records), start=1):
+    assert len(recorded) == len(files) == 8 and recorded[3]["cam/img"] == "img_3.jpg"
+    for i, (f, r) in enumerate(zip(files, recorded)):
         (tmp_path / f"img_{i}.jpg").write_bytes(f)
         (tmp_path / f"record_{i}.json").write_text(json.dumps(r))
-    assert tub.count_records(str(tmp_path)) == len(records) == 7
-    for i, f in enumerate(files):
+    assert tub.count_records(str(tmp_path)) == 7                                              # records 1 .. 7
+    records = recorded[1:]
+    for i, f in enumerate(files[1:]):
         assert np.array_equal(np.asarray(Image.open(io.BytesIO(f))), g["frames_u8"][i]) and tub.jpeg_size(f) == g["frames_u8"].shape[1:3]
     for cname in ("DataLoader", "SpeedFeatureDataLoader", "SpeedCtlDataLoader", "FullHouseDataLoader"):
         lab, ft = tub.labels_and_features(records, cname)
