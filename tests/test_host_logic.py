@@ -271,3 +271,16 @@ def test_reference_arm_prints_a_contract_line():
                              timeout=600, cwd=ROOT)
         assert not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]          # no number without the GPU
         assert "no CPU path" in (out.stdout + out.stderr)
+
+
+def test_grid_walk_fuzz_under_the_sanitizers(tmp_path):
+    """csrc/loc_grid.h built for the host with -fsanitize=address,undefined: 300 random centre lines x 400 cars against the reference's loop
+    (tests/host_locate_fuzz.cpp) — exact indices, no out-of-bounds cell access, no integer overflow in the ring arithmetic."""
+    import subprocess
+    exe = tmp_path / "loc_fuzz"
+    build = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer", "-o", str(exe),
+                            os.path.join(ROOT, "tests", "host_locate_fuzz.cpp")], capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("no sanitizer runtime in this toolchain: " + build.stderr[-200:])
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and run.stdout.strip() == "ok 120000 cars", (run.stdout[-500:], run.stderr[-2000:])

@@ -74,3 +74,24 @@ def test_parser_rejects_what_the_kernels_do_not_decode(host_lib):
     Image.fromarray(f[..., 0]).save(buf, format="JPEG")          # greyscale
     assert host_decode(host_lib, buf.getvalue(), 32, 32)[0] == 111
     assert host_decode(host_lib, b"not a jpeg at all", 32, 32)[0] == 110
+
+
+def test_host_decoder_survives_corrupted_files_under_the_address_sanitizer(tmp_path):
+    """Telemetry JPEGs are external input: 3,000 corrupted files (random bytes, truncation, runs of 0xff, damaged tables, inserted bytes; all three
+    chroma subsamplings) through the product's parser / entropy decoder / IDCT built with -fsanitize=address.  A malformed file may give an error
+    code or garbage pixels, never an access outside its buffers."""
+    exe = tmp_path / "jpeg_fuzz"
+    build = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-o", str(exe),
+                            os.path.join(ROOT, "tests", "host_jpeg_fuzz.cpp")], capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("no AddressSanitizer runtime in this toolchain: " + build.stderr[-200:])
+    files = []
+    for i, (q, sub) in enumerate(((75, 2), (90, 1), (60, 0))):
+        buf = io.BytesIO()
+        Image.fromarray(synth.frame_pool(1, 120, 160, seed=50 + i)[0]).save(buf, format="JPEG", quality=q, subsampling=sub)
+        p = tmp_path / f"f{i}.jpg"
+        p.write_bytes(buf.getvalue())
+        files.append(str(p))
+    run = subprocess.run([str(exe), "120", "160", "1000"] + files, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr[-3000:]
+    assert run.stdout.startswith("runs 3000 decoded")
