@@ -1,0 +1,46 @@
+// Host build of the product's per-pixel arithmetic (csrc/pixel_math.cuh: pure host / device functions, the source the generic kernel compiles) for
+// the CPU-side check against the oracle and against OpenCV itself (tests/test_host_logic.py).  Test infrastructure.
+#include <math.h>
+
+#include "../triton-racer-sim_b200/csrc/pixel_math.cuh"
+using namespace trs;
+
+// every colour of [first, first + n): (r, g, b) = (c >> 16, c >> 8, c) -> h, s, v bytes
+extern "C" void math_rgb2hsv_range(unsigned first, unsigned n, uint8_t* hsv)
+{
+    int32_t sdiv[256], hdiv[256];
+    for (int i = 0; i < 256; ++i) {
+        sdiv[i] = i ? (int32_t)rint((255 << 12) / (double)i) : 0;
+        hdiv[i] = i ? (int32_t)rint((180 << 12) / (6.0 * i)) : 0;
+    }
+    for (unsigned k = 0; k < n; ++k) {
+        const unsigned c = first + k;
+        int h, s, v;
+        rgb2hsv_px((c >> 16) & 255, (c >> 8) & 255, c & 255, sdiv, hdiv, h, s, v);
+        hsv[3 * k] = (uint8_t)h; hsv[3 * k + 1] = (uint8_t)s; hsv[3 * k + 2] = (uint8_t)v;
+    }
+}
+
+extern "C" int math_in_range(int h, int s, int v, const int32_t* lo, const int32_t* hi)
+{
+    HsvRange r;
+    for (int c = 0; c < 3; ++c) { r.lo[c] = lo[c]; r.hi[c] = hi[c]; }
+    return in_range_px(h, s, v, r) ? 1 : 0;
+}
+
+// direction classes of all gradients (dx, dy) in [-m, m]^2, row-major in dy then dx
+extern "C" void math_canny_dirs(int m, uint8_t* out)
+{
+    for (int dy = -m; dy <= m; ++dy)
+        for (int dx = -m; dx <= m; ++dx) *out++ = (uint8_t)canny_dir(dx, dy);
+}
+
+extern "C" void math_adjust_table(int dynamic, float fdelta, float foff, float fratio, uint8_t* lut)
+{
+    for (int i = 0; i < 256; ++i) lut[i] = adjust_entry(i, dynamic != 0, fdelta, foff, fratio);
+}
+
+extern "C" double math_brightness_delta(unsigned long long s0, unsigned long long s1, unsigned long long s2, double npx, double baseline)
+{
+    return brightness_delta(s0, s1, s2, npx, baseline);
+}

@@ -284,3 +284,63 @@ def test_grid_walk_fuzz_under_the_sanitizers(tmp_path):
         pytest.skip("no sanitizer runtime in this toolchain: " + build.stderr[-200:])
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0 and run.stdout.strip() == "ok 120000 cars", (run.stdout[-500:], run.stderr[-2000:])
+
+
+# ---- per-pixel arithmetic of the kernels (csrc/pixel_math.cuh compiled for the host) ---------------------------------------------------------------
+@pytest.fixture(scope="module")
+def math_host(tmp_path_factory):
+    import ctypes as C
+    import subprocess
+    out = tmp_path_factory.mktemp("math") / "libmathchk.so"
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", str(out), os.path.join(ROOT, "tests", "host_math_check.cpp")])
+    lib = C.CDLL(str(out))
+    lib.math_rgb2hsv_range.argtypes = [C.c_uint, C.c_uint, C.c_void_p]
+    lib.math_in_range.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.math_canny_dirs.argtypes = [C.c_int, C.c_void_p]
+    lib.math_adjust_table.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    lib.math_brightness_delta.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_double, C.c_double]
+    lib.math_brightness_delta.restype = C.c_double
+    return lib
+
+
+def test_pixel_math_header_against_opencv_and_the_oracle(math_host):
+    """The header the kernels compile, built for the host: RGB -> HSV over all 2^24 colours against cv2.cvtColor itself, the direction classes of
+    all gradients in [-400, 400]^2 against the angle they stand for, the brightness / contrast table and the dynamic-brightness statistic against
+    the oracle (which test_oracle_golden.py holds to the reference's own outputs)."""
+    import cv2
+
+    import oracle
+    from tests.helpers import cfg_for
+    # (1) every colour, in slabs of 2^20
+    for first in range(0, 1 << 24, 1 << 20):
+        got = np.empty((1 << 20, 3), np.uint8)
+        math_host.math_rgb2hsv_range(first, 1 << 20, got.ctypes.data)
+        c = np.arange(first, first + (1 << 20), dtype=np.uint32)
+        rgb = np.stack([(c >> 16) & 255, (c >> 8) & 255, c & 255], 1).astype(np.uint8)
+        want = cv2.cvtColor(rgb.reshape(1024, 1024, 3), cv2.COLOR_RGB2HSV).reshape(-1, 3)
+        assert np.array_equal(got, want), first
+    # (2) direction classes: 0 within 22.5 degrees of the x axis, 1 within 22.5 degrees of the y axis, else the diagonal with the sign of dx dy;
+    # gradients within 0.01 degrees of a sector boundary are left to the integer rule (tan 22.5 as 13573 / 2^15)
+    m = 400
+    dirs = np.empty((2 * m + 1, 2 * m + 1), np.uint8)
+    math_host.math_canny_dirs(m, dirs.ctypes.data)
+    dy, dx = np.mgrid[-m:m + 1, -m:m + 1]
+    ang = np.degrees(np.arctan2(np.abs(dy), np.abs(dx)))
+    want = np.where(ang < 22.5, 0, np.where(ang > 67.5, 1, np.where((dx ^ dy) < 0, 3, 2)))
+    clear = (np.abs(ang - 22.5) > 0.01) & (np.abs(ang - 67.5) > 0.01) & ((dx != 0) | (dy != 0))      # (the zero gradient never passes the magnitude test)
+    assert np.array_equal(dirs[clear], want[clear])
+    # (3) brightness / contrast tables against the oracle's, static and dynamic
+    rng = np.random.default_rng(12)
+    from triton_racer_sim_b200 import synth
+    for over in (dict(preprocessing_contrast_enhancement_ratio=1.3, preprocessing_contrast_enhancement_offset=100.5),
+                 dict(preprocessing_dynamic_brightness_enabled=True, preprocessing_brightness_baseline=400.25, preprocessing_contrast_enhancement_ratio=0.7),
+                 dict(preprocessing_dynamic_brightness_enabled=True, preprocessing_brightness_baseline=550)):
+        cfg = cfg_for(over)
+        for img in synth.frame_pool(6, 120, 160, seed=int(rng.integers(1000))):
+            lut, sums = oracle.brightness_lut(img, cfg)
+            dyn = bool(cfg["preprocessing_dynamic_brightness_enabled"])
+            delta = math_host.math_brightness_delta(int(sums[0]), int(sums[1]), int(sums[2]), 79.0 * 160, float(cfg["preprocessing_brightness_baseline"]))
+            got = np.zeros(256, np.uint8)
+            math_host.math_adjust_table(int(dyn), np.float32(delta), np.float32(cfg["preprocessing_contrast_enhancement_offset"]),
+                                        np.float32(cfg["preprocessing_contrast_enhancement_ratio"]), got.ctypes.data)
+            assert np.array_equal(got, lut), over
