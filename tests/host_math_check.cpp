@@ -44,3 +44,40 @@ extern "C" double math_brightness_delta(unsigned long long s0, unsigned long lon
 {
     return brightness_delta(s0, s1, s2, npx, baseline);
 }
+
+// Exhaustive check of the threshold tables the fast kernels use instead of computing saturation and hue (csrc/preproc_fast.cuh, init_tables):
+// returns the number of (v, d, K) triples for which "s <= K" and "d <= T_K[v]" disagree, K over [k_lo, k_hi].
+extern "C" long long math_check_sat_thresholds(int k_lo, int k_hi)
+{
+    long long bad = 0;
+    for (int v = 0; v < 256; ++v) {
+        const int sd = hsv_sdiv_entry(v);
+        for (long long K = k_lo; K <= k_hi; ++K) {
+            const uint32_t T = sat_threshold_entry(K, v, sd);
+            const int t = T == 0x8001u ? -1 : (int)T;                       // the packed compare reads 0x8001 as -1
+            for (int d = 0; d <= v; ++d) {
+                const int s = (d * sd + 2048) >> 12;
+                bad += (s <= K) != (d <= t);
+            }
+        }
+    }
+    return bad;
+}
+
+// ... and of the hue thresholds for one range [lo, hi] with hi <= 149: every delta d and every numerator h0 the three formulas can produce
+// (g - b in [-d, d], b - r + 2d in [d, 3d], r - g + 4d in [3d, 5d]); the wrapped hue of a negative numerator is h + 180.
+extern "C" long long math_check_hue_thresholds(int lo, int hi)
+{
+    long long bad = 0;
+    for (int d = 0; d < 256; ++d) {
+        const int hd = hsv_hdiv_entry(d);
+        const uint32_t e = hue_threshold_entry(lo, hi, hd);
+        const int a_lo = (int)(e & 0xffffu) - 2048, a_hi = (int)(e >> 16) - 2048;
+        for (int h0 = -d; h0 <= 5 * d; ++h0) {
+            int h = (h0 * hd + 2048) >> 12;
+            h += h < 0 ? 180 : 0;
+            bad += (lo <= h && h <= hi) != (a_lo <= h0 && h0 <= a_hi);
+        }
+    }
+    return bad;
+}

@@ -300,6 +300,10 @@ def math_host(tmp_path_factory):
     lib.math_adjust_table.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
     lib.math_brightness_delta.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_double, C.c_double]
     lib.math_brightness_delta.restype = C.c_double
+    lib.math_check_sat_thresholds.argtypes = [C.c_int, C.c_int]
+    lib.math_check_sat_thresholds.restype = C.c_longlong
+    lib.math_check_hue_thresholds.argtypes = [C.c_int, C.c_int]
+    lib.math_check_hue_thresholds.restype = C.c_longlong
     return lib
 
 
@@ -344,3 +348,15 @@ def test_pixel_math_header_against_opencv_and_the_oracle(math_host):
             math_host.math_adjust_table(int(dyn), np.float32(delta), np.float32(cfg["preprocessing_contrast_enhancement_offset"]),
                                         np.float32(cfg["preprocessing_contrast_enhancement_ratio"]), got.ctypes.data)
             assert np.array_equal(got, lut), over
+
+
+def test_threshold_tables_replace_saturation_and_hue_exactly(math_host):
+    """The fast kernels never compute the saturation, and for the reference's default ranges not the hue either: they compare the delta / the hue
+    numerator with per-value thresholds (csrc/pixel_math.cuh sat_threshold_entry / hue_threshold_entry, the functions init_tables calls).  Exhaustive
+    proof on the host build: every (value, delta) pair against every saturation bound from -2 to 300, and every (delta, numerator) pair against every
+    hue interval with a lower bound >= 0 and an upper bound up to 149 (the variant's conditions: both hue bounds live, so the lower one is positive;
+    the host picks it for upper bounds below 60 only)."""
+    assert math_host.math_check_sat_thresholds(-2, 300) == 0
+    for lo in list(range(0, 151, 7)) + [1, 25]:                  # (a live lower bound is positive; a negative one would admit wrapped hues)
+        for hi in (0, 12, 43, 59, 90, 120, 149):
+            assert math_host.math_check_hue_thresholds(lo, hi) == 0, (lo, hi)

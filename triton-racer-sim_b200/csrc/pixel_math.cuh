@@ -32,6 +32,56 @@ TRS_HD void rgb2hsv_px(int r, int g, int b, const int32_t* sdiv, const int32_t* 
     h += (h < 0) ? 180 : 0;
 }
 
+// The two division tables of the 8-bit RGB -> HSV path, entry i (0 at i = 0).
+TRS_HD int hsv_sdiv_entry(int i)
+{
+#if defined(__CUDA_ARCH__)
+    return i ? __double2int_rn((double)(255 << 12) / (double)i) : 0;
+#else
+    return i ? (int)__builtin_rint((double)(255 << 12) / (double)i) : 0;
+#endif
+}
+TRS_HD int hsv_hdiv_entry(int i)
+{
+#if defined(__CUDA_ARCH__)
+    return i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
+#else
+    return i ? (int)__builtin_rint((double)(180 << 12) / (6.0 * (double)i)) : 0;
+#endif
+}
+
+// Saturation bounds without computing the saturation (preproc_fast.cuh, SatThresholds): s = (d sdiv[v] + 2048) >> 12 is monotone in the delta d, so
+// "s <= K" is "d <= T_K[v]".  Returns T_K[v] as the 16-bit pattern the packed compares use: 0x8001 compares as -1 (no delta qualifies).
+// A lower bound "s >= L" is "d > T_{L-1}[v]": pass K = L - 1.
+TRS_HD uint32_t sat_threshold_entry(long long K, int v, int sd)
+{
+    if (K < 0) return 0x8001u;                                    // no d qualifies (compares as -1)
+    if (v == 0) return 0u;                                        // v = 0: d = 0, s = 0
+    const long long q = (4096 * K + 2047) / sd;
+    return (uint32_t)(q < v ? q : v);
+}
+
+// Hue bounds without computing the hue (preproc_fast.cuh, HueThresholds): h = (h0 hdiv[d] + 2048) >> 12 is monotone in the numerator h0, and a
+// wrapped hue (h0 < 0: h + 180 >= 150) cannot pass an upper bound <= 149, so "lo <= h <= hi" is "a_lo <= h0 <= a_hi" for such a bound: the smallest
+// numerator with h0 hd + 2048 >= 4096 lo and the largest with h0 hd + 2048 <= 4096 hi + 4095.  Returned biased by 2048 like the packed numerators, as
+// (a_lo + 2048) | (a_hi + 2048) << 16.  Needs lo >= 0 as well (a negative lower bound would admit the unwrapped values lo .. -1, whose hue is 177 .. 179):
+// the variant is only used when the lower bound can fail, i.e. is positive.
+TRS_HD uint32_t hue_threshold_entry(long long lo, long long hi, int hd)
+{
+    long long a_lo, a_hi;
+    if (hd == 0) {                                                // grey pixel: h = 0
+        const bool pass = lo <= 0 && 0 <= hi;
+        a_lo = pass ? -2048 : 1; a_hi = pass ? 4000 : 0;
+    } else {
+        const long long nl = 4096 * lo - 2048, nh = 4096 * hi + 2047;
+        a_lo = nl >= 0 ? (nl + hd - 1) / hd : -((-nl) / hd);      // ceiling
+        a_hi = nh >= 0 ? nh / hd : -((-nh + hd - 1) / hd);        // floor
+    }
+    a_lo = a_lo < -2048 ? -2048 : (a_lo > 20000 ? 20000 : a_lo);
+    a_hi = a_hi < -2048 ? -2048 : (a_hi > 20000 ? 20000 : a_hi);
+    return (uint32_t)(a_lo + 2048) | ((uint32_t)(a_hi + 2048) << 16);
+}
+
 // ---- inRange with pre-rounded integer bounds (img_preprocessing.py:71, cv2.inRange) --------------------
 // OpenCV rounds each scalar bound to int32 (half-to-even; out of range -> INT_MIN) before comparing.
 struct HsvRange {

@@ -1048,7 +1048,7 @@ template <int NR, int F0, int F1>
 __device__ __forceinline__ void init_tables(const PreKParams& p, const SmemMap& S, int t0, int tstride)
 {
     for (int i = t0; i < 256; i += tstride) {
-        const int sd = i ? __double2int_rn((double)(255 << 12) / (double)i) : 0;
+        const int sd = hsv_sdiv_entry(i);
         if (SatThresholds<NR, F0, F1>::use) {
             // the live saturation bounds in table order (see SatThresholds); K = the largest admissible saturation of "s <= K"
             uint32_t entry = 0;
@@ -1060,11 +1060,7 @@ __device__ __forceinline__ void init_tables(const PreKParams& p, const SmemMap& 
                 for (int side = 0; side < 2; ++side) {
                     if (!(fl & (4 << side))) continue;
                     const long long K = side == 0 ? (long long)p.ranges[r].lo[1] - 1 : (long long)p.ranges[r].hi[1];
-                    uint32_t T;
-                    if (K < 0) T = 0x8001u;                                   // no d qualifies (compares as -1)
-                    else if (i == 0) T = 0u;                                  // v = 0: d = 0, s = 0
-                    else { const long long q = (4096 * K + 2047) / sd; T = (uint32_t)(q < i ? q : i); }
-                    entry |= T << (16 * (slot & 1));
+                    entry |= sat_threshold_entry(K, i, sd) << (16 * (slot & 1));
                     ++slot;
                 }
             }
@@ -1072,22 +1068,9 @@ __device__ __forceinline__ void init_tables(const PreKParams& p, const SmemMap& 
         } else {
             sts32(S.sdiv + 4 * i, (uint32_t)sd);
         }
-        const int hd = i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
+        const int hd = hsv_hdiv_entry(i);
         if (HueThresholds<NR, F0, F1>::use) {
-            // numerators h0 of a delta i that land in [lo, hi]: smallest with h0 hd + 2048 >= 4096 lo, largest with h0 hd + 2048 <= 4096 hi + 4095
-            const long long lo = p.ranges[HueThresholds<NR, F0, F1>::range].lo[0], hi = p.ranges[HueThresholds<NR, F0, F1>::range].hi[0];
-            long long a_lo, a_hi;
-            if (hd == 0) {                                                     // grey pixel: h = 0
-                const bool pass = lo <= 0 && 0 <= hi;
-                a_lo = pass ? -2048 : 1; a_hi = pass ? 4000 : 0;
-            } else {
-                const long long nl = 4096 * lo - 2048, nh = 4096 * hi + 2047;
-                a_lo = nl >= 0 ? (nl + hd - 1) / hd : -((-nl) / hd);           // ceiling
-                a_hi = nh >= 0 ? nh / hd : -((-nh + hd - 1) / hd);             // floor
-            }
-            a_lo = a_lo < -2048 ? -2048 : (a_lo > 20000 ? 20000 : a_lo);
-            a_hi = a_hi < -2048 ? -2048 : (a_hi > 20000 ? 20000 : a_hi);
-            sts32(S.hue + 4 * i, (uint32_t)(a_lo + 2048) | ((uint32_t)(a_hi + 2048) << 16));
+            sts32(S.hue + 4 * i, hue_threshold_entry(p.ranges[HueThresholds<NR, F0, F1>::range].lo[0], p.ranges[HueThresholds<NR, F0, F1>::range].hi[0], hd));
         } else {
             sts32(S.hue + 4 * i, (uint32_t)hd);
         }
